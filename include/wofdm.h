@@ -1,0 +1,158 @@
+/* wofdm.h -- C-ABI of libwofdm.so, the B200-native replacement for the Monte-Carlo BER/SER
+ * chain and the interference-power evaluation of felipescoelho/w-ofdm-optimization.
+ *
+ * The reference has no FFI: its boundary is function level.  Each entry point below names the
+ * reference function it replaces (paths relative to the reference root).  Bindings: ctypes
+ * (w-ofdm-optimization_b200/capi.py) for python/ofdm_utils, MEX gateway (mex/wofdm_mex.cpp) for
+ * matlab/main_BER_calculation.m and matlab/main_interference_calculation.m; see INTEGRATION.md.
+ *
+ * Conventions: plain C, host pointers unless a parameter is named d_*; the caller owns every
+ * buffer; complex = interleaved (re,im) doubles; matrices are column-major where MATLAB passes
+ * matrices; every function returns 0 or a negative WOFDM_E* code and never throws; a handle is
+ * not thread-safe, different handles are.  There is no CPU fallback: without a CUDA device
+ * wofdm_create fails with WOFDM_ENODEV.
+ */
+#ifndef WOFDM_H_
+#define WOFDM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WOFDM_VERSION 100
+
+#if defined(__GNUC__)
+#define WOFDM_API __attribute__((visibility("default")))
+#else
+#define WOFDM_API
+#endif
+
+enum {
+    WOFDM_OK = 0,
+    WOFDM_EINVAL = -1,       /* bad argument (see wofdm_last_error) */
+    WOFDM_ECUDA = -2,        /* CUDA runtime error */
+    WOFDM_ENOMEM = -3,       /* host or device allocation failed */
+    WOFDM_ENODEV = -4,       /* no usable CUDA device */
+    WOFDM_EUNSUPPORTED = -5  /* valid request outside the compiled kernel set */
+};
+
+typedef struct wofdm_ctx* wofdm_handle;
+typedef struct wofdm_ber_plan_s* wofdm_ber_plan;
+
+/* One w-OFDM system.  n_tx = N+cp+cs, stride = n_rx = N+tail_rx+rm = n_tx-tail_tx. */
+typedef struct {
+    int32_t N;             /* DFT length, power of two in [16, 1024] */
+    int32_t cp;            /* cyclic prefix */
+    int32_t cs;            /* cyclic suffix */
+    int32_t tail_tx;       /* Tx window tail */
+    int32_t tail_rx;       /* Rx window tail (even) */
+    int32_t rm;            /* samples dropped in front of each Rx block */
+    int32_t shift;         /* circular shift before the DFT */
+    int32_t bits;          /* bits per sub-carrier: 2, 4, 6 or 8 (square QAM) */
+    int32_t S;             /* OFDM symbols per frame; symbol 0 is the pilot */
+    int32_t noise_norm;    /* 0 = python: SNR fixed on the truncated signal (wofdm_simulation.py:208-215)
+                              1 = matlab: on the full convolution (main_BER_calculation.m:260-261) */
+    int32_t constellation; /* 0 = python: natural-order un-normalised list (wofdm_simulation.py:179-182)
+                              1 = matlab: qammod Gray, unit average power (main_BER_calculation.m:248) */
+    int32_t precision;     /* 0 = fp32, 1 = fp64 */
+} wofdm_sys_t;
+
+/* ---- library / device ------------------------------------------------------------------- */
+WOFDM_API int wofdm_version(void);
+WOFDM_API int wofdm_device_count(int* n);
+/* n_gpus = 0: every visible device; n > 0: devices 0..n-1. */
+WOFDM_API int wofdm_create(wofdm_handle* h, int n_gpus);
+/* Explicit device list (one process per GPU under torchrun: {LOCAL_RANK}). */
+WOFDM_API int wofdm_create_on(wofdm_handle* h, const int* device_ids, int n);
+WOFDM_API int wofdm_destroy(wofdm_handle h);
+WOFDM_API const char* wofdm_last_error(wofdm_handle h);
+/* Kernels of this library launched through the handle so far. */
+WOFDM_API int64_t wofdm_launch_count(wofdm_handle h);
+
+/* Diagnostic: FMA-only micro-benchmark on device slot 0 (mode 0 scalar FFMA, 1 packed FFMA2).
+ * tflops = measured FP32 rate, the denominator of the BER kernel's roofline; sm_mhz_equiv (optional)
+ * = the SM clock at which 128 FMA lanes per SM would deliver that rate. */
+WOFDM_API int wofdm_diag_fp32_peak(wofdm_handle h, int mode, double* tflops, double* sm_mhz_equiv);
+
+/* ---- parameter table and windows (host, tiny) -------------------------------------------- */
+/* Replaces wOFDMSystem.__init__'s table (python/ofdm_utils/wofdm_simulation.py:391-418) and
+ * calculate_parameters (matlab/main_BER_calculation.m:457-493).  name: CP, wtx, CPwtx, wrx, CPwrx,
+ * WOLA, CPW.  Fills N, cp, cs, tail_tx, tail_rx, rm, shift; leaves the other fields alone. */
+WOFDM_API int wofdm_params_from_name(const char* name, int N, int cp, int tail_tx, int tail_rx, wofdm_sys_t* out);
+/* gen_rc_window_tx / gen_rc_window_rx (python/ofdm_utils/transmitter.py:61-87, receiver.py:36-56;
+ * matlab/functions/transmitter_rc_window.m, receiver_rc_window.m).  out: n_tx resp. N+tail_rx. */
+WOFDM_API int wofdm_rc_window_tx(const wofdm_sys_t* sys, double* out);
+WOFDM_API int wofdm_rc_window_rx(const wofdm_sys_t* sys, double* out);
+/* reduce_variable_tx/rx applied to a stored tail vector (python/optimization_tools/utils.py:13-73):
+ * x has tail_tx+1 resp. tail_rx/2+1 entries. */
+WOFDM_API int wofdm_expand_window_tx(const wofdm_sys_t* sys, const double* x, double* out);
+WOFDM_API int wofdm_expand_window_rx(const wofdm_sys_t* sys, const double* x, double* out);
+
+/* ---- Monte-Carlo BER/SER chain ----------------------------------------------------------- */
+/* Replaces wOFDMSystem.__run_sim_mc / __run_sim_cp_mc (python/ofdm_utils/wofdm_simulation.py:85-366)
+ * and run_simulation (matlab/main_BER_calculation.m:230-274) for ONE window pair.  On-device Philox
+ * draws.  Frames are indexed f = (snr_idx*C + chan_idx)*ensemble + e; symbols depend on (seed, f),
+ * noise on (seed, f, variant): calling twice with the same seed and variant 0/1 evaluates two window
+ * pairs on the same symbols with independent noise, as the reference does for optimised vs RC.
+ * Counters are summed over channels x ensemble, one entry per SNR point; *_tot are the totals
+ * (frames * N*bits*(S-1) resp. frames * N*(S-1)).  Uses every device of the handle.
+ *   win_tx: n_tx doubles, win_rx: N+tail_rx doubles, chan: complex L x C column-major. */
+WOFDM_API int wofdm_ber_run(wofdm_handle h, const wofdm_sys_t* sys, const double* win_tx, const double* win_rx,
+                  const double* chan, int L, int C, const double* snr_db, int n_snr, int64_t ensemble,
+                  uint64_t seed, uint32_t variant,
+                  int64_t* bit_err, int64_t* bit_tot, int64_t* sym_err, int64_t* sym_tot);
+/* Same, but only frames f = shard_index (mod shard_count): one process per GPU sums the results
+ * with a single all-reduce of the int64 counters. */
+WOFDM_API int wofdm_ber_run_shard(wofdm_handle h, const wofdm_sys_t* sys, const double* win_tx, const double* win_rx,
+                        const double* chan, int L, int C, const double* snr_db, int n_snr, int64_t ensemble,
+                        uint64_t seed, uint32_t variant, int shard_index, int shard_count,
+                        int64_t* bit_err, int64_t* bit_tot, int64_t* sym_err, int64_t* sym_tot);
+
+/* Device-resident form: inputs are uploaded once, launches are asynchronous. */
+WOFDM_API int wofdm_ber_plan_create(wofdm_handle h, const wofdm_sys_t* sys, const double* win_tx, const double* win_rx,
+                          const double* chan, int L, int C, const double* snr_db, int n_snr,
+                          wofdm_ber_plan* plan);
+/* Zeroes the plan's device counters and launches the shard on device slot `slot` of the handle,
+ * on `stream` (a cudaStream_t; NULL = the plan's own stream).  Returns without synchronising.
+ * d_counters (optional out) = device pointer to int64[n_snr][2] = {bit_err, sym_err}. */
+WOFDM_API int wofdm_ber_plan_launch(wofdm_ber_plan plan, int slot, int64_t ensemble, uint64_t seed, uint32_t variant,
+                          int shard_index, int shard_count, void* stream, void** d_counters);
+/* Waits for the launches and adds the counters of every slot launched since the last read. */
+WOFDM_API int wofdm_ber_plan_read(wofdm_ber_plan plan, int64_t* bit_err, int64_t* sym_err);
+/* Name of the kernel variant the plan dispatches to (for logs / profiles). */
+WOFDM_API const char* wofdm_ber_plan_kernel(wofdm_ber_plan plan);
+WOFDM_API int wofdm_ber_plan_destroy(wofdm_ber_plan plan);
+
+/* Verify mode: the caller injects every draw for F frames and gets the intermediates back.
+ * Same chain and same kernels as wofdm_ber_run.
+ *   chan: complex L x F (one channel per frame), snr_db: F, sym_idx: N x S x F constellation indices
+ *   in the convention's own order, noise: complex len x F unit-variance draws with
+ *   len = S*stride (noise_norm 0) or tail_tx + S*stride + L - 1 (noise_norm 1),
+ *   eq_out: complex N x (S-1) x F, dec_idx: N x (S-1) x F, bit_err/sym_err: F.
+ *   variant_kernel: 0 = the kernel wofdm_ber_run would pick, 1 = force the generic staged kernel. */
+WOFDM_API int wofdm_ber_verify(wofdm_handle h, const wofdm_sys_t* sys, const double* win_tx, const double* win_rx,
+                     const double* chan, int L, int F, const double* snr_db,
+                     const int32_t* sym_idx, const double* noise, int variant_kernel,
+                     double* eq_out, int32_t* dec_idx, int64_t* bit_err, int64_t* sym_err);
+/* Exports the on-device draws of production frames frame_ids[0..F) so a production run can be
+ * replayed through wofdm_ber_verify or a CPU oracle.  sym_idx: N x S x F, noise: complex len x F. */
+WOFDM_API int wofdm_ber_draws(wofdm_handle h, const wofdm_sys_t* sys, int L, uint64_t seed, uint32_t variant,
+                    const int64_t* frame_ids, int F, int32_t* sym_idx, double* noise);
+
+/* ---- interference power ------------------------------------------------------------------ */
+/* Replaces interf_power (python/ofdm_utils/interf_calc.py:20-113) per channel realisation:
+ * P[k + N*c] = sum_{j!=k} |A_0[k,j]|^2 + sum_{m>=1} sum_j |A_m[k,j]|^2,  A_m = Rx_mat . H_m(h_c) . Tx_mat.
+ * mode 0 = fp64 (DMMA), 1 = TF32-split tensor cores.  chan: complex L x C, P: N x C column-major. */
+WOFDM_API int wofdm_interf_power(wofdm_handle h, const wofdm_sys_t* sys, const double* win_tx, const double* win_rx,
+                       const double* chan, int L, int C, int mode, double* P);
+/* MATLAB semantics (calculate_interference, matlab/main_interference_calculation.m:177-225):
+ * scalar per channel, ISI slices summed before squaring.  P: C doubles. */
+WOFDM_API int wofdm_interf_power_scalar(wofdm_handle h, const wofdm_sys_t* sys, const double* win_tx,
+                              const double* win_rx, const double* chan, int L, int C, int mode, double* P);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WOFDM_H_ */

@@ -1,0 +1,161 @@
+"""GPU parity tests of K1 through the C-ABI (ctypes), against the oracle and the golden vectors.
+
+Verify mode injects the reference's own draws (np.random replayed in the reference's call order):
+  fp64: equalised symbols <= 1e-9 relative, decisions and error counts bit-exact;
+  fp32: equalised symbols <= 1e-4 relative (frame norm), decisions bit-exact wherever the oracle's
+        equalised symbol is farther than 1e-3 (lattice units) from a decision boundary.
+"""
+import numpy as np
+import pytest
+
+import wofdm_b200 as W
+from oracle import wofdm_oracle as O
+from helpers import golden_params, golden_windows, load_ser_golden, replay_frames
+
+pytestmark = pytest.mark.gpu
+
+TOL = {0: 1e-4, 1: 1e-9}
+
+
+@pytest.fixture(scope="module")
+def handle():
+    with W.Handle([0]) as h:
+        yield h
+
+
+def to_sys(p, precision):
+    return W.SysT(N=p.N, cp=p.cp, cs=p.cs, tail_tx=p.tail_tx, tail_rx=p.tail_rx, rm=p.rm, shift=p.shift,
+                  bits=p.bits, S=p.S, noise_norm=p.noise_norm, constellation=p.constellation, precision=precision)
+
+
+def boundary_distance(eq_lattice, m):
+    """distance of each equalised symbol (lattice units) to the nearest decision boundary"""
+    def ax(v):
+        b = np.arange(-(m - 2), m - 1, 2.0)          # boundaries at even integers
+        return np.min(np.abs(v[..., None] - b), axis=-1) if b.size else np.full(v.shape, np.inf)
+    return np.minimum(ax(eq_lattice.real), ax(eq_lattice.imag))
+
+
+def check_frames(handle, p, vt, vr, frames_in, precision, force_staged=False):
+    """frames_in: list of (chan, snr, sym_idx (N,S), noise)"""
+    s = to_sys(p, precision)
+    F = len(frames_in)
+    chan = np.stack([f[0] for f in frames_in], axis=1)
+    snr = np.array([f[1] for f in frames_in])
+    sym = np.stack([f[2].T for f in frames_in])                      # (F, S, N)
+    nz = np.stack([f[3] for f in frames_in])
+    eq, dec, be, se = handle.ber_verify(s, vt, vr, chan, snr, sym, nz, force_staged=force_staged)
+    m = O.qam_levels(p.bits)
+    sc = O.qam_scale(p.bits, p.constellation)
+    for i, (h, snr_i, idx, noise) in enumerate(frames_in):
+        ref = O.frame_chain_structured(p, vt, vr, h, snr_i, idx, noise)
+        got = eq[i].T                                                # (N, S-1)
+        rel = np.linalg.norm(got - ref.eq) / np.linalg.norm(ref.eq)
+        assert rel < TOL[precision], (i, rel)
+        d = dec[i].T
+        if precision == 1:
+            assert np.array_equal(d, ref.dec_idx), i
+            assert se[i] == ref.sym_err and be[i] == ref.bit_err, i
+        else:
+            safe = boundary_distance(ref.eq / sc, m) > 1e-3 * np.maximum(1.0, np.abs(ref.eq / sc))
+            assert np.array_equal(d[safe], ref.dec_idx[safe]), i
+            assert (~safe).sum() <= max(3, 0.03 * safe.size)
+            assert abs(int(se[i]) - ref.sym_err) <= int((~safe).sum())
+        # counters are consistent with the returned decisions
+        assert se[i] == np.count_nonzero(d != idx[:, 1:])
+        assert be[i] == O.bit_errors(idx[:, 1:], d)
+
+
+@pytest.mark.parametrize("precision", [1, 0])
+@pytest.mark.parametrize("name", O.SYSTEMS)
+def test_verify_against_reference_draws(handle, name, precision):
+    """Golden case B: single frames drawn exactly as the reference draws them; the reference's own
+    SER pins the symbol-error count of every frame."""
+    g = load_ser_golden(name)
+    p = golden_params(g, g["B_S"])
+    wins = golden_windows(g, p)
+    for i, snr in enumerate(g["B_snr"]):
+        fr = replay_frames(p, wins, g["B_channels"], 1, [snr], int(g["B_seed"][i]))[0]
+        for w, (vt, vr) in enumerate(wins):
+            check_frames(handle, p, vt, vr, [(fr["chan"], fr["snr"], fr["sym_idx"], fr["noise"][w])], precision)
+            if precision == 1:
+                s = to_sys(p, 1)
+                _, _, _, se = handle.ber_verify(s, vt, vr, fr["chan"][:, None], [fr["snr"]],
+                                                fr["sym_idx"].T[None], fr["noise"][w][None])
+                assert int(se[0]) == int(round(g["B_ser"][i][w] * p.N * (p.S - 1)))
+
+
+@pytest.mark.parametrize("precision", [1, 0])
+@pytest.mark.parametrize("N,S,bits,conv,nn", [(16, 3, 2, 0, 0), (32, 5, 4, 1, 1), (64, 16, 6, 1, 0), (128, 7, 8, 0, 1),
+                                              (256, 16, 4, 1, 1), (512, 4, 6, 0, 0), (1024, 16, 6, 1, 0)])
+def test_verify_shapes_and_conventions(handle, N, S, bits, conv, nn, precision):
+    rng = np.random.default_rng(N + S)
+    cp, ttx, trx = N // 16, N // 32, 2 * (N // 64) if N >= 64 else 0
+    for name in ("WOLA", "CPW", "CP"):
+        a, b = (0, 0) if name == "CP" else (ttx, trx)
+        p = O.system_params(name, N, max(cp, a + b), a, b, S=S, bits=bits, noise_norm=nn, constellation=conv)
+        vt, vr, _, _ = O.perturbed_windows(p, seed=N)
+        L = 21 if N >= 64 else 5
+        frames = []
+        for k in range(3):
+            h = O.synth_channels(1, L, seed=k)[:, 0]
+            n = O.noise_len(p, L)
+            frames.append((h, 5.0 + 12 * k, rng.integers(0, 1 << bits, size=(N, S)),
+                           rng.standard_normal(n) + 1j * rng.standard_normal(n)))
+        check_frames(handle, p, vt, vr, frames, precision)
+        check_frames(handle, p, vt, vr, frames, precision, force_staged=True)
+
+
+def test_production_replay_matches_oracle(handle):
+    """Production mode: export the on-device Philox draws of some frames, replay them through the
+    oracle and require the same error counts (fp64 exact; fp32 up to boundary flips)."""
+    g = load_ser_golden("WOLA")
+    chans = np.concatenate([g["A_channels"], g["B_channels"]], axis=1)      # (21, 3)
+    snr = np.array([6.0, 18.0])
+    ens = 2
+    for precision in (1, 0):
+        for conv, nn in ((0, 0), (1, 1)):
+            p = golden_params(g, 16, constellation=conv, noise_norm=nn)
+            vt, vr = golden_windows(g, p)[0]
+            s = to_sys(p, precision)
+            res = handle.ber_run(s, vt, vr, chans, snr, ens, seed=1234, variant=1)
+            F = len(snr) * chans.shape[1] * ens
+            ids = np.arange(F)
+            sym, nz = handle.ber_draws(s, chans.shape[0], 1234, 1, ids)
+            assert sym.min() >= 0 and sym.max() < 16 and len(np.unique(sym)) == 16
+            assert abs(np.mean(np.abs(nz) ** 2) - 2.0) < 0.05
+            want_sym = np.zeros(len(snr), dtype=np.int64)
+            want_bit = np.zeros(len(snr), dtype=np.int64)
+            for f in ids:
+                e = f % ens
+                c = (f // ens) % chans.shape[1]
+                si = f // (ens * chans.shape[1])
+                r = O.frame_chain_structured(p, vt, vr, chans[:, c], snr[si], sym[f].T, nz[f])
+                want_sym[si] += r.sym_err
+                want_bit[si] += r.bit_err
+            assert np.array_equal(res["sym_tot"], np.full(len(snr), chans.shape[1] * ens * p.N * (p.S - 1)))
+            assert np.array_equal(res["bit_tot"], res["sym_tot"] * p.bits)
+            if precision == 1:
+                assert np.array_equal(res["sym_err"], want_sym) and np.array_equal(res["bit_err"], want_bit)
+            else:
+                assert np.all(np.abs(res["sym_err"] - want_sym) <= 3 + 0.002 * want_sym)
+                assert np.all(np.abs(res["bit_err"] - want_bit) <= 4 + 0.002 * want_bit)
+
+
+def test_sharding_is_exact(handle):
+    """Counters of disjoint shards add up to the unsharded run (same seeds, global frame ids)."""
+    g = load_ser_golden("wtx")
+    p = golden_params(g, 16)
+    vt, vr = golden_windows(g, p)[0]
+    s = to_sys(p, 0)
+    chans = O.synth_channels(5, 21, seed=3)
+    snr = np.array([0.0, 10.0, 20.0])
+    full = handle.ber_run(s, vt, vr, chans, snr, 7, seed=99)
+    acc = {k: np.zeros(3, dtype=np.int64) for k in full}
+    for i in range(3):
+        part = handle.ber_run(s, vt, vr, chans, snr, 7, seed=99, shard=(i, 3))
+        for k in acc:
+            acc[k] += part[k]
+    for k in full:
+        assert np.array_equal(full[k], acc[k]), k
+    assert np.all(np.diff(full["sym_err"]) < 0)      # SER falls with SNR

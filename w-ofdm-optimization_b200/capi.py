@@ -1,0 +1,322 @@
+"""ctypes binding of libwofdm.so (include/wofdm.h).
+
+The library is the product; this file only marshals numpy arrays into the C-ABI.  There is no
+CPU fallback: importing works anywhere (so host logic and symbol exports can be tested), but
+creating a handle without a CUDA device raises ``WofdmError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libwofdm.so")
+
+OK, EINVAL, ECUDA, ENOMEM, ENODEV, EUNSUPPORTED = 0, -1, -2, -3, -4, -5
+_ERRNAME = {EINVAL: "WOFDM_EINVAL", ECUDA: "WOFDM_ECUDA", ENOMEM: "WOFDM_ENOMEM", ENODEV: "WOFDM_ENODEV",
+            EUNSUPPORTED: "WOFDM_EUNSUPPORTED"}
+
+
+class WofdmError(RuntimeError):
+    def __init__(self, code, msg=""):
+        self.code = code
+        super().__init__(f"{_ERRNAME.get(code, code)}: {msg}")
+
+
+class SysT(C.Structure):
+    """wofdm_sys_t"""
+    _fields_ = [(n, C.c_int32) for n in ("N", "cp", "cs", "tail_tx", "tail_rx", "rm", "shift", "bits", "S",
+                                         "noise_norm", "constellation", "precision")]
+
+    @property
+    def n_tx(self):
+        return self.N + self.cp + self.cs
+
+    @property
+    def stride(self):
+        return self.n_tx - self.tail_tx
+
+    def noise_len(self, L):
+        return self.S * self.stride if self.noise_norm == 0 else self.tail_tx + self.S * self.stride + L - 1
+
+    def copy(self, **kw):
+        o = SysT()
+        C.memmove(C.byref(o), C.byref(self), C.sizeof(SysT))
+        for k, v in kw.items():
+            setattr(o, k, v)
+        return o
+
+
+_P = C.POINTER
+_dp, _i32p, _i64p = _P(C.c_double), _P(C.c_int32), _P(C.c_int64)
+
+# name -> (restype, argtypes); every symbol include/wofdm.h declares
+SIGNATURES = {
+    "wofdm_version": (C.c_int, []),
+    "wofdm_device_count": (C.c_int, [_P(C.c_int)]),
+    "wofdm_create": (C.c_int, [_P(C.c_void_p), C.c_int]),
+    "wofdm_create_on": (C.c_int, [_P(C.c_void_p), _P(C.c_int), C.c_int]),
+    "wofdm_destroy": (C.c_int, [C.c_void_p]),
+    "wofdm_last_error": (C.c_char_p, [C.c_void_p]),
+    "wofdm_launch_count": (C.c_int64, [C.c_void_p]),
+    "wofdm_diag_fp32_peak": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp]),
+    "wofdm_params_from_name": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, _P(SysT)]),
+    "wofdm_rc_window_tx": (C.c_int, [_P(SysT), _dp]),
+    "wofdm_rc_window_rx": (C.c_int, [_P(SysT), _dp]),
+    "wofdm_expand_window_tx": (C.c_int, [_P(SysT), _dp, _dp]),
+    "wofdm_expand_window_rx": (C.c_int, [_P(SysT), _dp, _dp]),
+    "wofdm_ber_run": (C.c_int, [C.c_void_p, _P(SysT), _dp, _dp, _dp, C.c_int, C.c_int, _dp, C.c_int, C.c_int64,
+                                C.c_uint64, C.c_uint32, _i64p, _i64p, _i64p, _i64p]),
+    "wofdm_ber_run_shard": (C.c_int, [C.c_void_p, _P(SysT), _dp, _dp, _dp, C.c_int, C.c_int, _dp, C.c_int, C.c_int64,
+                                      C.c_uint64, C.c_uint32, C.c_int, C.c_int, _i64p, _i64p, _i64p, _i64p]),
+    "wofdm_ber_plan_create": (C.c_int, [C.c_void_p, _P(SysT), _dp, _dp, _dp, C.c_int, C.c_int, _dp, C.c_int,
+                                        _P(C.c_void_p)]),
+    "wofdm_ber_plan_launch": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_uint32, C.c_int, C.c_int,
+                                        C.c_void_p, _P(C.c_void_p)]),
+    "wofdm_ber_plan_read": (C.c_int, [C.c_void_p, _i64p, _i64p]),
+    "wofdm_ber_plan_kernel": (C.c_char_p, [C.c_void_p]),
+    "wofdm_ber_plan_destroy": (C.c_int, [C.c_void_p]),
+    "wofdm_ber_verify": (C.c_int, [C.c_void_p, _P(SysT), _dp, _dp, _dp, C.c_int, C.c_int, _dp, _i32p, _dp, C.c_int,
+                                   _dp, _i32p, _i64p, _i64p]),
+    "wofdm_ber_draws": (C.c_int, [C.c_void_p, _P(SysT), C.c_int, C.c_uint64, C.c_uint32, _i64p, C.c_int, _i32p, _dp]),
+    "wofdm_interf_power": (C.c_int, [C.c_void_p, _P(SysT), _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, _dp]),
+    "wofdm_interf_power_scalar": (C.c_int, [C.c_void_p, _P(SysT), _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, _dp]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen libwofdm.so (built by ``__graft_entry__.build()`` / ``make -C csrc``)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise WofdmError(ENODEV, f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
+                                     f"g.build()'` (nvcc, sm_100a). There is no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _cplx(a):
+    """complex array -> contiguous complex128 (interleaved re, im doubles)"""
+    return np.ascontiguousarray(a, dtype=np.complex128)
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(t)
+
+
+def params_from_name(name, N, cp, tail_tx, tail_rx, bits=4, S=16, noise_norm=0, constellation=0, precision=0):
+    s = SysT(bits=bits, S=S, noise_norm=noise_norm, constellation=constellation, precision=precision)
+    rc = load().wofdm_params_from_name(name.encode(), N, cp, tail_tx, tail_rx, C.byref(s))
+    if rc:
+        raise WofdmError(rc, f"unknown system {name!r}")
+    return s
+
+
+def rc_window_tx(s):
+    out = np.empty(s.n_tx)
+    rc = load().wofdm_rc_window_tx(C.byref(s), _ptr(out, _dp))
+    if rc:
+        raise WofdmError(rc, "rc_window_tx")
+    return out
+
+
+def rc_window_rx(s):
+    out = np.empty(s.N + s.tail_rx)
+    rc = load().wofdm_rc_window_rx(C.byref(s), _ptr(out, _dp))
+    if rc:
+        raise WofdmError(rc, "rc_window_rx")
+    return out
+
+
+def expand_window_tx(s, x):
+    x = _f64(np.ravel(x))
+    if x.size != s.tail_tx + 1:
+        raise WofdmError(EINVAL, "Tx tail vector must hold tail_tx+1 values")
+    out = np.empty(s.n_tx)
+    rc = load().wofdm_expand_window_tx(C.byref(s), _ptr(x, _dp), _ptr(out, _dp))
+    if rc:
+        raise WofdmError(rc, "expand_window_tx")
+    return out
+
+
+def expand_window_rx(s, x):
+    x = _f64(np.ravel(x))
+    if x.size != s.tail_rx // 2 + 1:
+        raise WofdmError(EINVAL, "Rx tail vector must hold tail_rx/2+1 values")
+    out = np.empty(s.N + s.tail_rx)
+    rc = load().wofdm_expand_window_rx(C.byref(s), _ptr(x, _dp), _ptr(out, _dp))
+    if rc:
+        raise WofdmError(rc, "expand_window_rx")
+    return out
+
+
+class Handle:
+    """wofdm_handle.  devices: None = all visible, int n = first n, list = explicit ids."""
+
+    def __init__(self, devices=None):
+        lib = load()
+        self._h = C.c_void_p()
+        if devices is None or isinstance(devices, int):
+            rc = lib.wofdm_create(C.byref(self._h), 0 if devices is None else int(devices))
+        else:
+            ids = (C.c_int * len(devices))(*devices)
+            rc = lib.wofdm_create_on(C.byref(self._h), ids, len(devices))
+        if rc:
+            self._h = None
+            raise WofdmError(rc, "wofdm_create failed (no CUDA device? this library has no CPU path)")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load().wofdm_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc:
+            raise WofdmError(rc, (load().wofdm_last_error(self._h) or b"").decode())
+
+    @property
+    def launches(self):
+        return int(load().wofdm_launch_count(self._h))
+
+    def fp32_peak(self, mode=0):
+        """(TFLOP/s, equivalent SM MHz) of the FMA-only micro-benchmark (0 scalar FFMA, 1 FFMA2)."""
+        t, m = C.c_double(), C.c_double()
+        self._check(load().wofdm_diag_fp32_peak(self._h, int(mode), C.byref(t), C.byref(m)))
+        return t.value, m.value
+
+    # ---- BER ----
+    def _win_chan(self, s, win_tx, win_rx, chan):
+        wt, wr = _f64(np.ravel(win_tx)), _f64(np.ravel(win_rx))
+        if wt.size != s.n_tx or wr.size != s.N + s.tail_rx:
+            raise WofdmError(EINVAL, f"window sizes must be n_tx={s.n_tx} and N+tail_rx={s.N + s.tail_rx}")
+        ch = np.asarray(chan)
+        if ch.ndim == 1:
+            ch = ch[:, None]
+        L, Cn = ch.shape
+        chf = _cplx(ch.T)          # (C, L) row-major == L x C column-major
+        return wt, wr, chf, L, Cn
+
+    def ber_run(self, s, win_tx, win_rx, chan, snr_db, ensemble, seed=0, variant=0, shard=(0, 1)):
+        wt, wr, chf, L, Cn = self._win_chan(s, win_tx, win_rx, chan)
+        snr = _f64(np.ravel(snr_db))
+        n = snr.size
+        out = [np.zeros(n, dtype=np.int64) for _ in range(4)]
+        rc = load().wofdm_ber_run_shard(self._h, C.byref(s), _ptr(wt, _dp), _ptr(wr, _dp), _ptr(chf, _dp), L, Cn,
+                                        _ptr(snr, _dp), n, int(ensemble), int(seed), int(variant),
+                                        int(shard[0]), int(shard[1]), *[_ptr(o, _i64p) for o in out])
+        self._check(rc)
+        return dict(bit_err=out[0], bit_tot=out[1], sym_err=out[2], sym_tot=out[3])
+
+    def ber_plan(self, s, win_tx, win_rx, chan, snr_db):
+        return BerPlan(self, s, win_tx, win_rx, chan, snr_db)
+
+    def ber_verify(self, s, win_tx, win_rx, chan, snr_db, sym_idx, noise, force_staged=False):
+        """chan (L, F); snr_db (F,); sym_idx (F, S, N) ints; noise (F, noise_len) complex.
+        Returns eq (F, S-1, N) complex, dec (F, S-1, N) int32, bit_err (F,), sym_err (F,)."""
+        wt, wr, chf, L, F = self._win_chan(s, win_tx, win_rx, chan)
+        snr = _f64(np.ravel(snr_db))
+        si = np.ascontiguousarray(sym_idx, dtype=np.int32)
+        nz = _cplx(noise)
+        if snr.size != F or si.shape != (F, s.S, s.N) or nz.shape != (F, s.noise_len(L)):
+            raise WofdmError(EINVAL, "verify: inconsistent shapes")
+        eq = np.empty((F, s.S - 1, s.N), dtype=np.complex128)
+        dec = np.empty((F, s.S - 1, s.N), dtype=np.int32)
+        be, se = np.zeros(F, dtype=np.int64), np.zeros(F, dtype=np.int64)
+        rc = load().wofdm_ber_verify(self._h, C.byref(s), _ptr(wt, _dp), _ptr(wr, _dp), _ptr(chf, _dp), L, F,
+                                     _ptr(snr, _dp), _ptr(si, _i32p), _ptr(nz, _dp), 1 if force_staged else 0,
+                                     _ptr(eq, _dp), _ptr(dec, _i32p), _ptr(be, _i64p), _ptr(se, _i64p))
+        self._check(rc)
+        return eq, dec, be, se
+
+    def ber_draws(self, s, L, seed, variant, frame_ids):
+        ids = np.ascontiguousarray(frame_ids, dtype=np.int64)
+        F = ids.size
+        si = np.empty((F, s.S, s.N), dtype=np.int32)
+        nz = np.empty((F, s.noise_len(L)), dtype=np.complex128)
+        rc = load().wofdm_ber_draws(self._h, C.byref(s), L, int(seed), int(variant), _ptr(ids, _i64p), F,
+                                    _ptr(si, _i32p), _ptr(nz, _dp))
+        self._check(rc)
+        return si, nz
+
+    # ---- interference ----
+    def interf_power(self, s, win_tx, win_rx, chan, mode=0, scalar=False):
+        wt, wr, chf, L, Cn = self._win_chan(s, win_tx, win_rx, chan)
+        if scalar:
+            P = np.empty(Cn)
+            rc = load().wofdm_interf_power_scalar(self._h, C.byref(s), _ptr(wt, _dp), _ptr(wr, _dp), _ptr(chf, _dp),
+                                                  L, Cn, int(mode), _ptr(P, _dp))
+        else:
+            P = np.empty((Cn, s.N))
+            rc = load().wofdm_interf_power(self._h, C.byref(s), _ptr(wt, _dp), _ptr(wr, _dp), _ptr(chf, _dp),
+                                           L, Cn, int(mode), _ptr(P, _dp))
+        self._check(rc)
+        return P
+
+
+class BerPlan:
+    """Device-resident inputs of one (system, windows, channel set, SNR grid); asynchronous launches."""
+
+    def __init__(self, handle, s, win_tx, win_rx, chan, snr_db):
+        self.handle, self.sys = handle, s
+        wt, wr, chf, L, Cn = handle._win_chan(s, win_tx, win_rx, chan)
+        snr = _f64(np.ravel(snr_db))
+        self.n_snr, self.L, self.C = snr.size, L, Cn
+        self._p = C.c_void_p()
+        rc = load().wofdm_ber_plan_create(handle._h, C.byref(s), _ptr(wt, _dp), _ptr(wr, _dp), _ptr(chf, _dp), L, Cn,
+                                          _ptr(snr, _dp), snr.size, C.byref(self._p))
+        handle._check(rc)
+
+    @property
+    def kernel(self):
+        return load().wofdm_ber_plan_kernel(self._p).decode()
+
+    def launch(self, ensemble, seed=0, variant=0, shard=(0, 1), slot=0, stream=None):
+        """Asynchronous.  Returns the device address of the int64[n_snr][2] counters."""
+        d = C.c_void_p()
+        rc = load().wofdm_ber_plan_launch(self._p, slot, int(ensemble), int(seed), int(variant), int(shard[0]),
+                                          int(shard[1]), C.c_void_p(stream) if stream else None, C.byref(d))
+        self.handle._check(rc)
+        return d.value
+
+    def read(self):
+        be, se = np.zeros(self.n_snr, dtype=np.int64), np.zeros(self.n_snr, dtype=np.int64)
+        self.handle._check(load().wofdm_ber_plan_read(self._p, _ptr(be, _i64p), _ptr(se, _i64p)))
+        return be, se
+
+    def totals(self, ensemble, shard=(0, 1)):
+        """(bit_tot, sym_tot) per SNR point for frames f = shard[0] mod shard[1]."""
+        per = self.C * int(ensemble)
+        i, n = shard
+
+        def upto(x):
+            return (x - i + n - 1) // n if x > i else 0
+        frames = np.array([upto((k + 1) * per) - upto(k * per) for k in range(self.n_snr)], dtype=np.int64)
+        sym = frames * self.sys.N * (self.sys.S - 1)
+        return sym * self.sys.bits, sym
+
+    def close(self):
+        if getattr(self, "_p", None):
+            load().wofdm_ber_plan_destroy(self._p)
+            self._p = None
+
+    __del__ = close

@@ -1,0 +1,444 @@
+// ber_host.cu -- host side of K1: variant selection, device tables, plans, and the
+// wofdm_ber_* entry points of include/wofdm.h.
+#include <algorithm>
+#include <cstring>
+#include <new>
+
+#include "host_common.h"
+
+using namespace wofdm;
+
+struct PlanDev {
+    void *d_wtx = nullptr, *d_wrx = nullptr, *d_tw = nullptr, *d_chan = nullptr, *d_snr = nullptr;
+    unsigned long long* d_cnt = nullptr;
+    void* d_scratch = nullptr;
+    size_t scratch_bytes = 0;
+    int blocks_per_sm = 0;
+    bool pending = false;
+    cudaStream_t last_stream = nullptr;
+};
+
+struct wofdm_ber_plan_s {
+    wofdm_ctx* ctx = nullptr;
+    wofdm_sys_t sys{};
+    int L = 0, C = 0, n_snr = 0;
+    const BerVariant* var = nullptr;
+    BerSmem lay{};
+    int chunk = 0, use_global = 0;
+    std::vector<PlanDev> devs;
+};
+
+namespace {
+
+struct Choice {
+    const BerVariant* var = nullptr;
+    BerSmem lay{};
+    int chunk = 0, use_global = 0;
+};
+
+int choose_variant(wofdm_ctx* h, const wofdm_sys_t& s, int L, bool verify, bool force_staged, size_t smem_cap,
+                   Choice* out) {
+    const int stride = s.N + s.cp + s.cs - s.tail_tx;
+    const int sec = s.S * stride;
+    const bool fp64 = s.precision == 1;
+    Choice best;
+    if (!fp64 && !force_staged) {
+        for (const auto& v : h->variants) {
+            if (v.TC == 0 || v.fp64 || v.verify != verify || v.N != s.N) continue;
+            const int chunk = ((sec + v.NT - 1) / v.NT) | 1;
+            if (chunk > v.TC) continue;
+            const BerSmem lay = v.layout(s.S, stride, s.tail_tx, s.tail_rx, L, chunk, 0);
+            if (lay.bytes > smem_cap) continue;
+            if (!best.var || v.TC < best.var->TC) { best.var = &v; best.lay = lay; best.chunk = chunk; }
+        }
+    }
+    if (!best.var) {
+        for (const auto& v : h->variants) {
+            if (v.TC != 0 || v.fp64 != fp64 || v.verify != verify || v.N != s.N) continue;
+            best.var = &v;
+            best.lay = v.layout(s.S, stride, s.tail_tx, s.tail_rx, L, 0, 0);
+            best.use_global = 0;
+            if (best.lay.bytes > smem_cap) {
+                best.use_global = 1;
+                best.lay = v.layout(s.S, stride, s.tail_tx, s.tail_rx, L, 0, 1);
+                if (best.lay.bytes > smem_cap) return fail(h, WOFDM_EUNSUPPORTED, "frame does not fit the staged kernel's shared memory");
+            }
+            break;
+        }
+    }
+    if (!best.var) return fail(h, WOFDM_EUNSUPPORTED, "no compiled kernel variant for this N / precision");
+    *out = best;
+    return WOFDM_OK;
+}
+
+template <typename T> void cast_vec(const std::vector<double>& src, std::vector<unsigned char>& dst) {
+    dst.resize(src.size() * sizeof(T));
+    T* p = reinterpret_cast<T*>(dst.data());
+    for (size_t i = 0; i < src.size(); ++i) p[i] = (T)src[i];
+}
+void cast_any(bool fp64, const std::vector<double>& src, std::vector<unsigned char>& dst) {
+    if (fp64) cast_vec<double>(src, dst); else cast_vec<float>(src, dst);
+}
+
+// host tables shared by plans and the verify path
+struct HostTables {
+    std::vector<unsigned char> wtx, wrx, tw;
+};
+
+void build_tables(const wofdm_sys_t& s, const double* win_tx, const double* win_rx, HostTables& t) {
+    const bool fp64 = s.precision == 1;
+    const int n_tx = s.N + s.cp + s.cs;
+    const double k = qam_scale(s) / (double)s.N;   // IDFT 1/N (transmitter.py:58) and constellation scale
+    std::vector<double> a(n_tx), b(s.N + s.tail_rx);
+    for (int i = 0; i < n_tx; ++i) a[i] = win_tx[i] * k;
+    for (int i = 0; i < s.N + s.tail_rx; ++i) b[i] = win_rx[i];
+    cast_any(fp64, a, t.wtx);
+    cast_any(fp64, b, t.wrx);
+    cast_any(fp64, build_twiddles(s.N), t.tw);
+}
+
+// channel matrix L x C column-major complex double -> [C][L] V2<T> (same memory order, cast only)
+void cast_chan(bool fp64, const double* chan, size_t n_complex, std::vector<unsigned char>& dst) {
+    std::vector<double> v(chan, chan + 2 * n_complex);
+    cast_any(fp64, v, dst);
+}
+
+void fill_sys(BerParams& p, const wofdm_sys_t& s, int L) {
+    memset(&p, 0, sizeof(p));
+    p.N = s.N; p.cp = s.cp; p.cs = s.cs; p.tail_tx = s.tail_tx; p.tail_rx = s.tail_rx; p.rm = s.rm;
+    p.shift = s.shift; p.bits = s.bits; p.S = s.S;
+    p.n_tx = s.N + s.cp + s.cs;
+    p.stride = p.n_tx - s.tail_tx;
+    p.L = L;
+    p.noise_norm = s.noise_norm; p.constellation = s.constellation;
+    p.noise_len = noise_len(s, L);
+    p.qscale = qam_scale(s);
+}
+
+int prepare_kernel(wofdm_ctx* h, const BerVariant& v, size_t smem, int* blocks_per_sm) {
+    WOFDM_CUDA(h, cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int nb = 0;
+    WOFDM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, v.fn, v.NT, smem));
+    if (nb < 1) return fail(h, WOFDM_EUNSUPPORTED, "kernel variant cannot be resident on this device");
+    *blocks_per_sm = nb;
+    return WOFDM_OK;
+}
+
+size_t elem_bytes(const wofdm_sys_t& s) { return s.precision == 1 ? sizeof(double2) : sizeof(float2); }
+
+}  // namespace
+
+extern "C" {
+
+int wofdm_ber_plan_create(wofdm_handle h, const wofdm_sys_t* sys, const double* win_tx, const double* win_rx,
+                          const double* chan, int L, int C, const double* snr_db, int n_snr,
+                          wofdm_ber_plan* out) {
+    if (!h) return WOFDM_EINVAL;
+    if (!out) return fail(h, WOFDM_EINVAL, "plan out pointer is NULL");
+    *out = nullptr;
+    int rc = validate_sys(h, sys, L);
+    if (rc) return rc;
+    if (!win_tx || !win_rx || !chan || !snr_db) return fail(h, WOFDM_EINVAL, "NULL input buffer");
+    if (C < 1 || n_snr < 1) return fail(h, WOFDM_EINVAL, "C and n_snr must be >= 1");
+    const bool fp64 = sys->precision == 1;
+
+    wofdm_ber_plan_s* p = new (std::nothrow) wofdm_ber_plan_s();
+    if (!p) return fail(h, WOFDM_ENOMEM, "host allocation failed");
+    p->ctx = h; p->sys = *sys; p->L = L; p->C = C; p->n_snr = n_snr;
+    Choice ch;
+    size_t cap = h->devs[0].smem_optin;
+    for (auto& d : h->devs) cap = std::min(cap, d.smem_optin);
+    rc = choose_variant(h, *sys, L, false, false, cap, &ch);
+    if (rc) { delete p; return rc; }
+    p->var = ch.var; p->lay = ch.lay; p->chunk = ch.chunk; p->use_global = ch.use_global;
+
+    HostTables t;
+    build_tables(*sys, win_tx, win_rx, t);
+    std::vector<unsigned char> hchan, hsnr;
+    cast_chan(fp64, chan, (size_t)L * C, hchan);
+    std::vector<double> lin(n_snr);
+    for (int i = 0; i < n_snr; ++i) lin[i] = std::pow(10.0, -0.1 * snr_db[i]);   // wofdm_simulation.py:138
+    cast_any(fp64, lin, hsnr);
+
+    p->devs.resize(h->devs.size());
+    for (size_t i = 0; i < h->devs.size(); ++i) {
+        DeviceCtx& d = h->devs[i];
+        PlanDev& pd = p->devs[i];
+        auto up = [&](void** dst, const std::vector<unsigned char>& src) -> cudaError_t {
+            cudaError_t e = cudaMalloc(dst, std::max<size_t>(src.size(), 16));
+            if (e != cudaSuccess) return e;
+            return cudaMemcpyAsync(*dst, src.data(), src.size(), cudaMemcpyHostToDevice, d.stream);
+        };
+        cudaError_t e = cudaSetDevice(d.dev);
+        if (e == cudaSuccess) e = up(&pd.d_wtx, t.wtx);
+        if (e == cudaSuccess) e = up(&pd.d_wrx, t.wrx);
+        if (e == cudaSuccess) e = up(&pd.d_tw, t.tw);
+        if (e == cudaSuccess) e = up(&pd.d_chan, hchan);
+        if (e == cudaSuccess) e = up(&pd.d_snr, hsnr);
+        if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&pd.d_cnt), (size_t)n_snr * 2 * sizeof(unsigned long long));
+        if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);   // host vectors go out of scope
+        if (e == cudaSuccess) {
+            rc = prepare_kernel(h, *p->var, p->lay.bytes, &pd.blocks_per_sm);
+            if (rc) { wofdm_ber_plan_destroy(p); return rc; }
+        }
+        if (e == cudaSuccess && p->use_global) {
+            const size_t elems = (size_t)p->lay.pad + sys->tail_tx + (size_t)sys->S * (sys->N + sys->cp + sys->cs - sys->tail_tx) + 64;
+            pd.scratch_bytes = (size_t)pd.blocks_per_sm * d.sm_count * 2 * elems * elem_bytes(*sys);
+            e = cudaMalloc(&pd.d_scratch, pd.scratch_bytes);
+        }
+        if (e != cudaSuccess) {
+            std::string msg = std::string("plan upload: ") + cudaGetErrorString(e);
+            wofdm_ber_plan_destroy(p);
+            return fail(h, e == cudaErrorMemoryAllocation ? WOFDM_ENOMEM : WOFDM_ECUDA, msg);
+        }
+    }
+    *out = p;
+    return WOFDM_OK;
+}
+
+int wofdm_ber_plan_launch(wofdm_ber_plan p, int slot, int64_t ensemble, uint64_t seed, uint32_t variant,
+                          int shard_index, int shard_count, void* stream, void** d_counters) {
+    if (!p) return WOFDM_EINVAL;
+    wofdm_ctx* h = p->ctx;
+    if (slot < 0 || slot >= (int)p->devs.size()) return fail(h, WOFDM_EINVAL, "device slot out of range");
+    if (ensemble < 1) return fail(h, WOFDM_EINVAL, "ensemble must be >= 1");
+    if (shard_count < 1 || shard_index < 0 || shard_index >= shard_count) return fail(h, WOFDM_EINVAL, "bad shard");
+    if (variant > 0xfffffff0u) return fail(h, WOFDM_EINVAL, "variant too large");
+    DeviceCtx& d = h->devs[slot];
+    PlanDev& pd = p->devs[slot];
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : d.stream;
+    WOFDM_CUDA(h, cudaSetDevice(d.dev));
+
+    const long long total = (long long)p->n_snr * p->C * ensemble;
+    const long long mine = total > shard_index ? (total - shard_index + shard_count - 1) / shard_count : 0;
+    BerParams prm;
+    fill_sys(prm, p->sys, p->L);
+    prm.chunk = p->chunk; prm.use_global = p->use_global;
+    prm.win_tx = pd.d_wtx; prm.win_rx = pd.d_wrx; prm.tw = pd.d_tw; prm.chan = pd.d_chan; prm.snr_lin = pd.d_snr;
+    prm.C = p->C; prm.n_snr = p->n_snr; prm.ensemble = ensemble;
+    prm.seed = seed; prm.variant = variant;
+    prm.frame_begin = shard_index; prm.frame_step = shard_count; prm.n_frames = mine;
+    prm.counters = pd.d_cnt;
+    prm.scratch = pd.d_scratch;
+    prm.scratch_elems = p->use_global ? (long long)(pd.scratch_bytes / ((size_t)pd.blocks_per_sm * d.sm_count * 2 * elem_bytes(p->sys))) : 0;
+
+    WOFDM_CUDA(h, cudaMemsetAsync(pd.d_cnt, 0, (size_t)p->n_snr * 2 * sizeof(unsigned long long), st));
+    if (mine > 0) {
+        const long long cap = (long long)pd.blocks_per_sm * d.sm_count;
+        const int grid = (int)std::min<long long>(mine, cap);
+        WOFDM_CUDA(h, p->var->launch(prm, grid, p->lay.bytes, st));
+        h->launches += 1;
+    }
+    pd.pending = true;
+    pd.last_stream = st;
+    if (d_counters) *d_counters = pd.d_cnt;
+    return WOFDM_OK;
+}
+
+int wofdm_ber_plan_read(wofdm_ber_plan p, int64_t* bit_err, int64_t* sym_err) {
+    if (!p) return WOFDM_EINVAL;
+    wofdm_ctx* h = p->ctx;
+    if (!bit_err || !sym_err) return fail(h, WOFDM_EINVAL, "NULL output buffer");
+    for (int i = 0; i < p->n_snr; ++i) { bit_err[i] = 0; sym_err[i] = 0; }
+    std::vector<unsigned long long> tmp((size_t)p->n_snr * 2);
+    for (size_t s = 0; s < p->devs.size(); ++s) {
+        PlanDev& pd = p->devs[s];
+        if (!pd.pending) continue;
+        WOFDM_CUDA(h, cudaSetDevice(h->devs[s].dev));
+        WOFDM_CUDA(h, cudaMemcpyAsync(tmp.data(), pd.d_cnt, tmp.size() * sizeof(unsigned long long),
+                                      cudaMemcpyDeviceToHost, pd.last_stream));
+        WOFDM_CUDA(h, cudaStreamSynchronize(pd.last_stream));
+        for (int i = 0; i < p->n_snr; ++i) { bit_err[i] += (int64_t)tmp[2 * i]; sym_err[i] += (int64_t)tmp[2 * i + 1]; }
+        pd.pending = false;
+    }
+    return WOFDM_OK;
+}
+
+const char* wofdm_ber_plan_kernel(wofdm_ber_plan p) { return (p && p->var) ? p->var->name : ""; }
+
+int wofdm_ber_plan_destroy(wofdm_ber_plan p) {
+    if (!p) return WOFDM_EINVAL;
+    for (size_t s = 0; s < p->devs.size(); ++s) {
+        PlanDev& pd = p->devs[s];
+        cudaSetDevice(p->ctx->devs[s].dev);
+        if (pd.pending && pd.last_stream) cudaStreamSynchronize(pd.last_stream);
+        cudaFree(pd.d_wtx); cudaFree(pd.d_wrx); cudaFree(pd.d_tw); cudaFree(pd.d_chan); cudaFree(pd.d_snr);
+        cudaFree(pd.d_cnt); cudaFree(pd.d_scratch);
+    }
+    cudaGetLastError();
+    delete p;
+    return WOFDM_OK;
+}
+
+int wofdm_ber_run_shard(wofdm_handle h, const wofdm_sys_t* sys, const double* win_tx, const double* win_rx,
+                        const double* chan, int L, int C, const double* snr_db, int n_snr, int64_t ensemble,
+                        uint64_t seed, uint32_t variant, int shard_index, int shard_count,
+                        int64_t* bit_err, int64_t* bit_tot, int64_t* sym_err, int64_t* sym_tot) {
+    if (!h) return WOFDM_EINVAL;
+    if (!bit_err || !bit_tot || !sym_err || !sym_tot) return fail(h, WOFDM_EINVAL, "NULL output buffer");
+    if (shard_count < 1 || shard_index < 0 || shard_index >= shard_count) return fail(h, WOFDM_EINVAL, "bad shard");
+    if (ensemble < 1) return fail(h, WOFDM_EINVAL, "ensemble must be >= 1");
+    wofdm_ber_plan p = nullptr;
+    int rc = wofdm_ber_plan_create(h, sys, win_tx, win_rx, chan, L, C, snr_db, n_snr, &p);
+    if (rc) return rc;
+    // the handle's devices split this shard's frames between them: device i takes the sub-shard
+    // shard_index + shard_count*i of shard_count*ndev, so results do not depend on the GPU count
+    const int nd = (int)h->devs.size();
+    for (int i = 0; i < nd && rc == WOFDM_OK; ++i)
+        rc = wofdm_ber_plan_launch(p, i, ensemble, seed, variant, shard_index + shard_count * i, shard_count * nd,
+                                   nullptr, nullptr);
+    if (rc == WOFDM_OK) rc = wofdm_ber_plan_read(p, bit_err, sym_err);
+    wofdm_ber_plan_destroy(p);
+    if (rc) return rc;
+    // frames of this shard per SNR point: f = (snr*C + c)*ensemble + e, f = shard_index (mod shard_count)
+    const long long per_snr = (long long)C * ensemble;
+    for (int i = 0; i < n_snr; ++i) {
+        const long long lo = (long long)i * per_snr, hi = lo + per_snr;   // [lo, hi)
+        auto count_upto = [&](long long x) -> long long {                  // #{f < x : f = shard_index mod shard_count}
+            return x > shard_index ? (x - shard_index + shard_count - 1) / shard_count : 0;
+        };
+        const long long frames = count_upto(hi) - count_upto(lo);
+        sym_tot[i] = frames * (long long)sys->N * (sys->S - 1);
+        bit_tot[i] = sym_tot[i] * sys->bits;
+    }
+    return WOFDM_OK;
+}
+
+int wofdm_ber_run(wofdm_handle h, const wofdm_sys_t* sys, const double* win_tx, const double* win_rx,
+                  const double* chan, int L, int C, const double* snr_db, int n_snr, int64_t ensemble,
+                  uint64_t seed, uint32_t variant,
+                  int64_t* bit_err, int64_t* bit_tot, int64_t* sym_err, int64_t* sym_tot) {
+    return wofdm_ber_run_shard(h, sys, win_tx, win_rx, chan, L, C, snr_db, n_snr, ensemble, seed, variant, 0, 1,
+                               bit_err, bit_tot, sym_err, sym_tot);
+}
+
+int wofdm_ber_verify(wofdm_handle h, const wofdm_sys_t* sys, const double* win_tx, const double* win_rx,
+                     const double* chan, int L, int F, const double* snr_db,
+                     const int32_t* sym_idx, const double* noise, int variant_kernel,
+                     double* eq_out, int32_t* dec_idx, int64_t* bit_err, int64_t* sym_err) {
+    if (!h) return WOFDM_EINVAL;
+    int rc = validate_sys(h, sys, L);
+    if (rc) return rc;
+    if (!win_tx || !win_rx || !chan || !snr_db || !sym_idx || !noise || !eq_out || !dec_idx || !bit_err || !sym_err)
+        return fail(h, WOFDM_EINVAL, "NULL buffer");
+    if (F < 1) return fail(h, WOFDM_EINVAL, "F must be >= 1");
+    const bool fp64 = sys->precision == 1;
+    const int M = 1 << sys->bits;
+    const size_t n_sym = (size_t)sys->N * sys->S * F;
+    for (size_t i = 0; i < n_sym; ++i)
+        if (sym_idx[i] < 0 || sym_idx[i] >= M) return fail(h, WOFDM_EINVAL, "sym_idx entry outside the constellation");
+
+    DeviceCtx& d = h->devs[0];
+    WOFDM_CUDA(h, cudaSetDevice(d.dev));
+    Choice ch;
+    rc = choose_variant(h, *sys, L, true, variant_kernel == 1, d.smem_optin, &ch);
+    if (rc) return rc;
+    int nb = 0;
+    rc = prepare_kernel(h, *ch.var, ch.lay.bytes, &nb);
+    if (rc) return rc;
+    const int grid = (int)std::min<long long>(F, (long long)nb * d.sm_count);
+
+    HostTables t;
+    build_tables(*sys, win_tx, win_rx, t);
+    std::vector<unsigned char> hchan, hsnr;
+    cast_chan(fp64, chan, (size_t)L * F, hchan);
+    std::vector<double> lin(F);
+    for (int i = 0; i < F; ++i) lin[i] = std::pow(10.0, -0.1 * snr_db[i]);
+    cast_any(fp64, lin, hsnr);
+    const size_t nlen = (size_t)noise_len(*sys, L);
+    const size_t n_eq = (size_t)sys->N * (sys->S - 1) * F;
+    const size_t scratch_elems = (size_t)ch.lay.pad + sys->tail_tx + (size_t)sys->S * (sys->N + sys->cp + sys->cs - sys->tail_tx) + 64;
+    const size_t scratch_bytes = ch.use_global ? (size_t)grid * 2 * scratch_elems * elem_bytes(*sys) : 0;
+
+    const size_t total = t.wtx.size() + t.wrx.size() + t.tw.size() + hchan.size() + hsnr.size() + n_sym * 4 +
+                         nlen * F * 16 + n_eq * 16 + n_eq * 4 + (size_t)F * 16 + scratch_bytes;
+    rc = arena_reserve(h, d, total);
+    if (rc) return rc;
+    auto put = [&](const void* src, size_t bytes, void** dst) -> cudaError_t {
+        *dst = arena_take(d, std::max<size_t>(bytes, 16));
+        if (!*dst) return cudaErrorMemoryAllocation;
+        return src ? cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, d.stream) : cudaSuccess;
+    };
+    void *d_wtx, *d_wrx, *d_tw, *d_chan, *d_snr, *d_sym, *d_noise, *d_eq, *d_dec, *d_be, *d_se, *d_scr = nullptr;
+    WOFDM_CUDA(h, put(t.wtx.data(), t.wtx.size(), &d_wtx));
+    WOFDM_CUDA(h, put(t.wrx.data(), t.wrx.size(), &d_wrx));
+    WOFDM_CUDA(h, put(t.tw.data(), t.tw.size(), &d_tw));
+    WOFDM_CUDA(h, put(hchan.data(), hchan.size(), &d_chan));
+    WOFDM_CUDA(h, put(hsnr.data(), hsnr.size(), &d_snr));
+    WOFDM_CUDA(h, put(sym_idx, n_sym * 4, &d_sym));
+    WOFDM_CUDA(h, put(noise, nlen * F * 16, &d_noise));
+    WOFDM_CUDA(h, put(nullptr, n_eq * 16, &d_eq));
+    WOFDM_CUDA(h, put(nullptr, n_eq * 4, &d_dec));
+    WOFDM_CUDA(h, put(nullptr, (size_t)F * 8, &d_be));
+    WOFDM_CUDA(h, put(nullptr, (size_t)F * 8, &d_se));
+    if (scratch_bytes) WOFDM_CUDA(h, put(nullptr, scratch_bytes, &d_scr));
+    WOFDM_CUDA(h, cudaMemsetAsync(d_be, 0, (size_t)F * 8, d.stream));
+    WOFDM_CUDA(h, cudaMemsetAsync(d_se, 0, (size_t)F * 8, d.stream));
+
+    BerParams prm;
+    fill_sys(prm, *sys, L);
+    prm.chunk = ch.chunk; prm.use_global = ch.use_global;
+    prm.win_tx = d_wtx; prm.win_rx = d_wrx; prm.tw = d_tw; prm.chan = d_chan; prm.snr_lin = d_snr;
+    prm.C = F; prm.n_snr = F; prm.ensemble = 1;
+    prm.frame_begin = 0; prm.frame_step = 1; prm.n_frames = F;
+    prm.sym_idx = static_cast<const int32_t*>(d_sym);
+    prm.noise_in = static_cast<const double2*>(d_noise);
+    prm.eq_out = static_cast<double2*>(d_eq);
+    prm.dec_out = static_cast<int32_t*>(d_dec);
+    prm.bit_err_f = static_cast<long long*>(d_be);
+    prm.sym_err_f = static_cast<long long*>(d_se);
+    prm.scratch = d_scr; prm.scratch_elems = (long long)scratch_elems;
+    WOFDM_CUDA(h, ch.var->launch(prm, grid, ch.lay.bytes, d.stream));
+    h->launches += 1;
+    WOFDM_CUDA(h, cudaMemcpyAsync(eq_out, d_eq, n_eq * 16, cudaMemcpyDeviceToHost, d.stream));
+    WOFDM_CUDA(h, cudaMemcpyAsync(dec_idx, d_dec, n_eq * 4, cudaMemcpyDeviceToHost, d.stream));
+    WOFDM_CUDA(h, cudaMemcpyAsync(bit_err, d_be, (size_t)F * 8, cudaMemcpyDeviceToHost, d.stream));
+    WOFDM_CUDA(h, cudaMemcpyAsync(sym_err, d_se, (size_t)F * 8, cudaMemcpyDeviceToHost, d.stream));
+    WOFDM_CUDA(h, cudaStreamSynchronize(d.stream));
+    return WOFDM_OK;
+}
+
+int wofdm_ber_draws(wofdm_handle h, const wofdm_sys_t* sys, int L, uint64_t seed, uint32_t variant,
+                    const int64_t* frame_ids, int F, int32_t* sym_idx, double* noise) {
+    if (!h) return WOFDM_EINVAL;
+    int rc = validate_sys(h, sys, L);
+    if (rc) return rc;
+    if (!frame_ids || !sym_idx || !noise || F < 1) return fail(h, WOFDM_EINVAL, "bad buffer");
+    DeviceCtx& d = h->devs[0];
+    WOFDM_CUDA(h, cudaSetDevice(d.dev));
+    const size_t nlen = (size_t)noise_len(*sys, L);
+    const size_t n_sym = (size_t)sys->N * sys->S * F;
+    rc = arena_reserve(h, d, (size_t)F * 8 + n_sym * 4 + nlen * F * 16);
+    if (rc) return rc;
+    long long* d_ids = static_cast<long long*>(arena_take(d, (size_t)F * 8));
+    int32_t* d_sym = static_cast<int32_t*>(arena_take(d, n_sym * 4));
+    double2* d_noise = static_cast<double2*>(arena_take(d, nlen * F * 16));
+    if (!d_ids || !d_sym || !d_noise) return fail(h, WOFDM_ENOMEM, "arena exhausted");
+    WOFDM_CUDA(h, cudaMemcpyAsync(d_ids, frame_ids, (size_t)F * 8, cudaMemcpyHostToDevice, d.stream));
+    BerParams prm;
+    fill_sys(prm, *sys, L);
+    prm.seed = seed; prm.variant = variant;
+    const dim3 gs(sys->S, F);
+    switch (sys->N) {
+        case 16: draws_sym_kernel<16><<<gs, 32, 0, d.stream>>>(prm, d_ids, d_sym); break;
+        case 32: draws_sym_kernel<32><<<gs, 32, 0, d.stream>>>(prm, d_ids, d_sym); break;
+        case 64: draws_sym_kernel<64><<<gs, 32, 0, d.stream>>>(prm, d_ids, d_sym); break;
+        case 128: draws_sym_kernel<128><<<gs, 32, 0, d.stream>>>(prm, d_ids, d_sym); break;
+        case 256: draws_sym_kernel<256><<<gs, 32, 0, d.stream>>>(prm, d_ids, d_sym); break;
+        case 512: draws_sym_kernel<512><<<gs, 32, 0, d.stream>>>(prm, d_ids, d_sym); break;
+        case 1024: draws_sym_kernel<1024><<<gs, 64, 0, d.stream>>>(prm, d_ids, d_sym); break;
+        default: return fail(h, WOFDM_EUNSUPPORTED, "N");
+    }
+    WOFDM_CUDA(h, cudaGetLastError());
+    const dim3 gn((unsigned)((nlen / 2 + 1 + 127) / 128), F);
+    if (sys->precision == 1) draws_noise_kernel<double><<<gn, 128, 0, d.stream>>>(prm, d_ids, d_noise);
+    else draws_noise_kernel<float><<<gn, 128, 0, d.stream>>>(prm, d_ids, d_noise);
+    WOFDM_CUDA(h, cudaGetLastError());
+    h->launches += 2;
+    WOFDM_CUDA(h, cudaMemcpyAsync(sym_idx, d_sym, n_sym * 4, cudaMemcpyDeviceToHost, d.stream));
+    WOFDM_CUDA(h, cudaMemcpyAsync(noise, d_noise, nlen * F * 16, cudaMemcpyDeviceToHost, d.stream));
+    WOFDM_CUDA(h, cudaStreamSynchronize(d.stream));
+    return WOFDM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,472 @@
+// ber_kernel.cuh -- K1, the fused Monte-Carlo BER/SER frame kernel (sm_100a).
+//
+// One CTA processes one frame at a time (S OFDM symbols, symbol 0 = pilot) entirely in shared
+// memory and registers, then moves on to its next frame (persistent grid).  Replaces the loop
+// body of wOFDMSystem.__run_sim_mc / __run_sim_cp_mc (python/ofdm_utils/wofdm_simulation.py:171-240,
+// 328-364) and run_simulation (matlab/main_BER_calculation.m:245-273), in the structured form of
+// SURVEY.md App. A.2 instead of the reference's dense tx_mat / rx_mat products:
+//
+//   draws (Philox or injected) -> QAM map -> IFFT -> CP/CS + Tx window -> overlap-add of the Tx
+//   tails into the frame stream -> L-tap channel convolution -> exact-SNR AWGN (frame-wide power
+//   sums) -> Rx window -> overlap-add -> circular shift -> FFT -> pilot one-tap equaliser ->
+//   hard slicing -> XOR/popcount error counters (warp shuffles, one atomic per warp).
+//
+// Two policies share this source:
+//   TC == 0  "staged": any L, any tail sizes; convolution output staged in a second buffer, noise
+//            regenerated in the second pass.  Used for fp64 and for shapes without a tuned variant.
+//   TC  > 0  "regs"  : each thread owns one chunk of <= TC consecutive stream samples; the chunk's
+//            convolution output AND its noise stay in registers across the frame-wide power
+//            reduction, taps live in registers LB at a time.  fp32 production path.
+// VERIFY = true replaces the Philox draws by caller-injected symbols/noise/channel per frame and
+// writes the equalised symbols and decisions back (same arithmetic, same code).
+#pragma once
+#include "common.cuh"
+#include "fft_regs.cuh"
+
+namespace wofdm {
+
+struct BerParams {
+    // system
+    int N, cp, cs, tail_tx, tail_rx, rm, shift, bits, S;
+    int n_tx, stride, L;
+    int noise_norm, constellation;
+    int chunk;                 // samples of the frame stream owned by one thread (regs policy)
+    int use_global;            // staged policy: frame buffers live in global scratch
+    // device tables, element type T / V2<T>
+    const void* win_tx;        // [n_tx]   v_tx * qam_scale / N
+    const void* win_rx;        // [N + tail_rx]
+    const void* tw;            // FFT twiddle sections
+    const void* chan;          // V2<T>[C][L]      (verify: [F][L])
+    const void* snr_lin;       // T[n_snr] = 10^(-snr/10)   (verify: [F])
+    int C, n_snr;
+    long long ensemble;
+    // production
+    unsigned long long seed;
+    unsigned variant;
+    long long frame_begin, frame_step, n_frames;   // frame ids f = frame_begin + j*frame_step, j < n_frames
+    unsigned long long* counters;                  // [n_snr][2] = {bit_err, sym_err}
+    // verify
+    const int32_t* sym_idx;    // [F][S][N]
+    const double2* noise_in;   // [F][noise_len]
+    double2* eq_out;           // [F][S-1][N]
+    int32_t* dec_out;          // [F][S-1][N]
+    long long* bit_err_f;      // [F]
+    long long* sym_err_f;      // [F]
+    long long noise_len;
+    double qscale;             // constellation amplitude factor (eq_out is reported in signal units)
+    // staged policy with use_global: 2 * scratch_elems V2<T> per CTA
+    void* scratch;
+    long long scratch_elems;
+};
+
+// ---- constellation helpers (oracle/wofdm_oracle.py: idx_to_levels / levels_to_idx) --------------
+__device__ __forceinline__ int gray_dec4(int g) { g ^= g >> 1; g ^= g >> 2; return g; }
+__device__ __forceinline__ int gray_enc(int v) { return v ^ (v >> 1); }
+
+__device__ __forceinline__ void idx_to_levels(int idx, int hb, int m, int conv, int& a, int& c) {
+    if (conv == 0) { a = idx >> hb; c = idx & (m - 1); }
+    else { a = gray_dec4(idx >> hb); c = (m - 1) - gray_dec4(idx & (m - 1)); }
+}
+__device__ __forceinline__ int levels_to_idx(int a, int c, int hb, int m, int conv) {
+    return conv == 0 ? ((a << hb) | c) : ((gray_enc(a) << hb) | gray_enc((m - 1) - c));
+}
+// nearest level on the odd-integer lattice, ties towards the lower level (first minimum of the
+// reference's argmin, wofdm_simulation.py:163)
+template <typename T> __device__ __forceinline__ int slice_level(T v, int m) {
+    const T lv = ceil((v + (T)(m - 1)) * (T)0.5 - (T)0.5);
+    return (int)fmin(fmax(lv, (T)0), (T)(m - 1));
+}
+
+// 16 constellation indices (one byte each) of OFDM symbol s for thread t: sub-carriers t + q*TPF
+template <int N, bool VERIFY>
+__device__ __forceinline__ void load_sym_idx(const BerParams& prm, long long f, int s, int t, uint32_t (&w)[4]) {
+    constexpr int TPF = N / 16;
+    if constexpr (VERIFY) {
+        const int32_t* src = prm.sym_idx + ((size_t)f * prm.S + s) * N;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t x = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) x |= ((uint32_t)src[t + (4 * j + b) * TPF] & 0xffu) << (8 * b);
+            w[j] = x;
+        }
+    } else {
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)f, (uint32_t)((unsigned long long)f >> 32),
+                                                 (uint32_t)(s * TPF + t), STREAM_SYM),
+                                      (uint32_t)prm.seed, (uint32_t)(prm.seed >> 32));
+        const uint32_t mask = ((1u << prm.bits) - 1u) * 0x01010101u;
+        w[0] = r.x & mask; w[1] = r.y & mask; w[2] = r.z & mask; w[3] = r.w & mask;
+    }
+}
+__device__ __forceinline__ int sym_byte(const uint32_t (&w)[4], int q) { return (w[q >> 2] >> (8 * (q & 3))) & 0xff; }
+
+// complex noise samples 2q and 2q+1 of frame f
+template <typename T>
+__device__ __forceinline__ void noise_pair(const BerParams& prm, long long f, uint32_t q, V2<T>& n0, V2<T>& n1) {
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)f, (uint32_t)((unsigned long long)f >> 32), q,
+                                             STREAM_NOISE + prm.variant),
+                                  (uint32_t)prm.seed, (uint32_t)(prm.seed >> 32));
+    n0 = gauss_pair(r.x, r.y, T());
+    n1 = gauss_pair(r.z, r.w, T());
+}
+
+template <typename T> __device__ __forceinline__ V2<T> to_v2(double2 d) { return mk2<T>((T)d.x, (T)d.y); }
+
+// shared-memory carve-up, computed identically on host (for the launch) and device
+struct BerSmem {
+    int pad;        // zero samples in front of the frame stream (covers every negative tap index)
+    int flen;       // frame-stream buffer elements incl. pad and tail slack (0: lives in global scratch)
+    int xlen;       // second buffer elements (staged: conv output / FFT exchange; regs: 0 if aliased)
+    int off_x, off_tw, off_geq, off_taps, off_wtx, off_wrx, off_red;   // byte offsets
+    size_t bytes;
+};
+
+template <typename T, int N, int NT, int TC, int LB>
+__host__ __device__ inline BerSmem ber_smem_layout(int S, int stride, int tail_tx, int tail_rx, int L, int chunk,
+                                                   int use_global) {
+    using P = FftPlan<N>;
+    constexpr int FPP = NT / P::TPF;
+    constexpr int E = (int)sizeof(V2<T>);
+    BerSmem m;
+    constexpr int lbs = LB > 0 ? LB : 1;
+    const int lpad = TC > 0 ? ((L + lbs - 1) / lbs) * lbs : L;
+    m.pad = (lpad + 1) & ~1;
+    const int body = tail_tx + S * stride;
+    const int exch = FPP * P::XLEN;
+    const int rounds = (S + FPP - 1) / FPP;
+    if (TC > 0) {
+        int need = body > NT * chunk ? body : NT * chunk;
+        if (rounds == 1 && exch > need) need = exch;       // exchange aliases the stream buffer
+        m.flen = m.pad + need + TC + 2;
+        m.xlen = rounds == 1 ? 0 : exch;
+    } else {
+        m.flen = use_global ? 0 : m.pad + body + 2;
+        const int sec = S * stride;
+        m.xlen = use_global ? exch : (exch > sec ? exch : sec);
+    }
+    m.flen = (m.flen + 1) & ~1;
+    m.xlen = (m.xlen + 1) & ~1;
+    int o = 0;
+    o += m.flen * E;                 m.off_x = o;
+    o += m.xlen * E;                 m.off_tw = o;
+    o += P::NTW * E;                 m.off_geq = o;
+    o += N * E;                      m.off_taps = o;
+    o += (L + (L & 1)) * E;          m.off_wtx = o;
+    o += ((stride + tail_tx + 3) & ~3) * (int)sizeof(T);   m.off_wrx = o;
+    o += ((N + tail_rx + 3) & ~3) * (int)sizeof(T);        m.off_red = o;
+    o += 64 * (int)sizeof(T);
+    m.bytes = ((size_t)o + 15) & ~(size_t)15;
+    return m;
+}
+
+template <typename T, int N, int NT, int TC, int LB, bool VERIFY>
+__global__ void __launch_bounds__(NT, (TC > 0 && NT <= 256 && sizeof(T) == 4) ? 2 : 1)
+ber_frame_kernel(const BerParams prm) {
+    using P = FftPlan<N>;
+    using C2 = V2<T>;
+    constexpr int TPF = P::TPF;
+    constexpr int FPP = NT / TPF;
+    static_assert(NT % TPF == 0 && NT % 32 == 0, "threads per CTA must be a multiple of N/16 and 32");
+    constexpr bool REGS = TC > 0;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x;
+    const int slot = tid / TPF, t = tid % TPF;
+    const int S = prm.S, stride = prm.stride, n_tx = prm.n_tx, beta = prm.tail_tx, L = prm.L;
+    const int hh = prm.tail_rx >> 1;
+    const int hb = prm.bits >> 1, m = 1 << hb;
+    const int sec = S * stride;                 // samples kept after the channel
+    const int body = beta + sec;                // serialised Tx stream length
+    const int rounds = (S + FPP - 1) / FPP;
+
+    const BerSmem lay = ber_smem_layout<T, N, NT, TC, LB>(S, stride, beta, prm.tail_rx, L, prm.chunk, prm.use_global);
+    C2* fbuf = reinterpret_cast<C2*>(smem_raw);
+    C2* xbuf = reinterpret_cast<C2*>(smem_raw + lay.off_x);
+    C2* tw = reinterpret_cast<C2*>(smem_raw + lay.off_tw);
+    C2* geq = reinterpret_cast<C2*>(smem_raw + lay.off_geq);
+    C2* taps = reinterpret_cast<C2*>(smem_raw + lay.off_taps);
+    T* wtx = reinterpret_cast<T*>(smem_raw + lay.off_wtx);
+    T* wrx = reinterpret_cast<T*>(smem_raw + lay.off_wrx);
+    T* red = reinterpret_cast<T*>(smem_raw + lay.off_red);
+    C2* rbuf = xbuf;                            // staged: conv output (aliases the exchange buffer)
+    if (!REGS && prm.use_global) {
+        C2* g = reinterpret_cast<C2*>(prm.scratch) + (size_t)blockIdx.x * 2 * prm.scratch_elems;
+        fbuf = g;
+        rbuf = g + prm.scratch_elems;
+    }
+    if (REGS && rounds == 1) xbuf = fbuf + lay.pad;   // exchange aliases the stream body
+    C2* const ub = fbuf + lay.pad;              // ub[i] = stream sample i, ub[-pad..-1] = 0
+    C2* const xb = xbuf + slot * P::XLEN;
+
+    // ---- one-time tables ----
+    for (int i = tid; i < P::NTW; i += NT) tw[i] = reinterpret_cast<const C2*>(prm.tw)[i];
+    for (int i = tid; i < n_tx; i += NT) wtx[i] = reinterpret_cast<const T*>(prm.win_tx)[i];
+    for (int i = tid; i < N + prm.tail_rx; i += NT) wrx[i] = reinterpret_cast<const T*>(prm.win_rx)[i];
+    for (int i = tid; i < lay.pad; i += NT) fbuf[i] = mk2<T>(0, 0);
+    __syncthreads();
+
+    for (long long j = blockIdx.x; j < prm.n_frames; j += gridDim.x) {
+        const long long f = prm.frame_begin + j * prm.frame_step;
+        long long ci, si;
+        if constexpr (VERIFY) { ci = f; si = f; }
+        else { ci = (f / prm.ensemble) % prm.C; si = f / (prm.ensemble * prm.C); }
+        const T snr_lin = reinterpret_cast<const T*>(prm.snr_lin)[si];
+        if (tid < L) taps[tid] = reinterpret_cast<const C2*>(prm.chan)[ci * L + tid];
+
+        // =========================== transmitter ===========================
+        for (int s0 = 0; s0 < S; s0 += FPP) {
+            const int s = s0 + slot;
+            const bool act = s < S;
+            C2 v[16];
+            {
+                uint32_t w[4] = {0, 0, 0, 0};
+                if (act) load_sym_idx<N, VERIFY>(prm, f, s, t, w);
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    int a, c;
+                    idx_to_levels(sym_byte(w, q), hb, m, prm.constellation, a, c);
+                    v[q] = act ? mk2<T>((T)(2 * a - (m - 1)), (T)(2 * c - (m - 1))) : mk2<T>(0, 0);
+                }
+            }
+            fft_regs<T, N, +1>(v, t, xb, tw);
+            if (REGS && rounds == 1) __syncthreads();   // exchange buffer becomes the stream
+            // CP/CS insertion + Tx window: sample i of symbol s is wtx[i] * x[(i - cp) mod N]
+            // (transmitter.py:13-35, 61-87).  Head samples i < tail_tx overlap the previous
+            // symbol's falling tail (wofdm_simulation.py:190-203) and are added after the sync.
+            C2* const us = ub + s * stride;
+            if (act) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const int n = t + q * TPF;
+                    int i = n + prm.cp;
+                    if (i >= beta || s == 0) us[i] = mk2<T>(v[q].x * wtx[i], v[q].y * wtx[i]);
+                    if (n >= N - prm.cp) {
+                        i = n - (N - prm.cp);
+                        if (i >= beta || s == 0) us[i] = mk2<T>(v[q].x * wtx[i], v[q].y * wtx[i]);
+                    }
+                    if (n < prm.cs) {
+                        i = n + prm.cp + N;
+                        us[i] = mk2<T>(v[q].x * wtx[i], v[q].y * wtx[i]);
+                    }
+                }
+            }
+            __syncthreads();
+            if (act && s > 0 && beta > 0) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const int n = t + q * TPF;
+                    int i = n + prm.cp;
+                    if (i < beta) { us[i].x += v[q].x * wtx[i]; us[i].y += v[q].y * wtx[i]; }
+                    if (n >= N - prm.cp) {
+                        i = n - (N - prm.cp);
+                        if (i < beta) { us[i].x += v[q].x * wtx[i]; us[i].y += v[q].y * wtx[i]; }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // =========================== channel + AWGN ===========================
+        // r = conv(h, u)[0:sec] (wofdm_simulation.py:206-209); y = r + sqrt(Pr*10^(-snr/10)/Pn) n
+        // with Pr, Pn summed over the whole frame (:135-138).  noise_norm 1: sums over the full
+        // convolution, beta+sec+L-1 samples (main_BER_calculation.m:260-261,289-292).
+        T pr = 0, pn = 0;
+        if constexpr (REGS) {
+            const int i0 = tid * prm.chunk;
+            C2 acc[TC];
+#pragma unroll
+            for (int o = 0; o < TC; ++o) acc[o] = mk2<T>(0, 0);
+#pragma unroll 1
+            for (int lb = 0; lb < L; lb += LB) {
+                C2 h[LB];
+#pragma unroll
+                for (int l = 0; l < LB; ++l) h[l] = (lb + l < L) ? taps[lb + l] : mk2<T>(0, 0);
+                const C2* src = ub + i0 - lb - (LB - 1);
+                // input c feeds output o through tap lb + (LB-1) - (c - o), 0 <= c - o <= LB-1
+#pragma unroll
+                for (int c = 0; c < TC + LB - 1; ++c) {
+                    const C2 x = src[c];
+#pragma unroll
+                    for (int o = 0; o < TC; ++o)
+                        if (c - o >= 0 && c - o <= LB - 1) cmac(acc[o], h[LB - 1 - (c - o)], x);
+                }
+            }
+            // noise for samples [i0 & ~1, ...): generated in aligned pairs, then shifted by parity
+            C2 nz[TC];
+            {
+                C2 nn[TC + 2];
+                const int par = i0 & 1;
+                if constexpr (VERIFY) {
+                    const double2* src = prm.noise_in + (size_t)f * prm.noise_len;
+#pragma unroll
+                    for (int o = 0; o < TC; ++o)
+                        nz[o] = (o < prm.chunk && i0 + o < sec) ? to_v2<T>(src[i0 + o]) : mk2<T>(0, 0);
+                } else {
+#pragma unroll
+                    for (int p2 = 0; p2 < (TC + 2) / 2; ++p2)
+                        noise_pair<T>(prm, f, (uint32_t)((i0 >> 1) + p2), nn[2 * p2], nn[2 * p2 + 1]);
+#pragma unroll
+                    for (int o = 0; o < TC; ++o) {
+                        nz[o] = par ? nn[o + 1] : nn[o];
+                        if (!(o < prm.chunk && i0 + o < sec)) nz[o] = mk2<T>(0, 0);
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 0; o < TC; ++o) {
+                if (!(o < prm.chunk && i0 + o < sec)) acc[o] = mk2<T>(0, 0);
+                pr = fma(acc[o].x, acc[o].x, pr); pr = fma(acc[o].y, acc[o].y, pr);
+                pn = fma(nz[o].x, nz[o].x, pn); pn = fma(nz[o].y, nz[o].y, pn);
+            }
+            if (prm.noise_norm == 1) {
+                // the L-1+beta samples the reference truncates still count in both power sums
+                for (int i = sec + tid; i < body + L - 1; i += NT) {
+                    C2 a = mk2<T>(0, 0);
+                    for (int l = 0; l < L; ++l)
+                        if (i - l < body) cmac(a, taps[l], ub[i - l]);
+                    C2 n0, n1;
+                    if constexpr (VERIFY) n0 = to_v2<T>(prm.noise_in[(size_t)f * prm.noise_len + i]);
+                    else { noise_pair<T>(prm, f, (uint32_t)(i >> 1), n0, n1); if (i & 1) n0 = n1; }
+                    pr += a.x * a.x + a.y * a.y;
+                    pn += n0.x * n0.x + n0.y * n0.y;
+                }
+            }
+            // frame-wide sums
+            pr = warp_sum(pr); pn = warp_sum(pn);
+            if ((tid & 31) == 0) { red[tid >> 5] = pr; red[32 + (tid >> 5)] = pn; }
+            __syncthreads();                       // also: every conv read of the stream is done
+            pr = 0; pn = 0;
+#pragma unroll
+            for (int wq = 0; wq < NT / 32; ++wq) { pr += red[wq]; pn += red[32 + wq]; }
+            const T g = sqrt(pr * snr_lin / pn);
+#pragma unroll
+            for (int o = 0; o < TC; ++o)
+                if (o < prm.chunk && i0 + o < sec)
+                    ub[i0 + o] = mk2<T>(fma(g, nz[o].x, acc[o].x), fma(g, nz[o].y, acc[o].y));
+        } else {
+            const int total = prm.noise_norm == 1 ? body + L - 1 : sec;
+            for (int i = tid; i < total; i += NT) {
+                C2 a = mk2<T>(0, 0);
+                for (int l = 0; l < L; ++l)
+                    if (i - l < body) cmac(a, taps[l], ub[i - l]);
+                if (i < sec) rbuf[i] = a;
+                C2 n0, n1;
+                if constexpr (VERIFY) n0 = to_v2<T>(prm.noise_in[(size_t)f * prm.noise_len + i]);
+                else { noise_pair<T>(prm, f, (uint32_t)(i >> 1), n0, n1); if (i & 1) n0 = n1; }
+                pr += a.x * a.x + a.y * a.y;
+                pn += n0.x * n0.x + n0.y * n0.y;
+            }
+            pr = warp_sum(pr); pn = warp_sum(pn);
+            if ((tid & 31) == 0) { red[tid >> 5] = pr; red[32 + (tid >> 5)] = pn; }
+            __syncthreads();
+            pr = 0; pn = 0;
+#pragma unroll
+            for (int wq = 0; wq < NT / 32; ++wq) { pr += red[wq]; pn += red[32 + wq]; }
+            const T g = sqrt(pr * snr_lin / pn);
+            for (int i = tid; i < sec; i += NT) {
+                C2 n0, n1;
+                if constexpr (VERIFY) n0 = to_v2<T>(prm.noise_in[(size_t)f * prm.noise_len + i]);
+                else { noise_pair<T>(prm, f, (uint32_t)(i >> 1), n0, n1); if (i & 1) n0 = n1; }
+                const C2 a = rbuf[i];
+                ub[i] = mk2<T>(fma(g, n0.x, a.x), fma(g, n0.y, a.y));
+            }
+        }
+        __syncthreads();
+
+        // =========================== receiver ===========================
+        // block s: z[k] = wrx[k]*y[s*stride + rm + k]; o[n] = sum_{k = n + hh (mod N)} z[k];
+        // q[n] = o[(n + shift) mod N]; Y = DFT(q)   (receiver.py:13-133)
+        unsigned bit_cnt = 0, sym_cnt = 0;
+        for (int s0 = 0; s0 < S; s0 += FPP) {
+            const int s = s0 + slot;
+            const bool act = s < S;
+            C2 v[16];
+            const C2* ys = ub + s * stride + prm.rm;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                C2 o = mk2<T>(0, 0);
+                if (act) {
+                    const int n = (t + q * TPF + prm.shift) & (N - 1);
+                    const C2 y0 = ys[n + hh];
+                    const T w0 = wrx[n + hh];
+                    o = mk2<T>(w0 * y0.x, w0 * y0.y);
+                    if (n < hh) { const C2 y1 = ys[n + hh + N]; const T w1 = wrx[n + hh + N]; o.x += w1 * y1.x; o.y += w1 * y1.y; }
+                    if (n >= N - hh) { const C2 y1 = ys[n + hh - N]; const T w1 = wrx[n + hh - N]; o.x += w1 * y1.x; o.y += w1 * y1.y; }
+                }
+                v[q] = o;
+            }
+            if (REGS && rounds == 1) __syncthreads();   // the stream body is about to become the exchange buffer
+            fft_regs<T, N, -1>(v, t, xb, tw);
+            // pilot: G = X0 / Y0 (wofdm_simulation.py:223), in lattice units
+            uint32_t w[4] = {0, 0, 0, 0};
+            if (act) load_sym_idx<N, VERIFY>(prm, f, s, t, w);
+            if (s == 0) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    int a, c;
+                    idx_to_levels(sym_byte(w, q), hb, m, prm.constellation, a, c);
+                    const C2 x0 = mk2<T>((T)(2 * a - (m - 1)), (T)(2 * c - (m - 1)));
+                    const T d = (T)1 / (v[q].x * v[q].x + v[q].y * v[q].y);
+                    const C2 num = cmulc(x0, v[q]);
+                    geq[t + q * TPF] = mk2<T>(num.x * d, num.y * d);
+                }
+            }
+            __syncthreads();
+            if (act && s > 0) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const int k = t + q * TPF;
+                    const C2 e = cmul(v[q], geq[k]);                       // :231
+                    const int da = slice_level<T>(e.x, m), dc = slice_level<T>(e.y, m);   // :233
+                    const int dec = levels_to_idx(da, dc, hb, m, prm.constellation);
+                    const int txi = sym_byte(w, q);
+                    sym_cnt += (dec != txi);                               // :235
+                    bit_cnt += __popc(dec ^ txi);
+                    if constexpr (VERIFY) {
+                        const size_t o = ((size_t)f * (S - 1) + (s - 1)) * N + k;
+                        prm.eq_out[o] = make_double2((double)e.x * prm.qscale, (double)e.y * prm.qscale);
+                        prm.dec_out[o] = dec;
+                    }
+                }
+            }
+        }
+        bit_cnt = warp_sum(bit_cnt);
+        sym_cnt = warp_sum(sym_cnt);
+        if ((tid & 31) == 0) {
+            if constexpr (VERIFY) {
+                atomicAdd(reinterpret_cast<unsigned long long*>(prm.bit_err_f) + f, (unsigned long long)bit_cnt);
+                atomicAdd(reinterpret_cast<unsigned long long*>(prm.sym_err_f) + f, (unsigned long long)sym_cnt);
+            } else {
+                atomicAdd(prm.counters + 2 * si, (unsigned long long)bit_cnt);
+                atomicAdd(prm.counters + 2 * si + 1, (unsigned long long)sym_cnt);
+            }
+        }
+        __syncthreads();   // taps / stream / geq are rewritten by the next frame
+    }
+}
+
+// ---- export of the on-device draws (wofdm_ber_draws) ------------------------------------------
+template <int N>
+__global__ void draws_sym_kernel(BerParams prm, const long long* frame_ids, int32_t* out) {
+    constexpr int TPF = N / 16;
+    const long long f = frame_ids[blockIdx.y];
+    const int s = blockIdx.x;
+    for (int t = threadIdx.x; t < TPF; t += blockDim.x) {
+        uint32_t w[4];
+        load_sym_idx<N, false>(prm, f, s, t, w);
+        for (int q = 0; q < 16; ++q) out[((size_t)blockIdx.y * prm.S + s) * N + t + q * TPF] = sym_byte(w, q);
+    }
+}
+template <typename T>
+__global__ void draws_noise_kernel(BerParams prm, const long long* frame_ids, double2* out) {
+    const long long f = frame_ids[blockIdx.y];
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (2 * q >= prm.noise_len) return;
+    V2<T> n0, n1;
+    noise_pair<T>(prm, f, (uint32_t)q, n0, n1);
+    double2* o = out + (size_t)blockIdx.y * prm.noise_len;
+    o[2 * q] = make_double2((double)n0.x, (double)n0.y);
+    if (2 * q + 1 < prm.noise_len) o[2 * q + 1] = make_double2((double)n1.x, (double)n1.y);
+}
+
+}  // namespace wofdm

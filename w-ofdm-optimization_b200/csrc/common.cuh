@@ -1,0 +1,89 @@
+// common.cuh -- small device helpers shared by the w-OFDM kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace wofdm {
+
+template <typename T> struct V2sel;
+template <> struct V2sel<float> { typedef float2 type; };
+template <> struct V2sel<double> { typedef double2 type; };
+template <typename T> using V2 = typename V2sel<T>::type;
+
+template <typename T> __host__ __device__ __forceinline__ V2<T> mk2(T x, T y) { V2<T> r; r.x = x; r.y = y; return r; }
+template <typename V> __device__ __forceinline__ V cadd(V a, V b) { a.x += b.x; a.y += b.y; return a; }
+template <typename V> __device__ __forceinline__ V csub(V a, V b) { a.x -= b.x; a.y -= b.y; return a; }
+template <typename V> __device__ __forceinline__ V cmul(V a, V b) {
+    V r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r;
+}
+// a * conj(b)
+template <typename V> __device__ __forceinline__ V cmulc(V a, V b) {
+    V r; r.x = a.x * b.x + a.y * b.y; r.y = a.y * b.x - a.x * b.y; return r;
+}
+// acc += a*b, four FMAs
+template <typename V> __device__ __forceinline__ void cmac(V& acc, V a, V b) {
+    acc.x = fma(a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x);
+    acc.y = fma(a.x, b.y, acc.y); acc.y = fma(a.y, b.x, acc.y);
+}
+__device__ __forceinline__ void cmac(float2& acc, float2 a, float2 b) {
+    acc.x = fmaf(a.x, b.x, acc.x); acc.x = fmaf(-a.y, b.y, acc.x);
+    acc.y = fmaf(a.x, b.y, acc.y); acc.y = fmaf(a.y, b.x, acc.y);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11), counter-based: draws depend only on (key, counter).
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+
+__host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const uint32_t hi0 = mulhi32(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = mulhi32(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return c;
+}
+
+// Counter layout: (frame_lo, frame_hi, index, stream).
+//   stream 0            : constellation indices, index = s*(N/16) + t  -> 16 bytes = sub-carriers
+//                         t + q*(N/16), q = 0..15 of OFDM symbol s (low `bits` bits of byte q)
+//   stream 1 + variant  : noise, index = q -> complex samples 2q (words x,y) and 2q+1 (words z,w)
+enum { STREAM_SYM = 0, STREAM_NOISE = 1 };
+
+// Box-Muller: one complex sample with independent N(0,1) parts from two 32-bit words.
+__device__ __forceinline__ float2 gauss_pair(uint32_t w0, uint32_t w1, float) {
+    // u in (0,1]: (w0 + 0.5) * 2^-32, exact enough in fp32; theta in [-pi, pi)
+    const float u = fmaf(__uint2float_rn(w0), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+    float lg, r, s, c;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(u));
+    const float t = fmaxf(lg * -1.3862943611198906f, 0.0f);  // -2 ln u
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));
+    const float th = __int2float_rn((int32_t)w1) * 1.4629180792671596e-09f;  // 2*pi * 2^-32
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(th));
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(th));
+    return make_float2(r * c, r * s);
+}
+__device__ __forceinline__ double2 gauss_pair(uint32_t w0, uint32_t w1, double) {
+    const double u = ((double)w0 + 0.5) * 2.3283064365386963e-10;
+    const double r = sqrt(-2.0 * log(u));
+    double s, c;
+    sincospi((double)(int32_t)w1 * 4.656612873077393e-10, &s, &c);  // 2 * 2^-32
+    return make_double2(r * c, r * s);
+}
+
+template <typename T> __device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace wofdm
