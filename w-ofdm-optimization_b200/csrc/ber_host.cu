@@ -56,6 +56,7 @@ int choose_variant(wofdm_ctx* h, const wofdm_sys_t& s, int L, bool verify, bool 
         for (const auto& v : h->variants) {
             if (v.TC != 0 || v.fp64 != fp64 || v.verify != verify || v.N != s.N) continue;
             best.var = &v;
+            best.chunk = ((sec + 255) / 256) | 1;   // noise block B of the staged policy (any odd number)
             best.lay = v.layout(s.S, stride, s.tail_tx, s.tail_rx, L, 0, 0);
             best.use_global = 0;
             if (best.lay.bytes > smem_cap) {
@@ -418,6 +419,12 @@ int wofdm_ber_draws(wofdm_handle h, const wofdm_sys_t* sys, int L, uint64_t seed
     BerParams prm;
     fill_sys(prm, *sys, L);
     prm.seed = seed; prm.variant = variant;
+    {   // the noise block B is a property of the kernel variant production mode dispatches to
+        Choice ch;
+        rc = choose_variant(h, *sys, L, false, false, d.smem_optin, &ch);
+        if (rc) return rc;
+        prm.chunk = ch.chunk;
+    }
     const dim3 gs(sys->S, F);
     switch (sys->N) {
         case 16: draws_sym_kernel<16><<<gs, 32, 0, d.stream>>>(prm, d_ids, d_sym); break;
@@ -430,7 +437,7 @@ int wofdm_ber_draws(wofdm_handle h, const wofdm_sys_t* sys, int L, uint64_t seed
         default: return fail(h, WOFDM_EUNSUPPORTED, "N");
     }
     WOFDM_CUDA(h, cudaGetLastError());
-    const dim3 gn((unsigned)((nlen / 2 + 1 + 127) / 128), F);
+    const dim3 gn((unsigned)((nlen + 127) / 128), F);
     if (sys->precision == 1) draws_noise_kernel<double><<<gn, 128, 0, d.stream>>>(prm, d_ids, d_noise);
     else draws_noise_kernel<float><<<gn, 128, 0, d.stream>>>(prm, d_ids, d_noise);
     WOFDM_CUDA(h, cudaGetLastError());

@@ -30,7 +30,8 @@ struct BerParams {
     int N, cp, cs, tail_tx, tail_rx, rm, shift, bits, S;
     int n_tx, stride, L;
     int noise_norm, constellation;
-    int chunk;                 // samples of the frame stream owned by one thread (regs policy)
+    int chunk;                 // B: noise block = samples of the frame stream owned by one thread (regs policy);
+                               // stream sample i uses draw (i/B)*(B+1) + i%B (B odd: blocks start on a Philox pair)
     int use_global;            // staged policy: frame buffers live in global scratch
     // device tables, element type T / V2<T>
     const void* win_tx;        // [n_tx]   v_tx * qam_scale / N
@@ -71,10 +72,14 @@ __device__ __forceinline__ int levels_to_idx(int a, int c, int hb, int m, int co
     return conv == 0 ? ((a << hb) | c) : ((gray_enc(a) << hb) | gray_enc((m - 1) - c));
 }
 // nearest level on the odd-integer lattice, ties towards the lower level (first minimum of the
-// reference's argmin, wofdm_simulation.py:163)
-template <typename T> __device__ __forceinline__ int slice_level(T v, int m) {
-    const T lv = ceil((v + (T)(m - 1)) * (T)0.5 - (T)0.5);
-    return (int)fmin(fmax(lv, (T)0), (T)(m - 1));
+// reference's argmin, wofdm_simulation.py:163): ceil(v/2 + (m-2)/2), clamped to [0, m-1]
+__device__ __forceinline__ int slice_level(float v, int m) {
+    const int lv = __float2int_ru(fmaf(v, 0.5f, 0.5f * (float)(m - 2)));
+    return min(max(lv, 0), m - 1);
+}
+__device__ __forceinline__ int slice_level(double v, int m) {
+    const int lv = __double2int_ru(fma(v, 0.5, 0.5 * (double)(m - 2)));
+    return min(max(lv, 0), m - 1);
 }
 
 // 16 constellation indices (one byte each) of OFDM symbol s for thread t: sub-carriers t + q*TPF
@@ -100,7 +105,7 @@ __device__ __forceinline__ void load_sym_idx(const BerParams& prm, long long f, 
 }
 __device__ __forceinline__ int sym_byte(const uint32_t (&w)[4], int q) { return (w[q >> 2] >> (8 * (q & 3))) & 0xff; }
 
-// complex noise samples 2q and 2q+1 of frame f
+// complex noise draws 2q and 2q+1 of frame f
 template <typename T>
 __device__ __forceinline__ void noise_pair(const BerParams& prm, long long f, uint32_t q, V2<T>& n0, V2<T>& n1) {
     const uint4 r = philox4x32_10(make_uint4((uint32_t)f, (uint32_t)((unsigned long long)f >> 32), q,
@@ -108,6 +113,16 @@ __device__ __forceinline__ void noise_pair(const BerParams& prm, long long f, ui
                                   (uint32_t)prm.seed, (uint32_t)(prm.seed >> 32));
     n0 = gauss_pair(r.x, r.y, T());
     n1 = gauss_pair(r.z, r.w, T());
+}
+// noise of stream sample i (any policy): draw index (i/B)*(B+1) + i%B
+template <typename T>
+__device__ __forceinline__ V2<T> noise_at(const BerParams& prm, long long f, int i) {
+    const int B = prm.chunk;
+    const int k = i / B;
+    const int d = k * (B + 1) + (i - k * B);
+    V2<T> n0, n1;
+    noise_pair<T>(prm, f, (uint32_t)(d >> 1), n0, n1);
+    return (d & 1) ? n1 : n0;
 }
 
 template <typename T> __device__ __forceinline__ V2<T> to_v2(double2 d) { return mk2<T>((T)d.x, (T)d.y); }
@@ -117,7 +132,7 @@ struct BerSmem {
     int pad;        // zero samples in front of the frame stream (covers every negative tap index)
     int flen;       // frame-stream buffer elements incl. pad and tail slack (0: lives in global scratch)
     int xlen;       // second buffer elements (staged: conv output / FFT exchange; regs: 0 if aliased)
-    int off_x, off_tw, off_geq, off_taps, off_wtx, off_wrx, off_red;   // byte offsets
+    int off_x, off_tw, off_geq, off_taps, off_wtx, off_wrx, off_red, off_qlut, off_dlut;   // byte offsets
     size_t bytes;
 };
 
@@ -154,7 +169,9 @@ __host__ __device__ inline BerSmem ber_smem_layout(int S, int stride, int tail_t
     o += (L + (L & 1)) * E;          m.off_wtx = o;
     o += ((stride + tail_tx + 3) & ~3) * (int)sizeof(T);   m.off_wrx = o;
     o += ((N + tail_rx + 3) & ~3) * (int)sizeof(T);        m.off_red = o;
-    o += 64 * (int)sizeof(T);
+    o += 64 * (int)sizeof(T);                              m.off_qlut = o;
+    o += 256 * E;                                          m.off_dlut = o;
+    o += 256;
     m.bytes = ((size_t)o + 15) & ~(size_t)15;
     return m;
 }
@@ -173,6 +190,7 @@ ber_frame_kernel(const BerParams prm) {
     const int tid = threadIdx.x;
     const int slot = tid / TPF, t = tid % TPF;
     const int S = prm.S, stride = prm.stride, n_tx = prm.n_tx, beta = prm.tail_tx, L = prm.L;
+    const int cp = prm.cp, cs = prm.cs;
     const int hh = prm.tail_rx >> 1;
     const int hb = prm.bits >> 1, m = 1 << hb;
     const int sec = S * stride;                 // samples kept after the channel
@@ -188,6 +206,8 @@ ber_frame_kernel(const BerParams prm) {
     T* wtx = reinterpret_cast<T*>(smem_raw + lay.off_wtx);
     T* wrx = reinterpret_cast<T*>(smem_raw + lay.off_wrx);
     T* red = reinterpret_cast<T*>(smem_raw + lay.off_red);
+    C2* qlut = reinterpret_cast<C2*>(smem_raw + lay.off_qlut);          // constellation index -> lattice point
+    unsigned char* dlut = smem_raw + lay.off_dlut;                       // (re level)*m + (im level) -> index
     C2* rbuf = xbuf;                            // staged: conv output (aliases the exchange buffer)
     if (!REGS && prm.use_global) {
         C2* g = reinterpret_cast<C2*>(prm.scratch) + (size_t)blockIdx.x * 2 * prm.scratch_elems;
@@ -203,6 +223,12 @@ ber_frame_kernel(const BerParams prm) {
     for (int i = tid; i < n_tx; i += NT) wtx[i] = reinterpret_cast<const T*>(prm.win_tx)[i];
     for (int i = tid; i < N + prm.tail_rx; i += NT) wrx[i] = reinterpret_cast<const T*>(prm.win_rx)[i];
     for (int i = tid; i < lay.pad; i += NT) fbuf[i] = mk2<T>(0, 0);
+    for (int i = tid; i < (1 << prm.bits); i += NT) {
+        int a, c;
+        idx_to_levels(i, hb, m, prm.constellation, a, c);
+        qlut[i] = mk2<T>((T)(2 * a - (m - 1)), (T)(2 * c - (m - 1)));
+        dlut[a * m + c] = (unsigned char)i;
+    }
     __syncthreads();
 
     for (long long j = blockIdx.x; j < prm.n_frames; j += gridDim.x) {
@@ -217,49 +243,53 @@ ber_frame_kernel(const BerParams prm) {
         for (int s0 = 0; s0 < S; s0 += FPP) {
             const int s = s0 + slot;
             const bool act = s < S;
+            const int se = act ? s : S - 1;     // idle slots shadow the last symbol (identical stores)
+            const bool first = se == 0;
             C2 v[16];
             {
-                uint32_t w[4] = {0, 0, 0, 0};
-                if (act) load_sym_idx<N, VERIFY>(prm, f, s, t, w);
+                uint32_t w[4];
+                load_sym_idx<N, VERIFY>(prm, f, se, t, w);
 #pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                    int a, c;
-                    idx_to_levels(sym_byte(w, q), hb, m, prm.constellation, a, c);
-                    v[q] = act ? mk2<T>((T)(2 * a - (m - 1)), (T)(2 * c - (m - 1))) : mk2<T>(0, 0);
-                }
+                for (int q = 0; q < 16; ++q) v[q] = qlut[sym_byte(w, q)];
             }
             fft_regs<T, N, +1>(v, t, xb, tw);
             if (REGS && rounds == 1) __syncthreads();   // exchange buffer becomes the stream
             // CP/CS insertion + Tx window: sample i of symbol s is wtx[i] * x[(i - cp) mod N]
             // (transmitter.py:13-35, 61-87).  Head samples i < tail_tx overlap the previous
             // symbol's falling tail (wofdm_simulation.py:190-203) and are added after the sync.
-            C2* const us = ub + s * stride;
-            if (act) {
+            C2* const us = ub + se * stride;
+            if (cp >= beta) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) { const int i = t + q * TPF + cp; us[i] = cscale(wtx[i], v[q]); }
+            } else {
 #pragma unroll
                 for (int q = 0; q < 16; ++q) {
-                    const int n = t + q * TPF;
-                    int i = n + prm.cp;
-                    if (i >= beta || s == 0) us[i] = mk2<T>(v[q].x * wtx[i], v[q].y * wtx[i]);
-                    if (n >= N - prm.cp) {
-                        i = n - (N - prm.cp);
-                        if (i >= beta || s == 0) us[i] = mk2<T>(v[q].x * wtx[i], v[q].y * wtx[i]);
-                    }
-                    if (n < prm.cs) {
-                        i = n + prm.cp + N;
-                        us[i] = mk2<T>(v[q].x * wtx[i], v[q].y * wtx[i]);
-                    }
+                    const int i = t + q * TPF + cp;
+                    if (i >= beta || first) us[i] = cscale(wtx[i], v[q]);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                if (q * TPF + TPF > N - cp) {             // uniform: this register row reaches the prefix
+                    const int i = t + q * TPF - (N - cp);
+                    if (i >= 0 && (i >= beta || first)) us[i] = cscale(wtx[i], v[q]);
+                }
+                if (q * TPF < cs) {                        // uniform: ... the suffix
+                    const int i = t + q * TPF + cp + N;
+                    if (i < n_tx) us[i] = cscale(wtx[i], v[q]);
                 }
             }
             __syncthreads();
-            if (act && s > 0 && beta > 0) {
+            if (beta > 0 && act && !first) {
 #pragma unroll
                 for (int q = 0; q < 16; ++q) {
-                    const int n = t + q * TPF;
-                    int i = n + prm.cp;
-                    if (i < beta) { us[i].x += v[q].x * wtx[i]; us[i].y += v[q].y * wtx[i]; }
-                    if (n >= N - prm.cp) {
-                        i = n - (N - prm.cp);
-                        if (i < beta) { us[i].x += v[q].x * wtx[i]; us[i].y += v[q].y * wtx[i]; }
+                    if (q * TPF + TPF > N - cp) {
+                        const int i = t + q * TPF - (N - cp);
+                        if (i >= 0 && i < beta) us[i] = caxpy(wtx[i], v[q], us[i]);
+                    }
+                    if (cp < beta) {
+                        const int i = t + q * TPF + cp;
+                        if (i < beta) us[i] = caxpy(wtx[i], v[q], us[i]);
                     }
                 }
             }
@@ -270,9 +300,12 @@ ber_frame_kernel(const BerParams prm) {
         // r = conv(h, u)[0:sec] (wofdm_simulation.py:206-209); y = r + sqrt(Pr*10^(-snr/10)/Pn) n
         // with Pr, Pn summed over the whole frame (:135-138).  noise_norm 1: sums over the full
         // convolution, beta+sec+L-1 samples (main_BER_calculation.m:260-261,289-292).
-        T pr = 0, pn = 0;
+        C2 pr2 = mk2<T>(0, 0), pn2 = mk2<T>(0, 0);
         if constexpr (REGS) {
-            const int i0 = tid * prm.chunk;
+            const int B = prm.chunk;
+            const int i0 = tid * B;
+            const bool full = (B == TC) && (NT * TC == sec);     // every register of every thread is a live sample
+            const int nvalid = min(B, max(sec - i0, 0));
             C2 acc[TC];
 #pragma unroll
             for (int o = 0; o < TC; ++o) acc[o] = mk2<T>(0, 0);
@@ -291,58 +324,57 @@ ber_frame_kernel(const BerParams prm) {
                         if (c - o >= 0 && c - o <= LB - 1) cmac(acc[o], h[LB - 1 - (c - o)], x);
                 }
             }
-            // noise for samples [i0 & ~1, ...): generated in aligned pairs, then shifted by parity
             C2 nz[TC];
-            {
-                C2 nn[TC + 2];
-                const int par = i0 & 1;
-                if constexpr (VERIFY) {
-                    const double2* src = prm.noise_in + (size_t)f * prm.noise_len;
+            if constexpr (VERIFY) {
+                const double2* src = prm.noise_in + (size_t)f * prm.noise_len;
 #pragma unroll
-                    for (int o = 0; o < TC; ++o)
-                        nz[o] = (o < prm.chunk && i0 + o < sec) ? to_v2<T>(src[i0 + o]) : mk2<T>(0, 0);
-                } else {
+                for (int o = 0; o < TC; ++o) nz[o] = (o < nvalid) ? to_v2<T>(src[i0 + o]) : mk2<T>(0, 0);
+            } else {
+                const uint32_t q0 = (uint32_t)tid * (uint32_t)((B + 1) >> 1);   // block tid starts at draw tid*(B+1)
 #pragma unroll
-                    for (int p2 = 0; p2 < (TC + 2) / 2; ++p2)
-                        noise_pair<T>(prm, f, (uint32_t)((i0 >> 1) + p2), nn[2 * p2], nn[2 * p2 + 1]);
-#pragma unroll
-                    for (int o = 0; o < TC; ++o) {
-                        nz[o] = par ? nn[o + 1] : nn[o];
-                        if (!(o < prm.chunk && i0 + o < sec)) nz[o] = mk2<T>(0, 0);
-                    }
+                for (int p2 = 0; p2 < (TC + 1) / 2; ++p2) {
+                    C2 n0, n1;
+                    noise_pair<T>(prm, f, q0 + p2, n0, n1);
+                    nz[2 * p2] = n0;
+                    if (2 * p2 + 1 < TC) nz[2 * p2 + 1] = n1;
                 }
             }
+            if (!full) {
 #pragma unroll
-            for (int o = 0; o < TC; ++o) {
-                if (!(o < prm.chunk && i0 + o < sec)) acc[o] = mk2<T>(0, 0);
-                pr = fma(acc[o].x, acc[o].x, pr); pr = fma(acc[o].y, acc[o].y, pr);
-                pn = fma(nz[o].x, nz[o].x, pn); pn = fma(nz[o].y, nz[o].y, pn);
+                for (int o = 0; o < TC; ++o)
+                    if (o >= nvalid) { acc[o] = mk2<T>(0, 0); nz[o] = mk2<T>(0, 0); }
             }
+#pragma unroll
+            for (int o = 0; o < TC; ++o) { pr2 = csq_acc(acc[o], pr2); pn2 = csq_acc(nz[o], pn2); }
             if (prm.noise_norm == 1) {
                 // the L-1+beta samples the reference truncates still count in both power sums
                 for (int i = sec + tid; i < body + L - 1; i += NT) {
                     C2 a = mk2<T>(0, 0);
                     for (int l = 0; l < L; ++l)
                         if (i - l < body) cmac(a, taps[l], ub[i - l]);
-                    C2 n0, n1;
+                    C2 n0;
                     if constexpr (VERIFY) n0 = to_v2<T>(prm.noise_in[(size_t)f * prm.noise_len + i]);
-                    else { noise_pair<T>(prm, f, (uint32_t)(i >> 1), n0, n1); if (i & 1) n0 = n1; }
-                    pr += a.x * a.x + a.y * a.y;
-                    pn += n0.x * n0.x + n0.y * n0.y;
+                    else n0 = noise_at<T>(prm, f, i);
+                    pr2 = csq_acc(a, pr2);
+                    pn2 = csq_acc(n0, pn2);
                 }
             }
             // frame-wide sums
-            pr = warp_sum(pr); pn = warp_sum(pn);
+            T pr = warp_sum(pr2.x + pr2.y), pn = warp_sum(pn2.x + pn2.y);
             if ((tid & 31) == 0) { red[tid >> 5] = pr; red[32 + (tid >> 5)] = pn; }
             __syncthreads();                       // also: every conv read of the stream is done
             pr = 0; pn = 0;
 #pragma unroll
             for (int wq = 0; wq < NT / 32; ++wq) { pr += red[wq]; pn += red[32 + wq]; }
             const T g = sqrt(pr * snr_lin / pn);
+            if (full) {
 #pragma unroll
-            for (int o = 0; o < TC; ++o)
-                if (o < prm.chunk && i0 + o < sec)
-                    ub[i0 + o] = mk2<T>(fma(g, nz[o].x, acc[o].x), fma(g, nz[o].y, acc[o].y));
+                for (int o = 0; o < TC; ++o) ub[i0 + o] = caxpy(g, nz[o], acc[o]);
+            } else {
+#pragma unroll
+                for (int o = 0; o < TC; ++o)
+                    if (o < nvalid) ub[i0 + o] = caxpy(g, nz[o], acc[o]);
+            }
         } else {
             const int total = prm.noise_norm == 1 ? body + L - 1 : sec;
             for (int i = tid; i < total; i += NT) {
@@ -350,13 +382,13 @@ ber_frame_kernel(const BerParams prm) {
                 for (int l = 0; l < L; ++l)
                     if (i - l < body) cmac(a, taps[l], ub[i - l]);
                 if (i < sec) rbuf[i] = a;
-                C2 n0, n1;
+                C2 n0;
                 if constexpr (VERIFY) n0 = to_v2<T>(prm.noise_in[(size_t)f * prm.noise_len + i]);
-                else { noise_pair<T>(prm, f, (uint32_t)(i >> 1), n0, n1); if (i & 1) n0 = n1; }
-                pr += a.x * a.x + a.y * a.y;
-                pn += n0.x * n0.x + n0.y * n0.y;
+                else n0 = noise_at<T>(prm, f, i);
+                pr2 = csq_acc(a, pr2);
+                pn2 = csq_acc(n0, pn2);
             }
-            pr = warp_sum(pr); pn = warp_sum(pn);
+            T pr = warp_sum(pr2.x + pr2.y), pn = warp_sum(pn2.x + pn2.y);
             if ((tid & 31) == 0) { red[tid >> 5] = pr; red[32 + (tid >> 5)] = pn; }
             __syncthreads();
             pr = 0; pn = 0;
@@ -364,11 +396,10 @@ ber_frame_kernel(const BerParams prm) {
             for (int wq = 0; wq < NT / 32; ++wq) { pr += red[wq]; pn += red[32 + wq]; }
             const T g = sqrt(pr * snr_lin / pn);
             for (int i = tid; i < sec; i += NT) {
-                C2 n0, n1;
+                C2 n0;
                 if constexpr (VERIFY) n0 = to_v2<T>(prm.noise_in[(size_t)f * prm.noise_len + i]);
-                else { noise_pair<T>(prm, f, (uint32_t)(i >> 1), n0, n1); if (i & 1) n0 = n1; }
-                const C2 a = rbuf[i];
-                ub[i] = mk2<T>(fma(g, n0.x, a.x), fma(g, n0.y, a.y));
+                else n0 = noise_at<T>(prm, f, i);
+                ub[i] = caxpy(g, n0, rbuf[i]);
             }
         }
         __syncthreads();
@@ -380,35 +411,33 @@ ber_frame_kernel(const BerParams prm) {
         for (int s0 = 0; s0 < S; s0 += FPP) {
             const int s = s0 + slot;
             const bool act = s < S;
+            const int se = act ? s : S - 1;
             C2 v[16];
-            const C2* ys = ub + s * stride + prm.rm;
+            const C2* ys = ub + se * stride + prm.rm + hh;
+            const T* wr = wrx + hh;
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
-                C2 o = mk2<T>(0, 0);
-                if (act) {
-                    const int n = (t + q * TPF + prm.shift) & (N - 1);
-                    const C2 y0 = ys[n + hh];
-                    const T w0 = wrx[n + hh];
-                    o = mk2<T>(w0 * y0.x, w0 * y0.y);
-                    if (n < hh) { const C2 y1 = ys[n + hh + N]; const T w1 = wrx[n + hh + N]; o.x += w1 * y1.x; o.y += w1 * y1.y; }
-                    if (n >= N - hh) { const C2 y1 = ys[n + hh - N]; const T w1 = wrx[n + hh - N]; o.x += w1 * y1.x; o.y += w1 * y1.y; }
+                const int a0 = (q * TPF + prm.shift) & (N - 1);          // first n of this register row
+                const int n = (t + q * TPF + prm.shift) & (N - 1);
+                C2 o = cscale(wr[n], ys[n]);
+                if (hh > 0) {                                             // uniform
+                    const bool wraps = a0 + TPF > N;
+                    if (wraps || a0 < hh) { if (n < hh) o = caxpy(wr[n + N], ys[n + N], o); }
+                    if (wraps || a0 + TPF > N - hh) { if (n >= N - hh) o = caxpy(wr[n - N], ys[n - N], o); }
                 }
                 v[q] = o;
             }
             if (REGS && rounds == 1) __syncthreads();   // the stream body is about to become the exchange buffer
             fft_regs<T, N, -1>(v, t, xb, tw);
-            // pilot: G = X0 / Y0 (wofdm_simulation.py:223), in lattice units
-            uint32_t w[4] = {0, 0, 0, 0};
-            if (act) load_sym_idx<N, VERIFY>(prm, f, s, t, w);
-            if (s == 0) {
+            uint32_t w[4];
+            load_sym_idx<N, VERIFY>(prm, f, se, t, w);
+            if (se == 0) {
+                // pilot: G = X0 / Y0 (wofdm_simulation.py:223), in lattice units
 #pragma unroll
                 for (int q = 0; q < 16; ++q) {
-                    int a, c;
-                    idx_to_levels(sym_byte(w, q), hb, m, prm.constellation, a, c);
-                    const C2 x0 = mk2<T>((T)(2 * a - (m - 1)), (T)(2 * c - (m - 1)));
+                    const C2 x0 = qlut[sym_byte(w, q)];
                     const T d = (T)1 / (v[q].x * v[q].x + v[q].y * v[q].y);
-                    const C2 num = cmulc(x0, v[q]);
-                    geq[t + q * TPF] = mk2<T>(num.x * d, num.y * d);
+                    geq[t + q * TPF] = cscale(d, cmulc(x0, v[q]));
                 }
             }
             __syncthreads();
@@ -416,11 +445,10 @@ ber_frame_kernel(const BerParams prm) {
 #pragma unroll
                 for (int q = 0; q < 16; ++q) {
                     const int k = t + q * TPF;
-                    const C2 e = cmul(v[q], geq[k]);                       // :231
-                    const int da = slice_level<T>(e.x, m), dc = slice_level<T>(e.y, m);   // :233
-                    const int dec = levels_to_idx(da, dc, hb, m, prm.constellation);
+                    const C2 e = cmul(v[q], geq[k]);                                       // :231
+                    const int dec = dlut[slice_level(e.x, m) * m + slice_level(e.y, m)];   // :233
                     const int txi = sym_byte(w, q);
-                    sym_cnt += (dec != txi);                               // :235
+                    sym_cnt += (dec != txi);                                               // :235
                     bit_cnt += __popc(dec ^ txi);
                     if constexpr (VERIFY) {
                         const size_t o = ((size_t)f * (S - 1) + (s - 1)) * N + k;
@@ -460,13 +488,10 @@ __global__ void draws_sym_kernel(BerParams prm, const long long* frame_ids, int3
 template <typename T>
 __global__ void draws_noise_kernel(BerParams prm, const long long* frame_ids, double2* out) {
     const long long f = frame_ids[blockIdx.y];
-    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (2 * q >= prm.noise_len) return;
-    V2<T> n0, n1;
-    noise_pair<T>(prm, f, (uint32_t)q, n0, n1);
-    double2* o = out + (size_t)blockIdx.y * prm.noise_len;
-    o[2 * q] = make_double2((double)n0.x, (double)n0.y);
-    if (2 * q + 1 < prm.noise_len) o[2 * q + 1] = make_double2((double)n1.x, (double)n1.y);
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // stream position
+    if (i >= prm.noise_len) return;
+    const V2<T> n0 = noise_at<T>(prm, f, (int)i);
+    out[(size_t)blockIdx.y * prm.noise_len + i] = make_double2((double)n0.x, (double)n0.y);
 }
 
 }  // namespace wofdm

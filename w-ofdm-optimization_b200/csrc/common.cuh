@@ -11,24 +11,50 @@ template <> struct V2sel<double> { typedef double2 type; };
 template <typename T> using V2 = typename V2sel<T>::type;
 
 template <typename T> __host__ __device__ __forceinline__ V2<T> mk2(T x, T y) { V2<T> r; r.x = x; r.y = y; return r; }
-template <typename V> __device__ __forceinline__ V cadd(V a, V b) { a.x += b.x; a.y += b.y; return a; }
-template <typename V> __device__ __forceinline__ V csub(V a, V b) { a.x -= b.x; a.y -= b.y; return a; }
-template <typename V> __device__ __forceinline__ V cmul(V a, V b) {
-    V r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r;
+// ---------------------------------------------------------------------------------------------
+// Complex arithmetic.  double2: plain scalar code.  float2: Blackwell packed-FP32 instructions
+// (add/mul/fma.f32x2 -> SASS FADD2/FMUL2/FFMA2): one issue slot per complex add, two per complex
+// multiply-accumulate.  The "(-a.y, a.x)" operands below cost nothing: ptxas folds the half swap
+// and the sign into the FFMA2/FADD2 operand modifiers (.F32x2.LO_HI.NP), and a duplicated scalar
+// into the broadcast form (.F32).
+// ---------------------------------------------------------------------------------------------
+typedef unsigned long long pk64;
+__device__ __forceinline__ pk64 pk(float x, float y) { pk64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y)); return r; }
+__device__ __forceinline__ pk64 pk(float2 a) { return pk(a.x, a.y); }
+__device__ __forceinline__ float2 upk(pk64 r) { float2 d; asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(r)); return d; }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { pk64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk(a)), "l"(pk(b))); return upk(d); }
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { pk64 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk(a)), "l"(pk(b))); return upk(d); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { pk64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk(a)), "l"(pk(b))); return upk(d); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { pk64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pk(a)), "l"(pk(b)), "l"(pk(c))); return upk(d); }
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return add2(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return sub2(a, b); }
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { a.x += b.x; a.y += b.y; return a; }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { a.x -= b.x; a.y -= b.y; return a; }
+// i*a and -i*a
+template <typename V> __device__ __forceinline__ V rotj(V a) { V r; r.x = -a.y; r.y = a.x; return r; }
+template <typename V> __device__ __forceinline__ V rotmj(V a) { V r; r.x = a.y; r.y = -a.x; return r; }
+// real scalar times complex
+__device__ __forceinline__ float2 cscale(float s, float2 a) { return mul2(a, make_float2(s, s)); }
+__device__ __forceinline__ double2 cscale(double s, double2 a) { a.x *= s; a.y *= s; return a; }
+// c + s*a (s real)
+__device__ __forceinline__ float2 caxpy(float s, float2 a, float2 c) { return fma2(a, make_float2(s, s), c); }
+__device__ __forceinline__ double2 caxpy(double s, double2 a, double2 c) { c.x = fma(s, a.x, c.x); c.y = fma(s, a.y, c.y); return c; }
+// a*b = b.x*a + b.y*(i a)
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return caxpy(b.y, rotj(a), cscale(b.x, a)); }
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) { double2 r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r; }
+// a*conj(b) = b.x*a + b.y*(-i a)
+__device__ __forceinline__ float2 cmulc(float2 a, float2 b) { return caxpy(b.y, rotmj(a), cscale(b.x, a)); }
+__device__ __forceinline__ double2 cmulc(double2 a, double2 b) { double2 r; r.x = a.x * b.x + a.y * b.y; r.y = a.y * b.x - a.x * b.y; return r; }
+// acc += h*x
+__device__ __forceinline__ void cmac(float2& acc, float2 h, float2 x) { acc = caxpy(h.x, x, acc); acc = caxpy(h.y, rotj(x), acc); }
+__device__ __forceinline__ void cmac(double2& acc, double2 h, double2 x) {
+    acc.x = fma(h.x, x.x, acc.x); acc.x = fma(-h.y, x.y, acc.x);
+    acc.y = fma(h.x, x.y, acc.y); acc.y = fma(h.y, x.x, acc.y);
 }
-// a * conj(b)
-template <typename V> __device__ __forceinline__ V cmulc(V a, V b) {
-    V r; r.x = a.x * b.x + a.y * b.y; r.y = a.y * b.x - a.x * b.y; return r;
-}
-// acc += a*b, four FMAs
-template <typename V> __device__ __forceinline__ void cmac(V& acc, V a, V b) {
-    acc.x = fma(a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x);
-    acc.y = fma(a.x, b.y, acc.y); acc.y = fma(a.y, b.x, acc.y);
-}
-__device__ __forceinline__ void cmac(float2& acc, float2 a, float2 b) {
-    acc.x = fmaf(a.x, b.x, acc.x); acc.x = fmaf(-a.y, b.y, acc.x);
-    acc.y = fmaf(a.x, b.y, acc.y); acc.y = fmaf(a.y, b.x, acc.y);
-}
+// p += (a.x^2, a.y^2): running |a|^2 in two lanes, summed by the caller
+__device__ __forceinline__ float2 csq_acc(float2 a, float2 p) { return fma2(a, a, p); }
+__device__ __forceinline__ double2 csq_acc(double2 a, double2 p) { p.x = fma(a.x, a.x, p.x); p.y = fma(a.y, a.y, p.y); return p; }
 
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al., SC'11), counter-based: draws depend only on (key, counter).

@@ -36,21 +36,22 @@ template <typename T, int DIR, int E> __device__ __forceinline__ V2<T> mul_w16(V
     constexpr T C1 = (T)0.92387953251128673848, S1 = (T)0.38268343236508978178, R2 = (T)0.70710678118654752440;
     if constexpr (e == 0) return a;
     else if constexpr (e == 8) return mk2<T>(-a.x, -a.y);
-    else if constexpr (e == 4) return DIR > 0 ? mk2<T>(-a.y, a.x) : mk2<T>(a.y, -a.x);
-    else if constexpr (e == 12) return DIR > 0 ? mk2<T>(a.y, -a.x) : mk2<T>(-a.y, a.x);
+    else if constexpr (e == 4) return DIR > 0 ? rotj(a) : rotmj(a);
+    else if constexpr (e == 12) return DIR > 0 ? rotmj(a) : rotj(a);
     else if constexpr (e == 2 || e == 6 || e == 10 || e == 14) {
-        // (c + i s) with |c| = |s| = R2
-        constexpr T sc = (e == 2 || e == 14) ? (T)1 : (T)-1;
-        constexpr T ss0 = (e == 2 || e == 6) ? (T)1 : (T)-1;
-        constexpr T ss = DIR > 0 ? ss0 : -ss0;
-        // (a.x + i a.y)(sc + i ss) * R2
-        return mk2<T>(R2 * (sc * a.x - ss * a.y), R2 * (ss * a.x + sc * a.y));
+        // R2 * (sc + i ss) * a = R2 * (sc*a + ss*(i a)), sc, ss = +-1
+        constexpr bool sc_pos = (e == 2 || e == 14);
+        constexpr bool ss_pos0 = (e == 2 || e == 6);
+        constexpr bool ss_pos = DIR > 0 ? ss_pos0 : !ss_pos0;
+        const V2<T> u = sc_pos ? a : mk2<T>(-a.x, -a.y);
+        const V2<T> w = ss_pos ? rotj(a) : rotmj(a);
+        return cscale(R2, cadd(u, w));
     } else {
         constexpr T ctab[16] = {1, C1, R2, S1, 0, -S1, -R2, -C1, -1, -C1, -R2, -S1, 0, S1, R2, C1};
         constexpr T stab[16] = {0, S1, R2, C1, 1, C1, R2, S1, 0, -S1, -R2, -C1, -1, -C1, -R2, -S1};
         constexpr T c = ctab[e];
         constexpr T s = DIR > 0 ? stab[e] : -stab[e];
-        return mk2<T>(a.x * c - a.y * s, a.x * s + a.y * c);
+        return cmul(a, mk2<T>(c, s));
     }
 }
 
@@ -64,11 +65,11 @@ template <typename T, int DIR> __device__ __forceinline__ void bfly4(V2<T>& a0, 
     a0 = cadd(s02, s13);
     a2 = csub(s02, s13);
     if constexpr (DIR < 0) {  // X1 = d02 - i d13, X3 = d02 + i d13
-        a1 = mk2<T>(d02.x + d13.y, d02.y - d13.x);
-        a3 = mk2<T>(d02.x - d13.y, d02.y + d13.x);
+        a1 = cadd(d02, rotmj(d13));
+        a3 = cadd(d02, rotj(d13));
     } else {
-        a1 = mk2<T>(d02.x - d13.y, d02.y + d13.x);
-        a3 = mk2<T>(d02.x + d13.y, d02.y - d13.x);
+        a1 = cadd(d02, rotj(d13));
+        a3 = cadd(d02, rotmj(d13));
     }
 }
 
