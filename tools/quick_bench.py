@@ -16,7 +16,7 @@ def main():
     if name in ("CP", "wtx", "CPwtx"): trx = 0
     s = W.params_from_name(name, N, cp, ttx, trx, bits=4 if N == 256 else 6, S=16)
     h = W.Handle([0])
-    print("fp32 peak scalar", h.fp32_peak(0), "ffma2", h.fp32_peak(1))
+    print("fp32 peak scalar", h.fp32_peak(0), "ffma2", h.fp32_peak(1), "cmac pattern", h.fp32_peak(2), "ffma2+lop3 1:1", h.fp32_peak(3))
     vt, vr = capi.rc_window_tx(s), capi.rc_window_rx(s)
     rng = np.random.default_rng(0)
     C = 250

@@ -1,6 +1,7 @@
 // ber_host.cu -- host side of K1: variant selection, device tables, plans, and the
 // wofdm_ber_* entry points of include/wofdm.h.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -42,14 +43,18 @@ int choose_variant(wofdm_ctx* h, const wofdm_sys_t& s, int L, bool verify, bool 
     const int sec = s.S * stride;
     const bool fp64 = s.precision == 1;
     Choice best;
+    // WOFDM_VARIANT=<substring> restricts the tuned candidates (kernel tuning aid, e.g. "_b2")
+    const char* want = getenv("WOFDM_VARIANT");
     if (!fp64 && !force_staged) {
         for (const auto& v : h->variants) {
             if (v.TC == 0 || v.fp64 || v.verify != verify || v.N != s.N) continue;
+            if (want && !strstr(v.name, want)) continue;
             const int chunk = ((sec + v.NT - 1) / v.NT) | 1;
-            if (chunk > v.TC) continue;
+            if (chunk > v.TC || L > v.LB) continue;
+            if (v.full && !(chunk == v.TC && v.NT * v.TC == sec)) continue;
             const BerSmem lay = v.layout(s.S, stride, s.tail_tx, s.tail_rx, L, chunk, 0);
             if (lay.bytes > smem_cap) continue;
-            if (!best.var || v.TC < best.var->TC) { best.var = &v; best.lay = lay; best.chunk = chunk; }
+            if (!best.var || v.TC < best.var->TC || (v.TC == best.var->TC && v.full && !best.var->full)) { best.var = &v; best.lay = lay; best.chunk = chunk; }
         }
     }
     if (!best.var) {

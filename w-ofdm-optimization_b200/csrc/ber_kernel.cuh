@@ -131,8 +131,8 @@ template <typename T> __device__ __forceinline__ V2<T> to_v2(double2 d) { return
 struct BerSmem {
     int pad;        // zero samples in front of the frame stream (covers every negative tap index)
     int flen;       // frame-stream buffer elements incl. pad and tail slack (0: lives in global scratch)
-    int xlen;       // second buffer elements (staged: conv output / FFT exchange; regs: 0 if aliased)
-    int off_x, off_tw, off_geq, off_taps, off_wtx, off_wrx, off_red, off_qlut, off_dlut;   // byte offsets
+    int xlen;       // second buffer elements: staged -> conv output / FFT exchange; regs -> noise / FFT exchange
+    int off_x, off_tw, off_geq, off_taps, off_wtx, off_wrx, off_red, off_qlut, off_dlut, off_symw;   // byte offsets
     size_t bytes;
 };
 
@@ -148,12 +148,10 @@ __host__ __device__ inline BerSmem ber_smem_layout(int S, int stride, int tail_t
     m.pad = (lpad + 1) & ~1;
     const int body = tail_tx + S * stride;
     const int exch = FPP * P::XLEN;
-    const int rounds = (S + FPP - 1) / FPP;
     if (TC > 0) {
-        int need = body > NT * chunk ? body : NT * chunk;
-        if (rounds == 1 && exch > need) need = exch;       // exchange aliases the stream buffer
+        const int need = body > NT * chunk ? body : NT * chunk;
         m.flen = m.pad + need + TC + 2;
-        m.xlen = rounds == 1 ? 0 : exch;
+        m.xlen = exch > NT * chunk + 2 ? exch : NT * chunk + 2;   // noise of the frame; FFT exchange in Tx/Rx
     } else {
         m.flen = use_global ? 0 : m.pad + body + 2;
         const int sec = S * stride;
@@ -171,13 +169,17 @@ __host__ __device__ inline BerSmem ber_smem_layout(int S, int stride, int tail_t
     o += ((N + tail_rx + 3) & ~3) * (int)sizeof(T);        m.off_red = o;
     o += 64 * (int)sizeof(T);                              m.off_qlut = o;
     o += 256 * E;                                          m.off_dlut = o;
-    o += 256;
+    o += 256;                                              m.off_symw = o;
+    o += S * P::TPF * 16;                                  // constellation-index words of every (symbol, thread)
     m.bytes = ((size_t)o + 15) & ~(size_t)15;
     return m;
 }
 
-template <typename T, int N, int NT, int TC, int LB, bool VERIFY>
-__global__ void __launch_bounds__(NT, (TC > 0 && NT <= 256 && sizeof(T) == 4) ? 2 : 1)
+__device__ __forceinline__ float recip(float x) { return __fdividef(1.0f, x); }
+__device__ __forceinline__ double recip(double x) { return 1.0 / x; }
+
+template <typename T, int N, int NT, int TC, int LB, int MINB, bool FULL, bool VERIFY>
+__global__ void __launch_bounds__(NT, MINB)
 ber_frame_kernel(const BerParams prm) {
     using P = FftPlan<N>;
     using C2 = V2<T>;
@@ -195,7 +197,6 @@ ber_frame_kernel(const BerParams prm) {
     const int hb = prm.bits >> 1, m = 1 << hb;
     const int sec = S * stride;                 // samples kept after the channel
     const int body = beta + sec;                // serialised Tx stream length
-    const int rounds = (S + FPP - 1) / FPP;
 
     const BerSmem lay = ber_smem_layout<T, N, NT, TC, LB>(S, stride, beta, prm.tail_rx, L, prm.chunk, prm.use_global);
     C2* fbuf = reinterpret_cast<C2*>(smem_raw);
@@ -208,13 +209,13 @@ ber_frame_kernel(const BerParams prm) {
     T* red = reinterpret_cast<T*>(smem_raw + lay.off_red);
     C2* qlut = reinterpret_cast<C2*>(smem_raw + lay.off_qlut);          // constellation index -> lattice point
     unsigned char* dlut = smem_raw + lay.off_dlut;                       // (re level)*m + (im level) -> index
-    C2* rbuf = xbuf;                            // staged: conv output (aliases the exchange buffer)
+    uint4* symw = reinterpret_cast<uint4*>(smem_raw + lay.off_symw);     // Tx -> Rx: the frame's constellation indices
+    C2* rbuf = xbuf;                            // staged: conv output; regs: the frame's noise (both alias the exchange)
     if (!REGS && prm.use_global) {
         C2* g = reinterpret_cast<C2*>(prm.scratch) + (size_t)blockIdx.x * 2 * prm.scratch_elems;
         fbuf = g;
         rbuf = g + prm.scratch_elems;
     }
-    if (REGS && rounds == 1) xbuf = fbuf + lay.pad;   // exchange aliases the stream body
     C2* const ub = fbuf + lay.pad;              // ub[i] = stream sample i, ub[-pad..-1] = 0
     C2* const xb = xbuf + slot * P::XLEN;
 
@@ -231,13 +232,21 @@ ber_frame_kernel(const BerParams prm) {
     }
     __syncthreads();
 
+    // frame id f = (si*C + ci)*ensemble + e, advanced without per-frame divisions
+    long long f = prm.frame_begin + (long long)blockIdx.x * prm.frame_step;
+    const long long df = (long long)gridDim.x * prm.frame_step;
+    long long fe = 0, de = 0;
+    int ci = 0, si = 0, dc = 0, ds = 0;
+    if constexpr (!VERIFY) {
+        const long long q = f / prm.ensemble, dq = df / prm.ensemble;
+        fe = f - q * prm.ensemble;   de = df - dq * prm.ensemble;
+        si = (int)(q / prm.C);       ci = (int)(q - (long long)si * prm.C);
+        ds = (int)(dq / prm.C);      dc = (int)(dq - (long long)ds * prm.C);
+    }
     for (long long j = blockIdx.x; j < prm.n_frames; j += gridDim.x) {
-        const long long f = prm.frame_begin + j * prm.frame_step;
-        long long ci, si;
-        if constexpr (VERIFY) { ci = f; si = f; }
-        else { ci = (f / prm.ensemble) % prm.C; si = f / (prm.ensemble * prm.C); }
+        if constexpr (VERIFY) { ci = (int)f; si = (int)f; }
         const T snr_lin = reinterpret_cast<const T*>(prm.snr_lin)[si];
-        if (tid < L) taps[tid] = reinterpret_cast<const C2*>(prm.chan)[ci * L + tid];
+        if (tid < L) taps[tid] = reinterpret_cast<const C2*>(prm.chan)[(size_t)ci * L + tid];
 
         // =========================== transmitter ===========================
         for (int s0 = 0; s0 < S; s0 += FPP) {
@@ -249,11 +258,11 @@ ber_frame_kernel(const BerParams prm) {
             {
                 uint32_t w[4];
                 load_sym_idx<N, VERIFY>(prm, f, se, t, w);
+                symw[se * TPF + t] = make_uint4(w[0], w[1], w[2], w[3]);
 #pragma unroll
                 for (int q = 0; q < 16; ++q) v[q] = qlut[sym_byte(w, q)];
             }
             fft_regs<T, N, +1>(v, t, xb, tw);
-            if (REGS && rounds == 1) __syncthreads();   // exchange buffer becomes the stream
             // CP/CS insertion + Tx window: sample i of symbol s is wtx[i] * x[(i - cp) mod N]
             // (transmitter.py:13-35, 61-87).  Head samples i < tail_tx overlap the previous
             // symbol's falling tail (wofdm_simulation.py:190-203) and are added after the sync.
@@ -302,50 +311,55 @@ ber_frame_kernel(const BerParams prm) {
         // convolution, beta+sec+L-1 samples (main_BER_calculation.m:260-261,289-292).
         C2 pr2 = mk2<T>(0, 0), pn2 = mk2<T>(0, 0);
         if constexpr (REGS) {
+            // Each thread owns the B = prm.chunk stream samples [i0, i0+B).  Their convolution outputs stay
+            // in registers across the frame-wide power reduction; their noise is generated INSIDE the
+            // convolution loop (one Philox pair every few inputs: integer/MUFU work fills the issue slots
+            // the 2-cycle FFMA2s leave free) and parked in shared memory until the gain is known.
             const int B = prm.chunk;
             const int i0 = tid * B;
-            const bool full = (B == TC) && (NT * TC == sec);     // every register of every thread is a live sample
-            const int nvalid = min(B, max(sec - i0, 0));
-            C2 acc[TC];
+            const int nvalid = FULL ? TC : min(B, max(sec - i0, 0));
+            C2 acc[TC], h[LB];
 #pragma unroll
             for (int o = 0; o < TC; ++o) acc[o] = mk2<T>(0, 0);
-#pragma unroll 1
-            for (int lb = 0; lb < L; lb += LB) {
-                C2 h[LB];
 #pragma unroll
-                for (int l = 0; l < LB; ++l) h[l] = (lb + l < L) ? taps[lb + l] : mk2<T>(0, 0);
-                const C2* src = ub + i0 - lb - (LB - 1);
-                // input c feeds output o through tap lb + (LB-1) - (c - o), 0 <= c - o <= LB-1
+            for (int l = 0; l < LB; ++l) h[l] = (l < L) ? taps[l] : mk2<T>(0, 0);
+            const C2* src = ub + i0 - (LB - 1);
+            C2* const nb = rbuf + i0;
+            constexpr int NPAIR = (TC + 1) / 2, NSTEP = (TC + LB - 1) / NPAIR;
+            const uint32_t q0 = (uint32_t)tid * (uint32_t)((B + 1) >> 1);   // block tid starts at draw tid*(B+1)
+            // input c feeds output o through tap (LB-1) - (c - o), 0 <= c - o <= LB-1
 #pragma unroll
-                for (int c = 0; c < TC + LB - 1; ++c) {
-                    const C2 x = src[c];
-#pragma unroll
-                    for (int o = 0; o < TC; ++o)
-                        if (c - o >= 0 && c - o <= LB - 1) cmac(acc[o], h[LB - 1 - (c - o)], x);
-                }
-            }
-            C2 nz[TC];
-            if constexpr (VERIFY) {
-                const double2* src = prm.noise_in + (size_t)f * prm.noise_len;
-#pragma unroll
-                for (int o = 0; o < TC; ++o) nz[o] = (o < nvalid) ? to_v2<T>(src[i0 + o]) : mk2<T>(0, 0);
-            } else {
-                const uint32_t q0 = (uint32_t)tid * (uint32_t)((B + 1) >> 1);   // block tid starts at draw tid*(B+1)
-#pragma unroll
-                for (int p2 = 0; p2 < (TC + 1) / 2; ++p2) {
-                    C2 n0, n1;
-                    noise_pair<T>(prm, f, q0 + p2, n0, n1);
-                    nz[2 * p2] = n0;
-                    if (2 * p2 + 1 < TC) nz[2 * p2 + 1] = n1;
-                }
-            }
-            if (!full) {
+            for (int c = 0; c < TC + LB - 1; ++c) {
+                const C2 x = src[c];
 #pragma unroll
                 for (int o = 0; o < TC; ++o)
-                    if (o >= nvalid) { acc[o] = mk2<T>(0, 0); nz[o] = mk2<T>(0, 0); }
+                    if (c - o >= 0 && c - o <= LB - 1) cmac(acc[o], h[LB - 1 - (c - o)], x);
+                if (c % NSTEP == 0 && c / NSTEP < NPAIR) {
+                    const int p2 = c / NSTEP;
+                    C2 n0, n1;
+                    if constexpr (VERIFY) {
+                        const double2* nin = prm.noise_in + (size_t)f * prm.noise_len + i0;
+                        n0 = (2 * p2 < nvalid) ? to_v2<T>(nin[2 * p2]) : mk2<T>(0, 0);
+                        n1 = (2 * p2 + 1 < nvalid) ? to_v2<T>(nin[2 * p2 + 1]) : mk2<T>(0, 0);
+                    } else {
+                        noise_pair<T>(prm, f, q0 + p2, n0, n1);
+                        if (!FULL) {
+                            if (2 * p2 >= nvalid) n0 = mk2<T>(0, 0);
+                            if (2 * p2 + 1 >= nvalid) n1 = mk2<T>(0, 0);
+                        }
+                    }
+                    pn2 = csq_acc(n0, pn2);
+                    nb[2 * p2] = n0;
+                    if (2 * p2 + 1 < TC) { pn2 = csq_acc(n1, pn2); nb[2 * p2 + 1] = n1; }
+                }
+            }
+            if (!FULL) {
+#pragma unroll
+                for (int o = 0; o < TC; ++o)
+                    if (o >= nvalid) acc[o] = mk2<T>(0, 0);
             }
 #pragma unroll
-            for (int o = 0; o < TC; ++o) { pr2 = csq_acc(acc[o], pr2); pn2 = csq_acc(nz[o], pn2); }
+            for (int o = 0; o < TC; ++o) pr2 = csq_acc(acc[o], pr2);
             if (prm.noise_norm == 1) {
                 // the L-1+beta samples the reference truncates still count in both power sums
                 for (int i = sec + tid; i < body + L - 1; i += NT) {
@@ -367,14 +381,9 @@ ber_frame_kernel(const BerParams prm) {
 #pragma unroll
             for (int wq = 0; wq < NT / 32; ++wq) { pr += red[wq]; pn += red[32 + wq]; }
             const T g = sqrt(pr * snr_lin / pn);
-            if (full) {
 #pragma unroll
-                for (int o = 0; o < TC; ++o) ub[i0 + o] = caxpy(g, nz[o], acc[o]);
-            } else {
-#pragma unroll
-                for (int o = 0; o < TC; ++o)
-                    if (o < nvalid) ub[i0 + o] = caxpy(g, nz[o], acc[o]);
-            }
+            for (int o = 0; o < TC; ++o)
+                if (FULL || o < nvalid) ub[i0 + o] = caxpy(g, nb[o], acc[o]);
         } else {
             const int total = prm.noise_norm == 1 ? body + L - 1 : sec;
             for (int i = tid; i < total; i += NT) {
@@ -427,20 +436,25 @@ ber_frame_kernel(const BerParams prm) {
                 }
                 v[q] = o;
             }
-            if (REGS && rounds == 1) __syncthreads();   // the stream body is about to become the exchange buffer
             fft_regs<T, N, -1>(v, t, xb, tw);
-            uint32_t w[4];
-            load_sym_idx<N, VERIFY>(prm, f, se, t, w);
-            if (se == 0) {
-                // pilot: G = X0 / Y0 (wofdm_simulation.py:223), in lattice units
+            const uint4 wv = symw[se * TPF + t];
+            const uint32_t w[4] = {wv.x, wv.y, wv.z, wv.w};
+            if (s0 == 0) {
+                // pilot (wofdm_simulation.py:223): the pilot's threads publish Y0, then every thread turns one
+                // bin into the equaliser tap G[k] = X0[k] / Y0[k] (lattice units), so nobody waits on one warp
+                if (se == 0) {
 #pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                    const C2 x0 = qlut[sym_byte(w, q)];
-                    const T d = (T)1 / (v[q].x * v[q].x + v[q].y * v[q].y);
-                    geq[t + q * TPF] = cscale(d, cmulc(x0, v[q]));
+                    for (int q = 0; q < 16; ++q) geq[t + q * TPF] = v[q];
                 }
+                __syncthreads();
+                const unsigned char* pil = reinterpret_cast<const unsigned char*>(symw);   // symbol 0: thread k%TPF, byte k/TPF
+                for (int k = tid; k < N; k += NT) {
+                    const C2 y0 = geq[k];
+                    const C2 x0 = qlut[pil[(k % TPF) * 16 + k / TPF]];
+                    geq[k] = cscale(recip(y0.x * y0.x + y0.y * y0.y), cmulc(x0, y0));
+                }
+                __syncthreads();
             }
-            __syncthreads();
             if (act && s > 0) {
 #pragma unroll
                 for (int q = 0; q < 16; ++q) {
@@ -470,6 +484,14 @@ ber_frame_kernel(const BerParams prm) {
             }
         }
         __syncthreads();   // taps / stream / geq are rewritten by the next frame
+        f += df;
+        if constexpr (!VERIFY) {
+            fe += de;
+            if (fe >= prm.ensemble) { fe -= prm.ensemble; ++ci; }
+            ci += dc;
+            if (ci >= prm.C) { ci -= prm.C; ++si; }
+            si += ds;
+        }
     }
 }
 

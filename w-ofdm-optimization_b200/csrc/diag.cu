@@ -38,6 +38,51 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(float* out, int iters, fl
     if (s == 12345.678f) out[0] = s;   // keeps the chains alive, never true in practice
 }
 
+// mode 3: 8 FFMA2 chains interleaved 1:1 with 8 integer (ALU-pipe) chains: do packed FMAs leave issue
+// slots for the other pipes?  Reported as the FFMA2 flop rate only.
+__global__ void __launch_bounds__(256) mix_peak_kernel(float* out, int iters, float a, float b, unsigned k) {
+    pk64 v[8], ab = pk(a, a), bb = pk(b, b);
+    unsigned z[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { v[i] = pk((float)(threadIdx.x + i) * 1e-3f, 1.0f); z[i] = threadIdx.x * 2654435761u + i; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(v[i]) : "l"(ab), "l"(bb));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(z[i]) : "r"(k), "r"(z[(i + 1) & 7]));
+            }
+    }
+    float s = 0; unsigned zz = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { float2 f = upk(v[i]); s += f.x + f.y; zz ^= z[i]; }
+    if (s == 12345.678f || zz == 0x12345u) out[0] = s;
+}
+
+// mode 2: the convolution's register pattern -- 17 complex accumulators, 21 complex taps, each input
+// feeds 17 complex MACs (2 FFMA2 each: acc += h.x*x; acc += h.y*(i x)); no memory traffic.
+__global__ void __launch_bounds__(256) cmac_peak_kernel(float2* out, int iters, float a, float b) {
+    float2 h[21], acc[17];
+#pragma unroll
+    for (int l = 0; l < 21; ++l) h[l] = make_float2(a + 1e-3f * l, b - 1e-3f * l);
+#pragma unroll
+    for (int o = 0; o < 17; ++o) acc[o] = make_float2(0.f, 0.f);
+    float2 x = make_float2((float)threadIdx.x * 1e-3f, 1.0f);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int c = 0; c < 21; ++c) {
+            x = make_float2(x.y, x.x + 1e-6f);
+#pragma unroll
+            for (int o = 0; o < 17; ++o) cmac(acc[o], h[(c + o) % 21], x);
+        }
+    }
+    float2 s = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int o = 0; o < 17; ++o) s = cadd(s, acc[o]);
+    if (s.x == 12345.678f) out[0] = s;
+}
+
 }  // namespace wofdm
 
 using namespace wofdm;
@@ -56,7 +101,9 @@ extern "C" WOFDM_API int wofdm_diag_fp32_peak(wofdm_handle h, int mode, double* 
     for (int rep = 0; rep < 6; ++rep) {
         WOFDM_CUDA(h, cudaEventRecord(e0, d.stream));
         if (mode == 0) fma_peak_kernel<0><<<grid, 256, 0, d.stream>>>(out, iters, 0.999f, 1e-4f);
-        else fma_peak_kernel<1><<<grid, 256, 0, d.stream>>>(out, iters, 0.999f, 1e-4f);
+        else if (mode == 1) fma_peak_kernel<1><<<grid, 256, 0, d.stream>>>(out, iters, 0.999f, 1e-4f);
+        else if (mode == 3) mix_peak_kernel<<<grid, 256, 0, d.stream>>>(out, iters, 0.999f, 1e-4f, 0x9E3779B9u);
+        else cmac_peak_kernel<<<grid, 256, 0, d.stream>>>(reinterpret_cast<float2*>(out), iters / 4, 0.01f, 0.02f);
         WOFDM_CUDA(h, cudaEventRecord(e1, d.stream));
         WOFDM_CUDA(h, cudaEventSynchronize(e1));
         float ms = 0;
@@ -64,7 +111,8 @@ extern "C" WOFDM_API int wofdm_diag_fp32_peak(wofdm_handle h, int mode, double* 
         if (rep > 0 && ms < best) best = ms;
         h->launches += 1;
     }
-    const double flops = 2.0 * 16 * 8 * (double)iters * 256.0 * grid;
+    const double flops = mode == 3 ? 2.0 * 16 * 8 * (double)iters * 256.0 * grid : mode == 2 ? 8.0 * 21 * 17 * (double)(iters / 4) * 256.0 * grid
+                                   : 2.0 * 16 * 8 * (double)iters * 256.0 * grid;
     *tflops = flops / (best * 1e-3) / 1e12;
     if (sm_mhz_equiv) *sm_mhz_equiv = *tflops * 1e12 / (2.0 * 128 * d.sm_count) / 1e6;   // clock that 128 FMA lanes/SM would need
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
