@@ -1,0 +1,88 @@
+"""GPU parity tests of K2 (interference power) through the C-ABI.
+
+fp64 tensor path (mode 0): <= 1e-9 relative against (i) the reference's own interf_power outputs on the mean
+channel (tests/golden/interf_*.npz), (ii) the dense oracle per channel, (iii) the independent Gram-form
+oracle; MATLAB scalar semantics against the restated calculate_interference."""
+import numpy as np
+import pytest
+
+import wofdm_b200 as W
+from oracle import wofdm_oracle as O
+from helpers import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def handle():
+    with W.Handle([0]) as h:
+        yield h
+
+
+def to_sys(p):
+    return W.SysT(N=p.N, cp=p.cp, cs=p.cs, tail_tx=p.tail_tx, tail_rx=p.tail_rx, rm=p.rm, shift=p.shift,
+                  bits=p.bits, S=p.S, noise_norm=0, constellation=0, precision=1)
+
+
+def rel(a, b):
+    return np.max(np.abs(a - b)) / np.max(np.abs(b))
+
+
+@pytest.mark.parametrize("name", O.SYSTEMS)
+def test_golden_mean_channel(handle, name):
+    """The reference evaluates the MEAN impulse response (interf_calc.py:80-83): same call, one column."""
+    g = np.load(f"{GOLDEN}/interf_{name}.npz")
+    ttx, trx = (0, 0) if name == "CP" else (int(g["tail_tx"]), int(g["tail_rx"]))
+    p = O.system_params(name, int(g["N"]), int(g["cp"]), ttx, trx)
+    h = g["channels"].mean(axis=1)
+    vt, vr = (np.ones(p.n_tx), np.ones(p.N)) if name == "CP" else (g["v_tx"], g["v_rx"])
+    P = handle.interf_power(to_sys(p), vt, vr, h[:, None], mode=0)
+    assert P.shape == (1, p.N)
+    assert rel(P[0], g["P_opt"]) < 1e-9
+    if name != "CP":
+        Prc = handle.interf_power(to_sys(p), O.rc_window_tx(p), O.rc_window_rx(p), h[:, None], mode=0)
+        assert rel(Prc[0], g["P_rc"]) < 1e-9
+
+
+@pytest.mark.parametrize("name", ["wtx", "WOLA", "CPW", "CPwrx"])
+def test_per_channel_batch(handle, name):
+    """Every channel realisation at once (the new capability): oracle = the same function per column."""
+    g = np.load(f"{GOLDEN}/interf_{name}.npz")
+    p = O.system_params(name, 256, 16, int(g["tail_tx"]), int(g["tail_rx"]))
+    chans = g["channels"][:, :6]
+    P = handle.interf_power(to_sys(p), g["v_tx"], g["v_rx"], chans, mode=0)
+    for c in range(chans.shape[1]):
+        want = O.interf_power_dense(p, g["v_tx"], g["v_rx"], chans[:, c])
+        assert rel(P[c], want) < 1e-9, c
+    want = O.interf_power_gram(p, g["v_tx"], g["v_rx"], chans[:, 0])
+    assert rel(P[0], want) < 1e-9
+
+
+@pytest.mark.parametrize("N,cp,ttx,trx,L", [(64, 8, 2, 2, 9), (128, 16, 4, 4, 21), (512, 24, 8, 8, 33), (64, 8, 2, 2, 80)])
+def test_other_sizes_and_long_channels(handle, N, cp, ttx, trx, L):
+    """Other DFT sizes; L = 80 > n_rx gives more than one ISI slice (M = 3)."""
+    p = O.system_params("WOLA", N, cp, ttx, trx)
+    vt, vr, _, _ = O.perturbed_windows(p, seed=N)
+    chans = O.synth_channels(3, L, seed=L)
+    assert O.n_slices(p, L) == (3 if L == 80 else 2)
+    P = handle.interf_power(to_sys(p), vt, vr, chans, mode=0)
+    for c in range(3):
+        assert rel(P[c], O.interf_power_dense(p, vt, vr, chans[:, c])) < 1e-9
+
+
+def test_matlab_scalar_semantics(handle):
+    """calculate_interference (main_interference_calculation.m:177-225): ISI slices summed before squaring."""
+    p = O.system_params("WOLA", 64, 8, 2, 2)
+    vt, vr, _, _ = O.perturbed_windows(p, seed=4)
+    chans = O.synth_channels(4, 80, seed=9)          # M = 3: the two conventions differ
+    S = handle.interf_power(to_sys(p), vt, vr, chans, mode=0, scalar=True)
+    Pv = handle.interf_power(to_sys(p), vt, vr, chans, mode=0)
+    for c in range(4):
+        want = O.interf_power_matlab(p, vt, vr, chans[:, c])
+        assert abs(S[c] - want) < 1e-9 * want
+        assert abs(Pv[c].sum() - want) > 1e-6 * want
+    p2 = O.system_params("wtx", 256, 16, 8, 0)
+    ch2 = O.synth_channels(2, 21, seed=1)
+    S2 = handle.interf_power(to_sys(p2), O.rc_window_tx(p2), O.rc_window_rx(p2), ch2, mode=0, scalar=True)
+    P2 = handle.interf_power(to_sys(p2), O.rc_window_tx(p2), O.rc_window_rx(p2), ch2, mode=0)
+    assert np.allclose(S2, P2.sum(axis=1), rtol=1e-12)     # one ISI slice: identical

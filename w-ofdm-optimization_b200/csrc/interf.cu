@@ -1,11 +1,258 @@
-// interf.cu -- K2, interference power (placeholder until the tensor-core contraction lands).
+// interf.cu -- K2/K3: interference power of the w-OFDM systems over every channel realisation.
+//
+//   A_m(c) = Rx_mat . H_m(h_c) . Tx_mat,   P_k(c) = sum_{j != k} |A_0[k,j]|^2 + sum_{m>=1} sum_j |A_m[k,j]|^2
+//
+// replacing interf_power (python/ofdm_utils/interf_calc.py:20-113) and calculate_interference
+// (matlab/main_interference_calculation.m:177-225), which evaluate ONE (mean) channel with eight dense
+// N x n products per A matrix.  Here:
+//   K3  build_tx_matrix / build_rx_matrix: Tx_mat = Vtx.Gamma.W^-1 (n_tx x N) and Rx_mat = W.K.P.Vrx.R
+//       (N x n_rx) written in closed form (one sincospi per entry) -- the matrix builders of
+//       transmitter.py / receiver.py / matlab/functions/*_matrix.m.
+//   K2a build_b: B_m(c) = H_m(h_c).Tx_mat.  H_m is banded Toeplitz (channel.py:15-53), so this is an
+//       L-tap convolution down the columns of Tx_mat; written to HBM as the real matrix [Re B; Im B].
+//   K2b gemm_power_f64: the dense contraction [Re A; Im A] = [Rr -Ri; Ri Rr] . [Re B; Im B] on the FP64
+//       tensor path (mma.sync m8n8k4 f64 = DMMA), all channels and slices side by side as the N
+//       dimension, with the off-diagonal mask and the row-wise sum of |.|^2 fused into the epilogue.
+// The TF32-split tensor path (mode 1) lives in interf_tf32.cu.
+#include <algorithm>
+
 #include "host_common.h"
+#include "interf.h"
+
+namespace wofdm {
+
+// ---- K3: matrix builders ----------------------------------------------------------------------
+// Tx_mat[i][k] = vtx[i]/N * exp(+2 pi i k n / N), n = (i - cp) mod N      (transmitter.py:13-58)
+__global__ void build_tx_matrix(double2* __restrict__ T, const double* __restrict__ vtx, int N, int cp, int n_tx) {
+    const int i = blockIdx.x, n = ((i - cp) % N + N) % N;
+    for (int k = threadIdx.x; k < N; k += blockDim.x) {
+        double s, c;
+        sincospi(2.0 * (double)(((long long)k * n) % N) / (double)N, &s, &c);
+        const double w = vtx[i] / (double)N;
+        T[(size_t)i * N + k] = make_double2(w * c, w * s);
+    }
+}
+
+// Rbig = [Rr -Ri; Ri Rr] (2N x Kp), R[k][b] = vrx[b-rm] * exp(-2 pi i k n(b) / N) for rm <= b < rm+N+d,
+// n(b) = ((b - rm - d/2) mod N - shift) mod N                              (receiver.py:13-133)
+__global__ void build_rx_matrix(double* __restrict__ Rbig, const double* __restrict__ vrx, int N, int tail_rx,
+                                int rm, int shift, int n_rx, int Kp) {
+    const int k = blockIdx.x;
+    const int hh = tail_rx / 2;
+    for (int b = threadIdx.x; b < Kp; b += blockDim.x) {
+        double re = 0.0, im = 0.0;
+        const int col = b < n_rx ? b : b - n_rx;     // second half of K multiplies Im B
+        if (b < 2 * n_rx && col >= rm && col - rm < N + tail_rx) {
+            const int np = ((col - rm - hh) % N + N) % N;
+            const int n = ((np - shift) % N + N) % N;
+            double s, c;
+            sincospi(2.0 * (double)(((long long)k * n) % N) / (double)N, &s, &c);
+            re = vrx[col - rm] * c;
+            im = -vrx[col - rm] * s;
+        }
+        // row k: Re A = Rr.Br - Ri.Bi ; row N+k: Im A = Ri.Br + Rr.Bi
+        Rbig[(size_t)k * Kp + b] = b < n_rx ? re : -im;
+        Rbig[(size_t)(N + k) * Kp + b] = b < n_rx ? im : re;
+        if (b >= 2 * n_rx) { Rbig[(size_t)k * Kp + b] = 0.0; Rbig[(size_t)(N + k) * Kp + b] = 0.0; }
+    }
+}
+
+// ---- K2a: B = H_m(h_c) . Tx_mat ------------------------------------------------------------------
+// slice s of a batch: channel c0 + s / Ms, slice index m = s % Ms.  sum_isi (MATLAB semantics,
+// main_interference_calculation.m:198): Ms = 2 and slice 1 holds sum_{m>=1} H_m.
+// Bbig[s][kk][j], kk < n_rx: Re B[kk][j]; n_rx <= kk < 2 n_rx: Im B[kk-n_rx][j]; zero up to Kp.
+__global__ void __launch_bounds__(256) build_b(double* __restrict__ Bbig, const double2* __restrict__ T,
+                                               const double2* __restrict__ chan, int L, int N, int n_tx, int n_rx,
+                                               int N0, int Kp, int Ms, int M, int c0, int sum_isi) {
+    const int s = blockIdx.z, b = blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    const int c = c0 + s / Ms, ms = s % Ms;
+    const double2* h = chan + (size_t)c * L;
+    double2 acc = make_double2(0.0, 0.0);
+    const int m_lo = ms, m_hi = (sum_isi && ms == 1) ? M - 1 : ms;
+    for (int m = m_lo; m <= m_hi; ++m)
+        for (int l = 0; l < L; ++l) {
+            const int row = m * N0 + b - l;                 // H_m[b][row] = h[l]            (channel.py:49-52)
+            if (row >= 0 && row < n_tx) cmac(acc, h[l], T[(size_t)row * N + j]);
+        }
+    double* out = Bbig + (size_t)s * Kp * N;
+    out[(size_t)b * N + j] = acc.x;
+    out[(size_t)(n_rx + b) * N + j] = acc.y;
+    if (b == 0)
+        for (int kk = 2 * n_rx; kk < Kp; ++kk) out[(size_t)kk * N + j] = 0.0;
+}
+
+// ---- K2b: FP64 tensor-core contraction with fused power epilogue ----------------------------------
+constexpr int BM = 128, BN = 64, BK = 16, AS = BK + 4, BS = BN + 4;
+
+__device__ __forceinline__ void dmma8x8x4(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// grid (N / BN column tiles of a slice, 2N / BM row tiles, slices); P[c][k] += row power
+__global__ void __launch_bounds__(256) gemm_power_f64(const double* __restrict__ Rbig, const double* __restrict__ Bbig,
+                                                      double* __restrict__ P, int N, int Kp, int Ms, int c0, int scalar) {
+    extern __shared__ __align__(16) double gsm[];
+    double (*As)[BM * AS] = reinterpret_cast<double (*)[BM * AS]>(gsm);
+    double (*Bs)[BK * BS] = reinterpret_cast<double (*)[BK * BS]>(gsm + 2 * BM * AS);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+    const int row0 = blockIdx.y * BM, col0 = blockIdx.x * BN, s = blockIdx.z;
+    const double* A = Rbig + (size_t)row0 * Kp;
+    const double* B = Bbig + (size_t)s * Kp * N + col0;
+    const int ar = tid >> 1, ak = (tid & 1) * 8;          // A tile: 128 rows x 16, 8 doubles per thread
+    const int br = tid >> 4, bc = (tid & 15) * 4;         // B tile: 16 rows x 64, 4 doubles per thread
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int jn = 0; jn < 4; ++jn) acc[i][jn][0] = acc[i][jn][1] = 0.0;
+    double ra[8], rb[4];
+    auto gload = [&](int k0) {
+        const double4* pa = reinterpret_cast<const double4*>(A + (size_t)ar * Kp + k0 + ak);
+        const double4 a0 = pa[0], a1 = pa[1];
+        ra[0] = a0.x; ra[1] = a0.y; ra[2] = a0.z; ra[3] = a0.w; ra[4] = a1.x; ra[5] = a1.y; ra[6] = a1.z; ra[7] = a1.w;
+        const double4 b0 = *reinterpret_cast<const double4*>(B + (size_t)(k0 + br) * N + bc);
+        rb[0] = b0.x; rb[1] = b0.y; rb[2] = b0.z; rb[3] = b0.w;
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) As[buf][ar * AS + ak + i] = ra[i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) Bs[buf][br * BS + bc + i] = rb[i];
+    };
+    gload(0);
+    sstore(0);
+    __syncthreads();
+    const int nk = Kp / BK;
+    for (int kt = 0; kt < nk; ++kt) {
+        const int buf = kt & 1;
+        if (kt + 1 < nk) gload((kt + 1) * BK);
+#pragma unroll
+        for (int kk = 0; kk < BK; kk += 4) {
+            double fa[4], fb[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) fa[i] = As[buf][(wm + 8 * i + (lane >> 2)) * AS + kk + (lane & 3)];
+#pragma unroll
+            for (int jn = 0; jn < 4; ++jn) fb[jn] = Bs[buf][(kk + (lane & 3)) * BS + wn + 8 * jn + (lane >> 2)];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int jn = 0; jn < 4; ++jn) dmma8x8x4(acc[i][jn][0], acc[i][jn][1], fa[i], fb[jn]);
+        }
+        if (kt + 1 < nk) sstore(buf ^ 1);
+        __syncthreads();
+    }
+    // epilogue: rows r (Re) and N + r (Im) of big-A both belong to sub-carrier r; slice 0 drops j == k
+    const int c = c0 + s / Ms, ms = s % Ms;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = row0 + wm + 8 * i + (lane >> 2);
+        const int k = r % N;
+        double pw = 0.0;
+#pragma unroll
+        for (int jn = 0; jn < 4; ++jn)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int jcol = col0 + wn + 8 * jn + 2 * (lane & 3) + e;
+                const double v = acc[i][jn][e];
+                if (!(ms == 0 && jcol == k)) pw = fma(v, v, pw);
+            }
+        pw += __shfl_xor_sync(0xffffffffu, pw, 1);
+        pw += __shfl_xor_sync(0xffffffffu, pw, 2);
+        if ((lane & 3) == 0) atomicAdd(scalar ? &P[c] : &P[(size_t)c * N + k], pw);
+    }
+}
+
+int interf_upload(wofdm_ctx* h, const wofdm_sys_t* sys, const double* win_tx, const double* win_rx,
+                  const double* chan, int L, int C, InterfDev* out) {
+    DeviceCtx& d = h->devs[0];
+    const int N = sys->N, n_tx = N + sys->cp + sys->cs, n_rx = n_tx - sys->tail_tx;
+    InterfDev v;
+    v.N = N; v.n_tx = n_tx; v.n_rx = n_rx; v.N0 = n_rx;
+    v.Kp = ((2 * n_rx + 63) / 64) * 64;
+    v.M = 1 + (L - 1 + sys->tail_tx + n_rx - 1) / n_rx;     // channel.py:42
+    const size_t bytes = (size_t)(n_tx + N + sys->tail_rx) * 8 + (size_t)L * C * 16 + (size_t)n_tx * N * 16 +
+                         (size_t)2 * N * v.Kp * 8;
+    // batch of channels whose B matrices fit the staging budget (1 GiB of the arena)
+    const size_t per_chan = (size_t)v.M * v.Kp * N * 8;
+    v.batch = (int)std::max<size_t>(1, std::min<size_t>((size_t)C, ((size_t)1 << 30) / per_chan));
+    int rc = arena_reserve(h, d, bytes + (size_t)v.batch * per_chan + (size_t)C * N * 8);
+    if (rc) return rc;
+    v.vtx = static_cast<double*>(arena_take(d, (size_t)n_tx * 8));
+    v.vrx = static_cast<double*>(arena_take(d, (size_t)(N + sys->tail_rx) * 8));
+    v.chan = static_cast<double2*>(arena_take(d, (size_t)L * C * 16));
+    v.T = static_cast<double2*>(arena_take(d, (size_t)n_tx * N * 16));
+    v.Rbig = static_cast<double*>(arena_take(d, (size_t)2 * N * v.Kp * 8));
+    v.Bbig = static_cast<double*>(arena_take(d, (size_t)v.batch * per_chan));
+    v.P = static_cast<double*>(arena_take(d, (size_t)C * N * 8));
+    if (!v.vtx || !v.vrx || !v.chan || !v.T || !v.Rbig || !v.Bbig || !v.P) return fail(h, WOFDM_ENOMEM, "arena exhausted");
+    WOFDM_CUDA(h, cudaMemcpyAsync(v.vtx, win_tx, (size_t)n_tx * 8, cudaMemcpyHostToDevice, d.stream));
+    WOFDM_CUDA(h, cudaMemcpyAsync(v.vrx, win_rx, (size_t)(N + sys->tail_rx) * 8, cudaMemcpyHostToDevice, d.stream));
+    WOFDM_CUDA(h, cudaMemcpyAsync(v.chan, chan, (size_t)L * C * 16, cudaMemcpyHostToDevice, d.stream));
+    build_tx_matrix<<<n_tx, 256, 0, d.stream>>>(v.T, v.vtx, N, sys->cp, n_tx);
+    build_rx_matrix<<<N, 256, 0, d.stream>>>(v.Rbig, v.vrx, N, sys->tail_rx, sys->rm, sys->shift, n_rx, v.Kp);
+    WOFDM_CUDA(h, cudaGetLastError());
+    h->launches += 2;
+    *out = v;
+    return WOFDM_OK;
+}
+
+static int interf_run(wofdm_handle h, const wofdm_sys_t* sys, const double* win_tx, const double* win_rx,
+                      const double* chan, int L, int C, int mode, int scalar, double* P) {
+    if (!h) return WOFDM_EINVAL;
+    int rc = validate_sys(h, sys, L);
+    if (rc) return rc;
+    if (!win_tx || !win_rx || !chan || !P || C < 1) return fail(h, WOFDM_EINVAL, "bad buffer");
+    if (mode != 0 && mode != 1) return fail(h, WOFDM_EINVAL, "mode must be 0 (fp64) or 1 (TF32-split)");
+    if (sys->N % 64) return fail(h, WOFDM_EUNSUPPORTED, "interference path needs N to be a multiple of 64");
+    DeviceCtx& d = h->devs[0];
+    WOFDM_CUDA(h, cudaSetDevice(d.dev));
+    InterfDev v;
+    rc = interf_upload(h, sys, win_tx, win_rx, chan, L, C, &v);
+    if (rc) return rc;
+    const int N = sys->N;
+    const size_t pbytes = scalar ? (size_t)C * 8 : (size_t)C * N * 8;
+    WOFDM_CUDA(h, cudaMemsetAsync(v.P, 0, pbytes, d.stream));
+    const int Ms = scalar ? std::min(v.M, 2) : v.M;      // scalar: slice 1 = sum of the ISI slices
+    for (int c0 = 0; c0 < C; c0 += v.batch) {
+        const int nc = std::min(v.batch, C - c0);
+        const int slices = nc * Ms;
+        build_b<<<dim3((N + 255) / 256, v.n_rx, slices), 256, 0, d.stream>>>(v.Bbig, v.T, v.chan, L, N, v.n_tx, v.n_rx,
+                                                                         v.N0, v.Kp, Ms, v.M, c0, scalar);
+        WOFDM_CUDA(h, cudaGetLastError());
+        if (mode == 0) {
+            constexpr size_t smem = (size_t)(2 * BM * AS + 2 * BK * BS) * sizeof(double);
+            WOFDM_CUDA(h, cudaFuncSetAttribute(gemm_power_f64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            gemm_power_f64<<<dim3(N / BN, 2 * N / BM, slices), 256, smem, d.stream>>>(v.Rbig, v.Bbig, v.P, N, v.Kp, Ms, c0, scalar);
+            WOFDM_CUDA(h, cudaGetLastError());
+        } else {
+            rc = interf_gemm_tf32(h, sys, v, Ms, c0, slices, scalar);
+            if (rc) return rc;
+        }
+        h->launches += 2;
+    }
+    WOFDM_CUDA(h, cudaMemcpyAsync(P, v.P, pbytes, cudaMemcpyDeviceToHost, d.stream));
+    WOFDM_CUDA(h, cudaStreamSynchronize(d.stream));
+    return WOFDM_OK;
+}
+
+}  // namespace wofdm
+
 using namespace wofdm;
+
 extern "C" {
-int wofdm_interf_power(wofdm_handle h, const wofdm_sys_t*, const double*, const double*, const double*, int, int, int, double*) {
-    return fail(h, WOFDM_EUNSUPPORTED, "wofdm_interf_power: not built yet");
+
+int wofdm_interf_power(wofdm_handle h, const wofdm_sys_t* sys, const double* win_tx, const double* win_rx,
+                       const double* chan, int L, int C, int mode, double* P) {
+    return interf_run(h, sys, win_tx, win_rx, chan, L, C, mode, 0, P);
 }
-int wofdm_interf_power_scalar(wofdm_handle h, const wofdm_sys_t*, const double*, const double*, const double*, int, int, int, double*) {
-    return fail(h, WOFDM_EUNSUPPORTED, "wofdm_interf_power_scalar: not built yet");
+
+int wofdm_interf_power_scalar(wofdm_handle h, const wofdm_sys_t* sys, const double* win_tx, const double* win_rx,
+                              const double* chan, int L, int C, int mode, double* P) {
+    return interf_run(h, sys, win_tx, win_rx, chan, L, C, mode, 1, P);
 }
-}
+
+}  // extern "C"
