@@ -7,7 +7,8 @@ built into ``libwofdm.so``), ``capi`` (ctypes binding of include/wofdm.h) and ``
 The directory name contains hyphens, so import it as ``import wofdm_b200`` (alias module at the
 repo root) or ``importlib.import_module("w-ofdm-optimization_b200")``.
 """
-from . import capi  # noqa: F401
+from . import capi, sharding  # noqa: F401
+from . import ofdm_utils  # noqa: F401,E402
 from .capi import Handle, BerPlan, SysT, WofdmError, params_from_name  # noqa: F401
 
-__all__ = ["capi", "Handle", "BerPlan", "SysT", "WofdmError", "params_from_name"]
+__all__ = ["capi", "sharding", "ofdm_utils", "Handle", "BerPlan", "SysT", "WofdmError", "params_from_name"]

@@ -305,14 +305,8 @@ class BerPlan:
 
     def totals(self, ensemble, shard=(0, 1)):
         """(bit_tot, sym_tot) per SNR point for frames f = shard[0] mod shard[1]."""
-        per = self.C * int(ensemble)
-        i, n = shard
-
-        def upto(x):
-            return (x - i + n - 1) // n if x > i else 0
-        frames = np.array([upto((k + 1) * per) - upto(k * per) for k in range(self.n_snr)], dtype=np.int64)
-        sym = frames * self.sys.N * (self.sys.S - 1)
-        return sym * self.sys.bits, sym
+        from .sharding import totals
+        return totals(self.n_snr, self.C, ensemble, self.sys.N, self.sys.S, self.sys.bits, shard)
 
     def close(self):
         if getattr(self, "_p", None):
