@@ -1,0 +1,118 @@
+"""GPU tests of the reference-facing host mirror (w-ofdm-optimization_b200/ofdm_utils.py) and of production mode
+(on-device RNG): SER/BER must fall inside the 95 % confidence interval of the oracle at every SNR point
+(north star), file inputs/outputs keep the reference's schema."""
+import os
+
+import numpy as np
+import pytest
+
+import wofdm_b200 as W
+from wofdm_b200 import ofdm_utils as U
+from oracle import wofdm_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def handle():
+    with W.Handle([0]) as h:
+        U.set_handle(h)
+        yield h
+        U.set_handle(None)
+
+
+def oracle_frame_sers(p, vt, vr, chans, snr_arr, frames_per_chan, seed, bits_mode=False):
+    """per-frame error ratios from the numpy oracle with its own seeded draws -> mean and 95 % CI"""
+    rng = np.random.default_rng(seed)
+    L = chans.shape[0]
+    n = O.noise_len(p, L)
+    out = []
+    for snr in snr_arr:
+        vals = []
+        for c in range(chans.shape[1]):
+            for _ in range(frames_per_chan):
+                idx = rng.integers(0, 1 << p.bits, size=(p.N, p.S))
+                nz = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+                r = O.frame_chain_structured(p, vt, vr, chans[:, c], float(snr), idx, nz)
+                vals.append(r.bit_err / (p.N * p.bits * (p.S - 1)) if bits_mode else r.sym_err / (p.N * (p.S - 1)))
+        v = np.array(vals)
+        out.append((v.mean(), 1.96 * v.std(ddof=1) / np.sqrt(len(v))))
+    return out
+
+
+@pytest.mark.parametrize("name,conv,nn", [("wtx", 0, 0), ("WOLA", 1, 1), ("CP", 0, 0)])
+def test_production_ser_within_oracle_ci(handle, name, conv, nn):
+    ttx = 8 if name in U.TX_SYSTEMS else 0
+    trx = 10 if name in U.RX_SYSTEMS else 0
+    p = O.system_params(name, 256, 16, ttx, trx, S=16, constellation=conv, noise_norm=nn)
+    vt, vr, _, _ = O.perturbed_windows(p, seed=8)
+    chans = O.synth_channels(4, 21, seed=12)
+    snr = np.array([0.0, 10.0, 20.0, 30.0])
+    ref = oracle_frame_sers(p, vt, vr, chans, snr, 40, seed=77, bits_mode=(conv == 1))
+    s = W.SysT(N=p.N, cp=p.cp, cs=p.cs, tail_tx=p.tail_tx, tail_rx=p.tail_rx, rm=p.rm, shift=p.shift, bits=p.bits,
+               S=p.S, noise_norm=nn, constellation=conv, precision=0)
+    r = handle.ber_run(s, vt, vr, chans, snr, 2000, seed=5)
+    got = r["bit_err"] / r["bit_tot"] if conv == 1 else r["sym_err"] / r["sym_tot"]
+    # 95 % CI of the oracle's own Monte-Carlo estimate (160 frames per point).  Twelve two-sided 95 % checks
+    # would fail by chance every other run, so: every point inside the 99.9 % interval, >= 3 of 4 inside 95 %.
+    inside = 0
+    for k, (mean, ci) in enumerate(ref):
+        assert abs(got[k] - mean) <= ci * (3.29 / 1.96) + 1e-4, (name, snr[k], got[k], mean, ci)
+        inside += abs(got[k] - mean) <= ci + 1e-4
+    assert inside >= 3, (name, got, ref)
+
+
+def test_simulation_fun_files(handle, tmp_path):
+    """Same 11-tuple, same input files (<sys>_<cp>.npy reduced tails, channels .npy), same output files."""
+    win_dir, out_dir = tmp_path / "optimized_windows", tmp_path / "simulation_results"
+    os.makedirs(win_dir)
+    chans = O.synth_channels(3, 21, seed=2)
+    np.save(tmp_path / "vehicularA.npy", chans)
+    snr = np.arange(-21, 51, 12)
+    for name in ("WOLA", "wtx", "wrx", "CP"):
+        ttx = 8 if name in U.TX_SYSTEMS else 0
+        trx = 10 if name in U.RX_SYSTEMS else 0
+        p = O.system_params(name, 256, 16, ttx, trx)
+        _, _, xt, xr = O.perturbed_windows(p, seed=1)
+        if name in ("WOLA", "CPW"):
+            np.save(win_dir / f"{name}_16.npy", np.concatenate([xt, xr]))
+        elif name == "wtx":
+            np.save(win_dir / f"{name}_16.npy", xt)
+        elif name == "wrx":
+            np.save(win_dir / f"{name}_16.npy", xr)
+        U.simulation_fun((name, 256, 16, ttx, trx, str(tmp_path / "vehicularA.npy"), str(win_dir), 40, snr, 16,
+                          str(out_dir)))
+        files = [f"CP_16.npy"] if name == "CP" else [f"opt_{name}_16.npy", f"rc_{name}_16.npy"]
+        for f in files:
+            ser = np.load(out_dir / "ser" / f)
+            assert ser.shape == (len(snr),) and ser.dtype == np.float64
+            assert ser[0] > 0.8 and np.all(np.diff(ser) <= 0.02) and ser[-1] < 0.2
+
+
+def test_matlab_signatures(handle):
+    """run_simulation / calculate_interference with the MATLAB argument lists (diagonal-matrix windows)."""
+    p = O.system_params("WOLA", 256, 16, 8, 10, constellation=1, noise_norm=1)
+    vt, vr = O.rc_window_tx(p), O.rc_window_rx(p)
+    chans = O.synth_channels(5, 21, seed=3)
+    bers = [U.run_simulation(50, 16, 4, 256, 16, p.cs, np.diag(vt), chans[:, 0], snr, 8, 10, np.diag(vr), p.rm, p.shift)
+            for snr in (0.0, 15.0, 30.0)]
+    assert 0.2 < bers[0] < 0.5 and bers[0] > bers[1] > bers[2]
+    got = U.calculate_interference(16, "WOLA", np.diag(vt), np.diag(vr), 256, 8, 10, chans.T)
+    want = O.interf_power_matlab(p, vt, vr, chans.mean(axis=1))
+    assert abs(got - want) < 1e-9 * want
+
+
+def test_interf_power_mirror(handle, tmp_path):
+    chans = O.synth_channels(6, 21, seed=4)
+    path = tmp_path / "vehicularA.npy"
+    np.save(path, chans)
+    p = O.system_params("CPW", 256, 16, 8, 10)
+    vt, vr, _, _ = O.perturbed_windows(p, seed=6)
+    Po, Prc = U.interf_power("CPW", [np.diag(vt), np.diag(vr)], 256, 16, 8, 10, channel_path=str(path))
+    assert np.allclose(Po, O.interf_power_dense(p, vt, vr, chans.mean(axis=1)), rtol=1e-9)
+    assert np.allclose(Prc, O.interf_power_dense(p, O.rc_window_tx(p), O.rc_window_rx(p), chans.mean(axis=1)), rtol=1e-9)
+    Pc = U.interf_power("CP", [None, None], 256, 16, 0, 0, channel_path=str(path))
+    pc = O.system_params("CP", 256, 16, 0, 0)
+    assert np.allclose(Pc, O.interf_power_dense(pc, np.ones(pc.n_tx), np.ones(256), chans.mean(axis=1)), rtol=1e-9)
+    Pall, _ = U.interf_power("CPW", [vt, vr], 256, 16, 8, 10, channel_path=str(path), per_channel=True)
+    assert Pall.shape == (6, 256)
