@@ -86,3 +86,24 @@ def test_matlab_scalar_semantics(handle):
     S2 = handle.interf_power(to_sys(p2), O.rc_window_tx(p2), O.rc_window_rx(p2), ch2, mode=0, scalar=True)
     P2 = handle.interf_power(to_sys(p2), O.rc_window_tx(p2), O.rc_window_rx(p2), ch2, mode=0)
     assert np.allclose(S2, P2.sum(axis=1), rtol=1e-12)     # one ISI slice: identical
+
+
+@pytest.mark.parametrize("name", ["WOLA", "wtx", "CPW", "CP"])
+def test_tf32_split_tensor_path(handle, name):
+    """mode 1: tcgen05 kind::tf32 with the 3xTF32 split; fp32-grade accuracy against the fp64 path / oracle.
+    Stated bound: |P_tf32 - P_fp64| <= 2e-5 * max(P) + 5e-8 per sub-carrier (split error 2^-21 per product, fp32
+    accumulation over K = 544 and 256 columns; the absolute term covers systems whose interference is orders of magnitude
+    below the O(1) useful gain the same fp32 accumulators also hold, e.g. CP-OFDM)."""
+    g = np.load(f"{GOLDEN}/interf_{name}.npz")
+    ttx, trx = (0, 0) if name == "CP" else (int(g["tail_tx"]), int(g["tail_rx"]))
+    p = O.system_params(name, 256, 16, ttx, trx)
+    vt, vr = (np.ones(p.n_tx), np.ones(p.N)) if name == "CP" else (g["v_tx"], g["v_rx"])
+    chans = g["channels"][:, :5]
+    P64 = handle.interf_power(to_sys(p), vt, vr, chans, mode=0)
+    P32 = handle.interf_power(to_sys(p), vt, vr, chans, mode=1)
+    tol = 2e-5 * np.max(P64) + 5e-8
+    assert np.max(np.abs(P32 - P64)) < tol
+    want = O.interf_power_dense(p, vt, vr, chans[:, 2])
+    assert np.max(np.abs(P32[2] - want)) < tol
+    S32 = handle.interf_power(to_sys(p), vt, vr, chans, mode=1, scalar=True)
+    assert np.allclose(S32, P64.sum(axis=1), rtol=2e-5, atol=256 * 5e-8)

@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(256) gemm_power_f64(const double* __restrict__
 }
 
 int interf_upload(wofdm_ctx* h, const wofdm_sys_t* sys, const double* win_tx, const double* win_rx,
-                  const double* chan, int L, int C, InterfDev* out) {
+                  const double* chan, int L, int C, int mode, InterfDev* out) {
     DeviceCtx& d = h->devs[0];
     const int N = sys->N, n_tx = N + sys->cp + sys->cs, n_rx = n_tx - sys->tail_tx;
     InterfDev v;
@@ -178,8 +178,9 @@ int interf_upload(wofdm_ctx* h, const wofdm_sys_t* sys, const double* win_tx, co
                          (size_t)2 * N * v.Kp * 8;
     // batch of channels whose B matrices fit the staging budget (1 GiB of the arena)
     const size_t per_chan = (size_t)v.M * v.Kp * N * 8;
-    v.batch = (int)std::max<size_t>(1, std::min<size_t>((size_t)C, ((size_t)1 << 30) / per_chan));
-    int rc = arena_reserve(h, d, bytes + (size_t)v.batch * per_chan + (size_t)C * N * 8);
+    v.batch = (int)std::max<size_t>(1, std::min<size_t>((size_t)C, ((size_t)1 << 30) / per_chan));   // <= 1 GiB of B per batch
+    const size_t tf32_bytes = mode == 1 ? ((size_t)2 * 2 * N * v.Kp + (size_t)2 * v.batch * v.M * N * v.Kp) * 4 : 0;
+    int rc = arena_reserve(h, d, bytes + (size_t)v.batch * per_chan + (size_t)C * N * 8 + tf32_bytes);
     if (rc) return rc;
     v.vtx = static_cast<double*>(arena_take(d, (size_t)n_tx * 8));
     v.vrx = static_cast<double*>(arena_take(d, (size_t)(N + sys->tail_rx) * 8));
@@ -188,7 +189,8 @@ int interf_upload(wofdm_ctx* h, const wofdm_sys_t* sys, const double* win_tx, co
     v.Rbig = static_cast<double*>(arena_take(d, (size_t)2 * N * v.Kp * 8));
     v.Bbig = static_cast<double*>(arena_take(d, (size_t)v.batch * per_chan));
     v.P = static_cast<double*>(arena_take(d, (size_t)C * N * 8));
-    if (!v.vtx || !v.vrx || !v.chan || !v.T || !v.Rbig || !v.Bbig || !v.P) return fail(h, WOFDM_ENOMEM, "arena exhausted");
+    v.tf32_work = tf32_bytes ? static_cast<float*>(arena_take(d, tf32_bytes)) : nullptr;
+    if ((tf32_bytes && !v.tf32_work) || !v.vtx || !v.vrx || !v.chan || !v.T || !v.Rbig || !v.Bbig || !v.P) return fail(h, WOFDM_ENOMEM, "arena exhausted");
     WOFDM_CUDA(h, cudaMemcpyAsync(v.vtx, win_tx, (size_t)n_tx * 8, cudaMemcpyHostToDevice, d.stream));
     WOFDM_CUDA(h, cudaMemcpyAsync(v.vrx, win_rx, (size_t)(N + sys->tail_rx) * 8, cudaMemcpyHostToDevice, d.stream));
     WOFDM_CUDA(h, cudaMemcpyAsync(v.chan, chan, (size_t)L * C * 16, cudaMemcpyHostToDevice, d.stream));
@@ -211,7 +213,7 @@ static int interf_run(wofdm_handle h, const wofdm_sys_t* sys, const double* win_
     DeviceCtx& d = h->devs[0];
     WOFDM_CUDA(h, cudaSetDevice(d.dev));
     InterfDev v;
-    rc = interf_upload(h, sys, win_tx, win_rx, chan, L, C, &v);
+    rc = interf_upload(h, sys, win_tx, win_rx, chan, L, C, mode, &v);
     if (rc) return rc;
     const int N = sys->N;
     const size_t pbytes = scalar ? (size_t)C * 8 : (size_t)C * N * 8;

@@ -12,6 +12,7 @@ struct InterfDev {
     double* Rbig;          // [2N][Kp] = [Rr -Ri; Ri Rr]
     double* Bbig;          // [batch*Ms][Kp][N] = [Re B; Im B] per slice
     double* P;             // [C][N] (or [C] in scalar mode)
+    float* tf32_work;      // mode 1: Rhi, Rlo [2N][Kp] and Bhi, Blo [batch*M][N][Kp] (K-major hi/lo splits)
 };
 
 // TF32-split tensor-core contraction of one batch (interf_tf32.cu)
