@@ -6,12 +6,13 @@
 // TF32 number), lo = fp32(x - hi) (the tensor core reads its top 19 bits); A.B ~ Ahi.Bhi + Ahi.Blo + Alo.Bhi,
 // relative error ~2^-21 per product, accumulated in fp32 in tensor memory.
 //
-// One CTA (128 threads) owns a 128 x 256 accumulator tile in TMEM (256 of the 512 columns).  Per K block of 32:
-// all threads copy the hi/lo tiles of both operands into shared memory in the canonical K-major no-swizzle UMMA
-// layout (8-row x 16-byte core matrices; chunk c of a tile sits at byte 16*c), one elected thread issues the 12
-// tcgen05.mma (4 K-steps x 3 split terms) and commits them to an mbarrier; two stages, so the copy of block k+1
-// overlaps the MMAs of block k.  Epilogue: tcgen05.ld the accumulator rows, mask the diagonal of slice 0, square,
-// sum, one atomicAdd per row -- A itself is never written.
+// One CTA (128 threads) owns a 128 x 256 accumulator tile in TMEM (256 of the 512 columns).  The hi/lo operands are
+// stored in HBM PRE-TILED: every (row tile, K block of 32) is one contiguous block already in the canonical K-major
+// no-swizzle UMMA layout (8-row x 16-byte core matrices; chunk c = (row/8)*64 + kchunk*8 + row%8 at byte 16*c), so a
+// stage is filled by four cp.async.bulk copies (TMA engine, no tensor map) that complete on an mbarrier.
+// Warp-specialised: one producer thread (bulk copies), one MMA thread (12 tcgen05.mma per K block = 4 K-steps x 3
+// split terms, tcgen05.commit frees the stage), two stages.  Epilogue (all four warps): tcgen05.ld the accumulator
+// rows, mask the diagonal of slice 0, square, sum, one atomicAdd per row -- A itself is never written.
 #include "interf.h"
 
 namespace wofdm {
@@ -50,36 +51,34 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (!done) __trap();                          // never spin forever on a GPU we share
 }
 
-// chunk c (16 bytes) of a K-major tile: row (c/64)*8 + c%8, K chunk (c%64)/8; lands at shared byte 16*c
-__device__ __forceinline__ void copy_tile(unsigned char* dst, const float* __restrict__ src, int rows, int ld, int k0,
-                                          int tid, int nt) {
-    const int nchunk = rows * (KB / 4);
-    for (int c = tid; c < nchunk; c += nt) {
-        const int row = (c >> 6) * 8 + (c & 7), kc = (c & 63) >> 3;
-        const uint4 v = *reinterpret_cast<const uint4*>(src + (size_t)row * ld + k0 + kc * 4);
-        *reinterpret_cast<uint4*>(dst + (size_t)c * 16) = v;
-    }
+__device__ __forceinline__ void bulk_copy(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
 }  // namespace
 
-// grid (2N / TM, slices), 128 threads, dynamic smem NSTAGE * STAGE_BYTES
-__global__ void __launch_bounds__(128, 1) gemm_power_tf32(const float* __restrict__ Rhi, const float* __restrict__ Rlo,
-                                                         const float* __restrict__ Bhi, const float* __restrict__ Blo,
+// grid (2N / TM, slices), 128 threads, dynamic smem NSTAGE * STAGE_BYTES.
+// Rt: [2N/TM][nk][hi|lo][TM*KB] tiles, Bt: [slices][nk][hi|lo][TN*KB] tiles (see tile_split_* below)
+__global__ void __launch_bounds__(128, 1) gemm_power_tf32(const float* __restrict__ Rt, const float* __restrict__ Bt,
                                                          double* __restrict__ P, int N, int Kp, int Ms, int c0, int scalar) {
     extern __shared__ __align__(1024) unsigned char sm[];
-    __shared__ __align__(8) unsigned long long bars[NSTAGE];
+    __shared__ __align__(8) unsigned long long full_bar[NSTAGE], empty_bar[NSTAGE], acc_bar;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int m0 = blockIdx.x * TM, s = blockIdx.y;
+    const int mt = blockIdx.x, m0 = mt * TM, s = blockIdx.y;
+    const int nk = Kp / KB;
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(TN) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
-        for (int i = 0; i < NSTAGE; ++i)
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bars[i])) : "memory");
+        for (int i = 0; i < NSTAGE; ++i) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&full_bar[i])) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&empty_bar[i])) : "memory");
+        }
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&acc_bar)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -87,22 +86,25 @@ __global__ void __launch_bounds__(128, 1) gemm_power_tf32(const float* __restric
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_base_s;
 
-    const float* bh = Bhi + (size_t)s * TN * Kp;
-    const float* bl = Blo + (size_t)s * TN * Kp;
-    const int nk = Kp / KB;
-    for (int kb = 0; kb < nk; ++kb) {
-        const int st = kb & 1;
-        unsigned char* base = sm + (size_t)st * STAGE_BYTES;
-        if (kb >= NSTAGE) mbar_wait(smem_u32(&bars[st]), (uint32_t)(((kb >> 1) - 1) & 1));   // MMAs of block kb-2 have drained this stage
-        copy_tile(base, Rhi + (size_t)m0 * Kp, TM, Kp, kb * KB, tid, 128);
-        copy_tile(base + A_BYTES, Rlo + (size_t)m0 * Kp, TM, Kp, kb * KB, tid, 128);
-        copy_tile(base + 2 * A_BYTES, bh, TN, Kp, kb * KB, tid, 128);
-        copy_tile(base + 2 * A_BYTES + B_BYTES, bl, TN, Kp, kb * KB, tid, 128);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> visible to the tensor core
-        __syncthreads();
-        if (tid == 0) {
+    if (tid == 0) {
+        // ===== producer: four bulk copies per stage =====
+        const float* ra = Rt + (size_t)mt * nk * (2 * TM * KB);
+        const float* rb = Bt + (size_t)s * nk * (2 * TN * KB);
+        for (int kb = 0; kb < nk; ++kb) {
+            const int st = kb & 1;
+            if (kb >= NSTAGE) mbar_wait(smem_u32(&empty_bar[st]), (uint32_t)(((kb >> 1) - 1) & 1));
+            const uint32_t bar = smem_u32(&full_bar[st]), dst = smem_u32(sm + (size_t)st * STAGE_BYTES);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"((uint32_t)STAGE_BYTES) : "memory");
+            bulk_copy(dst, ra + (size_t)kb * (2 * TM * KB), 2 * A_BYTES, bar);                 // A hi | lo
+            bulk_copy(dst + 2 * A_BYTES, rb + (size_t)kb * (2 * TN * KB), 2 * B_BYTES, bar);    // B hi | lo
+        }
+    } else if (tid == 32) {
+        // ===== MMA issuer =====
+        for (int kb = 0; kb < nk; ++kb) {
+            const int st = kb & 1;
+            mbar_wait(smem_u32(&full_bar[st]), (uint32_t)((kb >> 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a_hi = smem_u32(base), a_lo = a_hi + A_BYTES, b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+            const uint32_t a_hi = smem_u32(sm + (size_t)st * STAGE_BYTES), a_lo = a_hi + A_BYTES, b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
 #pragma unroll
             for (int j = 0; j < KB / 8; ++j) {                             // one MMA consumes 8 TF32 = two 16-byte chunks
                 const uint32_t off = (uint32_t)j * 256u;
@@ -110,14 +112,14 @@ __global__ void __launch_bounds__(128, 1) gemm_power_tf32(const float* __restric
                 mma_tf32(tmem, umma_desc(a_hi + off), umma_desc(b_lo + off), 1u);
                 mma_tf32(tmem, umma_desc(a_lo + off), umma_desc(b_hi + off), 1u);
             }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&bars[st])) : "memory");
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&empty_bar[st])) : "memory");
         }
+        // completes exactly once, after every MMA of the tile (a parity wait on a recycled barrier would
+        // release the epilogue warps, which do not follow the pipeline, after the first K block)
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&acc_bar)) : "memory");
     }
-    // the last commit covers every MMA issued before it
-    {
-        const int kb = nk - 1;
-        mbar_wait(smem_u32(&bars[kb & 1]), (uint32_t)((kb >> 1) & 1));
-    }
+    __syncwarp();
+    mbar_wait(smem_u32(&acc_bar), 0u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
     // epilogue: thread = one row of the tile (TMEM lane 32*warp + lane)
@@ -151,31 +153,51 @@ __global__ void __launch_bounds__(128, 1) gemm_power_tf32(const float* __restric
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(TN) : "memory");
 }
 
-// x -> (hi, lo) fp32 pair, elementwise
-__global__ void split_tf32(const double* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, size_t n) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const float h = __uint_as_float(__float_as_uint((float)x[i]) & 0xffffe000u);
-        hi[i] = h;
-        lo[i] = (float)(x[i] - (double)h);
+__device__ __forceinline__ void split_hi_lo(double x, float& hi, float& lo) {
+    hi = __uint_as_float(__float_as_uint((float)x) & 0xffffe000u);
+    lo = (float)(x - (double)hi);
+}
+// offset (in floats) of element (row, kk) inside its [hi|lo] tile pair: tile = (row/rows_per_tile, kk/KB)
+__device__ __forceinline__ size_t tiled_off(int row, int kk, int rows_per_tile, int nk) {
+    const int rt = row / rows_per_tile, r = row % rows_per_tile, kb = kk / KB, k = kk % KB;
+    const int c = (r >> 3) * 64 + (k >> 2) * 8 + (r & 7);
+    return ((size_t)rt * nk + kb) * (2 * (size_t)rows_per_tile * KB) + (size_t)c * 4 + (k & 3);
+}
+
+// Rbig [2N][Kp] fp64 -> Rt tiles (tiny: 2N x Kp elements)
+__global__ void tile_split_r(const double* __restrict__ Rbig, float* __restrict__ Rt, int rows, int Kp) {
+    const int nk = Kp / KB;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)rows * Kp; i += (size_t)gridDim.x * blockDim.x) {
+        const int row = (int)(i / Kp), kk = (int)(i % Kp);
+        float hi, lo;
+        split_hi_lo(Rbig[i], hi, lo);
+        const size_t o = tiled_off(row, kk, TM, nk);
+        Rt[o] = hi;
+        Rt[o + (size_t)TM * KB] = lo;
     }
 }
 
-// [slice][kk][j] fp64 -> [slice][j][kk] hi/lo fp32 (K-major for the tensor core), 32x32 tiles through smem
-__global__ void __launch_bounds__(256) transpose_split_b(const double* __restrict__ Bbig, float* __restrict__ Bhi,
-                                                         float* __restrict__ Blo, int N, int Kp) {
+// Bbig [slice][kk][j] fp64 -> Bt tiles [slice][kb][hi|lo][chunk][4]: 32 x 32 (kk x j) tiles through smem, each thread
+// writes the float4 of 4 consecutive kk for one row j; a warp writes 512 contiguous bytes
+__global__ void __launch_bounds__(256) tile_split_b(const double* __restrict__ Bbig, float* __restrict__ Bt, int N, int Kp) {
     __shared__ double tile[32][33];
-    const int s = blockIdx.z, k0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+    const int s = blockIdx.z, kb = blockIdx.y, j0 = blockIdx.x * 32, nk = Kp / KB;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const double* src = Bbig + (size_t)s * Kp * N;
-    for (int i = ty; i < 32; i += 8) tile[i][tx] = src[(size_t)(k0 + i) * N + j0 + tx];
+    for (int i = ty; i < 32; i += 8) tile[i][tx] = src[(size_t)(kb * 32 + i) * N + j0 + tx];
     __syncthreads();
-    for (int i = ty; i < 32; i += 8) {
-        const double x = tile[tx][i];
-        const float h = __uint_as_float(__float_as_uint((float)x) & 0xffffe000u);
-        const size_t o = ((size_t)s * N + j0 + i) * Kp + k0 + tx;
-        Bhi[o] = h;
-        Blo[o] = (float)(x - (double)h);
-    }
+    const int t = threadIdx.x;
+    const int jl = (t & 7) | ((t >> 6) << 3), kc = (t >> 3) & 7;
+    float4 hi, lo;
+    split_hi_lo(tile[4 * kc + 0][jl], hi.x, lo.x);
+    split_hi_lo(tile[4 * kc + 1][jl], hi.y, lo.y);
+    split_hi_lo(tile[4 * kc + 2][jl], hi.z, lo.z);
+    split_hi_lo(tile[4 * kc + 3][jl], hi.w, lo.w);
+    const int j = j0 + jl;
+    const size_t c = (size_t)(j >> 3) * 64 + kc * 8 + (j & 7);
+    float* dst = Bt + ((size_t)s * nk + kb) * (2 * (size_t)TN * KB);
+    *reinterpret_cast<float4*>(dst + c * 4) = hi;
+    *reinterpret_cast<float4*>(dst + (size_t)TN * KB + c * 4) = lo;
 }
 
 int interf_gemm_tf32(wofdm_ctx* h, const wofdm_sys_t* sys, const InterfDev& v, int Ms, int c0, int slices, int scalar) {
@@ -183,18 +205,16 @@ int interf_gemm_tf32(wofdm_ctx* h, const wofdm_sys_t* sys, const InterfDev& v, i
     const int N = sys->N;
     if (N != TN) return fail(h, WOFDM_EUNSUPPORTED, "TF32-split interference path is built for N = 256");
     if (v.Kp % KB) return fail(h, WOFDM_EINVAL, "Kp must be a multiple of 32");
-    const size_t nr = (size_t)2 * N * v.Kp, nb = (size_t)slices * N * v.Kp;
+    const size_t nr = (size_t)2 * 2 * N * v.Kp;                      // Rt: hi + lo
     // fp32 work buffers live behind the fp64 B matrix of this batch (interf_upload reserved room for them)
-    float* Rhi = v.tf32_work;
-    float* Rlo = Rhi + nr;
-    float* Bhi = Rlo + nr;
-    float* Blo = Bhi + nb;
-    split_tf32<<<256, 256, 0, d.stream>>>(v.Rbig, Rhi, Rlo, nr);
-    transpose_split_b<<<dim3(N / 32, v.Kp / 32, slices), 256, 0, d.stream>>>(v.Bbig, Bhi, Blo, N, v.Kp);
+    float* Rt = v.tf32_work;
+    float* Bt = Rt + nr;
+    tile_split_r<<<128, 256, 0, d.stream>>>(v.Rbig, Rt, 2 * N, v.Kp);
+    tile_split_b<<<dim3(N / 32, v.Kp / KB, slices), 256, 0, d.stream>>>(v.Bbig, Bt, N, v.Kp);
     WOFDM_CUDA(h, cudaGetLastError());
     const size_t smem = (size_t)NSTAGE * STAGE_BYTES;
     WOFDM_CUDA(h, cudaFuncSetAttribute(gemm_power_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gemm_power_tf32<<<dim3(2 * N / TM, slices), 128, smem, d.stream>>>(Rhi, Rlo, Bhi, Blo, v.P, N, v.Kp, Ms, c0, scalar);
+    gemm_power_tf32<<<dim3(2 * N / TM, slices), 128, smem, d.stream>>>(Rt, Bt, v.P, N, v.Kp, Ms, c0, scalar);
     WOFDM_CUDA(h, cudaGetLastError());
     h->launches += 2;
     return WOFDM_OK;
