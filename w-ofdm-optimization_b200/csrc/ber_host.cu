@@ -230,7 +230,9 @@ int wofdm_ber_plan_launch(wofdm_ber_plan p, int slot, int64_t ensemble, uint64_t
 
     WOFDM_CUDA(h, cudaMemsetAsync(pd.d_cnt, 0, (size_t)p->n_snr * 2 * sizeof(unsigned long long), st));
     if (mine > 0) {
-        const long long cap = (long long)pd.blocks_per_sm * d.sm_count;
+        long long cap = (long long)pd.blocks_per_sm * d.sm_count;
+        if (const char* lim = getenv("WOFDM_MAX_CTAS_PER_SM"))            // tuning aid: occupancy sensitivity
+            cap = std::min<long long>(cap, (long long)std::max(1, atoi(lim)) * d.sm_count);
         const int grid = (int)std::min<long long>(mine, cap);
         WOFDM_CUDA(h, p->var->launch(prm, grid, p->lay.bytes, st));
         h->launches += 1;
