@@ -51,6 +51,10 @@ int choose_variant(wofdm_ctx* h, const wofdm_sys_t& s, int L, bool verify, bool 
             if (want && !strstr(v.name, want)) continue;
             const int chunk = ((sec + v.NT - 1) / v.NT) | 1;
             if (chunk > v.TC || L > v.LB) continue;
+            // the tuned kernels only look at the outer register rows for the prefix / suffix / heads / overlap-add
+            // (ber_kernel.cuh, ER): rows are N/16 samples wide
+            const int tpf = s.N / 16;
+            if (s.cp > 2 * tpf || s.cs > 2 * tpf || s.tail_tx > 2 * tpf || s.tail_rx / 2 > tpf || s.shift > tpf) continue;
             if (v.full && !(chunk == v.TC && v.NT * v.TC == sec)) continue;
             const BerSmem lay = v.layout(s.S, stride, s.tail_tx, s.tail_rx, L, chunk, 0);
             if (lay.bytes > smem_cap) continue;

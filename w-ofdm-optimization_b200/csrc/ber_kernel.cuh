@@ -73,13 +73,14 @@ __device__ __forceinline__ int levels_to_idx(int a, int c, int hb, int m, int co
 }
 // nearest level on the odd-integer lattice, ties towards the lower level (first minimum of the
 // reference's argmin, wofdm_simulation.py:163): ceil(v/2 + (m-2)/2), clamped to [0, m-1]
+// (the float -> unsigned conversion saturates at 0, which is the lower clamp)
 __device__ __forceinline__ int slice_level(float v, int m) {
-    const int lv = __float2int_ru(fmaf(v, 0.5f, 0.5f * (float)(m - 2)));
-    return min(max(lv, 0), m - 1);
+    const unsigned lv = __float2uint_ru(fmaf(v, 0.5f, 0.5f * (float)(m - 2)));
+    return (int)min(lv, (unsigned)(m - 1));
 }
 __device__ __forceinline__ int slice_level(double v, int m) {
-    const int lv = __double2int_ru(fma(v, 0.5, 0.5 * (double)(m - 2)));
-    return min(max(lv, 0), m - 1);
+    const unsigned lv = __double2uint_ru(fma(v, 0.5, 0.5 * (double)(m - 2)));
+    return (int)min(lv, (unsigned)(m - 1));
 }
 
 // 16 constellation indices (one byte each) of OFDM symbol s for thread t: sub-carriers t + q*TPF
@@ -164,7 +165,7 @@ __host__ __device__ inline BerSmem ber_smem_layout(int S, int stride, int tail_t
     o += m.xlen * E;                 m.off_tw = o;
     o += P::NTW * E;                 m.off_geq = o;
     o += N * E;                      m.off_taps = o;
-    o += (L + (L & 1)) * E;          m.off_wtx = o;
+    o += (((L > lpad ? L : lpad) + 1) & ~1) * E;   m.off_wtx = o;   // taps, zero-padded to the register block
     o += ((stride + tail_tx + 3) & ~3) * (int)sizeof(T);   m.off_wrx = o;
     o += ((N + tail_rx + 3) & ~3) * (int)sizeof(T);        m.off_red = o;
     o += 64 * (int)sizeof(T);                              m.off_qlut = o;
@@ -178,6 +179,34 @@ __host__ __device__ inline BerSmem ber_smem_layout(int S, int stride, int tail_t
 __device__ __forceinline__ float recip(float x) { return __fdividef(1.0f, x); }
 __device__ __forceinline__ double recip(double x) { return 1.0 / x; }
 
+// sum of the NW per-warp partials every thread reads after the frame-wide barrier (fixed order:
+// the result does not depend on scheduling); r is 16-byte aligned
+template <int NW> __device__ __forceinline__ float block_total(const float* r) {
+    float s = 0.0f;
+    if constexpr (NW % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < NW / 4; ++i) { const float4 v = reinterpret_cast<const float4*>(r)[i]; s += (v.x + v.y) + (v.z + v.w); }
+    } else {
+#pragma unroll
+        for (int i = 0; i < NW; ++i) s += r[i];
+    }
+    return s;
+}
+template <int NW> __device__ __forceinline__ double block_total(const double* r) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) s += r[i];
+    return s;
+}
+// g = sqrt(Pr * 10^(-snr/10) / Pn)   (wofdm_simulation.py:135-138)
+__device__ __forceinline__ float noise_gain(float pr, float snr_lin, float pn) {
+    float g;
+    const float q = __fdividef(pr * snr_lin, pn);
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(g) : "f"(q));
+    return g;
+}
+__device__ __forceinline__ double noise_gain(double pr, double snr_lin, double pn) { return sqrt(pr * snr_lin / pn); }
+
 template <typename T, int N, int NT, int TC, int LB, int MINB, bool FULL, bool VERIFY>
 __global__ void __launch_bounds__(NT, MINB)
 ber_frame_kernel(const BerParams prm) {
@@ -187,6 +216,10 @@ ber_frame_kernel(const BerParams prm) {
     constexpr int FPP = NT / TPF;
     static_assert(NT % TPF == 0 && NT % 32 == 0, "threads per CTA must be a multiple of N/16 and 32");
     constexpr bool REGS = TC > 0;
+    // Register row q of a thread = sub-carriers / samples t + q*TPF.  Only the outer rows can reach the cyclic
+    // prefix / suffix, the Tx heads and the Rx overlap-add; the tuned variants look at ER of them (the host
+    // checks cp, cs, tail_tx <= ER*TPF and tail_rx/2, shift <= TPF), the staged policy at all 16.
+    constexpr int ER = REGS ? 2 : 16;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x;
@@ -246,7 +279,8 @@ ber_frame_kernel(const BerParams prm) {
     for (long long j = blockIdx.x; j < prm.n_frames; j += gridDim.x) {
         if constexpr (VERIFY) { ci = (int)f; si = (int)f; }
         const T snr_lin = reinterpret_cast<const T*>(prm.snr_lin)[si];
-        if (tid < L) taps[tid] = reinterpret_cast<const C2*>(prm.chan)[(size_t)ci * L + tid];
+        if (tid < (REGS ? (LB > L ? LB : L) : L))   // regs policy: zero-padded to LB, loaded without predicates
+            taps[tid] = tid < L ? reinterpret_cast<const C2*>(prm.chan)[(size_t)ci * L + tid] : mk2<T>(0, 0);
 
         // =========================== transmitter ===========================
         for (int s0 = 0; s0 < S; s0 += FPP) {
@@ -274,15 +308,18 @@ ber_frame_kernel(const BerParams prm) {
 #pragma unroll
                 for (int q = 0; q < 16; ++q) {
                     const int i = t + q * TPF + cp;
-                    if (i >= beta || first) us[i] = cscale(wtx[i], v[q]);
+                    if (q >= ER || i >= beta || first) us[i] = cscale(wtx[i], v[q]);
                 }
             }
 #pragma unroll
-            for (int q = 0; q < 16; ++q) {
+            for (int q = 16 - ER; q < 16; ++q) {
                 if (q * TPF + TPF > N - cp) {             // uniform: this register row reaches the prefix
                     const int i = t + q * TPF - (N - cp);
                     if (i >= 0 && (i >= beta || first)) us[i] = cscale(wtx[i], v[q]);
                 }
+            }
+#pragma unroll
+            for (int q = 0; q < ER; ++q) {
                 if (q * TPF < cs) {                        // uniform: ... the suffix
                     const int i = t + q * TPF + cp + N;
                     if (i < n_tx) us[i] = cscale(wtx[i], v[q]);
@@ -291,12 +328,15 @@ ber_frame_kernel(const BerParams prm) {
             __syncthreads();
             if (beta > 0 && act && !first) {
 #pragma unroll
-                for (int q = 0; q < 16; ++q) {
+                for (int q = 16 - ER; q < 16; ++q) {
                     if (q * TPF + TPF > N - cp) {
                         const int i = t + q * TPF - (N - cp);
                         if (i >= 0 && i < beta) us[i] = caxpy(wtx[i], v[q], us[i]);
                     }
-                    if (cp < beta) {
+                }
+                if (cp < beta) {
+#pragma unroll
+                    for (int q = 0; q < ER; ++q) {
                         const int i = t + q * TPF + cp;
                         if (i < beta) us[i] = caxpy(wtx[i], v[q], us[i]);
                     }
@@ -322,7 +362,7 @@ ber_frame_kernel(const BerParams prm) {
 #pragma unroll
             for (int o = 0; o < TC; ++o) acc[o] = mk2<T>(0, 0);
 #pragma unroll
-            for (int l = 0; l < LB; ++l) h[l] = (l < L) ? taps[l] : mk2<T>(0, 0);
+            for (int l = 0; l < LB; ++l) h[l] = taps[l];
             const C2* src = ub + i0 - (LB - 1);
             C2* const nb = rbuf + i0;
             constexpr int NPAIR = (TC + 1) / 2, NSTEP = (TC + LB - 1) / NPAIR;
@@ -377,10 +417,7 @@ ber_frame_kernel(const BerParams prm) {
             T pr = warp_sum(pr2.x + pr2.y), pn = warp_sum(pn2.x + pn2.y);
             if ((tid & 31) == 0) { red[tid >> 5] = pr; red[32 + (tid >> 5)] = pn; }
             __syncthreads();                       // also: every conv read of the stream is done
-            pr = 0; pn = 0;
-#pragma unroll
-            for (int wq = 0; wq < NT / 32; ++wq) { pr += red[wq]; pn += red[32 + wq]; }
-            const T g = sqrt(pr * snr_lin / pn);
+            const T g = noise_gain(block_total<NT / 32>(red), snr_lin, block_total<NT / 32>(red + 32));
 #pragma unroll
             for (int o = 0; o < TC; ++o)
                 if (FULL || o < nvalid) ub[i0 + o] = caxpy(g, nb[o], acc[o]);
@@ -400,10 +437,7 @@ ber_frame_kernel(const BerParams prm) {
             T pr = warp_sum(pr2.x + pr2.y), pn = warp_sum(pn2.x + pn2.y);
             if ((tid & 31) == 0) { red[tid >> 5] = pr; red[32 + (tid >> 5)] = pn; }
             __syncthreads();
-            pr = 0; pn = 0;
-#pragma unroll
-            for (int wq = 0; wq < NT / 32; ++wq) { pr += red[wq]; pn += red[32 + wq]; }
-            const T g = sqrt(pr * snr_lin / pn);
+            const T g = noise_gain(block_total<NT / 32>(red), snr_lin, block_total<NT / 32>(red + 32));
             for (int i = tid; i < sec; i += NT) {
                 C2 n0;
                 if constexpr (VERIFY) n0 = to_v2<T>(prm.noise_in[(size_t)f * prm.noise_len + i]);
@@ -426,6 +460,12 @@ ber_frame_kernel(const BerParams prm) {
             const T* wr = wrx + hh;
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
+                if (REGS && q >= 1 && q <= 13) {
+                    // tail_rx/2, shift <= TPF: rows 1..13 neither wrap nor touch the overlap-add margins
+                    const int n = t + q * TPF + prm.shift;
+                    v[q] = cscale(wr[n], ys[n]);
+                    continue;
+                }
                 const int a0 = (q * TPF + prm.shift) & (N - 1);          // first n of this register row
                 const int n = (t + q * TPF + prm.shift) & (N - 1);
                 C2 o = cscale(wr[n], ys[n]);

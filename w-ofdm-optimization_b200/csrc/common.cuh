@@ -59,20 +59,13 @@ __device__ __forceinline__ double2 csq_acc(double2 a, double2 p) { p.x = fma(a.x
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al., SC'11), counter-based: draws depend only on (key, counter).
 // ---------------------------------------------------------------------------------------------
-__host__ __device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b) {
-#ifdef __CUDA_ARCH__
-    return __umulhi(a, b);
-#else
-    return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
-#endif
-}
-
+// One round = two 32x32->64 products (a single IMAD.WIDE.U32 each on the device) and two 3-input XORs.
 __host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
-        const uint32_t hi0 = mulhi32(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
-        const uint32_t hi1 = mulhi32(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
-        c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+        const uint64_t p0 = (uint64_t)0xD2511F53u * (uint64_t)c.x;
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * (uint64_t)c.z;
+        c = make_uint4((uint32_t)(p1 >> 32) ^ c.y ^ k0, (uint32_t)p1, (uint32_t)(p0 >> 32) ^ c.w ^ k1, (uint32_t)p0);
         k0 += 0x9E3779B9u;
         k1 += 0xBB67AE85u;
     }

@@ -107,10 +107,17 @@ template <typename T, int DIR> __device__ __forceinline__ V2<T> tw_apply(V2<T> a
     else return cmulc(a, w);
 }
 
+// Barrier between the threads of one transform: the N/16 threads of a group sit in one warp when
+// N <= 512 (groups are aligned to their size), so a warp barrier is enough and the CTA's other
+// warps run on; larger transforms span warps and use the CTA barrier.
+template <int TPF> __device__ __forceinline__ void fft_group_sync() {
+    if constexpr (TPF <= 32) __syncwarp(); else __syncthreads();
+}
+
 // One transform per group of N/16 threads; EVERY thread of the CTA must call this (it contains
-// __syncthreads()).  xb: this group's exchange buffer (FftPlan<N>::XLEN elements, shared memory);
-// tw: twiddle table (FftPlan<N>::NTW elements).  The buffer may be reused right after return only
-// after another __syncthreads() (the last reads are not fenced).
+// barriers).  xb: this group's exchange buffer (FftPlan<N>::XLEN elements, shared memory), private
+// to the group; tw: twiddle table (FftPlan<N>::NTW elements).  Memory that aliases xb and is
+// touched by OTHER groups needs a __syncthreads() of the caller on both sides of this call.
 template <typename T, int N, int DIR>
 __device__ __forceinline__ void fft_regs(V2<T> (&v)[16], const int t, V2<T>* __restrict__ xb,
                                          const V2<T>* __restrict__ tw) {
@@ -122,17 +129,20 @@ __device__ __forceinline__ void fft_regs(V2<T> (&v)[16], const int t, V2<T>* __r
         const int Ns = (p == 0) ? 1 : (p == 1) ? 16 : 256;
         const int k = t & (Ns - 1);
         if (p > 0) {
-            __syncthreads();
+            V2<T> w[15];                  // fetched before the barrier: they do not depend on the exchange
+#pragma unroll
+            for (int m = 1; m < 16; ++m) w[m - 1] = tw[tw_off + m * Ns + k];
+            fft_group_sync<TPF>();
 #pragma unroll
             for (int m = 0; m < 16; ++m) v[m] = xb[fft_pad(t + m * TPF)];
 #pragma unroll
-            for (int m = 1; m < 16; ++m) v[m] = tw_apply<T, DIR>(v[m], tw[tw_off + m * Ns + k]);
+            for (int m = 1; m < 16; ++m) v[m] = tw_apply<T, DIR>(v[m], w[m - 1]);
             tw_off += 16 * Ns;
         }
         dft16<T, DIR>(v);
         const bool last = (p == P::a - 1);
         if (!(last && P::r == 1)) {
-            if (p > 0) __syncthreads();   // everybody has finished reading the previous layout
+            fft_group_sync<TPF>();        // the group has finished reading the previous layout (also of an earlier call)
             const int base = (t - k) * 16 + k;
 #pragma unroll
             for (int m = 0; m < 16; ++m) xb[fft_pad(base + m * Ns)] = v[m];
@@ -140,7 +150,7 @@ __device__ __forceinline__ void fft_regs(V2<T> (&v)[16], const int t, V2<T>* __r
     }
     if constexpr (P::r > 1) {
         constexpr int r = P::r, G = 16 / r;   // G butterflies of radix r per thread
-        __syncthreads();
+        fft_group_sync<TPF>();
 #pragma unroll
         for (int q = 0; q < 16; ++q) v[q] = xb[fft_pad(t + q * TPF)];
 #pragma unroll
