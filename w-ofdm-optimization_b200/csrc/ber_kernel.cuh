@@ -82,6 +82,18 @@ __device__ __forceinline__ int slice_level(double v, int m) {
     const unsigned lv = __double2uint_ru(fma(v, 0.5, 0.5 * (double)(m - 2)));
     return (int)min(lv, (unsigned)(m - 1));
 }
+// (re level << hb) | (im level), m = 1 << hb levels per axis; float: one packed FMA for both axes
+__device__ __forceinline__ int slice_index(float2 e, int hb) {
+    const int m = 1 << hb;
+    const float off = 0.5f * (float)(m - 2);
+    const float2 y = fma2(e, make_float2(0.5f, 0.5f), make_float2(off, off));
+    const unsigned la = min(__float2uint_ru(y.x), (unsigned)(m - 1)), lc = min(__float2uint_ru(y.y), (unsigned)(m - 1));
+    return (int)((la << hb) | lc);
+}
+__device__ __forceinline__ int slice_index(double2 e, int hb) {
+    const int m = 1 << hb;
+    return (slice_level(e.x, m) << hb) | slice_level(e.y, m);
+}
 
 // 16 constellation indices (one byte each) of OFDM symbol s for thread t: sub-carriers t + q*TPF
 template <int N, bool VERIFY>
@@ -261,7 +273,7 @@ ber_frame_kernel(const BerParams prm) {
         int a, c;
         idx_to_levels(i, hb, m, prm.constellation, a, c);
         qlut[i] = mk2<T>((T)(2 * a - (m - 1)), (T)(2 * c - (m - 1)));
-        dlut[a * m + c] = (unsigned char)i;
+        dlut[(a << hb) | c] = (unsigned char)i;
     }
     __syncthreads();
 
@@ -302,8 +314,11 @@ ber_frame_kernel(const BerParams prm) {
             // symbol's falling tail (wofdm_simulation.py:190-203) and are added after the sync.
             C2* const us = ub + se * stride;
             if (cp >= beta) {
+                T wv[16];                                 // window loads ahead of the (possibly aliasing) stores
 #pragma unroll
-                for (int q = 0; q < 16; ++q) { const int i = t + q * TPF + cp; us[i] = cscale(wtx[i], v[q]); }
+                for (int q = 0; q < 16; ++q) wv[q] = wtx[t + q * TPF + cp];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) us[t + q * TPF + cp] = cscale(wv[q], v[q]);
             } else {
 #pragma unroll
                 for (int q = 0; q < 16; ++q) {
@@ -388,9 +403,10 @@ ber_frame_kernel(const BerParams prm) {
                             if (2 * p2 + 1 >= nvalid) n1 = mk2<T>(0, 0);
                         }
                     }
+                    // (slots >= B belong to the next thread's block: never written from here)
                     pn2 = csq_acc(n0, pn2);
-                    nb[2 * p2] = n0;
-                    if (2 * p2 + 1 < TC) { pn2 = csq_acc(n1, pn2); nb[2 * p2 + 1] = n1; }
+                    if (FULL || 2 * p2 < B) nb[2 * p2] = n0;
+                    if (2 * p2 + 1 < TC) { pn2 = csq_acc(n1, pn2); if (FULL || 2 * p2 + 1 < B) nb[2 * p2 + 1] = n1; }
                 }
             }
             if (!FULL) {
@@ -418,9 +434,13 @@ ber_frame_kernel(const BerParams prm) {
             if ((tid & 31) == 0) { red[tid >> 5] = pr; red[32 + (tid >> 5)] = pn; }
             __syncthreads();                       // also: every conv read of the stream is done
             const T g = noise_gain(block_total<NT / 32>(red), snr_lin, block_total<NT / 32>(red + 32));
+            // loads first, then stores: ptxas cannot prove that nb and ub do not overlap and would otherwise
+            // serialise every load behind the previous store
+#pragma unroll
+            for (int o = 0; o < TC; ++o) acc[o] = caxpy(g, nb[FULL ? o : min(o, B - 1)], acc[o]);
 #pragma unroll
             for (int o = 0; o < TC; ++o)
-                if (FULL || o < nvalid) ub[i0 + o] = caxpy(g, nb[o], acc[o]);
+                if (FULL || o < nvalid) ub[i0 + o] = acc[o];
         } else {
             const int total = prm.noise_norm == 1 ? body + L - 1 : sec;
             for (int i = tid; i < total; i += NT) {
@@ -500,7 +520,7 @@ ber_frame_kernel(const BerParams prm) {
                 for (int q = 0; q < 16; ++q) {
                     const int k = t + q * TPF;
                     const C2 e = cmul(v[q], geq[k]);                                       // :231
-                    const int dec = dlut[slice_level(e.x, m) * m + slice_level(e.y, m)];   // :233
+                    const int dec = dlut[slice_index(e, hb)];                              // :233
                     const int txi = sym_byte(w, q);
                     sym_cnt += (dec != txi);                                               // :235
                     bit_cnt += __popc(dec ^ txi);

@@ -59,13 +59,25 @@ __device__ __forceinline__ double2 csq_acc(double2 a, double2 p) { p.x = fma(a.x
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al., SC'11), counter-based: draws depend only on (key, counter).
 // ---------------------------------------------------------------------------------------------
-// One round = two 32x32->64 products (a single IMAD.WIDE.U32 each on the device) and two 3-input XORs.
+// One round = two 32x32->64 products (one IMAD.WIDE.U32 each on the device; the halves are taken with
+// mov.b64 so that no 64-bit shift is left for the compiler to lower) and two 3-input XORs.
+__host__ __device__ __forceinline__ void mul_wide32(uint32_t a, uint32_t b, uint32_t& lo, uint32_t& hi) {
+#ifdef __CUDA_ARCH__
+    unsigned long long p;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(p) : "r"(a), "r"(b));
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(p));
+#else
+    const uint64_t p = (uint64_t)a * (uint64_t)b;
+    lo = (uint32_t)p; hi = (uint32_t)(p >> 32);
+#endif
+}
 __host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
-        const uint64_t p0 = (uint64_t)0xD2511F53u * (uint64_t)c.x;
-        const uint64_t p1 = (uint64_t)0xCD9E8D57u * (uint64_t)c.z;
-        c = make_uint4((uint32_t)(p1 >> 32) ^ c.y ^ k0, (uint32_t)p1, (uint32_t)(p0 >> 32) ^ c.w ^ k1, (uint32_t)p0);
+        uint32_t lo0, hi0, lo1, hi1;
+        mul_wide32(0xD2511F53u, c.x, lo0, hi0);
+        mul_wide32(0xCD9E8D57u, c.z, lo1, hi1);
+        c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
         k0 += 0x9E3779B9u;
         k1 += 0xBB67AE85u;
     }
