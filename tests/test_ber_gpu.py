@@ -87,7 +87,7 @@ def test_verify_against_reference_draws(handle, name, precision):
 
 @pytest.mark.parametrize("precision", [1, 0])
 @pytest.mark.parametrize("N,S,bits,conv,nn", [(16, 3, 2, 0, 0), (32, 5, 4, 1, 1), (64, 16, 6, 1, 0), (128, 7, 8, 0, 1),
-                                              (256, 16, 4, 1, 1), (512, 4, 6, 0, 0), (1024, 16, 6, 1, 0)])
+                                              (256, 16, 4, 1, 1), (256, 4, 4, 0, 0), (256, 9, 4, 1, 1), (512, 4, 6, 0, 0), (1024, 16, 6, 1, 0)])
 def test_verify_shapes_and_conventions(handle, N, S, bits, conv, nn, precision):
     rng = np.random.default_rng(N + S)
     cp, ttx, trx = N // 16, N // 32, 2 * (N // 64) if N >= 64 else 0

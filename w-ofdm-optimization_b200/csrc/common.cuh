@@ -96,7 +96,7 @@ __device__ __forceinline__ float2 gauss_pair(uint32_t w0, uint32_t w1, float) {
     const float u = fmaf(__uint2float_rn(w0), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
     float lg, r, s, c;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(u));
-    const float t = fmaxf(lg * -1.3862943611198906f, 0.0f);  // -2 ln u
+    const float t = lg * -1.3862943611198906f;               // -2 ln u >= 0 (u <= 1 after rounding; -0 is harmless)
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));
     const float th = __int2float_rn((int32_t)w1) * 1.4629180792671596e-09f;  // 2*pi * 2^-32
     asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(th));
