@@ -15,6 +15,7 @@ struct PlanDev {
     void* d_scratch = nullptr;
     size_t scratch_bytes = 0;
     int blocks_per_sm = 0;
+    long long max_ctas = 0;
     bool pending = false;
     cudaStream_t last_stream = nullptr;
 };
@@ -37,6 +38,12 @@ struct Choice {
     int chunk = 0, use_global = 0;
 };
 
+// noise numbering of a frame shared by a cluster (BerParams::split)
+void fill_split(BerParams& prm, const BerVariant& v) {
+    prm.split = v.CL > 1 ? prm.S * prm.stride / v.CL : 0;
+    prm.split_nt = v.CL > 1 ? v.NT : 0;
+}
+
 int choose_variant(wofdm_ctx* h, const wofdm_sys_t& s, int L, bool verify, bool force_staged, size_t smem_cap,
                    Choice* out) {
     const int stride = s.N + s.cp + s.cs - s.tail_tx;
@@ -49,14 +56,17 @@ int choose_variant(wofdm_ctx* h, const wofdm_sys_t& s, int L, bool verify, bool 
         for (const auto& v : h->variants) {
             if (v.TC == 0 || v.fp64 || v.verify != verify || v.N != s.N) continue;
             if (want && !strstr(v.name, want)) continue;
-            const int chunk = ((sec + v.NT - 1) / v.NT) | 1;
+            // CL CTAs share a frame: S/CL consecutive symbols each, all of them in one pass of the CTA
+            if (s.S % v.CL != 0 || (v.CL > 1 && s.S / v.CL > v.NT / (v.N / 16))) continue;
+            const int S_cta = s.S / v.CL, sec_cta = sec / v.CL;
+            const int chunk = ((sec_cta + v.NT - 1) / v.NT) | 1;
             if (chunk > v.TC || L > v.LB) continue;
             // the tuned kernels only look at the outer register rows for the prefix / suffix / heads / overlap-add
             // (ber_kernel.cuh, ER): rows are N/16 samples wide
             const int tpf = s.N / 16;
             if (s.cp > 2 * tpf || s.cs > 2 * tpf || s.tail_tx > 2 * tpf || s.tail_rx / 2 > tpf || s.shift > tpf) continue;
-            if (v.full && !(chunk == v.TC && v.NT * v.TC == sec)) continue;
-            const BerSmem lay = v.layout(s.S, stride, s.tail_tx, s.tail_rx, L, chunk, 0);
+            if (v.full && !(chunk == v.TC && v.NT * v.TC == sec_cta)) continue;
+            const BerSmem lay = v.layout(S_cta, stride, s.tail_tx, s.tail_rx, L, chunk, 0);
             if (lay.bytes > smem_cap) continue;
             if (!best.var || v.TC < best.var->TC || (v.TC == best.var->TC && v.full && !best.var->full)) { best.var = &v; best.lay = lay; best.chunk = chunk; }
         }
@@ -125,12 +135,27 @@ void fill_sys(BerParams& p, const wofdm_sys_t& s, int L) {
     p.qscale = qam_scale(s);
 }
 
-int prepare_kernel(wofdm_ctx* h, const BerVariant& v, size_t smem, int* blocks_per_sm) {
+// max_ctas: CTAs of this variant that can be resident on the device at once (a multiple of the cluster size)
+int prepare_kernel(wofdm_ctx* h, const BerVariant& v, size_t smem, int sm_count, int* blocks_per_sm, long long* max_ctas) {
     WOFDM_CUDA(h, cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int nb = 0;
     WOFDM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, v.fn, v.NT, smem));
     if (nb < 1) return fail(h, WOFDM_EUNSUPPORTED, "kernel variant cannot be resident on this device");
     *blocks_per_sm = nb;
+    long long cap = (long long)nb * sm_count;
+    if (v.CL > 1) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(v.CL * sm_count); cfg.blockDim = dim3(v.NT); cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = v.CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int ncl = 0;
+        WOFDM_CUDA(h, cudaOccupancyMaxActiveClusters(&ncl, v.fn, &cfg));
+        if (ncl < 1) return fail(h, WOFDM_EUNSUPPORTED, "no thread-block cluster of this variant fits the device");
+        cap = (long long)ncl * v.CL;
+    }
+    if (max_ctas) *max_ctas = cap;
     return WOFDM_OK;
 }
 
@@ -188,7 +213,7 @@ int wofdm_ber_plan_create(wofdm_handle h, const wofdm_sys_t* sys, const double* 
         if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&pd.d_cnt), (size_t)n_snr * 2 * sizeof(unsigned long long));
         if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);   // host vectors go out of scope
         if (e == cudaSuccess) {
-            rc = prepare_kernel(h, *p->var, p->lay.bytes, &pd.blocks_per_sm);
+            rc = prepare_kernel(h, *p->var, p->lay.bytes, d.sm_count, &pd.blocks_per_sm, &pd.max_ctas);
             if (rc) { wofdm_ber_plan_destroy(p); return rc; }
         }
         if (e == cudaSuccess && p->use_global) {
@@ -224,6 +249,7 @@ int wofdm_ber_plan_launch(wofdm_ber_plan p, int slot, int64_t ensemble, uint64_t
     BerParams prm;
     fill_sys(prm, p->sys, p->L);
     prm.chunk = p->chunk; prm.use_global = p->use_global;
+    fill_split(prm, *p->var);
     prm.win_tx = pd.d_wtx; prm.win_rx = pd.d_wrx; prm.tw = pd.d_tw; prm.chan = pd.d_chan; prm.snr_lin = pd.d_snr;
     prm.C = p->C; prm.n_snr = p->n_snr; prm.ensemble = ensemble;
     prm.seed = seed; prm.variant = variant;
@@ -234,10 +260,11 @@ int wofdm_ber_plan_launch(wofdm_ber_plan p, int slot, int64_t ensemble, uint64_t
 
     WOFDM_CUDA(h, cudaMemsetAsync(pd.d_cnt, 0, (size_t)p->n_snr * 2 * sizeof(unsigned long long), st));
     if (mine > 0) {
-        long long cap = (long long)pd.blocks_per_sm * d.sm_count;
+        long long cap = pd.max_ctas;
         if (const char* lim = getenv("WOFDM_MAX_CTAS_PER_SM"))            // tuning aid: occupancy sensitivity
             cap = std::min<long long>(cap, (long long)std::max(1, atoi(lim)) * d.sm_count);
-        const int grid = (int)std::min<long long>(mine, cap);
+        const int cl = p->var->CL;
+        const int grid = (int)std::min<long long>(mine, std::max<long long>(cap / cl, 1)) * cl;   // CTAs = frames in flight x cluster size
         WOFDM_CUDA(h, p->var->launch(prm, grid, p->lay.bytes, st));
         h->launches += 1;
     }
@@ -346,9 +373,10 @@ int wofdm_ber_verify(wofdm_handle h, const wofdm_sys_t* sys, const double* win_t
     rc = choose_variant(h, *sys, L, true, variant_kernel == 1, d.smem_optin, &ch);
     if (rc) return rc;
     int nb = 0;
-    rc = prepare_kernel(h, *ch.var, ch.lay.bytes, &nb);
+    long long max_ctas = 0;
+    rc = prepare_kernel(h, *ch.var, ch.lay.bytes, d.sm_count, &nb, &max_ctas);
     if (rc) return rc;
-    const int grid = (int)std::min<long long>(F, (long long)nb * d.sm_count);
+    const int grid = (int)std::min<long long>(F, std::max<long long>(max_ctas / ch.var->CL, 1)) * ch.var->CL;
 
     HostTables t;
     build_tables(*sys, win_tx, win_rx, t);
@@ -390,6 +418,7 @@ int wofdm_ber_verify(wofdm_handle h, const wofdm_sys_t* sys, const double* win_t
     BerParams prm;
     fill_sys(prm, *sys, L);
     prm.chunk = ch.chunk; prm.use_global = ch.use_global;
+    fill_split(prm, *ch.var);
     prm.win_tx = d_wtx; prm.win_rx = d_wrx; prm.tw = d_tw; prm.chan = d_chan; prm.snr_lin = d_snr;
     prm.C = F; prm.n_snr = F; prm.ensemble = 1;
     prm.frame_begin = 0; prm.frame_step = 1; prm.n_frames = F;
@@ -435,6 +464,7 @@ int wofdm_ber_draws(wofdm_handle h, const wofdm_sys_t* sys, int L, uint64_t seed
         rc = choose_variant(h, *sys, L, false, false, d.smem_optin, &ch);
         if (rc) return rc;
         prm.chunk = ch.chunk;
+        fill_split(prm, *ch.var);
     }
     const dim3 gs(sys->S, F);
     switch (sys->N) {

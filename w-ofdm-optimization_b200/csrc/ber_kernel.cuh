@@ -17,9 +17,14 @@
 //   TC  > 0  "regs"  : each thread owns one chunk of <= TC consecutive stream samples; the chunk's
 //            convolution output AND its noise stay in registers across the frame-wide power
 //            reduction, taps live in registers LB at a time.  fp32 production path.
+// CL > 1 (regs policy): a thread-block cluster of CL CTAs shares one frame, S/CL consecutive OFDM symbols and
+// their part of the frame stream per CTA (N = 1024: the stream plus the parked noise is 278 KB, more than one SM
+// holds).  The CTAs meet three times per frame through distributed shared memory: the Tx tail and the L-1
+// convolution halo of the previous CTA's last symbol, the frame-wide power sums, and the pilot's equaliser taps.
 // VERIFY = true replaces the Philox draws by caller-injected symbols/noise/channel per frame and
 // writes the equalised symbols and decisions back (same arithmetic, same code).
 #pragma once
+#include <cooperative_groups.h>
 #include "common.cuh"
 #include "fft_regs.cuh"
 
@@ -33,6 +38,7 @@ struct BerParams {
     int chunk;                 // B: noise block = samples of the frame stream owned by one thread (regs policy);
                                // stream sample i uses draw (i/B)*(B+1) + i%B (B odd: blocks start on a Philox pair)
     int use_global;            // staged policy: frame buffers live in global scratch
+    int split, split_nt;       // CL > 1: stream samples per CTA and threads per CTA (noise block g = rank*NT + local/B); else 0
     // device tables, element type T / V2<T>
     const void* win_tx;        // [n_tx]   v_tx * qam_scale / N
     const void* win_rx;        // [N + tail_rx]
@@ -131,8 +137,15 @@ __device__ __forceinline__ void noise_pair(const BerParams& prm, long long f, ui
 template <typename T>
 __device__ __forceinline__ V2<T> noise_at(const BerParams& prm, long long f, int i) {
     const int B = prm.chunk;
-    const int k = i / B;
-    const int d = k * (B + 1) + (i - k * B);
+    int k0 = 0;
+    if (prm.split > 0) {       // frame shared by a cluster: blocks are numbered per CTA
+        const int r = min(i / prm.split, prm.S * prm.stride / prm.split - 1);
+        i -= r * prm.split;
+        k0 = r * prm.split_nt;
+    }
+    const int kl = i / B;
+    const int k = k0 + kl;
+    const int d = k * (B + 1) + (i - kl * B);
     V2<T> n0, n1;
     noise_pair<T>(prm, f, (uint32_t)(d >> 1), n0, n1);
     return (d & 1) ? n1 : n0;
@@ -219,7 +232,12 @@ __device__ __forceinline__ float noise_gain(float pr, float snr_lin, float pn) {
 }
 __device__ __forceinline__ double noise_gain(double pr, double snr_lin, double pn) { return sqrt(pr * snr_lin / pn); }
 
-template <typename T, int N, int NT, int TC, int LB, int MINB, bool FULL, bool VERIFY>
+// barrier over the CTAs of a frame (release/acquire at cluster scope: remote shared-memory traffic is ordered)
+template <int CL> __device__ __forceinline__ void frame_sync() {
+    if constexpr (CL > 1) cooperative_groups::this_cluster().sync(); else __syncthreads();
+}
+
+template <typename T, int N, int NT, int TC, int LB, int MINB, bool FULL, bool VERIFY, int CL = 1>
 __global__ void __launch_bounds__(NT, MINB)
 ber_frame_kernel(const BerParams prm) {
     using P = FftPlan<N>;
@@ -228,6 +246,7 @@ ber_frame_kernel(const BerParams prm) {
     constexpr int FPP = NT / TPF;
     static_assert(NT % TPF == 0 && NT % 32 == 0, "threads per CTA must be a multiple of N/16 and 32");
     constexpr bool REGS = TC > 0;
+    static_assert(CL == 1 || REGS, "clusters are a feature of the register-resident policy");
     // Register row q of a thread = sub-carriers / samples t + q*TPF.  Only the outer rows can reach the cyclic
     // prefix / suffix, the Tx heads and the Rx overlap-add; the tuned variants look at ER of them (the host
     // checks cp, cs, tail_tx <= ER*TPF and tail_rx/2, shift <= TPF), the staged policy at all 16.
@@ -236,12 +255,17 @@ ber_frame_kernel(const BerParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x;
     const int slot = tid / TPF, t = tid % TPF;
-    const int S = prm.S, stride = prm.stride, n_tx = prm.n_tx, beta = prm.tail_tx, L = prm.L;
+    // this CTA's share of the frame: S OFDM symbols starting at symbol sb (the whole frame when CL == 1)
+    int rank = 0;
+    if constexpr (CL > 1) rank = (int)cooperative_groups::this_cluster().block_rank();
+    const int S = prm.S / CL, sb = rank * S;
+    const int stride = prm.stride, n_tx = prm.n_tx, beta = prm.tail_tx, L = prm.L;
     const int cp = prm.cp, cs = prm.cs;
     const int hh = prm.tail_rx >> 1;
     const int hb = prm.bits >> 1, m = 1 << hb;
-    const int sec = S * stride;                 // samples kept after the channel
+    const int sec = S * stride;                 // samples kept after the channel (this CTA's)
     const int body = beta + sec;                // serialised Tx stream length
+    const bool last_rank = rank == CL - 1;
 
     const BerSmem lay = ber_smem_layout<T, N, NT, TC, LB>(S, stride, beta, prm.tail_rx, L, prm.chunk, prm.use_global);
     C2* fbuf = reinterpret_cast<C2*>(smem_raw);
@@ -261,8 +285,16 @@ ber_frame_kernel(const BerParams prm) {
         fbuf = g;
         rbuf = g + prm.scratch_elems;
     }
-    C2* const ub = fbuf + lay.pad;              // ub[i] = stream sample i, ub[-pad..-1] = 0
+    C2* const ub = fbuf + lay.pad;              // ub[i] = stream sample i (CTA-local), ub[-pad..-1] = 0 or the halo
     C2* const xb = xbuf + slot * P::XLEN;
+    // distributed shared memory: the previous CTA's stream (tail + halo), CTA 0's equaliser taps, every CTA's sums
+    const C2* prev_ub = ub;
+    const C2* geq0 = geq;
+    if constexpr (CL > 1) {
+        auto cluster = cooperative_groups::this_cluster();
+        if (rank > 0) prev_ub = cluster.map_shared_rank(ub, rank - 1);
+        geq0 = cluster.map_shared_rank(geq, 0);
+    }
 
     // ---- one-time tables ----
     for (int i = tid; i < P::NTW; i += NT) tw[i] = reinterpret_cast<const C2*>(prm.tw)[i];
@@ -278,8 +310,9 @@ ber_frame_kernel(const BerParams prm) {
     __syncthreads();
 
     // frame id f = (si*C + ci)*ensemble + e, advanced without per-frame divisions
-    long long f = prm.frame_begin + (long long)blockIdx.x * prm.frame_step;
-    const long long df = (long long)gridDim.x * prm.frame_step;
+    const long long fslot = blockIdx.x / CL, nslots = gridDim.x / CL;   // frames in flight on the grid
+    long long f = prm.frame_begin + fslot * prm.frame_step;
+    const long long df = nslots * prm.frame_step;
     long long fe = 0, de = 0;
     int ci = 0, si = 0, dc = 0, ds = 0;
     if constexpr (!VERIFY) {
@@ -288,7 +321,7 @@ ber_frame_kernel(const BerParams prm) {
         si = (int)(q / prm.C);       ci = (int)(q - (long long)si * prm.C);
         ds = (int)(dq / prm.C);      dc = (int)(dq - (long long)ds * prm.C);
     }
-    for (long long j = blockIdx.x; j < prm.n_frames; j += gridDim.x) {
+    for (long long j = fslot; j < prm.n_frames; j += nslots) {
         if constexpr (VERIFY) { ci = (int)f; si = (int)f; }
         const T snr_lin = reinterpret_cast<const T*>(prm.snr_lin)[si];
         if (tid < (REGS ? (LB > L ? LB : L) : L))   // regs policy: zero-padded to LB, loaded without predicates
@@ -299,11 +332,11 @@ ber_frame_kernel(const BerParams prm) {
             const int s = s0 + slot;
             const bool act = s < S;
             const int se = act ? s : S - 1;     // idle slots shadow the last symbol (identical stores)
-            const bool first = se == 0;
+            const bool first = sb + se == 0;    // the frame's first symbol has no predecessor
             C2 v[16];
             {
                 uint32_t w[4];
-                load_sym_idx<N, VERIFY>(prm, f, se, t, w);
+                load_sym_idx<N, VERIFY>(prm, f, sb + se, t, w);
                 symw[se * TPF + t] = make_uint4(w[0], w[1], w[2], w[3]);
 #pragma unroll
                 for (int q = 0; q < 16; ++q) v[q] = qlut[sym_byte(w, q)];
@@ -340,22 +373,29 @@ ber_frame_kernel(const BerParams prm) {
                     if (i < n_tx) us[i] = cscale(wtx[i], v[q]);
                 }
             }
-            __syncthreads();
+            frame_sync<CL>();
+            // the falling tail of the previous symbol: same buffer, or the previous CTA's (its slack past `sec`)
+            const C2* const tl = (CL > 1 && se == 0) ? prev_ub + sec : us;
             if (beta > 0 && act && !first) {
 #pragma unroll
                 for (int q = 16 - ER; q < 16; ++q) {
                     if (q * TPF + TPF > N - cp) {
                         const int i = t + q * TPF - (N - cp);
-                        if (i >= 0 && i < beta) us[i] = caxpy(wtx[i], v[q], us[i]);
+                        if (i >= 0 && i < beta) us[i] = caxpy(wtx[i], v[q], tl[i]);
                     }
                 }
                 if (cp < beta) {
 #pragma unroll
                     for (int q = 0; q < ER; ++q) {
                         const int i = t + q * TPF + cp;
-                        if (i < beta) us[i] = caxpy(wtx[i], v[q], us[i]);
+                        if (i < beta) us[i] = caxpy(wtx[i], v[q], tl[i]);
                     }
                 }
+            }
+            if constexpr (CL > 1) {
+                // convolution halo: the last `pad` stream samples of the previous CTA (none of them is a head)
+                // (CL > 1 requires a single pass, S/CL <= FPP: the previous CTA's last symbol is complete here)
+                if (rank > 0 && tid < lay.pad) fbuf[tid] = prev_ub[sec - lay.pad + tid];
             }
         }
         __syncthreads();
@@ -381,7 +421,7 @@ ber_frame_kernel(const BerParams prm) {
             const C2* src = ub + i0 - (LB - 1);
             C2* const nb = rbuf + i0;
             constexpr int NPAIR = (TC + 1) / 2, NSTEP = (TC + LB - 1) / NPAIR;
-            const uint32_t q0 = (uint32_t)tid * (uint32_t)((B + 1) >> 1);   // block tid starts at draw tid*(B+1)
+            const uint32_t q0 = (uint32_t)(rank * NT + tid) * (uint32_t)((B + 1) >> 1);   // block g starts at draw g*(B+1)
             // input c feeds output o through tap (LB-1) - (c - o), 0 <= c - o <= LB-1
 #pragma unroll
             for (int c = 0; c < TC + LB - 1; ++c) {
@@ -393,7 +433,7 @@ ber_frame_kernel(const BerParams prm) {
                     const int p2 = c / NSTEP;
                     C2 n0, n1;
                     if constexpr (VERIFY) {
-                        const double2* nin = prm.noise_in + (size_t)f * prm.noise_len + i0;
+                        const double2* nin = prm.noise_in + (size_t)f * prm.noise_len + (size_t)rank * sec + i0;
                         n0 = (2 * p2 < nvalid) ? to_v2<T>(nin[2 * p2]) : mk2<T>(0, 0);
                         n1 = (2 * p2 + 1 < nvalid) ? to_v2<T>(nin[2 * p2 + 1]) : mk2<T>(0, 0);
                     } else {
@@ -416,15 +456,15 @@ ber_frame_kernel(const BerParams prm) {
             }
 #pragma unroll
             for (int o = 0; o < TC; ++o) pr2 = csq_acc(acc[o], pr2);
-            if (prm.noise_norm == 1) {
+            if (prm.noise_norm == 1 && last_rank) {
                 // the L-1+beta samples the reference truncates still count in both power sums
                 for (int i = sec + tid; i < body + L - 1; i += NT) {
                     C2 a = mk2<T>(0, 0);
                     for (int l = 0; l < L; ++l)
                         if (i - l < body) cmac(a, taps[l], ub[i - l]);
                     C2 n0;
-                    if constexpr (VERIFY) n0 = to_v2<T>(prm.noise_in[(size_t)f * prm.noise_len + i]);
-                    else n0 = noise_at<T>(prm, f, i);
+                    if constexpr (VERIFY) n0 = to_v2<T>(prm.noise_in[(size_t)f * prm.noise_len + (size_t)rank * sec + i]);
+                    else n0 = noise_at<T>(prm, f, rank * sec + i);   // (same numbering: noise_at splits at prm.split = sec)
                     pr2 = csq_acc(a, pr2);
                     pn2 = csq_acc(n0, pn2);
                 }
@@ -432,12 +472,20 @@ ber_frame_kernel(const BerParams prm) {
             // frame-wide sums
             T pr = warp_sum(pr2.x + pr2.y), pn = warp_sum(pn2.x + pn2.y);
             if ((tid & 31) == 0) { red[tid >> 5] = pr; red[32 + (tid >> 5)] = pn; }
-            __syncthreads();                       // also: every conv read of the stream is done
-            const T g = noise_gain(block_total<NT / 32>(red), snr_lin, block_total<NT / 32>(red + 32));
+            frame_sync<CL>();                      // also: every conv read of the stream is done
+            T prt = 0, pnt = 0;                    // CTA partials in rank order: every CTA forms the same gain
+#pragma unroll
+            for (int r = 0; r < CL; ++r) {
+                const T* rr = red;
+                if constexpr (CL > 1) rr = cooperative_groups::this_cluster().map_shared_rank(red, r);
+                prt += block_total<NT / 32>(rr);
+                pnt += block_total<NT / 32>(rr + 32);
+            }
+            const T g = noise_gain(prt, snr_lin, pnt);
             // loads first, then stores: ptxas cannot prove that nb and ub do not overlap and would otherwise
             // serialise every load behind the previous store
 #pragma unroll
-            for (int o = 0; o < TC; ++o) acc[o] = caxpy(g, nb[FULL ? o : min(o, B - 1)], acc[o]);
+            for (int o = 0; o < TC; ++o) acc[o] = caxpy(g, nb[o], acc[o]);   // (o >= nvalid: reads a neighbour's slot, result discarded)
 #pragma unroll
             for (int o = 0; o < TC; ++o)
                 if (FULL || o < nvalid) ub[i0 + o] = acc[o];
@@ -502,30 +550,32 @@ ber_frame_kernel(const BerParams prm) {
             if (s0 == 0) {
                 // pilot (wofdm_simulation.py:223): the pilot's threads publish Y0, then every thread turns one
                 // bin into the equaliser tap G[k] = X0[k] / Y0[k] (lattice units), so nobody waits on one warp
-                if (se == 0) {
+                if (rank == 0) {
+                    if (se == 0) {
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) geq[t + q * TPF] = v[q];
+                        for (int q = 0; q < 16; ++q) geq[t + q * TPF] = v[q];
+                    }
+                    __syncthreads();
+                    const unsigned char* pil = reinterpret_cast<const unsigned char*>(symw);   // symbol 0: thread k%TPF, byte k/TPF
+                    for (int k = tid; k < N; k += NT) {
+                        const C2 y0 = geq[k];
+                        const C2 x0 = qlut[pil[(k % TPF) * 16 + k / TPF]];
+                        geq[k] = cscale(recip(y0.x * y0.x + y0.y * y0.y), cmulc(x0, y0));
+                    }
                 }
-                __syncthreads();
-                const unsigned char* pil = reinterpret_cast<const unsigned char*>(symw);   // symbol 0: thread k%TPF, byte k/TPF
-                for (int k = tid; k < N; k += NT) {
-                    const C2 y0 = geq[k];
-                    const C2 x0 = qlut[pil[(k % TPF) * 16 + k / TPF]];
-                    geq[k] = cscale(recip(y0.x * y0.x + y0.y * y0.y), cmulc(x0, y0));
-                }
-                __syncthreads();
+                frame_sync<CL>();
             }
-            if (act && s > 0) {
+            if (act && sb + s > 0) {
 #pragma unroll
                 for (int q = 0; q < 16; ++q) {
                     const int k = t + q * TPF;
-                    const C2 e = cmul(v[q], geq[k]);                                       // :231
+                    const C2 e = cmul(v[q], geq0[k]);                                      // :231
                     const int dec = dlut[slice_index(e, hb)];                              // :233
                     const int txi = sym_byte(w, q);
                     sym_cnt += (dec != txi);                                               // :235
                     bit_cnt += __popc(dec ^ txi);
                     if constexpr (VERIFY) {
-                        const size_t o = ((size_t)f * (S - 1) + (s - 1)) * N + k;
+                        const size_t o = ((size_t)f * (prm.S - 1) + (sb + s - 1)) * N + k;
                         prm.eq_out[o] = make_double2((double)e.x * prm.qscale, (double)e.y * prm.qscale);
                         prm.dec_out[o] = dec;
                     }
@@ -553,6 +603,7 @@ ber_frame_kernel(const BerParams prm) {
             si += ds;
         }
     }
+    if constexpr (CL > 1) cooperative_groups::this_cluster().sync();   // nobody leaves while a peer may still read its shared memory
 }
 
 // ---- export of the on-device draws (wofdm_ber_draws) ------------------------------------------

@@ -9,6 +9,7 @@ namespace wofdm {
 struct BerVariant {
     const char* name;
     int N, NT, TC, LB, MINB;
+    int CL;                    // CTAs per frame (thread-block cluster size)
     bool full;                 // every register of every thread is a live stream sample (NT*TC == S*stride)
     bool fp64, verify;
     BerSmem (*layout)(int S, int stride, int tail_tx, int tail_rx, int L, int chunk, int use_global);
@@ -16,18 +17,29 @@ struct BerVariant {
     cudaError_t (*launch)(const BerParams& prm, int grid, size_t smem, cudaStream_t st);
 };
 
-template <typename T, int N, int NT, int TC, int LB, int MINB, bool FULL, bool V>
+template <typename T, int N, int NT, int TC, int LB, int MINB, bool FULL, bool V, int CL = 1>
 struct BerVariantImpl {
+    // grid = CTAs (a multiple of CL); CL > 1 launches thread-block clusters of CL CTAs
     static cudaError_t launch(const BerParams& prm, int grid, size_t smem, cudaStream_t st) {
-        ber_frame_kernel<T, N, NT, TC, LB, MINB, FULL, V><<<grid, NT, smem, st>>>(prm);
-        return cudaGetLastError();
+        if constexpr (CL == 1) {
+            ber_frame_kernel<T, N, NT, TC, LB, MINB, FULL, V, 1><<<grid, NT, smem, st>>>(prm);
+            return cudaGetLastError();
+        } else {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            return cudaLaunchKernelEx(&cfg, ber_frame_kernel<T, N, NT, TC, LB, MINB, FULL, V, CL>, prm);
+        }
     }
     static BerVariant make(const char* name) {
         BerVariant v;
-        v.name = name; v.N = N; v.NT = NT; v.TC = TC; v.LB = LB; v.MINB = MINB; v.full = FULL;
+        v.name = name; v.N = N; v.NT = NT; v.TC = TC; v.LB = LB; v.MINB = MINB; v.CL = CL; v.full = FULL;
         v.fp64 = sizeof(T) == 8; v.verify = V;
         v.layout = &ber_smem_layout<T, N, NT, TC, LB>;
-        v.fn = reinterpret_cast<const void*>(&ber_frame_kernel<T, N, NT, TC, LB, MINB, FULL, V>);
+        v.fn = reinterpret_cast<const void*>(&ber_frame_kernel<T, N, NT, TC, LB, MINB, FULL, V, CL>);
         v.launch = &launch;
         return v;
     }
@@ -36,6 +48,11 @@ struct BerVariantImpl {
 #define WOFDM_VARIANT(T, N, NT, TC, LB, MINB, FULL, tag)                                            \
     out.push_back(BerVariantImpl<T, N, NT, TC, LB, MINB, FULL, false>::make("ber_" tag "_n" #N "_t" #NT "_c" #TC "_l" #LB "_b" #MINB "_f" #FULL)); \
     out.push_back(BerVariantImpl<T, N, NT, TC, LB, MINB, FULL, true>::make("ber_" tag "_n" #N "_t" #NT "_c" #TC "_l" #LB "_b" #MINB "_f" #FULL "_verify"));
+
+// CL CTAs per frame (thread-block cluster)
+#define WOFDM_VARIANT_CL(T, N, NT, TC, LB, MINB, FULL, CL, tag)                                     \
+    out.push_back(BerVariantImpl<T, N, NT, TC, LB, MINB, FULL, false, CL>::make("ber_" tag "_n" #N "_t" #NT "_c" #TC "_l" #LB "_b" #MINB "_f" #FULL "_cl" #CL)); \
+    out.push_back(BerVariantImpl<T, N, NT, TC, LB, MINB, FULL, true, CL>::make("ber_" tag "_n" #N "_t" #NT "_c" #TC "_l" #LB "_b" #MINB "_f" #FULL "_cl" #CL "_verify"));
 
 void register_ber_f32_staged(std::vector<BerVariant>& out);
 void register_ber_f64_staged(std::vector<BerVariant>& out);
