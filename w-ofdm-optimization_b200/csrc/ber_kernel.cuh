@@ -288,13 +288,13 @@ ber_frame_kernel(const BerParams prm) {
     C2* const ub = fbuf + lay.pad;              // ub[i] = stream sample i (CTA-local), ub[-pad..-1] = 0 or the halo
     C2* const xb = xbuf + slot * P::XLEN;
     // distributed shared memory: the previous CTA's stream (tail + halo), CTA 0's equaliser taps, every CTA's sums
+    // (pulled: a few dozen samples per frame; the power sums and the equaliser taps are PUSHED into every CTA's
+    // copy with remote stores, which do not stall, so all their reads are local)
     const C2* prev_ub = ub;
-    const C2* geq0 = geq;
     if constexpr (CL > 1) {
-        auto cluster = cooperative_groups::this_cluster();
-        if (rank > 0) prev_ub = cluster.map_shared_rank(ub, rank - 1);
-        geq0 = cluster.map_shared_rank(geq, 0);
+        if (rank > 0) prev_ub = cooperative_groups::this_cluster().map_shared_rank(ub, rank - 1);
     }
+    static_assert(CL * (NT / 32) <= 32, "per-warp partial sums of all CTAs must fit the reduction scratch");
 
     // ---- one-time tables ----
     for (int i = tid; i < P::NTW; i += NT) tw[i] = reinterpret_cast<const C2*>(prm.tw)[i];
@@ -471,17 +471,18 @@ ber_frame_kernel(const BerParams prm) {
             }
             // frame-wide sums
             T pr = warp_sum(pr2.x + pr2.y), pn = warp_sum(pn2.x + pn2.y);
-            if ((tid & 31) == 0) { red[tid >> 5] = pr; red[32 + (tid >> 5)] = pn; }
-            frame_sync<CL>();                      // also: every conv read of the stream is done
-            T prt = 0, pnt = 0;                    // CTA partials in rank order: every CTA forms the same gain
+            if ((tid & 31) == 0) {
+                // warp partials go to slot rank*NW + warp of EVERY CTA of the frame: same order, same gain everywhere
+                const int sl = rank * (NT / 32) + (tid >> 5);
 #pragma unroll
-            for (int r = 0; r < CL; ++r) {
-                const T* rr = red;
-                if constexpr (CL > 1) rr = cooperative_groups::this_cluster().map_shared_rank(red, r);
-                prt += block_total<NT / 32>(rr);
-                pnt += block_total<NT / 32>(rr + 32);
+                for (int r = 0; r < CL; ++r) {
+                    T* rr = red;
+                    if constexpr (CL > 1) rr = cooperative_groups::this_cluster().map_shared_rank(red, r);
+                    rr[sl] = pr; rr[32 + sl] = pn;
+                }
             }
-            const T g = noise_gain(prt, snr_lin, pnt);
+            frame_sync<CL>();                      // also: every conv read of the stream is done
+            const T g = noise_gain(block_total<CL * (NT / 32)>(red), snr_lin, block_total<CL * (NT / 32)>(red + 32));
             // loads first, then stores: ptxas cannot prove that nb and ub do not overlap and would otherwise
             // serialise every load behind the previous store
 #pragma unroll
@@ -560,7 +561,12 @@ ber_frame_kernel(const BerParams prm) {
                     for (int k = tid; k < N; k += NT) {
                         const C2 y0 = geq[k];
                         const C2 x0 = qlut[pil[(k % TPF) * 16 + k / TPF]];
-                        geq[k] = cscale(recip(y0.x * y0.x + y0.y * y0.y), cmulc(x0, y0));
+                        const C2 gk = cscale(recip(y0.x * y0.x + y0.y * y0.y), cmulc(x0, y0));
+                        geq[k] = gk;
+                        if constexpr (CL > 1) {
+#pragma unroll
+                            for (int r = 1; r < CL; ++r) cooperative_groups::this_cluster().map_shared_rank(geq, r)[k] = gk;
+                        }
                     }
                 }
                 frame_sync<CL>();
@@ -569,7 +575,7 @@ ber_frame_kernel(const BerParams prm) {
 #pragma unroll
                 for (int q = 0; q < 16; ++q) {
                     const int k = t + q * TPF;
-                    const C2 e = cmul(v[q], geq0[k]);                                      // :231
+                    const C2 e = cmul(v[q], geq[k]);                                       // :231
                     const int dec = dlut[slice_index(e, hb)];                              // :233
                     const int txi = sym_byte(w, q);
                     sym_cnt += (dec != txi);                                               // :235
