@@ -153,8 +153,8 @@ def main():
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
 
-    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":    # keeps NCCL's banner off stdout: ONE JSON line
-        os.environ["NCCL_DEBUG"] = "WARN"
+    if os.environ.get("NCCL_DEBUG"):                             # NCCL logs to stdout by default: ONE JSON line there
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
     import wofdm_b200 as W

@@ -6,13 +6,16 @@
 // TF32 number), lo = fp32(x - hi) (the tensor core reads its top 19 bits); A.B ~ Ahi.Bhi + Ahi.Blo + Alo.Bhi,
 // relative error ~2^-21 per product, accumulated in fp32 in tensor memory.
 //
-// One CTA (128 threads) owns a 128 x 256 accumulator tile in TMEM (256 of the 512 columns).  The hi/lo operands are
+// A persistent CTA (192 threads, one per SM) works through 128 x 256 output tiles with TWO accumulators in TMEM (all
+// 512 columns): the MMA issuer fills one while the four epilogue warps drain the other, so the tensor pipe does not
+// idle through the epilogue, the TMEM allocation and the pipeline fill of every tile.  The hi/lo operands are
 // stored in HBM PRE-TILED: every (row tile, K block of 32) is one contiguous block already in the canonical K-major
 // no-swizzle UMMA layout (8-row x 16-byte core matrices; chunk c = (row/8)*64 + kchunk*8 + row%8 at byte 16*c), so a
 // stage is filled by four cp.async.bulk copies (TMA engine, no tensor map) that complete on an mbarrier.
 // Warp-specialised: one producer thread (bulk copies), one MMA thread (12 tcgen05.mma per K block = 4 K-steps x 3
-// split terms, tcgen05.commit frees the stage), two stages.  Epilogue (all four warps): tcgen05.ld the accumulator
+// split terms, tcgen05.commit frees the stage), two stages.  Epilogue (four warps): tcgen05.ld the accumulator
 // rows, mask the diagonal of slice 0, square, sum, one atomicAdd per row -- A itself is never written.
+#include <algorithm>
 #include "interf.h"
 
 namespace wofdm {
@@ -58,19 +61,21 @@ __device__ __forceinline__ void bulk_copy(uint32_t dst, const void* src, uint32_
 
 }  // namespace
 
-// grid (2N / TM, slices), 128 threads, dynamic smem NSTAGE * STAGE_BYTES.
+// Persistent: grid = min(tiles, SMs) CTAs of 192 threads, tile t = (row tile t % (2N/TM), slice t / (2N/TM)), CTA b
+// takes tiles b, b + grid, ...  Warps 0-3 = epilogue (TMEM lanes 32w..32w+31), warp 4 = producer, warp 5 = MMA issuer.
 // Rt: [2N/TM][nk][hi|lo][TM*KB] tiles, Bt: [slices][nk][hi|lo][TN*KB] tiles (see tile_split_* below)
-__global__ void __launch_bounds__(128, 1) gemm_power_tf32(const float* __restrict__ Rt, const float* __restrict__ Bt,
-                                                         double* __restrict__ P, int N, int Kp, int Ms, int c0, int scalar) {
+constexpr int NTHREADS = 192;
+__global__ void __launch_bounds__(NTHREADS, 1) gemm_power_tf32(const float* __restrict__ Rt, const float* __restrict__ Bt,
+                                                              double* __restrict__ P, int N, int Kp, int Ms, int c0, int scalar,
+                                                              int n_tiles) {
     extern __shared__ __align__(1024) unsigned char sm[];
-    __shared__ __align__(8) unsigned long long full_bar[NSTAGE], empty_bar[NSTAGE], acc_bar;
+    __shared__ __align__(8) unsigned long long full_bar[NSTAGE], empty_bar[NSTAGE], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int mt = blockIdx.x, m0 = mt * TM, s = blockIdx.y;
-    const int nk = Kp / KB;
+    const int nk = Kp / KB, mtiles = 2 * N / TM;
 
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(TN) : "memory");
+    if (warp == 4) {   // both accumulators: all 512 columns (one CTA per SM: the stages take 192 KB of shared memory)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(2 * TN) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
@@ -78,7 +83,10 @@ __global__ void __launch_bounds__(128, 1) gemm_power_tf32(const float* __restric
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&full_bar[i])) : "memory");
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&empty_bar[i])) : "memory");
         }
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&acc_bar)) : "memory");
+        for (int i = 0; i < 2; ++i) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&acc_full[i])) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" :: "r"(smem_u32(&acc_empty[i])) : "memory");   // one arrival per epilogue warp
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -86,71 +94,94 @@ __global__ void __launch_bounds__(128, 1) gemm_power_tf32(const float* __restric
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_base_s;
 
-    if (tid == 0) {
-        // ===== producer: four bulk copies per stage =====
-        const float* ra = Rt + (size_t)mt * nk * (2 * TM * KB);
-        const float* rb = Bt + (size_t)s * nk * (2 * TN * KB);
-        for (int kb = 0; kb < nk; ++kb) {
-            const int st = kb & 1;
-            if (kb >= NSTAGE) mbar_wait(smem_u32(&empty_bar[st]), (uint32_t)(((kb >> 1) - 1) & 1));
-            const uint32_t bar = smem_u32(&full_bar[st]), dst = smem_u32(sm + (size_t)st * STAGE_BYTES);
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"((uint32_t)STAGE_BYTES) : "memory");
-            bulk_copy(dst, ra + (size_t)kb * (2 * TM * KB), 2 * A_BYTES, bar);                 // A hi | lo
-            bulk_copy(dst + 2 * A_BYTES, rb + (size_t)kb * (2 * TN * KB), 2 * B_BYTES, bar);    // B hi | lo
-        }
-    } else if (tid == 32) {
-        // ===== MMA issuer =====
-        for (int kb = 0; kb < nk; ++kb) {
-            const int st = kb & 1;
-            mbar_wait(smem_u32(&full_bar[st]), (uint32_t)((kb >> 1) & 1));
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a_hi = smem_u32(sm + (size_t)st * STAGE_BYTES), a_lo = a_hi + A_BYTES, b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
-#pragma unroll
-            for (int j = 0; j < KB / 8; ++j) {                             // one MMA consumes 8 TF32 = two 16-byte chunks
-                const uint32_t off = (uint32_t)j * 256u;
-                mma_tf32(tmem, umma_desc(a_hi + off), umma_desc(b_hi + off), (kb | j) != 0);
-                mma_tf32(tmem, umma_desc(a_hi + off), umma_desc(b_lo + off), 1u);
-                mma_tf32(tmem, umma_desc(a_lo + off), umma_desc(b_hi + off), 1u);
+    if (warp == 4) {
+        if (lane == 0) {
+            // ===== producer: two bulk copies per stage, K blocks numbered through all of this CTA's tiles =====
+            int it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const float* ra = Rt + (size_t)(tile % mtiles) * nk * (2 * TM * KB);
+                const float* rb = Bt + (size_t)(tile / mtiles) * nk * (2 * TN * KB);
+                for (int kb = 0; kb < nk; ++kb, ++it) {
+                    const int st = it % NSTAGE;
+                    if (it >= NSTAGE) mbar_wait(smem_u32(&empty_bar[st]), (uint32_t)(((it / NSTAGE) - 1) & 1));
+                    const uint32_t bar = smem_u32(&full_bar[st]), dst = smem_u32(sm + (size_t)st * STAGE_BYTES);
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"((uint32_t)STAGE_BYTES) : "memory");
+                    bulk_copy(dst, ra + (size_t)kb * (2 * TM * KB), 2 * A_BYTES, bar);                 // A hi | lo
+                    bulk_copy(dst + 2 * A_BYTES, rb + (size_t)kb * (2 * TN * KB), 2 * B_BYTES, bar);    // B hi | lo
+                }
             }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&empty_bar[st])) : "memory");
         }
-        // completes exactly once, after every MMA of the tile (a parity wait on a recycled barrier would
-        // release the epilogue warps, which do not follow the pipeline, after the first K block)
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&acc_bar)) : "memory");
-    }
-    __syncwarp();
-    mbar_wait(smem_u32(&acc_bar), 0u);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
-    // epilogue: thread = one row of the tile (TMEM lane 32*warp + lane)
-    const int r = m0 + warp * 32 + lane, k = r % N;
-    const int c = c0 + s / Ms, ms = s % Ms;
-    float pw = 0.f;
-#pragma unroll 1
-    for (int cc = 0; cc < TN / 32; ++cc) {
-        uint32_t v[32];
-        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cc * 32);
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-            : "r"(taddr) : "memory");
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    } else if (warp == 5) {
+        if (lane == 0) {
+            // ===== MMA issuer: tile tl accumulates into TMEM columns [(tl & 1) * TN, +TN) while the epilogue drains the other half =====
+            int it = 0, tl = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+                const int buf = tl & 1;
+                if (tl >= 2) {
+                    mbar_wait(smem_u32(&acc_empty[buf]), (uint32_t)(((tl >> 1) - 1) & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                const uint32_t tacc = tmem + (uint32_t)(buf * TN);
+                for (int kb = 0; kb < nk; ++kb, ++it) {
+                    const int st = it % NSTAGE;
+                    mbar_wait(smem_u32(&full_bar[st]), (uint32_t)((it / NSTAGE) & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_hi = smem_u32(sm + (size_t)st * STAGE_BYTES), a_lo = a_hi + A_BYTES, b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            const float x = __uint_as_float(v[i]);
-            if (!(ms == 0 && cc * 32 + i == k)) pw = fmaf(x, x, pw);
+                    for (int j = 0; j < KB / 8; ++j) {                             // one MMA consumes 8 TF32 = two 16-byte chunks
+                        const uint32_t off = (uint32_t)j * 256u;
+                        mma_tf32(tacc, umma_desc(a_hi + off), umma_desc(b_hi + off), (kb | j) != 0);
+                        mma_tf32(tacc, umma_desc(a_hi + off), umma_desc(b_lo + off), 1u);
+                        mma_tf32(tacc, umma_desc(a_lo + off), umma_desc(b_hi + off), 1u);
+                    }
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&empty_bar[st])) : "memory");
+                }
+                // completes once per tile, after every MMA of the tile
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&acc_full[buf])) : "memory");
+            }
+        }
+    } else {
+        // ===== epilogue warps: thread = one row of the tile (TMEM lane 32*warp + lane) =====
+        int tl = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+            const int buf = tl & 1;
+            const int m0 = (tile % mtiles) * TM, s = tile / mtiles;
+            mbar_wait(smem_u32(&acc_full[buf]), (uint32_t)((tl >> 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int r = m0 + warp * 32 + lane, k = r % N;
+            const int c = c0 + s / Ms, ms = s % Ms;
+            float pw = 0.f;
+#pragma unroll 1
+            for (int cc = 0; cc < TN / 32; ++cc) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * TN + cc * 32);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr) : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float x = __uint_as_float(v[i]);
+                    if (!(ms == 0 && cc * 32 + i == k)) pw = fmaf(x, x, pw);
+                }
+            }
+            // this warp's quarter of the accumulator has been read: hand the buffer back to the MMA issuer
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(&acc_empty[buf])) : "memory");
+            atomicAdd(scalar ? &P[c] : &P[(size_t)c * N + k], (double)pw);
         }
     }
-    atomicAdd(scalar ? &P[c] : &P[(size_t)c * N + k], (double)pw);
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(TN) : "memory");
+    if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(2 * TN) : "memory");
 }
 
 __device__ __forceinline__ void split_hi_lo(double x, float& hi, float& lo) {
@@ -214,7 +245,8 @@ int interf_gemm_tf32(wofdm_ctx* h, const wofdm_sys_t* sys, const InterfDev& v, i
     WOFDM_CUDA(h, cudaGetLastError());
     const size_t smem = (size_t)NSTAGE * STAGE_BYTES;
     WOFDM_CUDA(h, cudaFuncSetAttribute(gemm_power_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gemm_power_tf32<<<dim3(2 * N / TM, slices), 128, smem, d.stream>>>(Rt, Bt, v.P, N, v.Kp, Ms, c0, scalar);
+    const int n_tiles = (2 * N / TM) * slices;
+    gemm_power_tf32<<<std::min(n_tiles, d.sm_count), NTHREADS, smem, d.stream>>>(Rt, Bt, v.P, N, v.Kp, Ms, c0, scalar, n_tiles);
     WOFDM_CUDA(h, cudaGetLastError());
     h->launches += 2;
     return WOFDM_OK;
