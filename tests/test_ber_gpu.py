@@ -142,6 +142,38 @@ def test_production_replay_matches_oracle(handle):
                 assert np.all(np.abs(res["bit_err"] - want_bit) <= 4 + 0.002 * want_bit)
 
 
+@pytest.mark.parametrize("name,nn", [("WOLA", 0), ("CPW", 1), ("CP", 1)])
+def test_production_replay_cluster_kernel(handle, name, nn):
+    """N = 1024 (one frame per 2-CTA cluster): the exported Philox draws, replayed through the oracle, give the
+    production counters -- pins the per-CTA noise numbering, the DSMEM tail / halo and the cluster-wide sums."""
+    N, S, bits = 1024, 16, 6
+    a, b = (0, 0) if name == "CP" else (32, 40)
+    p = O.system_params(name, N, 64, a, b, S=S, bits=bits, noise_norm=nn, constellation=1)
+    vt, vr, _, _ = O.perturbed_windows(p, seed=5)
+    chans = O.synth_channels(2, 21, seed=11)
+    snr = np.array([12.0, 30.0])
+    ens = 2
+    for precision in (0, 1):
+        s = to_sys(p, precision)
+        res = handle.ber_run(s, vt, vr, chans, snr, ens, seed=77, variant=0)
+        F = len(snr) * chans.shape[1] * ens
+        ids = np.arange(F)
+        sym, nz = handle.ber_draws(s, chans.shape[0], 77, 0, ids)
+        want_sym = np.zeros(len(snr), dtype=np.int64)
+        want_bit = np.zeros(len(snr), dtype=np.int64)
+        for f in ids:
+            c = (f // ens) % chans.shape[1]
+            si = f // (ens * chans.shape[1])
+            r = O.frame_chain_structured(p, vt, vr, chans[:, c], snr[si], sym[f].T, nz[f])
+            want_sym[si] += r.sym_err
+            want_bit[si] += r.bit_err
+        if precision == 1:
+            assert np.array_equal(res["sym_err"], want_sym) and np.array_equal(res["bit_err"], want_bit)
+        else:
+            assert np.all(np.abs(res["sym_err"] - want_sym) <= 5 + 0.003 * want_sym), (res["sym_err"], want_sym)
+            assert np.all(np.abs(res["bit_err"] - want_bit) <= 8 + 0.003 * want_bit), (res["bit_err"], want_bit)
+
+
 def test_sharding_is_exact(handle):
     """Counters of disjoint shards add up to the unsharded run (same seeds, global frame ids)."""
     g = load_ser_golden("wtx")

@@ -16,6 +16,7 @@
 // split terms, tcgen05.commit frees the stage), two stages.  Epilogue (four warps): tcgen05.ld the accumulator
 // rows, mask the diagonal of slice 0, square, sum, one atomicAdd per row -- A itself is never written.
 #include <algorithm>
+#include <cstdlib>
 #include "interf.h"
 
 namespace wofdm {
@@ -23,6 +24,10 @@ namespace wofdm {
 namespace {
 
 constexpr int TM = 128, TN = 256, KB = 32, NSTAGE = 2;
+// Two CTAs that work on neighbouring row tiles of the same (channel, slice) form a thread-block cluster and share
+// the B operand: each fetches one half of a B stage and MULTICASTS it into both shared memories.  Without it the
+// persistent kernel pulls 96 KB per K block and SM out of L2 = 12.3 TB/s, which is the L2 limit, not the tensor pipe's.
+// (CLUSTER is a template parameter: 2 by default, WOFDM_TF32_CLUSTER=1 selects the non-multicast build for A/B runs)
 constexpr int A_BYTES = TM * KB * 4, B_BYTES = TN * KB * 4;            // one hi (or lo) tile
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;                 // 96 KiB
 constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
@@ -58,13 +63,22 @@ __device__ __forceinline__ void bulk_copy(uint32_t dst, const void* src, uint32_
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// the same copy delivered to the same offsets (data and mbarrier) of every CTA in `mask`
+__device__ __forceinline__ void bulk_copy_multicast(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 
 }  // namespace
 
-// Persistent: grid = min(tiles, SMs) CTAs of 192 threads, tile t = (row tile t % (2N/TM), slice t / (2N/TM)), CTA b
-// takes tiles b, b + grid, ...  Warps 0-3 = epilogue (TMEM lanes 32w..32w+31), warp 4 = producer, warp 5 = MMA issuer.
+// Persistent: grid = CLUSTER * min(tile pairs, resident clusters) CTAs of 192 threads; cluster q takes the tile pairs
+// q, q + clusters, ...; pair p = (slice p / (mtiles/2), row tiles 2*(p % (mtiles/2)) + rank).  Warps 0-3 = epilogue (TMEM lanes 32w..32w+31), warp 4 = producer, warp 5 = MMA issuer.
 // Rt: [2N/TM][nk][hi|lo][TM*KB] tiles, Bt: [slices][nk][hi|lo][TN*KB] tiles (see tile_split_* below)
 constexpr int NTHREADS = 192;
+template <int CLUSTER>
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_power_tf32(const float* __restrict__ Rt, const float* __restrict__ Bt,
                                                               double* __restrict__ P, int N, int Kp, int Ms, int c0, int scalar,
                                                               int n_tiles) {
@@ -72,7 +86,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_power_tf32(const float* __re
     __shared__ __align__(8) unsigned long long full_bar[NSTAGE], empty_bar[NSTAGE], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr uint16_t CL_MASK = (1u << CLUSTER) - 1u;
     const int nk = Kp / KB, mtiles = 2 * N / TM;
+    uint32_t rank = 0;
+    if (CLUSTER > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int q0 = blockIdx.x / CLUSTER, nq = gridDim.x / CLUSTER, n_pairs = n_tiles / CLUSTER, ppairs = mtiles / CLUSTER;
 
     if (warp == 4) {   // both accumulators: all 512 columns (one CTA per SM: the stages take 192 KB of shared memory)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(2 * TN) : "memory");
@@ -81,7 +99,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_power_tf32(const float* __re
     if (tid == 0) {
         for (int i = 0; i < NSTAGE; ++i) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&full_bar[i])) : "memory");
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&empty_bar[i])) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&empty_bar[i])), "r"(CLUSTER) : "memory");   // released by every CTA's MMAs
         }
         for (int i = 0; i < 2; ++i) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&acc_full[i])) : "memory");
@@ -91,6 +109,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_power_tf32(const float* __re
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (CLUSTER > 1) cluster_sync_all();          // the peer's barriers exist before anything is multicast onto them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_base_s;
 
@@ -98,16 +117,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_power_tf32(const float* __re
         if (lane == 0) {
             // ===== producer: two bulk copies per stage, K blocks numbered through all of this CTA's tiles =====
             int it = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const float* ra = Rt + (size_t)(tile % mtiles) * nk * (2 * TM * KB);
-                const float* rb = Bt + (size_t)(tile / mtiles) * nk * (2 * TN * KB);
+            for (int p = q0; p < n_pairs; p += nq) {
+                const float* ra = Rt + (size_t)((p % ppairs) * CLUSTER + rank) * nk * (2 * TM * KB);
+                const float* rb = Bt + (size_t)(p / ppairs) * nk * (2 * TN * KB);
                 for (int kb = 0; kb < nk; ++kb, ++it) {
                     const int st = it % NSTAGE;
                     if (it >= NSTAGE) mbar_wait(smem_u32(&empty_bar[st]), (uint32_t)(((it / NSTAGE) - 1) & 1));
                     const uint32_t bar = smem_u32(&full_bar[st]), dst = smem_u32(sm + (size_t)st * STAGE_BYTES);
                     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"((uint32_t)STAGE_BYTES) : "memory");
                     bulk_copy(dst, ra + (size_t)kb * (2 * TM * KB), 2 * A_BYTES, bar);                 // A hi | lo
-                    bulk_copy(dst + 2 * A_BYTES, rb + (size_t)kb * (2 * TN * KB), 2 * B_BYTES, bar);    // B hi | lo
+                    // B hi | lo: this CTA's share, delivered to every CTA of the cluster (each receives all of it)
+                    constexpr uint32_t QB = 2 * B_BYTES / CLUSTER;
+                    if (CLUSTER > 1)
+                        bulk_copy_multicast(dst + 2 * A_BYTES + rank * QB,
+                                            reinterpret_cast<const unsigned char*>(rb + (size_t)kb * (2 * TN * KB)) + (size_t)rank * QB, QB, bar, CL_MASK);
+                    else
+                        bulk_copy(dst + 2 * A_BYTES, rb + (size_t)kb * (2 * TN * KB), 2 * B_BYTES, bar);
                 }
             }
         }
@@ -115,7 +140,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_power_tf32(const float* __re
         if (lane == 0) {
             // ===== MMA issuer: tile tl accumulates into TMEM columns [(tl & 1) * TN, +TN) while the epilogue drains the other half =====
             int it = 0, tl = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+            for (int p = q0; p < n_pairs; p += nq, ++tl) {
                 const int buf = tl & 1;
                 if (tl >= 2) {
                     mbar_wait(smem_u32(&acc_empty[buf]), (uint32_t)(((tl >> 1) - 1) & 1));
@@ -134,7 +159,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_power_tf32(const float* __re
                         mma_tf32(tacc, umma_desc(a_hi + off), umma_desc(b_lo + off), 1u);
                         mma_tf32(tacc, umma_desc(a_lo + off), umma_desc(b_hi + off), 1u);
                     }
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&empty_bar[st])) : "memory");
+                    // frees stage st in every CTA of the cluster (each of them multicasts into it)
+                    if (CLUSTER > 1)
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                                     :: "r"(smem_u32(&empty_bar[st])), "h"(CL_MASK) : "memory");
+                    else
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&empty_bar[st])) : "memory");
                 }
                 // completes once per tile, after every MMA of the tile
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&acc_full[buf])) : "memory");
@@ -143,9 +173,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_power_tf32(const float* __re
     } else {
         // ===== epilogue warps: thread = one row of the tile (TMEM lane 32*warp + lane) =====
         int tl = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+        for (int p = q0; p < n_pairs; p += nq, ++tl) {
             const int buf = tl & 1;
-            const int m0 = (tile % mtiles) * TM, s = tile / mtiles;
+            const int m0 = ((p % ppairs) * CLUSTER + (int)rank) * TM, s = p / ppairs;
             mbar_wait(smem_u32(&acc_full[buf]), (uint32_t)((tl >> 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int r = m0 + warp * 32 + lane, k = r % N;
@@ -181,6 +211,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_power_tf32(const float* __re
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (CLUSTER > 1) cluster_sync_all();          // nobody leaves while the peer's releases can still land on its barriers
     if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(2 * TN) : "memory");
 }
 
@@ -244,9 +275,27 @@ int interf_gemm_tf32(wofdm_ctx* h, const wofdm_sys_t* sys, const InterfDev& v, i
     tile_split_b<<<dim3(N / 32, v.Kp / KB, slices), 256, 0, d.stream>>>(v.Bbig, Bt, N, v.Kp);
     WOFDM_CUDA(h, cudaGetLastError());
     const size_t smem = (size_t)NSTAGE * STAGE_BYTES;
-    WOFDM_CUDA(h, cudaFuncSetAttribute(gemm_power_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int n_tiles = (2 * N / TM) * slices;
-    gemm_power_tf32<<<std::min(n_tiles, d.sm_count), NTHREADS, smem, d.stream>>>(Rt, Bt, v.P, N, v.Kp, Ms, c0, scalar, n_tiles);
+    const char* env = getenv("WOFDM_TF32_CLUSTER");
+    const int cl = (env && atoi(env) == 1) ? 1 : 2;
+    auto launch = [&](auto kern, int CL) -> int {
+        WOFDM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(CL * d.sm_count); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = smem; cfg.stream = d.stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int ncl = 0;
+        WOFDM_CUDA(h, cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg));
+        if (ncl < 1) return fail(h, WOFDM_EUNSUPPORTED, "no cluster of the TF32 contraction kernel fits the device");
+        cfg.gridDim = dim3(CL * std::min(n_tiles / CL, ncl));
+        WOFDM_CUDA(h, cudaLaunchKernelEx(&cfg, kern, (const float*)Rt, (const float*)Bt, v.P, N, v.Kp, Ms, c0, scalar, n_tiles));
+        return WOFDM_OK;
+    };
+    static_assert((2 * TN / TM) % 2 == 0, "row tiles pair up inside a cluster");
+    const int rc = cl == 1 ? launch(gemm_power_tf32<1>, 1) : launch(gemm_power_tf32<2>, 2);
+    if (rc) return rc;
     WOFDM_CUDA(h, cudaGetLastError());
     h->launches += 2;
     return WOFDM_OK;
