@@ -36,7 +36,7 @@ def boundary_distance(eq_lattice, m):
     return np.minimum(ax(eq_lattice.real), ax(eq_lattice.imag))
 
 
-def check_frames(handle, p, vt, vr, frames_in, precision, force_staged=False):
+def check_frames(handle, p, vt, vr, frames_in, precision, force_staged=False, direct=False):
     """frames_in: list of (chan, snr, sym_idx (N,S), noise)"""
     s = to_sys(p, precision)
     F = len(frames_in)
@@ -44,7 +44,7 @@ def check_frames(handle, p, vt, vr, frames_in, precision, force_staged=False):
     snr = np.array([f[1] for f in frames_in])
     sym = np.stack([f[2].T for f in frames_in])                      # (F, S, N)
     nz = np.stack([f[3] for f in frames_in])
-    eq, dec, be, se = handle.ber_verify(s, vt, vr, chan, snr, sym, nz, force_staged=force_staged)
+    eq, dec, be, se = handle.ber_verify(s, vt, vr, chan, snr, sym, nz, force_staged=force_staged, direct=direct)
     m = O.qam_levels(p.bits)
     sc = O.qam_scale(p.bits, p.constellation)
     for i, (h, snr_i, idx, noise) in enumerate(frames_in):
@@ -104,6 +104,8 @@ def test_verify_shapes_and_conventions(handle, N, S, bits, conv, nn, precision):
                            rng.standard_normal(n) + 1j * rng.standard_normal(n)))
         check_frames(handle, p, vt, vr, frames, precision)
         check_frames(handle, p, vt, vr, frames, precision, force_staged=True)
+        if precision == 0:
+            check_frames(handle, p, vt, vr, frames, precision, direct=True)      # direct-form convolution over the whole frame
 
 
 def test_production_replay_matches_oracle(handle):

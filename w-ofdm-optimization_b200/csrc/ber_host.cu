@@ -44,12 +44,17 @@ void fill_split(BerParams& prm, const BerVariant& v) {
     prm.split_nt = v.CL > 1 ? v.NT : 0;
 }
 
+// win_tx (may be NULL): the circular-interior kernels need it flat between the tails; no_circ excludes them
 int choose_variant(wofdm_ctx* h, const wofdm_sys_t& s, int L, bool verify, bool force_staged, size_t smem_cap,
-                   Choice* out) {
+                   Choice* out, const double* win_tx = nullptr, bool no_circ = false) {
     const int stride = s.N + s.cp + s.cs - s.tail_tx;
     const int sec = s.S * stride;
     const bool fp64 = s.precision == 1;
     Choice best;
+    bool flat = win_tx != nullptr && !no_circ && !getenv("WOFDM_NO_CIRC");
+    if (flat)
+        for (int i = s.tail_tx; i < s.N + s.cp + s.cs - s.tail_tx; ++i)
+            if (win_tx[i] != win_tx[s.tail_tx]) { flat = false; break; }
     // WOFDM_VARIANT=<substring> restricts the tuned candidates (kernel tuning aid, e.g. "_b2")
     const char* want = getenv("WOFDM_VARIANT");
     if (!fp64 && !force_staged) {
@@ -66,9 +71,16 @@ int choose_variant(wofdm_ctx* h, const wofdm_sys_t& s, int L, bool verify, bool 
             const int tpf = s.N / 16;
             if (s.cp > 2 * tpf || s.cs > 2 * tpf || s.tail_tx > 2 * tpf || s.tail_rx / 2 > tpf || s.shift > tpf) continue;
             if (v.full && !(chunk == v.TC && v.NT * v.TC == sec_cta)) continue;
+            // circular interior: flat window, the tail_tx + L - 1 edge outputs of a symbol two per thread, one Tx pass
+            if (v.circ && !(flat && s.tail_tx + L - 1 <= 2 * tpf && s.S <= v.NT / tpf && s.cp + 2 * tpf >= s.tail_tx + L - 1)) continue;
             const BerSmem lay = v.layout(S_cta, stride, s.tail_tx, s.tail_rx, L, chunk, 0);
             if (lay.bytes > smem_cap) continue;
-            if (!best.var || v.TC < best.var->TC || (v.TC == best.var->TC && v.full && !best.var->full)) { best.var = &v; best.lay = lay; best.chunk = chunk; }
+            // measured order: the exact-fit direct kernel, then the circular-interior kernels
+            // (+8 % over a direct kernel whose chunk does not fit exactly, -2..+1 % against the exact fit), then the rest
+            auto rank = [](const BerVariant& x) { return (x.full && !x.circ) ? 0 : x.circ ? 1 : 2; };
+            const bool better = !best.var || rank(v) < rank(*best.var) ||
+                                (rank(v) == rank(*best.var) && (v.TC < best.var->TC || (v.TC == best.var->TC && v.full && !best.var->full)));
+            if (better) { best.var = &v; best.lay = lay; best.chunk = chunk; }
         }
     }
     if (!best.var) {
@@ -183,7 +195,7 @@ int wofdm_ber_plan_create(wofdm_handle h, const wofdm_sys_t* sys, const double* 
     Choice ch;
     size_t cap = h->devs[0].smem_optin;
     for (auto& d : h->devs) cap = std::min(cap, d.smem_optin);
-    rc = choose_variant(h, *sys, L, false, false, cap, &ch);
+    rc = choose_variant(h, *sys, L, false, false, cap, &ch, win_tx);
     if (rc) { delete p; return rc; }
     p->var = ch.var; p->lay = ch.lay; p->chunk = ch.chunk; p->use_global = ch.use_global;
 
@@ -370,7 +382,7 @@ int wofdm_ber_verify(wofdm_handle h, const wofdm_sys_t* sys, const double* win_t
     DeviceCtx& d = h->devs[0];
     WOFDM_CUDA(h, cudaSetDevice(d.dev));
     Choice ch;
-    rc = choose_variant(h, *sys, L, true, variant_kernel == 1, d.smem_optin, &ch);
+    rc = choose_variant(h, *sys, L, true, variant_kernel == 1, d.smem_optin, &ch, win_tx, variant_kernel == 2);
     if (rc) return rc;
     int nb = 0;
     long long max_ctas = 0;

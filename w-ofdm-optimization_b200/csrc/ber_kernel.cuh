@@ -17,6 +17,11 @@
 //   TC  > 0  "regs"  : each thread owns one chunk of <= TC consecutive stream samples; the chunk's
 //            convolution output AND its noise stay in registers across the frame-wide power
 //            reduction, taps live in registers LB at a time.  fp32 production path.
+// CIRC (regs policy, CL == 1): the ISI-free interior of every symbol -- outputs whose L inputs all lie in the flat part
+// of that symbol's own Tx window, stride - (tail_tx + L - 1) of stride samples -- is a CIRCULAR convolution of the
+// symbol with the taps, so it is taken as IFFT(H o X) (one more register FFT per symbol) instead of L complex MACs
+// per sample; only the first tail_tx + L - 1 outputs of every symbol (previous tail, prefix, window head) keep the
+// direct form.  Same results up to rounding; the host checks that the window really is flat there.
 // CL > 1 (regs policy): a thread-block cluster of CL CTAs shares one frame, S/CL consecutive OFDM symbols and
 // their part of the frame stream per CTA (N = 1024: the stream plus the parked noise is 278 KB, more than one SM
 // holds).  The CTAs meet three times per frame through distributed shared memory: the Tx tail and the L-1
@@ -158,7 +163,7 @@ struct BerSmem {
     int pad;        // zero samples in front of the frame stream (covers every negative tap index)
     int flen;       // frame-stream buffer elements incl. pad and tail slack (0: lives in global scratch)
     int xlen;       // second buffer elements: staged -> conv output / FFT exchange; regs -> noise / FFT exchange
-    int off_x, off_tw, off_geq, off_taps, off_wtx, off_wrx, off_red, off_qlut, off_dlut, off_symw;   // byte offsets
+    int off_x, off_tw, off_geq, off_hf, off_taps, off_wtx, off_wrx, off_red, off_qlut, off_dlut, off_symw;   // byte offsets
     size_t bytes;
 };
 
@@ -189,7 +194,8 @@ __host__ __device__ inline BerSmem ber_smem_layout(int S, int stride, int tail_t
     o += m.flen * E;                 m.off_x = o;
     o += m.xlen * E;                 m.off_tw = o;
     o += P::NTW * E;                 m.off_geq = o;
-    o += N * E;                      m.off_taps = o;
+    o += N * E;                      m.off_hf = o;     // channel frequency response x flat window value (CIRC)
+    o += (TC > 0 ? N : 0) * E;       m.off_taps = o;
     o += (((L > lpad ? L : lpad) + 1) & ~1) * E;   m.off_wtx = o;   // taps, zero-padded to the register block
     o += ((stride + tail_tx + 3) & ~3) * (int)sizeof(T);   m.off_wrx = o;
     o += ((N + tail_rx + 3) & ~3) * (int)sizeof(T);        m.off_red = o;
@@ -237,7 +243,7 @@ template <int CL> __device__ __forceinline__ void frame_sync() {
     if constexpr (CL > 1) cooperative_groups::this_cluster().sync(); else __syncthreads();
 }
 
-template <typename T, int N, int NT, int TC, int LB, int MINB, bool FULL, bool VERIFY, int CL = 1>
+template <typename T, int N, int NT, int TC, int LB, int MINB, bool FULL, bool VERIFY, int CL = 1, bool CIRC = false>
 __global__ void __launch_bounds__(NT, MINB)
 ber_frame_kernel(const BerParams prm) {
     using P = FftPlan<N>;
@@ -247,6 +253,7 @@ ber_frame_kernel(const BerParams prm) {
     static_assert(NT % TPF == 0 && NT % 32 == 0, "threads per CTA must be a multiple of N/16 and 32");
     constexpr bool REGS = TC > 0;
     static_assert(CL == 1 || REGS, "clusters are a feature of the register-resident policy");
+    static_assert(!CIRC || (REGS && CL == 1 && N <= NT), "circular-interior policy: regs, one CTA per frame, one bin per thread");
     // Register row q of a thread = sub-carriers / samples t + q*TPF.  Only the outer rows can reach the cyclic
     // prefix / suffix, the Tx heads and the Rx overlap-add; the tuned variants look at ER of them (the host
     // checks cp, cs, tail_tx <= ER*TPF and tail_rx/2, shift <= TPF), the staged policy at all 16.
@@ -272,6 +279,7 @@ ber_frame_kernel(const BerParams prm) {
     C2* xbuf = reinterpret_cast<C2*>(smem_raw + lay.off_x);
     C2* tw = reinterpret_cast<C2*>(smem_raw + lay.off_tw);
     C2* geq = reinterpret_cast<C2*>(smem_raw + lay.off_geq);
+    C2* hf = reinterpret_cast<C2*>(smem_raw + lay.off_hf);
     C2* taps = reinterpret_cast<C2*>(smem_raw + lay.off_taps);
     T* wtx = reinterpret_cast<T*>(smem_raw + lay.off_wtx);
     T* wrx = reinterpret_cast<T*>(smem_raw + lay.off_wrx);
@@ -309,6 +317,9 @@ ber_frame_kernel(const BerParams prm) {
     }
     __syncthreads();
 
+    C2 wk = mk2<T>(1, 0);                       // CIRC: exp(-2 pi i tid / N), the step of bin tid's DFT phasor
+    if constexpr (CIRC) { float sn, cs_; sincospif(-2.0f * (float)tid / (float)N, &sn, &cs_); wk = mk2<T>((T)cs_, (T)sn); }
+
     // frame id f = (si*C + ci)*ensemble + e, advanced without per-frame divisions
     const long long fslot = blockIdx.x / CL, nslots = gridDim.x / CL;   // frames in flight on the grid
     long long f = prm.frame_begin + fslot * prm.frame_step;
@@ -326,8 +337,19 @@ ber_frame_kernel(const BerParams prm) {
         const T snr_lin = reinterpret_cast<const T*>(prm.snr_lin)[si];
         if (tid < (REGS ? (LB > L ? LB : L) : L))   // regs policy: zero-padded to LB, loaded without predicates
             taps[tid] = tid < L ? reinterpret_cast<const C2*>(prm.chan)[(size_t)ci * L + tid] : mk2<T>(0, 0);
+        if constexpr (CIRC) {
+            // H'[k] = w_flat * sum_l h[l] exp(-2 pi i k l / N), one bin per thread, phasor by recurrence
+            __syncthreads();
+            if (tid < N) {
+                C2 ph = mk2<T>(1, 0), a = mk2<T>(0, 0);
+                for (int l = 0; l < L; ++l) { cmac(a, taps[l], ph); ph = cmul(ph, wk); }
+                hf[tid] = cscale(wtx[beta], a);
+            }
+            __syncthreads();
+        }
 
         // =========================== transmitter ===========================
+        C2 cv[16];                              // CIRC: interior of the channel output, c[t + q*TPF] (single Tx pass)
         for (int s0 = 0; s0 < S; s0 += FPP) {
             const int s = s0 + slot;
             const bool act = s < S;
@@ -338,6 +360,12 @@ ber_frame_kernel(const BerParams prm) {
                 uint32_t w[4];
                 load_sym_idx<N, VERIFY>(prm, f, sb + se, t, w);
                 symw[se * TPF + t] = make_uint4(w[0], w[1], w[2], w[3]);
+                if constexpr (CIRC) {
+                    // c = w_flat * (h circ x) = IFFT(H' o X)
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) cv[q] = cmul(qlut[sym_byte(w, q)], hf[t + q * TPF]);
+                    fft_regs<T, N, +1>(cv, t, xb, tw);
+                }
 #pragma unroll
                 for (int q = 0; q < 16; ++q) v[q] = qlut[sym_byte(w, q)];
             }
@@ -405,7 +433,116 @@ ber_frame_kernel(const BerParams prm) {
         // with Pr, Pn summed over the whole frame (:135-138).  noise_norm 1: sums over the full
         // convolution, beta+sec+L-1 samples (main_BER_calculation.m:260-261,289-292).
         C2 pr2 = mk2<T>(0, 0), pn2 = mk2<T>(0, 0);
-        if constexpr (REGS) {
+        if constexpr (CIRC) {
+            // ---- noise of this thread's block of B stream samples -> shared memory, |n|^2 partial (numbering as in regs)
+            const int B = prm.chunk;
+            const int i0 = tid * B;
+            const int nvalid = FULL ? TC : min(B, max(sec - i0, 0));
+            C2* const nb = rbuf + i0;
+            constexpr int NPAIR = (TC + 1) / 2;
+            const uint32_t q0 = (uint32_t)tid * (uint32_t)((B + 1) >> 1);
+#pragma unroll
+            for (int p2 = 0; p2 < NPAIR; ++p2) {
+                C2 n0, n1;
+                if constexpr (VERIFY) {
+                    const double2* nin = prm.noise_in + (size_t)f * prm.noise_len + i0;
+                    n0 = (2 * p2 < nvalid) ? to_v2<T>(nin[2 * p2]) : mk2<T>(0, 0);
+                    n1 = (2 * p2 + 1 < nvalid) ? to_v2<T>(nin[2 * p2 + 1]) : mk2<T>(0, 0);
+                } else {
+                    noise_pair<T>(prm, f, q0 + p2, n0, n1);
+                    if (!FULL) {
+                        if (2 * p2 >= nvalid) n0 = mk2<T>(0, 0);
+                        if (2 * p2 + 1 >= nvalid) n1 = mk2<T>(0, 0);
+                    }
+                }
+                pn2 = csq_acc(n0, pn2);
+                if (FULL || 2 * p2 < B) nb[2 * p2] = n0;
+                if (2 * p2 + 1 < TC) { pn2 = csq_acc(n1, pn2); if (FULL || 2 * p2 + 1 < B) nb[2 * p2 + 1] = n1; }
+            }
+            // ---- edge outputs 2t, 2t+1 < E = beta + L - 1 of this thread's symbol: direct form, taps in registers
+            const int E = beta + L - 1;
+            const bool act = slot < S;
+            const int se = act ? slot : S - 1;
+            const int ebase = se * stride;
+            C2 re0 = mk2<T>(0, 0), re1 = mk2<T>(0, 0);
+            {
+                C2 h[LB];
+#pragma unroll
+                for (int l = 0; l < LB; ++l) h[l] = taps[l];
+                const C2* src = ub + ebase + 2 * t - (LB - 1);
+#pragma unroll
+                for (int c = 0; c <= LB; ++c) {
+                    const C2 x = src[c];
+                    if (c < LB) cmac(re0, h[LB - 1 - c], x);
+                    if (c >= 1) cmac(re1, h[LB - c], x);
+                }
+            }
+            const bool e0 = act && 2 * t < E, e1 = act && 2 * t + 1 < E;
+            if (!e0) re0 = mk2<T>(0, 0);
+            if (!e1) re1 = mk2<T>(0, 0);
+            pr2 = csq_acc(re0, pr2);
+            pr2 = csq_acc(re1, pr2);
+            // ---- interior: c[m], m = t + q*TPF, sits at i = m + cp (and at i -+ N inside the prefix / suffix) if E <= i < stride
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const int i = t + q * TPF + cp;
+                bool mid = act;
+                if (q < ER) mid = mid && i >= E;
+                if (q >= 16 - ER) mid = mid && i < stride;
+                C2 cq = mid ? cv[q] : mk2<T>(0, 0);
+                pr2 = csq_acc(cq, pr2);
+                if (q >= 16 - ER) { if (act && i - N >= E) pr2 = csq_acc(cv[q], pr2); }
+                if (q < ER) { if (act && i + N < stride) pr2 = csq_acc(cv[q], pr2); }
+            }
+            if (prm.noise_norm == 1) {
+                // the L-1+beta samples the reference truncates still count in both power sums
+                for (int i = sec + tid; i < body + L - 1; i += NT) {
+                    C2 a = mk2<T>(0, 0);
+                    for (int l = 0; l < L; ++l)
+                        if (i - l < body) cmac(a, taps[l], ub[i - l]);
+                    C2 n0;
+                    if constexpr (VERIFY) n0 = to_v2<T>(prm.noise_in[(size_t)f * prm.noise_len + i]);
+                    else n0 = noise_at<T>(prm, f, i);
+                    pr2 = csq_acc(a, pr2);
+                    pn2 = csq_acc(n0, pn2);
+                }
+            }
+            T pr = warp_sum(pr2.x + pr2.y), pn = warp_sum(pn2.x + pn2.y);
+            if ((tid & 31) == 0) { red[tid >> 5] = pr; red[32 + (tid >> 5)] = pn; }
+            __syncthreads();                       // also: every read of the Tx stream is done
+            const T g = noise_gain(block_total<NT / 32>(red), snr_lin, block_total<NT / 32>(red + 32));
+            // ---- y = r + g n over the stream (noise loads ahead of the may-alias stores)
+            const C2* const nz = rbuf + ebase;     // noise by stream position
+            {
+                C2 y[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) y[q] = caxpy(g, nz[t + q * TPF + cp], cv[q]);
+                C2 ye0 = caxpy(g, nz[2 * t], re0), ye1 = caxpy(g, nz[2 * t + 1], re1);
+                C2 yp[ER], ys[ER];
+#pragma unroll
+                for (int q = 0; q < ER; ++q) {
+                    const int ip = t + (16 - ER + q) * TPF + cp - N, is = t + q * TPF + cp + N;
+                    yp[q] = caxpy(g, nz[max(ip, 0)], cv[16 - ER + q]);
+                    ys[q] = caxpy(g, nz[min(is, stride - 1)], cv[q]);
+                }
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const int i = t + q * TPF + cp;
+                    bool mid = act;
+                    if (q < ER) mid = mid && i >= E;
+                    if (q >= 16 - ER) mid = mid && i < stride;
+                    if (mid) ub[ebase + i] = y[q];
+                }
+#pragma unroll
+                for (int q = 0; q < ER; ++q) {
+                    const int ip = t + (16 - ER + q) * TPF + cp - N, is = t + q * TPF + cp + N;
+                    if (act && ip >= E) ub[ebase + ip] = yp[q];
+                    if (act && is < stride) ub[ebase + is] = ys[q];
+                }
+                if (e0) ub[ebase + 2 * t] = ye0;
+                if (e1) ub[ebase + 2 * t + 1] = ye1;
+            }
+        } else if constexpr (REGS) {
             // Each thread owns the B = prm.chunk stream samples [i0, i0+B).  Their convolution outputs stay
             // in registers across the frame-wide power reduction; their noise is generated INSIDE the
             // convolution loop (one Philox pair every few inputs: integer/MUFU work fills the issue slots

@@ -10,6 +10,7 @@ struct BerVariant {
     const char* name;
     int N, NT, TC, LB, MINB;
     int CL;                    // CTAs per frame (thread-block cluster size)
+    bool circ;                 // interior of the channel output as a circular convolution (needs a flat Tx window)
     bool full;                 // every register of every thread is a live stream sample (NT*TC == S*stride)
     bool fp64, verify;
     BerSmem (*layout)(int S, int stride, int tail_tx, int tail_rx, int L, int chunk, int use_global);
@@ -17,12 +18,12 @@ struct BerVariant {
     cudaError_t (*launch)(const BerParams& prm, int grid, size_t smem, cudaStream_t st);
 };
 
-template <typename T, int N, int NT, int TC, int LB, int MINB, bool FULL, bool V, int CL = 1>
+template <typename T, int N, int NT, int TC, int LB, int MINB, bool FULL, bool V, int CL = 1, bool CIRC = false>
 struct BerVariantImpl {
     // grid = CTAs (a multiple of CL); CL > 1 launches thread-block clusters of CL CTAs
     static cudaError_t launch(const BerParams& prm, int grid, size_t smem, cudaStream_t st) {
         if constexpr (CL == 1) {
-            ber_frame_kernel<T, N, NT, TC, LB, MINB, FULL, V, 1><<<grid, NT, smem, st>>>(prm);
+            ber_frame_kernel<T, N, NT, TC, LB, MINB, FULL, V, 1, CIRC><<<grid, NT, smem, st>>>(prm);
             return cudaGetLastError();
         } else {
             cudaLaunchConfig_t cfg = {};
@@ -31,15 +32,15 @@ struct BerVariantImpl {
             at[0].id = cudaLaunchAttributeClusterDimension;
             at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             cfg.attrs = at; cfg.numAttrs = 1;
-            return cudaLaunchKernelEx(&cfg, ber_frame_kernel<T, N, NT, TC, LB, MINB, FULL, V, CL>, prm);
+            return cudaLaunchKernelEx(&cfg, ber_frame_kernel<T, N, NT, TC, LB, MINB, FULL, V, CL, CIRC>, prm);
         }
     }
     static BerVariant make(const char* name) {
         BerVariant v;
-        v.name = name; v.N = N; v.NT = NT; v.TC = TC; v.LB = LB; v.MINB = MINB; v.CL = CL; v.full = FULL;
+        v.name = name; v.N = N; v.NT = NT; v.TC = TC; v.LB = LB; v.MINB = MINB; v.CL = CL; v.circ = CIRC; v.full = FULL;
         v.fp64 = sizeof(T) == 8; v.verify = V;
         v.layout = &ber_smem_layout<T, N, NT, TC, LB>;
-        v.fn = reinterpret_cast<const void*>(&ber_frame_kernel<T, N, NT, TC, LB, MINB, FULL, V, CL>);
+        v.fn = reinterpret_cast<const void*>(&ber_frame_kernel<T, N, NT, TC, LB, MINB, FULL, V, CL, CIRC>);
         v.launch = &launch;
         return v;
     }
@@ -53,6 +54,11 @@ struct BerVariantImpl {
 #define WOFDM_VARIANT_CL(T, N, NT, TC, LB, MINB, FULL, CL, tag)                                     \
     out.push_back(BerVariantImpl<T, N, NT, TC, LB, MINB, FULL, false, CL>::make("ber_" tag "_n" #N "_t" #NT "_c" #TC "_l" #LB "_b" #MINB "_f" #FULL "_cl" #CL)); \
     out.push_back(BerVariantImpl<T, N, NT, TC, LB, MINB, FULL, true, CL>::make("ber_" tag "_n" #N "_t" #NT "_c" #TC "_l" #LB "_b" #MINB "_f" #FULL "_cl" #CL "_verify"));
+
+// circular-interior policy (one CTA per frame)
+#define WOFDM_VARIANT_CIRC(T, N, NT, TC, LB, MINB, FULL, tag)                                       \
+    out.push_back(BerVariantImpl<T, N, NT, TC, LB, MINB, FULL, false, 1, true>::make("ber_" tag "_n" #N "_t" #NT "_c" #TC "_l" #LB "_b" #MINB "_f" #FULL "_circ")); \
+    out.push_back(BerVariantImpl<T, N, NT, TC, LB, MINB, FULL, true, 1, true>::make("ber_" tag "_n" #N "_t" #NT "_c" #TC "_l" #LB "_b" #MINB "_f" #FULL "_circ_verify"));
 
 void register_ber_f32_staged(std::vector<BerVariant>& out);
 void register_ber_f64_staged(std::vector<BerVariant>& out);
