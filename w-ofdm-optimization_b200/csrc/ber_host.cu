@@ -27,6 +27,7 @@ struct wofdm_ber_plan_s {
     const BerVariant* var = nullptr;
     BerSmem lay{};
     int chunk = 0, use_global = 0;
+    bool transient = false;    // buffers live in the devices' arenas (one-shot plan of wofdm_ber_run*): nothing to free
     std::vector<PlanDev> devs;
 };
 
@@ -175,11 +176,11 @@ size_t elem_bytes(const wofdm_sys_t& s) { return s.precision == 1 ? sizeof(doubl
 
 }  // namespace
 
-extern "C" {
-
-int wofdm_ber_plan_create(wofdm_handle h, const wofdm_sys_t* sys, const double* win_tx, const double* win_rx,
-                          const double* chan, int L, int C, const double* snr_db, int n_snr,
-                          wofdm_ber_plan* out) {
+// transient = true: device buffers come out of the per-device arena (no cudaMalloc / cudaFree per call); such a plan
+// must be destroyed before the arena is used again (wofdm_ber_run_shard does exactly that)
+static int plan_create_impl(wofdm_handle h, const wofdm_sys_t* sys, const double* win_tx, const double* win_rx,
+                            const double* chan, int L, int C, const double* snr_db, int n_snr,
+                            wofdm_ber_plan* out, bool transient) {
     if (!h) return WOFDM_EINVAL;
     if (!out) return fail(h, WOFDM_EINVAL, "plan out pointer is NULL");
     *out = nullptr;
@@ -191,7 +192,7 @@ int wofdm_ber_plan_create(wofdm_handle h, const wofdm_sys_t* sys, const double* 
 
     wofdm_ber_plan_s* p = new (std::nothrow) wofdm_ber_plan_s();
     if (!p) return fail(h, WOFDM_ENOMEM, "host allocation failed");
-    p->ctx = h; p->sys = *sys; p->L = L; p->C = C; p->n_snr = n_snr;
+    p->ctx = h; p->sys = *sys; p->L = L; p->C = C; p->n_snr = n_snr; p->transient = transient;
     Choice ch;
     size_t cap = h->devs[0].smem_optin;
     for (auto& d : h->devs) cap = std::min(cap, d.smem_optin);
@@ -211,28 +212,37 @@ int wofdm_ber_plan_create(wofdm_handle h, const wofdm_sys_t* sys, const double* 
     for (size_t i = 0; i < h->devs.size(); ++i) {
         DeviceCtx& d = h->devs[i];
         PlanDev& pd = p->devs[i];
+        auto dev_alloc = [&](void** dst, size_t bytes) -> cudaError_t {
+            if (!transient) return cudaMalloc(dst, std::max<size_t>(bytes, 16));
+            *dst = arena_take(d, std::max<size_t>(bytes, 16));
+            return *dst ? cudaSuccess : cudaErrorMemoryAllocation;
+        };
         auto up = [&](void** dst, const std::vector<unsigned char>& src) -> cudaError_t {
-            cudaError_t e = cudaMalloc(dst, std::max<size_t>(src.size(), 16));
+            cudaError_t e = dev_alloc(dst, src.size());
             if (e != cudaSuccess) return e;
             return cudaMemcpyAsync(*dst, src.data(), src.size(), cudaMemcpyHostToDevice, d.stream);
         };
         cudaError_t e = cudaSetDevice(d.dev);
+        if (e == cudaSuccess) {
+            rc = prepare_kernel(h, *p->var, p->lay.bytes, d.sm_count, &pd.blocks_per_sm, &pd.max_ctas);
+            if (rc) { delete p; return rc; }
+        }
+        // staged policy with frame buffers in global memory: two of them per resident CTA
+        const size_t scratch_elems = (size_t)p->lay.pad + sys->tail_tx + (size_t)sys->S * (sys->N + sys->cp + sys->cs - sys->tail_tx) + 64;
+        pd.scratch_bytes = p->use_global ? (size_t)pd.blocks_per_sm * d.sm_count * 2 * scratch_elems * elem_bytes(*sys) : 0;
+        if (e == cudaSuccess && transient) {
+            rc = arena_reserve(h, d, t.wtx.size() + t.wrx.size() + t.tw.size() + hchan.size() + hsnr.size() +
+                                         (size_t)n_snr * 16 + pd.scratch_bytes);
+            if (rc) { delete p; return rc; }
+        }
         if (e == cudaSuccess) e = up(&pd.d_wtx, t.wtx);
         if (e == cudaSuccess) e = up(&pd.d_wrx, t.wrx);
         if (e == cudaSuccess) e = up(&pd.d_tw, t.tw);
         if (e == cudaSuccess) e = up(&pd.d_chan, hchan);
         if (e == cudaSuccess) e = up(&pd.d_snr, hsnr);
-        if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&pd.d_cnt), (size_t)n_snr * 2 * sizeof(unsigned long long));
+        if (e == cudaSuccess) e = dev_alloc(reinterpret_cast<void**>(&pd.d_cnt), (size_t)n_snr * 2 * sizeof(unsigned long long));
         if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);   // host vectors go out of scope
-        if (e == cudaSuccess) {
-            rc = prepare_kernel(h, *p->var, p->lay.bytes, d.sm_count, &pd.blocks_per_sm, &pd.max_ctas);
-            if (rc) { wofdm_ber_plan_destroy(p); return rc; }
-        }
-        if (e == cudaSuccess && p->use_global) {
-            const size_t elems = (size_t)p->lay.pad + sys->tail_tx + (size_t)sys->S * (sys->N + sys->cp + sys->cs - sys->tail_tx) + 64;
-            pd.scratch_bytes = (size_t)pd.blocks_per_sm * d.sm_count * 2 * elems * elem_bytes(*sys);
-            e = cudaMalloc(&pd.d_scratch, pd.scratch_bytes);
-        }
+        if (e == cudaSuccess && p->use_global) e = dev_alloc(&pd.d_scratch, pd.scratch_bytes);
         if (e != cudaSuccess) {
             std::string msg = std::string("plan upload: ") + cudaGetErrorString(e);
             wofdm_ber_plan_destroy(p);
@@ -241,6 +251,14 @@ int wofdm_ber_plan_create(wofdm_handle h, const wofdm_sys_t* sys, const double* 
     }
     *out = p;
     return WOFDM_OK;
+}
+
+extern "C" {
+
+int wofdm_ber_plan_create(wofdm_handle h, const wofdm_sys_t* sys, const double* win_tx, const double* win_rx,
+                          const double* chan, int L, int C, const double* snr_db, int n_snr,
+                          wofdm_ber_plan* out) {
+    return plan_create_impl(h, sys, win_tx, win_rx, chan, L, C, snr_db, n_snr, out, false);
 }
 
 int wofdm_ber_plan_launch(wofdm_ber_plan p, int slot, int64_t ensemble, uint64_t seed, uint32_t variant,
@@ -313,6 +331,7 @@ int wofdm_ber_plan_destroy(wofdm_ber_plan p) {
         PlanDev& pd = p->devs[s];
         cudaSetDevice(p->ctx->devs[s].dev);
         if (pd.pending && pd.last_stream) cudaStreamSynchronize(pd.last_stream);
+        if (p->transient) continue;             // arena memory
         cudaFree(pd.d_wtx); cudaFree(pd.d_wrx); cudaFree(pd.d_tw); cudaFree(pd.d_chan); cudaFree(pd.d_snr);
         cudaFree(pd.d_cnt); cudaFree(pd.d_scratch);
     }
@@ -330,7 +349,7 @@ int wofdm_ber_run_shard(wofdm_handle h, const wofdm_sys_t* sys, const double* wi
     if (shard_count < 1 || shard_index < 0 || shard_index >= shard_count) return fail(h, WOFDM_EINVAL, "bad shard");
     if (ensemble < 1) return fail(h, WOFDM_EINVAL, "ensemble must be >= 1");
     wofdm_ber_plan p = nullptr;
-    int rc = wofdm_ber_plan_create(h, sys, win_tx, win_rx, chan, L, C, snr_db, n_snr, &p);
+    int rc = plan_create_impl(h, sys, win_tx, win_rx, chan, L, C, snr_db, n_snr, &p, true);
     if (rc) return rc;
     // the handle's devices split this shard's frames between them: device i takes the sub-shard
     // shard_index + shard_count*i of shard_count*ndev, so results do not depend on the GPU count
