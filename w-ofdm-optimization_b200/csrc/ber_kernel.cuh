@@ -364,12 +364,12 @@ ber_frame_kernel(const BerParams prm) {
                     // c = w_flat * (h circ x) = IFFT(H' o X)
 #pragma unroll
                     for (int q = 0; q < 16; ++q) cv[q] = cmul(qlut[sym_byte(w, q)], hf[t + q * TPF]);
-                    fft_regs<T, N, +1>(cv, t, xb, tw);
+                    fft_regs<T, N, +1, FPP>(cv, t, xb, tw, slot);
                 }
 #pragma unroll
                 for (int q = 0; q < 16; ++q) v[q] = qlut[sym_byte(w, q)];
             }
-            fft_regs<T, N, +1>(v, t, xb, tw);
+            fft_regs<T, N, +1, FPP>(v, t, xb, tw, slot);
             // CP/CS insertion + Tx window: sample i of symbol s is wtx[i] * x[(i - cp) mod N]
             // (transmitter.py:13-35, 61-87).  Head samples i < tail_tx overlap the previous
             // symbol's falling tail (wofdm_simulation.py:190-203) and are added after the sync.
@@ -682,7 +682,7 @@ ber_frame_kernel(const BerParams prm) {
                 }
                 v[q] = o;
             }
-            fft_regs<T, N, -1>(v, t, xb, tw);
+            fft_regs<T, N, -1, FPP>(v, t, xb, tw, slot);
             const uint4 wv = symw[se * TPF + t];
             const uint32_t w[4] = {wv.x, wv.y, wv.z, wv.w};
             if (s0 == 0) {

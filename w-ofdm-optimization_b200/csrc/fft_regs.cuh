@@ -110,17 +110,22 @@ template <typename T, int DIR> __device__ __forceinline__ V2<T> tw_apply(V2<T> a
 // Barrier between the threads of one transform: the N/16 threads of a group sit in one warp when
 // N <= 512 (groups are aligned to their size), so a warp barrier is enough and the CTA's other
 // warps run on; larger transforms span warps and use the CTA barrier.
-template <int TPF> __device__ __forceinline__ void fft_group_sync() {
-    if constexpr (TPF <= 32) __syncwarp(); else __syncthreads();
+// N = 1024: a transform spans two warps; with at most 15 transforms per CTA (NB) each group gets its own
+// named barrier (ids 1..NB, TPF threads) instead of stalling the whole CTA.
+template <int TPF, int NB> __device__ __forceinline__ void fft_group_sync(int group) {
+    if constexpr (TPF <= 32) __syncwarp();
+    else if constexpr (NB >= 1 && NB <= 15) asm volatile("bar.sync %0, %1;" :: "r"(group + 1), "n"(TPF) : "memory");
+    else __syncthreads();
 }
 
 // One transform per group of N/16 threads; EVERY thread of the CTA must call this (it contains
 // barriers).  xb: this group's exchange buffer (FftPlan<N>::XLEN elements, shared memory), private
 // to the group; tw: twiddle table (FftPlan<N>::NTW elements).  Memory that aliases xb and is
 // touched by OTHER groups needs a __syncthreads() of the caller on both sides of this call.
-template <typename T, int N, int DIR>
+// NB / group: number of transforms the CTA runs side by side and this thread's transform (for the named barriers).
+template <typename T, int N, int DIR, int NB = 0>
 __device__ __forceinline__ void fft_regs(V2<T> (&v)[16], const int t, V2<T>* __restrict__ xb,
-                                         const V2<T>* __restrict__ tw) {
+                                         const V2<T>* __restrict__ tw, const int group = 0) {
     using P = FftPlan<N>;
     constexpr int TPF = P::TPF;
     int tw_off = 0;
@@ -132,7 +137,7 @@ __device__ __forceinline__ void fft_regs(V2<T> (&v)[16], const int t, V2<T>* __r
             V2<T> w[15];                  // fetched before the barrier: they do not depend on the exchange
 #pragma unroll
             for (int m = 1; m < 16; ++m) w[m - 1] = tw[tw_off + m * Ns + k];
-            fft_group_sync<TPF>();
+            fft_group_sync<TPF, NB>(group);
 #pragma unroll
             for (int m = 0; m < 16; ++m) v[m] = xb[fft_pad(t + m * TPF)];
 #pragma unroll
@@ -142,7 +147,7 @@ __device__ __forceinline__ void fft_regs(V2<T> (&v)[16], const int t, V2<T>* __r
         dft16<T, DIR>(v);
         const bool last = (p == P::a - 1);
         if (!(last && P::r == 1)) {
-            fft_group_sync<TPF>();        // the group has finished reading the previous layout (also of an earlier call)
+            fft_group_sync<TPF, NB>(group);        // the group has finished reading the previous layout (also of an earlier call)
             const int base = (t - k) * 16 + k;
 #pragma unroll
             for (int m = 0; m < 16; ++m) xb[fft_pad(base + m * Ns)] = v[m];
@@ -150,7 +155,7 @@ __device__ __forceinline__ void fft_regs(V2<T> (&v)[16], const int t, V2<T>* __r
     }
     if constexpr (P::r > 1) {
         constexpr int r = P::r, G = 16 / r;   // G butterflies of radix r per thread
-        fft_group_sync<TPF>();
+        fft_group_sync<TPF, NB>(group);
 #pragma unroll
         for (int q = 0; q < 16; ++q) v[q] = xb[fft_pad(t + q * TPF)];
 #pragma unroll
