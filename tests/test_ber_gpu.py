@@ -176,6 +176,29 @@ def test_production_replay_cluster_kernel(handle, name, nn):
             assert np.all(np.abs(res["bit_err"] - want_bit) <= 8 + 0.003 * want_bit), (res["bit_err"], want_bit)
 
 
+@pytest.mark.parametrize("name,N,cp,ttx,trx,bits", [("wtx", 256, 16, 8, 0, 4), ("CPW", 256, 16, 8, 10, 4),
+                                                    ("WOLA", 1024, 64, 32, 40, 6), ("CPW", 1024, 64, 32, 40, 6)])
+def test_production_is_deterministic_and_grid_independent(handle, name, N, cp, ttx, trx, bits, monkeypatch):
+    """Every tuned policy (exact-fit direct, circular interior, 2-CTA cluster): same seed -> bit-identical counters,
+    run to run and for any number of resident CTAs (a shared-memory race or a grid-dependent draw would show here;
+    compute-sanitizer is not available on the GPU pool)."""
+    s = W.params_from_name(name, N, cp, ttx, trx, bits=bits, S=16, noise_norm=1, constellation=1)
+    vt, vr = W.capi.rc_window_tx(s), W.capi.rc_window_rx(s)
+    chans = O.synth_channels(7, 21, seed=2)
+    snr = np.array([3.0, 14.0, 27.0])
+    ens = 40 if N == 256 else 12
+    ref = handle.ber_run(s, vt, vr, chans, snr, ens, seed=4242)
+    assert ref["sym_err"][0] > ref["sym_err"][2] > 0
+    for lim in ("", "1", ""):
+        if lim:
+            monkeypatch.setenv("WOFDM_MAX_CTAS_PER_SM", lim)
+        else:
+            monkeypatch.delenv("WOFDM_MAX_CTAS_PER_SM", raising=False)
+        again = handle.ber_run(s, vt, vr, chans, snr, ens, seed=4242)
+        for k in ref:
+            assert np.array_equal(ref[k], again[k]), (k, lim)
+
+
 def test_sharding_is_exact(handle):
     """Counters of disjoint shards add up to the unsharded run (same seeds, global frame ids)."""
     g = load_ser_golden("wtx")
