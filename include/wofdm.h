@@ -153,6 +153,22 @@ WOFDM_API int wofdm_interf_power(wofdm_handle h, const wofdm_sys_t* sys, const d
 WOFDM_API int wofdm_interf_power_scalar(wofdm_handle h, const wofdm_sys_t* sys, const double* win_tx,
                               const double* win_rx, const double* chan, int L, int C, int mode, double* P);
 
+/* ---- Channel generation (next-row 8f-4) ------------------------------------------------------------------
+ * ITU-R tapped-delay-line channels with GMEDS_1 Rayleigh fading on the device: channel_model.gen_chan
+ * (python/channel_model/itur_channels.py:33-94 + rayleigh_fading.py:52-102), the producer of channels/<standard>.npy
+ * (python/wofdm_optimization.py:63-86).
+ *   wofdm_channel_profile: "vehicularA" | "vehicularB" | "outdoor-indoorA" | "outdoor-indoorB" -> index, or WOFDM_EINVAL.
+ *   One SET = one call of the reference's gen_chan: its own oscillator phases, no_frames time samples frame_duration
+ *   apart, every path scaled to ENERGY 10^(dB/10) over the set (the reference's adjust_power).  The reference's
+ *   driver stores C channels as C sets of one frame each: n_sets = C, no_frames = 1.
+ *   phases: NULL -> Philox4x32-10 + Box-Muller draws keyed by (seed, set); else the standard-normal draws themselves,
+ *   [n_sets][n_paths][21][2] in the reference's draw order (path, oscillator, real part / imaginary part).
+ *   chan: complex L x (n_sets*no_frames) column-major, column = set*no_frames + frame. */
+WOFDM_API int wofdm_channel_profile(const char* standard);
+WOFDM_API int wofdm_gen_channels(wofdm_handle h, int profile, int L, double doppler_freq, double sampling_rate,
+                       double frame_duration, int no_frames, int n_sets, uint64_t seed, const double* phases,
+                       double* chan);
+
 #ifdef __cplusplus
 }
 #endif

@@ -83,6 +83,9 @@ SIGNATURES = {
     "wofdm_ber_draws": (C.c_int, [C.c_void_p, _P(SysT), C.c_int, C.c_uint64, C.c_uint32, _i64p, C.c_int, _i32p, _dp]),
     "wofdm_interf_power": (C.c_int, [C.c_void_p, _P(SysT), _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, _dp]),
     "wofdm_interf_power_scalar": (C.c_int, [C.c_void_p, _P(SysT), _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, _dp]),
+    "wofdm_channel_profile": (C.c_int, [C.c_char_p]),
+    "wofdm_gen_channels": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
+                                     C.c_uint64, _dp, _dp]),
 }
 
 _lib = None
@@ -271,6 +274,26 @@ class Handle:
                                            L, Cn, int(mode), _ptr(P, _dp))
         self._check(rc)
         return P
+
+
+    def gen_channels(self, standard, L, doppler_freq, sampling_rate, frame_duration, no_frames=1, n_sets=1, seed=0,
+                     phases=None):
+        """ITU-R channels with GMEDS_1 fading (wofdm_gen_channels) -> (L, n_sets*no_frames) complex128.
+        phases: None (on-device Philox draws) or (n_sets, n_paths, 21, 2) standard-normal draws."""
+        prof = load().wofdm_channel_profile(str(standard).encode())
+        if prof < 0:
+            raise WofdmError(EINVAL, f"unknown ITU-R channel profile {standard!r}")
+        ph = None
+        if phases is not None:
+            ph = _f64(np.ascontiguousarray(phases, dtype=np.float64).ravel())
+            if ph.size % (int(n_sets) * 21 * 2):
+                raise WofdmError(EINVAL, "phases must have shape (n_sets, n_paths, 21, 2)")
+        out = np.empty((int(n_sets) * int(no_frames), int(L)), dtype=np.complex128)
+        rc = load().wofdm_gen_channels(self._h, prof, int(L), float(doppler_freq), float(sampling_rate),
+                                       float(frame_duration), int(no_frames), int(n_sets), int(seed),
+                                       _ptr(ph, _dp) if ph is not None else None, _ptr(out, _dp))
+        self._check(rc)
+        return out.T
 
 
 class BerPlan:
