@@ -153,6 +153,16 @@ WOFDM_API int wofdm_interf_power(wofdm_handle h, const wofdm_sys_t* sys, const d
 WOFDM_API int wofdm_interf_power_scalar(wofdm_handle h, const wofdm_sys_t* sys, const double* win_tx,
                               const double* win_rx, const double* chan, int L, int C, int mode, double* P);
 
+/* ---- Window-optimisation Hessian (next-row 8f-2) -------------------------------------------------------------
+ * The quadratic form of the interference power in the reduced window variables: OptimizerTx / OptimizerRx /
+ * OptimizerTxRx.gen_hessian (python/optimization_tools/optimizers.py:232-257, 387-410, 808-833) and
+ * quad_objective_tx / _rx (matlab/window_optimization.m:596-680), whose O(n^2 N^2) loops are the slowest part of the
+ * reference's run_opt.  chan: ONE impulse response, complex L (the reference passes the mean of the stored set).
+ * H: n_var x n_var doubles (symmetric), n_var = (tail_rx/2 + 1) * (tail_tx + 1), variable index
+ * u = a*(tail_tx+1) + b for Rx-tail variable a and Tx-tail variable b (OptimizerTxRx's flatten order; Tx-only and
+ * Rx-only systems have tail_rx = 0 or tail_tx = 0 and the index is b or a).  *n_var (may be NULL) returns n_var. */
+WOFDM_API int wofdm_window_hessian(wofdm_handle h, const wofdm_sys_t* sys, const double* chan, int L, double* H, int* n_var);
+
 /* ---- Channel generation (next-row 8f-4) ------------------------------------------------------------------
  * ITU-R tapped-delay-line channels with GMEDS_1 Rayleigh fading on the device: channel_model.gen_chan
  * (python/channel_model/itur_channels.py:33-94 + rayleigh_fading.py:52-102), the producer of channels/<standard>.npy

@@ -1,0 +1,73 @@
+"""Window-optimisation Hessian: the Gram-form oracle against the REFERENCE's own gen_hessian outputs
+(golden, N = 64, CPU) and the device path against the oracle through the C-ABI (GPU).  fp64; 1e-9 relative to the
+largest entry (the reference's loop-built DFT matrices carry ~1e-12 themselves)."""
+import os
+import time
+
+import numpy as np
+import pytest
+
+from oracle import wofdm_oracle as O
+
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hessian.npz"))
+SYSTEMS = ("wtx", "CPwtx", "wrx", "CPwrx", "WOLA", "CPW")
+
+
+def tails(name, ttx, trx):
+    return (ttx if name in ("wtx", "CPwtx", "WOLA", "CPW") else 0, trx if name in ("wrx", "CPwrx", "WOLA", "CPW") else 0)
+
+
+@pytest.mark.parametrize("name", SYSTEMS)
+def test_oracle_matches_reference_hessian(name):
+    a, b = tails(name, int(G["tail_tx"]), int(G["tail_rx"]))
+    p = O.system_params(name, int(G["N"]), int(G["cp"]), a, b)
+    H = O.window_hessian(p, G["h"])
+    ref = G[f"H_{name}"]
+    assert H.shape == ref.shape == ((b // 2 + 1) * (a + 1),) * 2
+    assert np.abs(H - ref).max() <= 1e-9 * np.abs(ref).max()
+    assert np.allclose(H, H.T) and np.linalg.eigvalsh(H).min() > -1e-9 * np.abs(H).max()     # a Gram matrix
+    # the quadratic form IS the interference power of the expanded window (summed over sub-carriers, the ISI slices
+    # summed before squaring: interf_power_matlab)
+    rng = np.random.default_rng(1)
+    xt = np.concatenate([[1.0], rng.uniform(0, 1, a)])
+    xr = np.concatenate([[1.0], rng.uniform(0.5, 1, b // 2)])
+    x = np.outer(xr, xt).ravel()
+    want = O.interf_power_matlab(p, O.expand_window_tx(xt, p), O.expand_window_rx(xr, p), G["h"])
+    assert abs(0.5 * x @ H @ x - want) <= 1e-9 * want
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", SYSTEMS)
+def test_device_matches_golden_and_oracle(name):
+    import wofdm_b200 as W
+    from wofdm_b200 import optimizers as OPT
+    a, b = tails(name, int(G["tail_tx"]), int(G["tail_rx"]))
+    with W.Handle([0]) as h:
+        if name in ("wtx", "CPwtx"):
+            opt = OPT.OptimizerTx(name, int(G["N"]), int(G["cp"]), a, handle=h)
+        elif name in ("wrx", "CPwrx"):
+            opt = OPT.OptimizerRx(name, int(G["N"]), int(G["cp"]), b, handle=h)
+        else:
+            opt = OPT.OptimizerTxRx(name, int(G["N"]), int(G["cp"]), a, b, handle=h)
+        H = opt.gen_hessian(opt.calculate_chann_matrices(G["h"]))
+        ref = G[f"H_{name}"]
+        assert np.abs(H - ref).max() <= 1e-9 * np.abs(ref).max()
+        # settingsData sizes (N = 256, tails 8 / 10, 21 taps): against the oracle's closed form
+        a2, b2 = tails(name, 8, 10)
+        p = O.system_params(name, 256, 16, a2, b2)
+        hch = O.synth_channels(8, 21, seed=4).mean(axis=1)
+        s = W.params_from_name(name, 256, 16, a2, b2)
+        h.window_hessian(s, hch)
+        t0 = time.perf_counter()
+        Hd = h.window_hessian(s, hch)
+        dt = time.perf_counter() - t0
+        Ho = O.window_hessian(p, hch)
+        assert np.abs(Hd - Ho).max() <= 1e-9 * np.abs(Ho).max()
+        print(f"{name}: {Hd.shape[0]} variables, device call {dt * 1e3:.2f} ms")
+
+
+@pytest.mark.gpu
+def test_bad_system_names_raise():
+    from wofdm_b200 import optimizers as OPT
+    with pytest.raises(ValueError):
+        OPT.OptimizerTx("WOLA", 256, 16, 8)

@@ -10,6 +10,7 @@ repo root) or ``importlib.import_module("w-ofdm-optimization_b200")``.
 from . import capi, sharding  # noqa: F401
 from . import ofdm_utils  # noqa: F401,E402
 from . import channel_model  # noqa: F401,E402
+from . import optimizers  # noqa: F401,E402
 from .capi import Handle, BerPlan, SysT, WofdmError, params_from_name  # noqa: F401
 
-__all__ = ["capi", "sharding", "ofdm_utils", "channel_model", "Handle", "BerPlan", "SysT", "WofdmError", "params_from_name"]
+__all__ = ["capi", "sharding", "ofdm_utils", "channel_model", "optimizers", "Handle", "BerPlan", "SysT", "WofdmError", "params_from_name"]

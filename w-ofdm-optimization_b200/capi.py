@@ -83,6 +83,7 @@ SIGNATURES = {
     "wofdm_ber_draws": (C.c_int, [C.c_void_p, _P(SysT), C.c_int, C.c_uint64, C.c_uint32, _i64p, C.c_int, _i32p, _dp]),
     "wofdm_interf_power": (C.c_int, [C.c_void_p, _P(SysT), _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, _dp]),
     "wofdm_interf_power_scalar": (C.c_int, [C.c_void_p, _P(SysT), _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, _dp]),
+    "wofdm_window_hessian": (C.c_int, [C.c_void_p, _P(SysT), _dp, C.c_int, _dp, _P(C.c_int)]),
     "wofdm_channel_profile": (C.c_int, [C.c_char_p]),
     "wofdm_gen_channels": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
                                      C.c_uint64, _dp, _dp]),
@@ -275,6 +276,18 @@ class Handle:
         self._check(rc)
         return P
 
+
+    def window_hessian(self, s, chan):
+        """Hessian of the interference power in the reduced window variables (wofdm_window_hessian) for ONE impulse
+        response chan (L,) -> (n_var, n_var), n_var = (tail_rx/2+1)*(tail_tx+1), index a*(tail_tx+1)+b."""
+        ch = _cplx(np.ravel(chan))
+        n_var = (s.tail_rx // 2 + 1) * (s.tail_tx + 1)
+        H = np.empty((n_var, n_var))
+        nv = C.c_int(0)
+        rc = load().wofdm_window_hessian(self._h, C.byref(s), _ptr(ch, _dp), ch.size, _ptr(H, _dp), C.byref(nv))
+        self._check(rc)
+        assert nv.value == n_var
+        return H
 
     def gen_channels(self, standard, L, doppler_freq, sampling_rate, frame_duration, no_frames=1, n_sets=1, seed=0,
                      phases=None):

@@ -91,7 +91,9 @@ __device__ __forceinline__ void dmma8x8x4(double& d0, double& d1, double a, doub
                  : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-// grid (N / BN column tiles of a slice, 2N / BM row tiles, slices); P[c][k] += row power
+// grid (N / BN column tiles of a slice, 2N / BM row tiles, slices); P[c][k] += row power.
+// STORE (window Hessian, K5): no power epilogue, [Re A; Im A] of slice s is written to P + s*2N*N instead.
+template <bool STORE>
 __global__ void __launch_bounds__(256) gemm_power_f64(const double* __restrict__ Rbig, const double* __restrict__ Bbig,
                                                       double* __restrict__ P, int N, int Kp, int Ms, int c0, int scalar) {
     extern __shared__ __align__(16) double gsm[];
@@ -144,6 +146,19 @@ __global__ void __launch_bounds__(256) gemm_power_f64(const double* __restrict__
         }
         if (kt + 1 < nk) sstore(buf ^ 1);
         __syncthreads();
+    }
+    if constexpr (STORE) {
+        double* out = P + (size_t)s * 2 * N * N;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = row0 + wm + 8 * i + (lane >> 2);
+#pragma unroll
+            for (int jn = 0; jn < 4; ++jn) {
+                const int jcol = col0 + wn + 8 * jn + 2 * (lane & 3);
+                *reinterpret_cast<double2*>(out + (size_t)r * N + jcol) = make_double2(acc[i][jn][0], acc[i][jn][1]);
+            }
+        }
+        return;
     }
     // epilogue: rows r (Re) and N + r (Im) of big-A both belong to sub-carrier r; slice 0 drops j == k
     const int c = c0 + s / Ms, ms = s % Ms;
@@ -227,8 +242,8 @@ static int interf_run(wofdm_handle h, const wofdm_sys_t* sys, const double* win_
         WOFDM_CUDA(h, cudaGetLastError());
         if (mode == 0) {
             constexpr size_t smem = (size_t)(2 * BM * AS + 2 * BK * BS) * sizeof(double);
-            WOFDM_CUDA(h, cudaFuncSetAttribute(gemm_power_f64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            gemm_power_f64<<<dim3(N / BN, 2 * N / BM, slices), 256, smem, d.stream>>>(v.Rbig, v.Bbig, v.P, N, v.Kp, Ms, c0, scalar);
+            WOFDM_CUDA(h, cudaFuncSetAttribute(gemm_power_f64<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            gemm_power_f64<false><<<dim3(N / BN, 2 * N / BM, slices), 256, smem, d.stream>>>(v.Rbig, v.Bbig, v.P, N, v.Kp, Ms, c0, scalar);
             WOFDM_CUDA(h, cudaGetLastError());
         } else {
             rc = interf_gemm_tf32(h, sys, v, Ms, c0, slices, scalar);
@@ -237,6 +252,107 @@ static int interf_run(wofdm_handle h, const wofdm_sys_t* sys, const double* win_
         h->launches += 2;
     }
     WOFDM_CUDA(h, cudaMemcpyAsync(P, v.P, pbytes, cudaMemcpyDeviceToHost, d.stream));
+    WOFDM_CUDA(h, cudaStreamSynchronize(d.stream));
+    return WOFDM_OK;
+}
+
+// ---- K5: window-optimisation Hessian ----------------------------------------
+// H[u,u'] = 2 Re( <offdiag A0_u, offdiag A0_u'> + <AS_u, AS_u'> ), A0_u / AS_u = the K2 contraction for the basis window
+// pair u = (Rx basis a, Tx basis b) on slice 0 / on the sum of the ISI slices.  Replaces the O(n^2 N^2) loops of
+// OptimizerTx/Rx/TxRx.gen_hessian (python/optimization_tools/optimizers.py:132-175, 232-257, 427-507, 808-833) and
+// quad_objective_tx/_rx (matlab/window_optimization.m:596-680).  X[u][ms][2N][N] holds [Re A; Im A].
+__global__ void __launch_bounds__(256) gram_offdiag(const double* __restrict__ X, double* __restrict__ H, int n_var, int N,
+                                                    int n_tb) {
+    __shared__ double red[256];
+    // pair index -> (u, u'), u' <= u
+    int u = 0, rem = blockIdx.x;
+    while (rem > u) { rem -= u + 1; ++u; }
+    const int up = rem;
+    const size_t mat = (size_t)2 * N * N;                    // one [Re A; Im A]
+    // X layout: [a][b][ms][2N][N] with u = a*n_tb + b
+    const double* x0 = X + (size_t)u * 2 * mat;
+    const double* y0 = X + (size_t)up * 2 * mat;
+    double acc = 0.0;
+    for (size_t e = threadIdx.x; e < 2 * mat; e += 256) {
+        const int ms = (int)(e / mat);
+        const size_t w = e - (size_t)ms * mat;
+        const int r = (int)(w / N), j = (int)(w - (size_t)r * N);
+        if (ms == 0 && j == r % N) continue;                  // slice 0: off-diagonal entries only
+        acc = fma(x0[e], y0[e], acc);
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int st = 128; st > 0; st >>= 1) {
+        if (threadIdx.x < st) red[threadIdx.x] += red[threadIdx.x + st];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { H[(size_t)u * n_var + up] = 2.0 * red[0]; H[(size_t)up * n_var + u] = 2.0 * red[0]; }
+    (void)n_tb;
+}
+
+static int window_hessian_run(wofdm_handle h, const wofdm_sys_t* sys, const double* chan, int L, double* H_out, int* n_var_out) {
+    if (!h) return WOFDM_EINVAL;
+    int rc = validate_sys(h, sys, L);
+    if (rc) return rc;
+    if (!chan || !H_out) return fail(h, WOFDM_EINVAL, "bad buffer");
+    if (sys->N % 64) return fail(h, WOFDM_EUNSUPPORTED, "interference path needs N to be a multiple of 64");
+    DeviceCtx& d = h->devs[0];
+    WOFDM_CUDA(h, cudaSetDevice(d.dev));
+    const int N = sys->N, n_tx = N + sys->cp + sys->cs, n_rx = n_tx - sys->tail_tx, n_w = N + sys->tail_rx;
+    const int n_tb = sys->tail_tx + 1, n_rb = sys->tail_rx / 2 + 1, n_var = n_tb * n_rb;
+    if (n_var_out) *n_var_out = n_var;
+    const int Kp = ((2 * n_rx + 63) / 64) * 64;
+    const int M = 1 + (L - 1 + sys->tail_tx + n_rx - 1) / n_rx;
+    const int Ms = 2;                                          // slice 0 and the sum of the ISI slices
+    // basis windows = columns of reduce_variable_tx / _rx (optimization_tools/utils.py:13-73)
+    std::vector<double> bt((size_t)n_tb * n_tx), br((size_t)n_rb * n_w), e(std::max(n_tb, n_rb));
+    for (int b = 0; b < n_tb; ++b) {
+        std::fill(e.begin(), e.end(), 0.0); e[b] = 1.0;
+        rc = wofdm_expand_window_tx(sys, e.data(), bt.data() + (size_t)b * n_tx);
+        if (rc) return fail(h, rc, "expand_window_tx");
+    }
+    for (int a = 0; a < n_rb; ++a) {
+        std::fill(e.begin(), e.end(), 0.0); e[a] = 1.0;
+        rc = wofdm_expand_window_rx(sys, e.data(), br.data() + (size_t)a * n_w);
+        if (rc) return fail(h, rc, "expand_window_rx");
+    }
+    const size_t matb = (size_t)2 * N * N * 8;
+    const size_t need = bt.size() * 8 + br.size() * 8 + (size_t)L * 16 + (size_t)n_tx * N * 16 + (size_t)2 * N * Kp * 8 +
+                        (size_t)n_tb * Ms * Kp * N * 8 + (size_t)n_var * Ms * matb + (size_t)n_var * n_var * 8;
+    rc = arena_reserve(h, d, need);
+    if (rc) return rc;
+    double* d_bt = static_cast<double*>(arena_take(d, bt.size() * 8));
+    double* d_br = static_cast<double*>(arena_take(d, br.size() * 8));
+    double2* d_chan = static_cast<double2*>(arena_take(d, (size_t)L * 16));
+    double2* d_T = static_cast<double2*>(arena_take(d, (size_t)n_tx * N * 16));
+    double* d_R = static_cast<double*>(arena_take(d, (size_t)2 * N * Kp * 8));
+    double* d_B = static_cast<double*>(arena_take(d, (size_t)n_tb * Ms * Kp * N * 8));
+    double* d_X = static_cast<double*>(arena_take(d, (size_t)n_var * Ms * matb));
+    double* d_H = static_cast<double*>(arena_take(d, (size_t)n_var * n_var * 8));
+    if (!d_bt || !d_br || !d_chan || !d_T || !d_R || !d_B || !d_X || !d_H) return fail(h, WOFDM_ENOMEM, "arena exhausted");
+    WOFDM_CUDA(h, cudaMemcpyAsync(d_bt, bt.data(), bt.size() * 8, cudaMemcpyHostToDevice, d.stream));
+    WOFDM_CUDA(h, cudaMemcpyAsync(d_br, br.data(), br.size() * 8, cudaMemcpyHostToDevice, d.stream));
+    WOFDM_CUDA(h, cudaMemcpyAsync(d_chan, chan, (size_t)L * 16, cudaMemcpyHostToDevice, d.stream));
+    // B_{b,ms} = H_ms . Tx_mat(t_b) for every Tx basis window
+    for (int b = 0; b < n_tb; ++b) {
+        build_tx_matrix<<<n_tx, 256, 0, d.stream>>>(d_T, d_bt + (size_t)b * n_tx, N, sys->cp, n_tx);
+        build_b<<<dim3((N + 255) / 256, n_rx, Ms), 256, 0, d.stream>>>(d_B + (size_t)b * Ms * Kp * N, d_T, d_chan, L, N, n_tx, n_rx,
+                                                                   n_rx, Kp, Ms, M, 0, 1);
+    }
+    WOFDM_CUDA(h, cudaGetLastError());
+    // X[a][b][ms] = Rbig(r_a) . B_{b,ms}: one stored contraction per Rx basis window over all Tx slices
+    constexpr size_t smem = (size_t)(2 * BM * AS + 2 * BK * BS) * sizeof(double);
+    WOFDM_CUDA(h, cudaFuncSetAttribute(gemm_power_f64<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int a = 0; a < n_rb; ++a) {
+        build_rx_matrix<<<N, 256, 0, d.stream>>>(d_R, d_br + (size_t)a * n_w, N, sys->tail_rx, sys->rm, sys->shift, n_rx, Kp);
+        gemm_power_f64<true><<<dim3(N / BN, 2 * N / BM, n_tb * Ms), 256, smem, d.stream>>>(
+            d_R, d_B, d_X + (size_t)a * n_tb * Ms * 2 * N * N, N, Kp, Ms, 0, 0);
+    }
+    WOFDM_CUDA(h, cudaGetLastError());
+    gram_offdiag<<<n_var * (n_var + 1) / 2, 256, 0, d.stream>>>(d_X, d_H, n_var, N, n_tb);
+    WOFDM_CUDA(h, cudaGetLastError());
+    h->launches += 2 * n_tb + 2 * n_rb + 1;
+    WOFDM_CUDA(h, cudaMemcpyAsync(H_out, d_H, (size_t)n_var * n_var * 8, cudaMemcpyDeviceToHost, d.stream));
     WOFDM_CUDA(h, cudaStreamSynchronize(d.stream));
     return WOFDM_OK;
 }
@@ -255,6 +371,10 @@ int wofdm_interf_power(wofdm_handle h, const wofdm_sys_t* sys, const double* win
 int wofdm_interf_power_scalar(wofdm_handle h, const wofdm_sys_t* sys, const double* win_tx, const double* win_rx,
                               const double* chan, int L, int C, int mode, double* P) {
     return interf_run(h, sys, win_tx, win_rx, chan, L, C, mode, 1, P);
+}
+
+int wofdm_window_hessian(wofdm_handle h, const wofdm_sys_t* sys, const double* chan, int L, double* H, int* n_var) {
+    return window_hessian_run(h, sys, chan, L, H, n_var);
 }
 
 }  // extern "C"
