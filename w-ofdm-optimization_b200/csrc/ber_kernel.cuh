@@ -238,6 +238,20 @@ __device__ __forceinline__ float noise_gain(float pr, float snr_lin, float pn) {
 }
 __device__ __forceinline__ double noise_gain(double pr, double snr_lin, double pn) { return sqrt(pr * snr_lin / pn); }
 
+// one output of the direct-form convolution past the kept samples (MATLAB's full-length noise normalisation): taps are
+// zero-padded to LB in shared memory, inputs at and beyond `body` do not exist.  Fully unrolled with two accumulators so
+// that the few threads which run it do not serialise 2*LB shared-memory latencies in front of the frame-wide barrier.
+template <typename T, int LB>
+__device__ __forceinline__ V2<T> tail_output(const V2<T>* taps, const V2<T>* ub, int i, int body) {
+    V2<T> a0 = mk2<T>(0, 0), a1 = mk2<T>(0, 0);
+#pragma unroll
+    for (int l = 0; l < LB; ++l) {
+        const V2<T> x = (i - l < body) ? ub[i - l] : mk2<T>(0, 0);
+        if (l & 1) cmac(a1, taps[l], x); else cmac(a0, taps[l], x);
+    }
+    return cadd(a0, a1);
+}
+
 // barrier over the CTAs of a frame (release/acquire at cluster scope: remote shared-memory traffic is ordered)
 template <int CL> __device__ __forceinline__ void frame_sync() {
     if constexpr (CL > 1) cooperative_groups::this_cluster().sync(); else __syncthreads();
@@ -497,9 +511,7 @@ ber_frame_kernel(const BerParams prm) {
             if (prm.noise_norm == 1) {
                 // the L-1+beta samples the reference truncates still count in both power sums
                 for (int i = sec + tid; i < body + L - 1; i += NT) {
-                    C2 a = mk2<T>(0, 0);
-                    for (int l = 0; l < L; ++l)
-                        if (i - l < body) cmac(a, taps[l], ub[i - l]);
+                    C2 a = tail_output<T, LB>(taps, ub, i, body);
                     C2 n0;
                     if constexpr (VERIFY) n0 = to_v2<T>(prm.noise_in[(size_t)f * prm.noise_len + i]);
                     else n0 = noise_at<T>(prm, f, i);
@@ -596,9 +608,7 @@ ber_frame_kernel(const BerParams prm) {
             if (prm.noise_norm == 1 && last_rank) {
                 // the L-1+beta samples the reference truncates still count in both power sums
                 for (int i = sec + tid; i < body + L - 1; i += NT) {
-                    C2 a = mk2<T>(0, 0);
-                    for (int l = 0; l < L; ++l)
-                        if (i - l < body) cmac(a, taps[l], ub[i - l]);
+                    C2 a = tail_output<T, LB>(taps, ub, i, body);
                     C2 n0;
                     if constexpr (VERIFY) n0 = to_v2<T>(prm.noise_in[(size_t)f * prm.noise_len + (size_t)rank * sec + i]);
                     else n0 = noise_at<T>(prm, f, rank * sec + i);   // (same numbering: noise_at splits at prm.split = sec)
