@@ -29,13 +29,28 @@ sys.path.insert(0, REPO)
 METRIC = "w-OFDM BER Monte Carlo OFDM symbols/s"
 UNIT = "OFDM symbols/s"
 CFG = dict(system="wtx", N=256, cp=16, tail_tx=8, tail_rx=0, bits=4, S=16, L=21, C=250, n_snr=30,
-           snr_lo=-20.0, snr_hi=50.0, ensemble_per_gpu=27, noise_norm=1, constellation=1)
+           snr_lo=-20.0, snr_hi=50.0, ensemble_per_gpu=27, noise_norm=1, constellation=1,
+           name="configs[1]: wtx-OFDM N=256 cp=16 tail_tx=8 16-QAM (Gray, BER), optimised-Tx-window stand-in, "
+                "250 VehA channels x 30 SNR points x ensemble 27 per GPU = 202500 frames = 3.24e6 OFDM symbols "
+                "(1.0e8 bits per SNR point) per GPU per step, S=16, L=21")
+# --workload configs4: BASELINE.json configs[4], the scaled stress case (not the headline line): N=1024, 64-QAM, WOLA with
+# 4x scaled tails, 10 000 synthetic VehA channels generated ON THE DEVICE (wofdm_gen_channels), 1e10 bits per SNR point
+CFG4 = dict(system="WOLA", N=1024, cp=64, tail_tx=32, tail_rx=40, bits=6, S=16, L=21, C=10000, n_snr=30,
+            snr_lo=-20.0, snr_hi=50.0, ensemble_per_gpu=11, noise_norm=1, constellation=1,
+            name="configs[4]: WOLA-OFDM N=1024 cp=64 tail_tx=32 tail_rx=40 64-QAM (Gray, BER), optimised-window stand-ins, "
+                 "10000 VehA channels (GMEDS_1, generated on the device) x 30 SNR points x ensemble 11 per GPU = 3.3e6 frames "
+                 "= 5.28e7 OFDM symbols (1.0e10 bits per SNR point) per GPU per step, S=16, L=21")
 
 
-def workload_inputs():
-    """Synthetic inputs of the named shapes (nothing ships with the reference).  Pure numpy."""
+def workload_inputs(handle=None):
+    """Synthetic inputs of the named shapes (nothing ships with the reference).  Pure numpy, except the
+    stress workload's 10 000 channels, which come from the device generator (K4) when a handle is given."""
     rng = np.random.default_rng(1)
     L, C = CFG["L"], CFG["C"]
+    if handle is not None and C > 1000:
+        fd, fs, frame = (100 / 3.6 / 299792458.0) * 2e9, 5e6, 16 * 256 * 200e-9        # wofdm_optimization.py:63-76
+        chan = handle.gen_channels("vehicularA", L, fd, fs, frame, no_frames=1, n_sets=C, seed=1)
+        return chan, np.linspace(CFG["snr_lo"], CFG["snr_hi"], CFG["n_snr"])
     d = np.array([0.0, 310, 710, 1090, 1730, 2510]) / 200.0            # ITU-R VehA delays in samples (Ts = 200 ns)
     pw = 10.0 ** (np.array([0.0, -1, -9, -10, -15, -20]) / 10.0)
     g = (rng.standard_normal((6, C)) + 1j * rng.standard_normal((6, C))) * np.sqrt(pw / 2)[:, None]
@@ -148,7 +163,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="configs1", choices=["configs1", "configs4"],
+                    help="configs1 = BASELINE's headline configuration (default); configs4 = the N=1024 stress case")
     args = ap.parse_args()
+    if args.workload == "configs4":
+        CFG.clear(); CFG.update(CFG4)
+        args.no_cpu_baseline = True          # the CPU port is dimensioned for the headline workload
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
@@ -174,7 +194,6 @@ def main():
     c = CFG
     s = W.params_from_name(c["system"], c["N"], c["cp"], c["tail_tx"], c["tail_rx"], bits=c["bits"], S=c["S"],
                            noise_norm=c["noise_norm"], constellation=c["constellation"], precision=0)
-    chan, snr = workload_inputs()
     rng = np.random.default_rng(7)
     x_tx = np.concatenate([[1.0], np.clip(capi.rc_window_tx(s)[-c["tail_tx"]:] * (1 + 0.1 * rng.uniform(-1, 1, c["tail_tx"])), 0, 1)])
     win_tx = capi.expand_window_tx(s, x_tx)                 # "optimised" Tx window stand-in
@@ -185,6 +204,7 @@ def main():
     syms_rank = frames_rank * c["S"]
 
     h = W.Handle([local])
+    chan, snr = workload_inputs(h)
     stream = torch.cuda.Stream()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
     peak_tflops, peak_mhz = h.fp32_peak(0)
@@ -264,9 +284,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[1]: wtx-OFDM N=256 cp=16 tail_tx=8 16-QAM (Gray, BER), optimised-Tx-window stand-in, "
-                                   "250 VehA channels x 30 SNR points x ensemble 27 per GPU = 202500 frames = 3.24e6 OFDM symbols "
-                                   "(1.0e8 bits per SNR point) per GPU per step, S=16, L=21",
+            "config": {"workload": c["name"],
                        "kernel": plan.kernel, "frames_per_gpu_per_step": frames_rank,
                        "l2": "256 MiB buffer rewritten between timed iterations (inputs are ~100 KB; the kernel is FP32-bound)",
                        "parallelism": f"frames sharded by global id over {world} GPU(s), one int64 all-reduce per step"},

@@ -4,6 +4,10 @@
 //                   csLength, windowTx, channel, snr, tailTx, tailRx, windowRx, prefixRemovalLength, ...
 //                   circularShiftLength [, seed])
 //       -- the positional arguments of run_simulation, matlab/main_BER_calculation.m:230-232.
+//   berSNR = wofdm_mex('run_simulation_sweep', <the same 14 arguments> [, seed])
+//       -- channel is now the whole C x L matrix (rows = realisations) and snr a vector: the triple loop of the
+//          driver, matlab/main_BER_calculation.m:66-87 (for snr, for channel: ber = ber + run_simulation(...);
+//          berSNR(snrIndex) = ber/numChannels), as ONE device job.  Returns n_snr x 1.
 //   P   = wofdm_mex('calculate_interference', cpLength, typeOFDM, windowTx, windowRx, numSubcar, tailTx, ...
 //                   tailRx, channels [, mode])
 //       -- calculate_interference, matlab/main_interference_calculation.m:177-180; the values the reference
@@ -66,7 +70,8 @@ static std::vector<double> interleave(const mxArray* a, size_t count, size_t str
     return z;
 }
 
-static void do_run_simulation(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+// sweep = false: one channel (vector), one SNR -> scalar; sweep = true: C x L channel matrix, SNR vector -> n_snr x 1
+static void do_run_simulation(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[], bool sweep) {
     if (nrhs < 14) mexErrMsgIdAndTxt("wofdm:nargin", "run_simulation needs 14 arguments");
     (void)nlhs;
     wofdm_sys_t s;
@@ -86,14 +91,32 @@ static void do_run_simulation(int nlhs, mxArray* plhs[], int nrhs, const mxArray
     s.precision = 0;
     const std::vector<double> wtx = diag_of(prhs[6], (size_t)(s.N + s.cp + s.cs));
     const std::vector<double> wrx = diag_of(prhs[11], (size_t)(s.N + s.tail_rx));
-    const int L = (int)mxGetNumberOfElements(prhs[7]);
-    const std::vector<double> chan = interleave(prhs[7], (size_t)L, 1, 0);
-    const double snr = mxGetScalar(prhs[8]);
     const unsigned long long seed = nrhs > 14 ? (unsigned long long)mxGetScalar(prhs[14]) : 0ull;
-    long long be = 0, bt = 0, se = 0, st = 0;
-    check(wofdm_ber_run(handle(), &s, wtx.data(), wrx.data(), chan.data(), L, 1, &snr, 1, ensemble, seed, 0,
-                        (int64_t*)&be, (int64_t*)&bt, (int64_t*)&se, (int64_t*)&st), "wofdm_ber_run");
-    plhs[0] = mxCreateDoubleScalar(bt ? (double)be / (double)bt : 0.0);   // ber, as [~, ber] = biterr(...) at :272
+    if (!sweep) {
+        const int L = (int)mxGetNumberOfElements(prhs[7]);
+        const std::vector<double> chan = interleave(prhs[7], (size_t)L, 1, 0);
+        const double snr = mxGetScalar(prhs[8]);
+        long long be = 0, bt = 0, se = 0, st = 0;
+        check(wofdm_ber_run(handle(), &s, wtx.data(), wrx.data(), chan.data(), L, 1, &snr, 1, ensemble, seed, 0,
+                            (int64_t*)&be, (int64_t*)&bt, (int64_t*)&se, (int64_t*)&st), "wofdm_ber_run");
+        plhs[0] = mxCreateDoubleScalar(bt ? (double)be / (double)bt : 0.0);   // ber, as [~, ber] = biterr(...) at :272
+        return;
+    }
+    // channels(channelIndex, :) -> column-major L x C complex
+    const size_t C = mxGetM(prhs[7]), L = mxGetN(prhs[7]);
+    std::vector<double> chan(2 * L * C);
+    for (size_t c = 0; c < C; ++c) {
+        const std::vector<double> row = interleave(prhs[7], L, C, c);
+        memcpy(chan.data() + 2 * L * c, row.data(), 2 * L * sizeof(double));
+    }
+    const size_t n_snr = mxGetNumberOfElements(prhs[8]);
+    const double* snr = mxGetPr(prhs[8]);
+    std::vector<long long> be(n_snr), bt(n_snr), se(n_snr), st(n_snr);
+    check(wofdm_ber_run(handle(), &s, wtx.data(), wrx.data(), chan.data(), (int)L, (int)C, snr, (int)n_snr, ensemble, seed, 0,
+                        (int64_t*)be.data(), (int64_t*)bt.data(), (int64_t*)se.data(), (int64_t*)st.data()), "wofdm_ber_run");
+    plhs[0] = mxCreateDoubleMatrix((mwSize)n_snr, 1, mxREAL);
+    double* out = mxGetPr(plhs[0]);
+    for (size_t i = 0; i < n_snr; ++i) out[i] = bt[i] ? (double)be[i] / (double)bt[i] : 0.0;
 }
 
 static void do_calculate_interference(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
@@ -126,8 +149,9 @@ static void do_calculate_interference(int nlhs, mxArray* plhs[], int nrhs, const
 extern "C" void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     char cmd[32];
     if (nrhs < 1 || !mxIsChar(prhs[0]) || mxGetString(prhs[0], cmd, sizeof(cmd)))
-        mexErrMsgIdAndTxt("wofdm:usage", "first argument must be 'run_simulation' or 'calculate_interference'");
-    if (!strcmp(cmd, "run_simulation")) do_run_simulation(nlhs, plhs, nrhs - 1, prhs + 1);
+        mexErrMsgIdAndTxt("wofdm:usage", "first argument must be 'run_simulation', 'run_simulation_sweep' or 'calculate_interference'");
+    if (!strcmp(cmd, "run_simulation")) do_run_simulation(nlhs, plhs, nrhs - 1, prhs + 1, false);
+    else if (!strcmp(cmd, "run_simulation_sweep")) do_run_simulation(nlhs, plhs, nrhs - 1, prhs + 1, true);
     else if (!strcmp(cmd, "calculate_interference")) do_calculate_interference(nlhs, plhs, nrhs - 1, prhs + 1);
     else mexErrMsgIdAndTxt("wofdm:usage", "unknown command '%s'", cmd);
 }
