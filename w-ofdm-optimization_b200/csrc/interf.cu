@@ -33,54 +33,109 @@ __global__ void build_tx_matrix(double2* __restrict__ T, const double* __restric
     }
 }
 
-// Rbig = [Rr -Ri; Ri Rr] (2N x Kp), R[k][b] = vrx[b-rm] * exp(-2 pi i k n(b) / N) for rm <= b < rm+N+d,
-// n(b) = ((b - rm - d/2) mod N - shift) mod N                              (receiver.py:13-133)
+// Rbig (2N x Kp), the real form of Rx_mat with the K dimension INTERLEAVED: column 2b multiplies Re B[b], column
+// 2b+1 multiplies Im B[b] (so the non-zero rows of an ISI slice are a prefix of K, see build_b):
+//   row k   (Re A): [ Rr[k][b], -Ri[k][b] ],   row N+k (Im A): [ Ri[k][b], Rr[k][b] ]
+// R[k][b] = vrx[b-rm] * exp(-2 pi i k n(b) / N) for rm <= b < rm+N+d, n(b) = ((b - rm - d/2) mod N - shift) mod N
+//                                                                                          (receiver.py:13-133)
 __global__ void build_rx_matrix(double* __restrict__ Rbig, const double* __restrict__ vrx, int N, int tail_rx,
                                 int rm, int shift, int n_rx, int Kp) {
     const int k = blockIdx.x;
     const int hh = tail_rx / 2;
-    for (int b = threadIdx.x; b < Kp; b += blockDim.x) {
+    for (int b = threadIdx.x; 2 * b < Kp; b += blockDim.x) {
         double re = 0.0, im = 0.0;
-        const int col = b < n_rx ? b : b - n_rx;     // second half of K multiplies Im B
-        if (b < 2 * n_rx && col >= rm && col - rm < N + tail_rx) {
-            const int np = ((col - rm - hh) % N + N) % N;
+        if (b < n_rx && b >= rm && b - rm < N + tail_rx) {
+            const int np = ((b - rm - hh) % N + N) % N;
             const int n = ((np - shift) % N + N) % N;
             double s, c;
             sincospi(2.0 * (double)(((long long)k * n) % N) / (double)N, &s, &c);
-            re = vrx[col - rm] * c;
-            im = -vrx[col - rm] * s;
+            re = vrx[b - rm] * c;
+            im = -vrx[b - rm] * s;
         }
-        // row k: Re A = Rr.Br - Ri.Bi ; row N+k: Im A = Ri.Br + Rr.Bi
-        Rbig[(size_t)k * Kp + b] = b < n_rx ? re : -im;
-        Rbig[(size_t)(N + k) * Kp + b] = b < n_rx ? im : re;
-        if (b >= 2 * n_rx) { Rbig[(size_t)k * Kp + b] = 0.0; Rbig[(size_t)(N + k) * Kp + b] = 0.0; }
+        *reinterpret_cast<double2*>(Rbig + (size_t)k * Kp + 2 * b) = make_double2(re, -im);
+        *reinterpret_cast<double2*>(Rbig + (size_t)(N + k) * Kp + 2 * b) = make_double2(im, re);
     }
 }
 
 // ---- K2a: B = H_m(h_c) . Tx_mat ------------------------------------------------------------------
 // slice s of a batch: channel c0 + s / Ms, slice index m = s % Ms.  sum_isi (MATLAB semantics,
 // main_interference_calculation.m:198): Ms = 2 and slice 1 holds sum_{m>=1} H_m.
-// Bbig[s][kk][j], kk < n_rx: Re B[kk][j]; n_rx <= kk < 2 n_rx: Im B[kk-n_rx][j]; zero up to Kp.
+// Bbig[s][kk][j], kk = 2b: Re B[b][j], kk = 2b+1: Im B[b][j]; zero from 2 n_rx up to Kp.
+// H_m[b][c] = h[m N0 + b - c] (channel.py:49-52) is non-zero only for b < L - 1 + n_tx - m N0: an ISI slice (m >= 1)
+// has isi_rows = L - 1 + tail_tx non-zero rows at most, a PREFIX of K in this layout.  Only round_up(2 isi_rows, 64)
+// rows of such a slice are written here and read by the contraction kernels (interf_isi_k).
+// Each thread forms BB consecutive rows b of one column j from the BB + L - 1 rows of Tx_mat they share.
+constexpr int BB = 8;
+__host__ __device__ inline int interf_isi_k(int L, int tail_tx, int n_rx, int Kp) {
+    const int rows = L - 1 + tail_tx < n_rx ? L - 1 + tail_tx : n_rx;
+    const int k = rows > 0 ? ((2 * rows + 63) / 64) * 64 : 64;   // never empty: the contraction initialises its accumulators
+    return k < Kp ? k : Kp;
+}
+// TILED: the TF32 path's operand is written directly (hi/lo split, UMMA tiles, float4 per 4 consecutive kk); Bbig is
+// then the float work buffer and the fp64 B matrix never exists.
+template <bool TILED>
 __global__ void __launch_bounds__(256) build_b(double* __restrict__ Bbig, const double2* __restrict__ T,
                                                const double2* __restrict__ chan, int L, int N, int n_tx, int n_rx,
-                                               int N0, int Kp, int Ms, int M, int c0, int sum_isi) {
-    const int s = blockIdx.z, b = blockIdx.y;
+                                               int N0, int Kp, int Ms, int M, int c0, int sum_isi, int k_isi) {
+    // taps of this slice's channel in shared memory, zero-padded by BB on both sides: the inner loop needs no
+    // range checks and reads them as broadcasts
+    extern __shared__ __align__(16) double2 hs_raw[];
+    const int s = blockIdx.z, b0 = blockIdx.y * BB;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= N) return;
     const int c = c0 + s / Ms, ms = s % Ms;
-    const double2* h = chan + (size_t)c * L;
-    double2 acc = make_double2(0.0, 0.0);
+    const int k_rows = ms == 0 ? Kp : k_isi;                 // rows of this slice that exist for the contraction
+    if (2 * b0 >= k_rows) return;                            // (uniform per block)
+    for (int l = threadIdx.x; l < L + 2 * BB; l += blockDim.x)
+        hs_raw[l] = (l >= BB && l < L + BB) ? chan[(size_t)c * L + l - BB] : make_double2(0.0, 0.0);
+    __syncthreads();
+    if (j >= N) return;
+    const double2* h = hs_raw + BB;                          // h[-BB .. L+BB)
+    double2 acc[BB];
+#pragma unroll
+    for (int i = 0; i < BB; ++i) acc[i] = make_double2(0.0, 0.0);
     const int m_lo = ms, m_hi = (sum_isi && ms == 1) ? M - 1 : ms;
-    for (int m = m_lo; m <= m_hi; ++m)
-        for (int l = 0; l < L; ++l) {
-            const int row = m * N0 + b - l;                 // H_m[b][row] = h[l]            (channel.py:49-52)
-            if (row >= 0 && row < n_tx) cmac(acc, h[l], T[(size_t)row * N + j]);
+    if (b0 < n_rx) {
+        for (int m = m_lo; m <= m_hi; ++m) {
+            // rows m N0 + b0 - (L-1) .. m N0 + b0 + BB - 1 of Tx_mat: row r feeds output i through tap l = m N0 + b0 + i - r
+            const int r_lo = m * N0 + b0 - (L - 1);
+            for (int rr = 0; rr < BB + L - 1; ++rr) {
+                const int row = r_lo + rr;
+                if (row < 0 || row >= n_tx) continue;
+                const double2 x = T[(size_t)row * N + j];
+                const double2* hw = h + (L - 1) - rr;         // tap of output i: hw[i] (zero outside [0, L))
+#pragma unroll
+                for (int i = 0; i < BB; ++i) cmac(acc[i], hw[i], x);
+            }
         }
-    double* out = Bbig + (size_t)s * Kp * N;
-    out[(size_t)b * N + j] = acc.x;
-    out[(size_t)(n_rx + b) * N + j] = acc.y;
-    if (b == 0)
-        for (int kk = 2 * n_rx; kk < Kp; ++kk) out[(size_t)kk * N + j] = 0.0;
+    }
+    if constexpr (TILED) {
+        static_assert(BB % 2 == 0, "two rows b = four consecutive kk = one 16-byte chunk");
+        float* bt = reinterpret_cast<float*>(Bbig);
+        const int nk = Kp / TF32_KB;
+#pragma unroll
+        for (int i = 0; i < BB; i += 2) {
+            const int kk = 2 * (b0 + i);
+            if (kk >= k_rows) break;
+            float4 hi, lo;
+            tf32_split(b0 + i < n_rx ? acc[i].x : 0.0, hi.x, lo.x);
+            tf32_split(b0 + i < n_rx ? acc[i].y : 0.0, hi.y, lo.y);
+            tf32_split(b0 + i + 1 < n_rx ? acc[i + 1].x : 0.0, hi.z, lo.z);
+            tf32_split(b0 + i + 1 < n_rx ? acc[i + 1].y : 0.0, hi.w, lo.w);
+            float* dst = bt + tf32_b_offset(s, nk, j, kk);
+            *reinterpret_cast<float4*>(dst) = hi;
+            *reinterpret_cast<float4*>(dst + (size_t)TF32_TN * TF32_KB) = lo;
+        }
+    } else {
+        double* out = Bbig + (size_t)s * Kp * N;
+#pragma unroll
+        for (int i = 0; i < BB; ++i) {
+            const int b = b0 + i;
+            if (2 * b >= k_rows) break;
+            const bool live = b < n_rx;
+            out[(size_t)(2 * b) * N + j] = live ? acc[i].x : 0.0;
+            out[(size_t)(2 * b + 1) * N + j] = live ? acc[i].y : 0.0;
+        }
+    }
 }
 
 // ---- K2b: FP64 tensor-core contraction with fused power epilogue ----------------------------------
@@ -95,7 +150,8 @@ __device__ __forceinline__ void dmma8x8x4(double& d0, double& d1, double a, doub
 // STORE (window Hessian, K5): no power epilogue, [Re A; Im A] of slice s is written to P + s*2N*N instead.
 template <bool STORE>
 __global__ void __launch_bounds__(256) gemm_power_f64(const double* __restrict__ Rbig, const double* __restrict__ Bbig,
-                                                      double* __restrict__ P, int N, int Kp, int Ms, int c0, int scalar) {
+                                                      double* __restrict__ P, int N, int Kp, int Ms, int c0, int scalar,
+                                                      int k_isi) {
     extern __shared__ __align__(16) double gsm[];
     double (*As)[BM * AS] = reinterpret_cast<double (*)[BM * AS]>(gsm);
     double (*Bs)[BK * BS] = reinterpret_cast<double (*)[BK * BS]>(gsm + 2 * BM * AS);
@@ -128,7 +184,7 @@ __global__ void __launch_bounds__(256) gemm_power_f64(const double* __restrict__
     gload(0);
     sstore(0);
     __syncthreads();
-    const int nk = Kp / BK;
+    const int nk = ((s % Ms) == 0 ? Kp : k_isi) / BK;        // ISI slices: only their non-zero K prefix (build_b)
     for (int kt = 0; kt < nk; ++kt) {
         const int buf = kt & 1;
         if (kt + 1 < nk) gload((kt + 1) * BK);
@@ -234,19 +290,27 @@ static int interf_run(wofdm_handle h, const wofdm_sys_t* sys, const double* win_
     const size_t pbytes = scalar ? (size_t)C * 8 : (size_t)C * N * 8;
     WOFDM_CUDA(h, cudaMemsetAsync(v.P, 0, pbytes, d.stream));
     const int Ms = scalar ? std::min(v.M, 2) : v.M;      // scalar: slice 1 = sum of the ISI slices
+    const int k_isi = interf_isi_k(L, sys->tail_tx, v.n_rx, v.Kp);
     for (int c0 = 0; c0 < C; c0 += v.batch) {
         const int nc = std::min(v.batch, C - c0);
         const int slices = nc * Ms;
-        build_b<<<dim3((N + 255) / 256, v.n_rx, slices), 256, 0, d.stream>>>(v.Bbig, v.T, v.chan, L, N, v.n_tx, v.n_rx,
-                                                                         v.N0, v.Kp, Ms, v.M, c0, scalar);
+        const dim3 bgrid((N + 255) / 256, (v.Kp / 2 + BB - 1) / BB, slices);
+        const size_t bsm = (size_t)(L + 2 * BB) * sizeof(double2);
+        const bool tiled = mode == 1 && N == TF32_TN;         // the TF32 operand straight from the band product
+        if (tiled)
+            build_b<true><<<bgrid, 256, bsm, d.stream>>>(reinterpret_cast<double*>(interf_tf32_b_tiles(v, N)), v.T, v.chan, L, N,
+                                                        v.n_tx, v.n_rx, v.N0, v.Kp, Ms, v.M, c0, scalar, k_isi);
+        else
+            build_b<false><<<bgrid, 256, bsm, d.stream>>>(v.Bbig, v.T, v.chan, L, N, v.n_tx, v.n_rx, v.N0, v.Kp, Ms, v.M, c0,
+                                                         scalar, k_isi);
         WOFDM_CUDA(h, cudaGetLastError());
         if (mode == 0) {
             constexpr size_t smem = (size_t)(2 * BM * AS + 2 * BK * BS) * sizeof(double);
             WOFDM_CUDA(h, cudaFuncSetAttribute(gemm_power_f64<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            gemm_power_f64<false><<<dim3(N / BN, 2 * N / BM, slices), 256, smem, d.stream>>>(v.Rbig, v.Bbig, v.P, N, v.Kp, Ms, c0, scalar);
+            gemm_power_f64<false><<<dim3(N / BN, 2 * N / BM, slices), 256, smem, d.stream>>>(v.Rbig, v.Bbig, v.P, N, v.Kp, Ms, c0, scalar, k_isi);
             WOFDM_CUDA(h, cudaGetLastError());
         } else {
-            rc = interf_gemm_tf32(h, sys, v, Ms, c0, slices, scalar);
+            rc = interf_gemm_tf32(h, sys, v, Ms, c0, slices, scalar, k_isi, tiled);
             if (rc) return rc;
         }
         h->launches += 2;
@@ -304,6 +368,7 @@ static int window_hessian_run(wofdm_handle h, const wofdm_sys_t* sys, const doub
     const int Kp = ((2 * n_rx + 63) / 64) * 64;
     const int M = 1 + (L - 1 + sys->tail_tx + n_rx - 1) / n_rx;
     const int Ms = 2;                                          // slice 0 and the sum of the ISI slices
+    const int k_isi = interf_isi_k(L, sys->tail_tx, n_rx, Kp);
     // basis windows = columns of reduce_variable_tx / _rx (optimization_tools/utils.py:13-73)
     std::vector<double> bt((size_t)n_tb * n_tx), br((size_t)n_rb * n_w), e(std::max(n_tb, n_rb));
     for (int b = 0; b < n_tb; ++b) {
@@ -336,8 +401,8 @@ static int window_hessian_run(wofdm_handle h, const wofdm_sys_t* sys, const doub
     // B_{b,ms} = H_ms . Tx_mat(t_b) for every Tx basis window
     for (int b = 0; b < n_tb; ++b) {
         build_tx_matrix<<<n_tx, 256, 0, d.stream>>>(d_T, d_bt + (size_t)b * n_tx, N, sys->cp, n_tx);
-        build_b<<<dim3((N + 255) / 256, n_rx, Ms), 256, 0, d.stream>>>(d_B + (size_t)b * Ms * Kp * N, d_T, d_chan, L, N, n_tx, n_rx,
-                                                                   n_rx, Kp, Ms, M, 0, 1);
+        build_b<false><<<dim3((N + 255) / 256, (Kp / 2 + BB - 1) / BB, Ms), 256, (size_t)(L + 2 * BB) * sizeof(double2), d.stream>>>(
+            d_B + (size_t)b * Ms * Kp * N, d_T, d_chan, L, N, n_tx, n_rx, n_rx, Kp, Ms, M, 0, 1, k_isi);
     }
     WOFDM_CUDA(h, cudaGetLastError());
     // X[a][b][ms] = Rbig(r_a) . B_{b,ms}: one stored contraction per Rx basis window over all Tx slices
@@ -346,7 +411,7 @@ static int window_hessian_run(wofdm_handle h, const wofdm_sys_t* sys, const doub
     for (int a = 0; a < n_rb; ++a) {
         build_rx_matrix<<<N, 256, 0, d.stream>>>(d_R, d_br + (size_t)a * n_w, N, sys->tail_rx, sys->rm, sys->shift, n_rx, Kp);
         gemm_power_f64<true><<<dim3(N / BN, 2 * N / BM, n_tb * Ms), 256, smem, d.stream>>>(
-            d_R, d_B, d_X + (size_t)a * n_tb * Ms * 2 * N * N, N, Kp, Ms, 0, 0);
+            d_R, d_B, d_X + (size_t)a * n_tb * Ms * 2 * N * N, N, Kp, Ms, 0, 0, k_isi);
     }
     WOFDM_CUDA(h, cudaGetLastError());
     gram_offdiag<<<n_var * (n_var + 1) / 2, 256, 0, d.stream>>>(d_X, d_H, n_var, N, n_tb);

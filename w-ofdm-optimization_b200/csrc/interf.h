@@ -9,13 +9,34 @@ struct InterfDev {
     double *vtx, *vrx;     // windows
     double2* chan;         // [C][L]
     double2* T;            // Tx_mat [n_tx][N]
-    double* Rbig;          // [2N][Kp] = [Rr -Ri; Ri Rr]
-    double* Bbig;          // [batch*Ms][Kp][N] = [Re B; Im B] per slice
+    double* Rbig;          // [2N][Kp], real form of Rx_mat, K interleaved (Re, Im) like Bbig's rows
+    double* Bbig;          // [batch*Ms][Kp][N], rows 2b / 2b+1 = Re / Im B[b] per slice
     double* P;             // [C][N] (or [C] in scalar mode)
     float* tf32_work;      // mode 1: Rhi, Rlo [2N][Kp] and Bhi, Blo [batch*M][N][Kp] (K-major hi/lo splits)
 };
 
 // TF32-split tensor-core contraction of one batch (interf_tf32.cu)
-int interf_gemm_tf32(wofdm_ctx* h, const wofdm_sys_t* sys, const InterfDev& v, int Ms, int c0, int slices, int scalar);
+// layout of the TF32 path's pre-tiled B operand (interf_tf32.cu): (row tile of TF32_TN columns j, K block of TF32_KB)
+// = one contiguous [hi | lo] pair of K-major no-swizzle UMMA tiles; element (j, kk) of slice s, nk = Kp / TF32_KB
+constexpr int TF32_TN = 256, TF32_KB = 32;
+__host__ __device__ inline size_t tf32_b_offset(int s, int nk, int j, int kk) {
+    const int kb = kk / TF32_KB, k = kk % TF32_KB;
+    const int c = (j >> 3) * (TF32_KB / 4 * 8) + (k >> 2) * 8 + (j & 7);      // 16-byte chunk inside the tile
+    return ((size_t)s * nk + kb) * (2 * (size_t)TF32_TN * TF32_KB) + (size_t)c * 4 + (k & 3);
+}
+// hi = fp32(x) with the 13 low mantissa bits cleared (a TF32 number), lo = fp32(x - hi)
+__host__ __device__ inline void tf32_split(double x, float& hi, float& lo) {
+    union { float f; unsigned u; } v;
+    v.f = (float)x;
+    v.u &= 0xffffe000u;
+    hi = v.f;
+    lo = (float)(x - (double)hi);
+}
+
+// k_isi: rows of K that exist for an ISI slice (interf.cu: interf_isi_k); slice 0 uses all Kp
+// b_tiled: build_b<true> already wrote the hi/lo tiles of B into the work buffer (no tile_split_b pass)
+int interf_gemm_tf32(wofdm_ctx* h, const wofdm_sys_t* sys, const InterfDev& v, int Ms, int c0, int slices, int scalar, int k_isi,
+                     bool b_tiled);
+float* interf_tf32_b_tiles(const InterfDev& v, int N);
 
 }  // namespace wofdm

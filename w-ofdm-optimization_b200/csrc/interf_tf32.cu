@@ -23,7 +23,7 @@ namespace wofdm {
 
 namespace {
 
-constexpr int TM = 128, TN = 256, KB = 32, NSTAGE = 2;
+constexpr int TM = 128, TN = TF32_TN, KB = TF32_KB, NSTAGE = 2;
 // Two CTAs that work on neighbouring row tiles of the same (channel, slice) form a thread-block cluster and share
 // the B operand: each fetches one half of a B stage and MULTICASTS it into both shared memories.  Without it the
 // persistent kernel pulls 96 KB per K block and SM out of L2 = 12.3 TB/s, which is the L2 limit, not the tensor pipe's.
@@ -81,7 +81,7 @@ constexpr int NTHREADS = 192;
 template <int CLUSTER>
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_power_tf32(const float* __restrict__ Rt, const float* __restrict__ Bt,
                                                               double* __restrict__ P, int N, int Kp, int Ms, int c0, int scalar,
-                                                              int n_tiles) {
+                                                              int n_tiles, int nk_isi) {
     extern __shared__ __align__(1024) unsigned char sm[];
     __shared__ __align__(8) unsigned long long full_bar[NSTAGE], empty_bar[NSTAGE], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_s;
@@ -120,7 +120,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_power_tf32(const float* __re
             for (int p = q0; p < n_pairs; p += nq) {
                 const float* ra = Rt + (size_t)((p % ppairs) * CLUSTER + rank) * nk * (2 * TM * KB);
                 const float* rb = Bt + (size_t)(p / ppairs) * nk * (2 * TN * KB);
-                for (int kb = 0; kb < nk; ++kb, ++it) {
+                const int nk_t = ((p / ppairs) % Ms) == 0 ? nk : nk_isi;        // ISI slices: non-zero K prefix only
+                for (int kb = 0; kb < nk_t; ++kb, ++it) {
                     const int st = it % NSTAGE;
                     if (it >= NSTAGE) mbar_wait(smem_u32(&empty_bar[st]), (uint32_t)(((it / NSTAGE) - 1) & 1));
                     const uint32_t bar = smem_u32(&full_bar[st]), dst = smem_u32(sm + (size_t)st * STAGE_BYTES);
@@ -147,7 +148,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_power_tf32(const float* __re
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
                 const uint32_t tacc = tmem + (uint32_t)(buf * TN);
-                for (int kb = 0; kb < nk; ++kb, ++it) {
+                const int nk_t = ((p / ppairs) % Ms) == 0 ? nk : nk_isi;
+                for (int kb = 0; kb < nk_t; ++kb, ++it) {
                     const int st = it % NSTAGE;
                     mbar_wait(smem_u32(&full_bar[st]), (uint32_t)((it / NSTAGE) & 1));
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -241,9 +243,11 @@ __global__ void tile_split_r(const double* __restrict__ Rbig, float* __restrict_
 
 // Bbig [slice][kk][j] fp64 -> Bt tiles [slice][kb][hi|lo][chunk][4]: 32 x 32 (kk x j) tiles through smem, each thread
 // writes the float4 of 4 consecutive kk for one row j; a warp writes 512 contiguous bytes
-__global__ void __launch_bounds__(256) tile_split_b(const double* __restrict__ Bbig, float* __restrict__ Bt, int N, int Kp) {
+__global__ void __launch_bounds__(256) tile_split_b(const double* __restrict__ Bbig, float* __restrict__ Bt, int N, int Kp,
+                                                    int Ms, int nk_isi) {
     __shared__ double tile[32][33];
     const int s = blockIdx.z, kb = blockIdx.y, j0 = blockIdx.x * 32, nk = Kp / KB;
+    if ((s % Ms) != 0 && kb >= nk_isi) return;               // K blocks an ISI slice does not have
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const double* src = Bbig + (size_t)s * Kp * N;
     for (int i = ty; i < 32; i += 8) tile[i][tx] = src[(size_t)(kb * 32 + i) * N + j0 + tx];
@@ -262,7 +266,10 @@ __global__ void __launch_bounds__(256) tile_split_b(const double* __restrict__ B
     *reinterpret_cast<float4*>(dst + (size_t)TN * KB + c * 4) = lo;
 }
 
-int interf_gemm_tf32(wofdm_ctx* h, const wofdm_sys_t* sys, const InterfDev& v, int Ms, int c0, int slices, int scalar) {
+float* interf_tf32_b_tiles(const InterfDev& v, int N) { return v.tf32_work + (size_t)2 * 2 * N * v.Kp; }
+
+int interf_gemm_tf32(wofdm_ctx* h, const wofdm_sys_t* sys, const InterfDev& v, int Ms, int c0, int slices, int scalar,
+                     int k_isi, bool b_tiled) {
     DeviceCtx& d = h->devs[0];
     const int N = sys->N;
     if (N != TN) return fail(h, WOFDM_EUNSUPPORTED, "TF32-split interference path is built for N = 256");
@@ -272,7 +279,8 @@ int interf_gemm_tf32(wofdm_ctx* h, const wofdm_sys_t* sys, const InterfDev& v, i
     float* Rt = v.tf32_work;
     float* Bt = Rt + nr;
     tile_split_r<<<128, 256, 0, d.stream>>>(v.Rbig, Rt, 2 * N, v.Kp);
-    tile_split_b<<<dim3(N / 32, v.Kp / KB, slices), 256, 0, d.stream>>>(v.Bbig, Bt, N, v.Kp);
+    const int nk_isi = k_isi / KB;
+    if (!b_tiled) tile_split_b<<<dim3(N / 32, v.Kp / KB, slices), 256, 0, d.stream>>>(v.Bbig, Bt, N, v.Kp, Ms, nk_isi);
     WOFDM_CUDA(h, cudaGetLastError());
     const size_t smem = (size_t)NSTAGE * STAGE_BYTES;
     const int n_tiles = (2 * N / TM) * slices;
@@ -290,7 +298,7 @@ int interf_gemm_tf32(wofdm_ctx* h, const wofdm_sys_t* sys, const InterfDev& v, i
         WOFDM_CUDA(h, cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg));
         if (ncl < 1) return fail(h, WOFDM_EUNSUPPORTED, "no cluster of the TF32 contraction kernel fits the device");
         cfg.gridDim = dim3(CL * std::min(n_tiles / CL, ncl));
-        WOFDM_CUDA(h, cudaLaunchKernelEx(&cfg, kern, (const float*)Rt, (const float*)Bt, v.P, N, v.Kp, Ms, c0, scalar, n_tiles));
+        WOFDM_CUDA(h, cudaLaunchKernelEx(&cfg, kern, (const float*)Rt, (const float*)Bt, v.P, N, v.Kp, Ms, c0, scalar, n_tiles, nk_isi));
         return WOFDM_OK;
     };
     static_assert((2 * TN / TM) % 2 == 0, "row tiles pair up inside a cluster");
