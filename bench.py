@@ -299,7 +299,11 @@ def main():
                                         "MEASURED_PEAKS.json has no FP32 entry (HBM/bf16 only); nominal 74.4 TFLOP/s",
                          "flops_per_symbol": {"fft": f_fft, "conv": f_conv, "misc": f_misc, "chain": f_chain},
                          "kernel_ms": kms, "achieved_fft_only": f_fft * syms_rank / (kms * 1e-3) / 1e12,
-                         "hbm_note": "HBM traffic ~0 (counters only): 'hbm'/'tensor' do not bound this kernel"},
+                         "hbm_note": "HBM traffic ~0 (counters only): 'hbm'/'tensor' do not bound this kernel",
+                         "bound_note": "on-chip bound: the denominator is the FP32 FMA peak the north star names; the kernel's real "
+                                       "limits are the math dispatch port (FFMA2/IMAD/LOP3 = 2 cycles per warp instruction, no "
+                                       "co-issue of integer work with packed FP32) and shared-memory wavefronts -- DESIGN.md section 3, "
+                                       "tools/ubench/pipes*.cu"},
             "ber_check": {"snr_db": [float(snr[k]) for k in (0, 10, 15, 20, 29)],
                           "ber": [float(be[k] / max(bt[k], 1)) if world == 1 else float(be[k] / (bt[k])) for k in (0, 10, 15, 20, 29)]},
         }
