@@ -216,3 +216,45 @@ def test_sharding_is_exact(handle):
     for k in full:
         assert np.array_equal(full[k], acc[k]), k
     assert np.all(np.diff(full["sym_err"]) < 0)      # SER falls with SNR
+
+
+@pytest.mark.parametrize("precision", [1, 0])
+def test_smallest_shapes_and_degenerate_jobs(handle, precision):
+    """Edge cases of the domain: a two-symbol frame (pilot + one data symbol), a one-tap (flat) channel, one channel,
+    one SNR point, ensemble 1, no windows at all (CP-OFDM) and windows with the shortest tails -- production counters
+    replayed through the oracle from the exported draws."""
+    for name, N, cp, ttx, trx, S, L, bits in (("CP", 256, 16, 0, 0, 2, 1, 4), ("WOLA", 256, 10, 2, 2, 2, 3, 2),
+                                               ("CPW", 64, 8, 2, 2, 3, 1, 6), ("wtx", 16, 4, 2, 0, 2, 2, 2)):
+        p = O.system_params(name, N, cp, ttx, trx, S=S, bits=bits, noise_norm=1, constellation=1)
+        vt, vr = O.rc_window_tx(p), O.rc_window_rx(p)
+        chan = O.synth_channels(1, max(L, 2), seed=9)[:L]
+        s = to_sys(p, precision)
+        res = handle.ber_run(s, vt, vr, chan, [17.0], 1, seed=8)
+        sym, nz = handle.ber_draws(s, L, 8, 0, np.arange(1))
+        r = O.frame_chain_structured(p, vt, vr, chan[:, 0], 17.0, sym[0].T, nz[0])
+        assert res["sym_tot"][0] == N * (S - 1) and res["bit_tot"][0] == N * (S - 1) * bits
+        tol = 0 if precision == 1 else 3
+        assert abs(int(res["sym_err"][0]) - r.sym_err) <= tol and abs(int(res["bit_err"][0]) - r.bit_err) <= tol + 1
+
+
+def test_invalid_arguments_are_rejected(handle):
+    """Error behaviour of the boundary: negative WOFDM_E* codes surface as WofdmError, nothing is launched."""
+    good = W.params_from_name("WOLA", 256, 16, 8, 10, bits=4, S=16)
+    vt, vr = W.capi.rc_window_tx(good), W.capi.rc_window_rx(good)
+    chan = O.synth_channels(2, 21, seed=1)
+    before = handle.launches
+    for field, value in (("N", 200), ("bits", 3), ("S", 1), ("tail_rx", 5), ("cp", -1), ("rm", 7), ("noise_norm", 2),
+                         ("constellation", 3), ("precision", 2), ("shift", 256)):
+        bad = W.SysT(**{f: getattr(good, f) for f, _ in good._fields_})
+        setattr(bad, field, value)
+        with pytest.raises(W.WofdmError):
+            handle.ber_run(bad, vt, vr, chan, [10.0], 1, seed=0)
+    with pytest.raises(W.WofdmError):
+        handle.ber_run(good, vt, vr, chan, [10.0], 0, seed=0)            # ensemble must be >= 1
+    with pytest.raises(W.WofdmError):
+        handle.ber_run(good, vt, vr, chan, [10.0], 1, seed=0, shard=(3, 2))
+    with pytest.raises(W.WofdmError):
+        handle.interf_power(good, vt, vr, chan, mode=5)
+    with pytest.raises(W.WofdmError):
+        W.params_from_name("OFDMA", 256, 16, 8, 10)
+    assert handle.launches == before
