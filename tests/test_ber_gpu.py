@@ -258,3 +258,26 @@ def test_invalid_arguments_are_rejected(handle):
     with pytest.raises(W.WofdmError):
         W.params_from_name("OFDMA", 256, 16, 8, 10)
     assert handle.launches == before
+
+
+def test_full_size_properties_configs1(handle):
+    """BASELINE configs[1] at its full size (250 channels x 30 SNR points x ensemble 27 = 202 500 frames, 1e8 bits per
+    point), checked through size-independent properties: exact totals, shard additivity, BER ~ 1/2 at -20 dB,
+    monotone in SNR up to its Monte-Carlo error, the error floor of the interference-limited regime at +50 dB."""
+    s = W.params_from_name("wtx", 256, 16, 8, 0, bits=4, S=16, noise_norm=1, constellation=1)
+    x_tx = np.concatenate([[1.0], np.clip(W.capi.rc_window_tx(s)[-8:] * (1 + 0.1 * np.random.default_rng(7).uniform(-1, 1, 8)), 0, 1)])
+    vt, vr = W.capi.expand_window_tx(s, x_tx), W.capi.rc_window_rx(s)
+    chan = O.synth_channels(250, 21, seed=1)
+    snr = np.linspace(-20, 50, 30)
+    full = handle.ber_run(s, vt, vr, chan, snr, 27, seed=2024)
+    assert np.all(full["bit_tot"] == 250 * 27 * 256 * 4 * 15) and np.all(full["sym_tot"] == 250 * 27 * 256 * 15)
+    parts = [handle.ber_run(s, vt, vr, chan, snr, 27, seed=2024, shard=(i, 2)) for i in range(2)]
+    for k in full:
+        assert np.array_equal(full[k], parts[0][k] + parts[1][k]), k
+    ber = full["bit_err"] / full["bit_tot"]
+    assert abs(ber[0] - 0.5) < 0.01
+    se = np.sqrt(ber * (1 - ber) / (250 * 27 * 15))              # per-frame granularity: a conservative standard error
+    assert np.all(np.diff(ber) <= 4 * (se[1:] + se[:-1]))
+    assert 0 < ber[-1] < 0.05 and ber[-1] < ber[10]
+    # symbol errors dominate bit errors, and a wrong symbol has 1..4 wrong bits
+    assert np.all(full["sym_err"] <= full["bit_err"]) and np.all(full["bit_err"] <= 4 * full["sym_err"])
