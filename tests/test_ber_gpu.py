@@ -281,3 +281,41 @@ def test_full_size_properties_configs1(handle):
     assert 0 < ber[-1] < 0.05 and ber[-1] < ber[10]
     # symbol errors dominate bit errors, and a wrong symbol has 1..4 wrong bits
     assert np.all(full["sym_err"] <= full["bit_err"]) and np.all(full["bit_err"] <= 4 * full["sym_err"])
+
+
+@pytest.mark.parametrize("cp", [10, 22, 32])
+@pytest.mark.parametrize("name", O.SYSTEMS)
+def test_verify_every_system_over_the_cp_range(handle, name, cp):
+    """settingsData's CP range (10..32) for all seven systems at N = 256, fp32, both channel policies: exercises the
+    prefix / suffix copies of the circular-interior kernel (cp > tail_tx + L - 1, cs > tail_tx) and the outer-row
+    logic of the direct kernels, which the CP = 16 goldens do not reach."""
+    ttx = 8 if name in ("CPW", "WOLA", "CPwtx", "wtx") else 0
+    trx = 10 if name in ("CPW", "WOLA", "CPwrx", "wrx") else 0
+    p = O.system_params(name, 256, cp, ttx, trx, S=16, bits=4, noise_norm=cp % 4 == 0, constellation=1)
+    vt, vr, _, _ = O.perturbed_windows(p, seed=cp)
+    rng = np.random.default_rng(cp)
+    frames = []
+    for k in range(2):
+        h = O.synth_channels(1, 21, seed=cp + k)[:, 0]
+        n = O.noise_len(p, 21)
+        frames.append((h, 8.0 + 15 * k, rng.integers(0, 16, size=(256, 16)), rng.standard_normal(n) + 1j * rng.standard_normal(n)))
+    check_frames(handle, p, vt, vr, frames, 0)
+    check_frames(handle, p, vt, vr, frames, 0, direct=True)
+
+
+@pytest.mark.parametrize("name,cp", [("WOLA", 40), ("CPW", 128), ("CPwtx", 96), ("wrx", 72), ("CP", 128)])
+def test_verify_cluster_kernel_over_shapes(handle, name, cp):
+    """N = 1024 (2-CTA cluster kernel), 4x scaled tails, other CP lengths than the stress configuration's 64."""
+    ttx = 32 if name in ("CPW", "WOLA", "CPwtx", "wtx") else 0
+    trx = 40 if name in ("CPW", "WOLA", "CPwrx", "wrx") else 0
+    p = O.system_params(name, 1024, cp, ttx, trx, S=16, bits=6, noise_norm=1, constellation=1)
+    vt, vr, _, _ = O.perturbed_windows(p, seed=cp)
+    rng = np.random.default_rng(cp)
+    h = O.synth_channels(1, 21, seed=cp)[:, 0]
+    n = O.noise_len(p, 21)
+    frames = [(h, 22.0, rng.integers(0, 64, size=(1024, 16)), rng.standard_normal(n) + 1j * rng.standard_normal(n))]
+    check_frames(handle, p, vt, vr, frames, 0)
+    s = to_sys(p, 0)
+    plan = handle.ber_plan(s, vt, vr, h[:, None], [22.0])
+    assert "_cl2" in plan.kernel, plan.kernel
+    plan.close()
