@@ -116,3 +116,28 @@ def test_interf_power_mirror(handle, tmp_path):
     assert np.allclose(Pc, O.interf_power_dense(pc, np.ones(pc.n_tx), np.ones(256), chans.mean(axis=1)), rtol=1e-9)
     Pall, _ = U.interf_power("CPW", [vt, vr], 256, 16, 8, 10, channel_path=str(path), per_channel=True)
     assert Pall.shape == (6, 256)
+
+
+@pytest.mark.parametrize("name", O.SYSTEMS)
+def test_production_ser_against_the_reference_itself(handle, name):
+    """North star: production-mode SER inside the reference's confidence interval at every SNR point.  The golden
+    holds SER curves from the REFERENCE's own jitted Monte-Carlo loops (tests/golden/make_golden_stat.py: 4 channels x
+    ensemble 150 = 600 frames per point).  The device repeats that experiment 24 times with different seeds (its own
+    Philox draws); the reference's estimate must be a plausible draw of that sampling distribution (|z| <= 3.5 at all
+    5 x 2 points) and agree with the device's long-run mean within 3.5 standard errors."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ser_statistical.npz"))
+    ttx = 8 if name in U.TX_SYSTEMS else 0
+    trx = 10 if name in U.RX_SYSTEMS else 0
+    p = O.system_params(name, int(g["N"]), int(g["cp"]), ttx, trx, S=int(g["S"]))
+    s = W.SysT(N=p.N, cp=p.cp, cs=p.cs, tail_tx=p.tail_tx, tail_rx=p.tail_rx, rm=p.rm, shift=p.shift, bits=4, S=p.S,
+               noise_norm=0, constellation=0, precision=0)
+    windows = [(g[f"vtx_{name}"], g[f"vrx_{name}"])]
+    if name != "CP":
+        windows.append((O.rc_window_tx(p), O.rc_window_rx(p)))
+    ref = g[f"ser_{name}"]
+    for w, (vt, vr) in enumerate(windows):
+        runs = np.array([(lambda r: r["sym_err"] / r["sym_tot"])(
+            handle.ber_run(s, vt, vr, g["channels"], g["snr"], int(g["ensemble"]), seed=1000 + k, variant=w)) for k in range(24)])
+        mean, std = runs.mean(axis=0), runs.std(axis=0, ddof=1)
+        z = (ref[w] - mean) / np.sqrt(std ** 2 * (1 + 1 / 24))
+        assert np.all(np.abs(z) <= 3.5), (name, w, z, ref[w], mean)
