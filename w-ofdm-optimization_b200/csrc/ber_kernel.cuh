@@ -135,8 +135,7 @@ __device__ __forceinline__ void noise_pair(const BerParams& prm, long long f, ui
     const uint4 r = philox4x32_10(make_uint4((uint32_t)f, (uint32_t)((unsigned long long)f >> 32), q,
                                              STREAM_NOISE + prm.variant),
                                   (uint32_t)prm.seed, (uint32_t)(prm.seed >> 32));
-    n0 = gauss_pair(r.x, r.y, T());
-    n1 = gauss_pair(r.z, r.w, T());
+    gauss_quad(r, n0, n1, T());
 }
 // noise of stream sample i (any policy): draw index (i/B)*(B+1) + i%B
 template <typename T>

@@ -103,6 +103,34 @@ __device__ __forceinline__ float2 gauss_pair(uint32_t w0, uint32_t w1, float) {
     asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(th));
     return make_float2(r * c, r * s);
 }
+// Two complex samples from one Philox call (words x,y -> n0; z,w -> n1): the same arithmetic as gauss_pair, with the
+// scalar FP32 steps of the two samples paired into packed instructions (a scalar FFMA/FMUL next to FFMA2s costs
+// almost as much dispatch time as a packed one).  Bit-identical to two gauss_pair calls.
+__device__ __forceinline__ void gauss_quad(uint4 r, float2& n0, float2& n1, float) {
+    const float2 u = fma2(make_float2(__uint2float_rn(r.x), __uint2float_rn(r.z)),
+                          make_float2(2.3283064365386963e-10f, 2.3283064365386963e-10f),
+                          make_float2(1.1641532182693481e-10f, 1.1641532182693481e-10f));
+    float2 lg, rr;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg.x) : "f"(u.x));
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg.y) : "f"(u.y));
+    const float2 t = mul2(lg, make_float2(-1.3862943611198906f, -1.3862943611198906f));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rr.x) : "f"(t.x));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rr.y) : "f"(t.y));
+    const float2 th = mul2(make_float2(__int2float_rn((int32_t)r.y), __int2float_rn((int32_t)r.w)),
+                           make_float2(1.4629180792671596e-09f, 1.4629180792671596e-09f));
+    float s0, c0, s1, c1;
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s0) : "f"(th.x));
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c0) : "f"(th.x));
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s1) : "f"(th.y));
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c1) : "f"(th.y));
+    n0 = mul2(make_float2(c0, s0), make_float2(rr.x, rr.x));
+    n1 = mul2(make_float2(c1, s1), make_float2(rr.y, rr.y));
+}
+__device__ __forceinline__ double2 gauss_pair(uint32_t w0, uint32_t w1, double);
+__device__ __forceinline__ void gauss_quad(uint4 r, double2& n0, double2& n1, double) {
+    n0 = gauss_pair(r.x, r.y, double());
+    n1 = gauss_pair(r.z, r.w, double());
+}
 __device__ __forceinline__ double2 gauss_pair(uint32_t w0, uint32_t w1, double) {
     const double u = ((double)w0 + 0.5) * 2.3283064365386963e-10;
     const double r = sqrt(-2.0 * log(u));
