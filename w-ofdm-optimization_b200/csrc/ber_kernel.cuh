@@ -127,7 +127,8 @@ __device__ __forceinline__ void load_sym_idx(const BerParams& prm, long long f, 
         w[0] = r.x & mask; w[1] = r.y & mask; w[2] = r.z & mask; w[3] = r.w & mask;
     }
 }
-__device__ __forceinline__ int sym_byte(const uint32_t (&w)[4], int q) { return (w[q >> 2] >> (8 * (q & 3))) & 0xff; }
+// (one PRMT: byte q&3 of the word, zero-extended)
+__device__ __forceinline__ int sym_byte(const uint32_t (&w)[4], int q) { return (int)__byte_perm(w[q >> 2], 0u, 0x4440u + (unsigned)(q & 3)); }
 
 // complex noise draws 2q and 2q+1 of frame f
 template <typename T>
