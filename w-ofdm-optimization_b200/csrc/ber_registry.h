@@ -63,5 +63,6 @@ struct BerVariantImpl {
 void register_ber_f32_staged(std::vector<BerVariant>& out);
 void register_ber_f64_staged(std::vector<BerVariant>& out);
 void register_ber_f32_regs(std::vector<BerVariant>& out);
+void register_ber_f32_regs_big(std::vector<BerVariant>& out);
 
 }  // namespace wofdm
