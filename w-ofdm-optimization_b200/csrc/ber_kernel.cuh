@@ -15,8 +15,9 @@
 //   TC == 0  "staged": any L, any tail sizes; convolution output staged in a second buffer, noise
 //            regenerated in the second pass.  Used for fp64 and for shapes without a tuned variant.
 //   TC  > 0  "regs"  : each thread owns one chunk of <= TC consecutive stream samples; the chunk's
-//            convolution output AND its noise stay in registers across the frame-wide power
-//            reduction, taps live in registers LB at a time.  fp32 production path.
+//            convolution output stays in registers across the frame-wide power reduction (its noise,
+//            generated inside the same loop, is parked in shared memory), all LB taps live in
+//            registers.  fp32 production path.
 // CIRC (regs policy, CL == 1): the ISI-free interior of every symbol -- outputs whose L inputs all lie in the flat part
 // of that symbol's own Tx window, stride - (tail_tx + L - 1) of stride samples -- is a CIRCULAR convolution of the
 // symbol with the taps, so it is taken as IFFT(H o X) (one more register FFT per symbol) instead of L complex MACs
