@@ -15,6 +15,7 @@
 //       dimension, with the off-diagonal mask and the row-wise sum of |.|^2 fused into the epilogue.
 // The TF32-split tensor path (mode 1) lives in interf_tf32.cu.
 #include <algorithm>
+#include <type_traits>
 
 #include "host_common.h"
 #include "interf.h"
@@ -72,7 +73,9 @@ __host__ __device__ inline int interf_isi_k(int L, int tail_tx, int n_rx, int Kp
     return k < Kp ? k : Kp;
 }
 // TILED: the TF32 path's operand is written directly (hi/lo split, UMMA tiles, float4 per 4 consecutive kk); Bbig is
-// then the float work buffer and the fp64 B matrix never exists.
+// then the float work buffer and the fp64 B matrix never exists.  That path is fp32-grade by contract (3xTF32), so
+// its band product runs in packed FP32 (taps and Tx_mat rounded to fp32, fp32 accumulation: ~1e-7 relative, far
+// inside the stated bound) instead of FP64 FMAs, which bound the fp64 variant of this kernel.
 template <bool TILED>
 __global__ void __launch_bounds__(256) build_b(double* __restrict__ Bbig, const double2* __restrict__ T,
                                                const double2* __restrict__ chan, int L, int N, int n_tx, int n_rx,
@@ -85,14 +88,18 @@ __global__ void __launch_bounds__(256) build_b(double* __restrict__ Bbig, const 
     const int c = c0 + s / Ms, ms = s % Ms;
     const int k_rows = ms == 0 ? Kp : k_isi;                 // rows of this slice that exist for the contraction
     if (2 * b0 >= k_rows) return;                            // (uniform per block)
-    for (int l = threadIdx.x; l < L + 2 * BB; l += blockDim.x)
-        hs_raw[l] = (l >= BB && l < L + BB) ? chan[(size_t)c * L + l - BB] : make_double2(0.0, 0.0);
+    using A2 = typename std::conditional<TILED, float2, double2>::type;    // accumulation type
+    A2* const hs = reinterpret_cast<A2*>(hs_raw);
+    for (int l = threadIdx.x; l < L + 2 * BB; l += blockDim.x) {
+        const double2 t = (l >= BB && l < L + BB) ? chan[(size_t)c * L + l - BB] : make_double2(0.0, 0.0);
+        hs[l].x = t.x; hs[l].y = t.y;
+    }
     __syncthreads();
     if (j >= N) return;
-    const double2* h = hs_raw + BB;                          // h[-BB .. L+BB)
-    double2 acc[BB];
+    const A2* h = hs + BB;                                   // h[-BB .. L+BB)
+    A2 acc[BB];
 #pragma unroll
-    for (int i = 0; i < BB; ++i) acc[i] = make_double2(0.0, 0.0);
+    for (int i = 0; i < BB; ++i) { acc[i].x = 0; acc[i].y = 0; }
     const int m_lo = ms, m_hi = (sum_isi && ms == 1) ? M - 1 : ms;
     if (b0 < n_rx) {
         for (int m = m_lo; m <= m_hi; ++m) {
@@ -101,8 +108,10 @@ __global__ void __launch_bounds__(256) build_b(double* __restrict__ Bbig, const 
             for (int rr = 0; rr < BB + L - 1; ++rr) {
                 const int row = r_lo + rr;
                 if (row < 0 || row >= n_tx) continue;
-                const double2 x = T[(size_t)row * N + j];
-                const double2* hw = h + (L - 1) - rr;         // tap of output i: hw[i] (zero outside [0, L))
+                const double2 xd = T[(size_t)row * N + j];
+                A2 x;
+                x.x = xd.x; x.y = xd.y;
+                const A2* hw = h + (L - 1) - rr;              // tap of output i: hw[i] (zero outside [0, L))
 #pragma unroll
                 for (int i = 0; i < BB; ++i) cmac(acc[i], hw[i], x);
             }
