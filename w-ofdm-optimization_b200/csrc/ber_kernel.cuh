@@ -511,12 +511,12 @@ ber_frame_kernel(const BerParams prm) {
             }
             if (prm.noise_norm == 1) {
                 // the L-1+beta samples the reference truncates still count in both power sums
-                for (int i = sec + tid; i < body + L - 1; i += NT) {
-                    C2 a = tail_output<T, LB>(taps, ub, i, body);
+                // (signal part on the first threads, noise part on the last ones: two warps share the extra latency)
+                for (int i = sec + tid; i < body + L - 1; i += NT) pr2 = csq_acc(tail_output<T, LB>(taps, ub, i, body), pr2);
+                for (int i = sec + (NT - 1 - tid); i < body + L - 1; i += NT) {
                     C2 n0;
                     if constexpr (VERIFY) n0 = to_v2<T>(prm.noise_in[(size_t)f * prm.noise_len + i]);
                     else n0 = noise_at<T>(prm, f, i);
-                    pr2 = csq_acc(a, pr2);
                     pn2 = csq_acc(n0, pn2);
                 }
             }
@@ -608,12 +608,12 @@ ber_frame_kernel(const BerParams prm) {
             for (int o = 0; o < TC; ++o) pr2 = csq_acc(acc[o], pr2);
             if (prm.noise_norm == 1 && last_rank) {
                 // the L-1+beta samples the reference truncates still count in both power sums
-                for (int i = sec + tid; i < body + L - 1; i += NT) {
-                    C2 a = tail_output<T, LB>(taps, ub, i, body);
+                // (signal part on the first threads, noise part on the last ones: two warps share the extra latency)
+                for (int i = sec + tid; i < body + L - 1; i += NT) pr2 = csq_acc(tail_output<T, LB>(taps, ub, i, body), pr2);
+                for (int i = sec + (NT - 1 - tid); i < body + L - 1; i += NT) {
                     C2 n0;
                     if constexpr (VERIFY) n0 = to_v2<T>(prm.noise_in[(size_t)f * prm.noise_len + (size_t)rank * sec + i]);
                     else n0 = noise_at<T>(prm, f, rank * sec + i);   // (same numbering: noise_at splits at prm.split = sec)
-                    pr2 = csq_acc(a, pr2);
                     pn2 = csq_acc(n0, pn2);
                 }
             }
