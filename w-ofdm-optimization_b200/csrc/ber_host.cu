@@ -181,6 +181,7 @@ size_t elem_bytes(const wofdm_sys_t& s) { return s.precision == 1 ? sizeof(doubl
 static int plan_create_impl(wofdm_handle h, const wofdm_sys_t* sys, const double* win_tx, const double* win_rx,
                             const double* chan, int L, int C, const double* snr_db, int n_snr,
                             wofdm_ber_plan* out, bool transient) {
+    NvtxRange nvtx_("wofdm_ber_plan_create");
     if (!h) return WOFDM_EINVAL;
     if (!out) return fail(h, WOFDM_EINVAL, "plan out pointer is NULL");
     *out = nullptr;
@@ -263,6 +264,7 @@ int wofdm_ber_plan_create(wofdm_handle h, const wofdm_sys_t* sys, const double* 
 
 int wofdm_ber_plan_launch(wofdm_ber_plan p, int slot, int64_t ensemble, uint64_t seed, uint32_t variant,
                           int shard_index, int shard_count, void* stream, void** d_counters) {
+    NvtxRange nvtx_("wofdm_ber_plan_launch");
     if (!p) return WOFDM_EINVAL;
     wofdm_ctx* h = p->ctx;
     if (slot < 0 || slot >= (int)p->devs.size()) return fail(h, WOFDM_EINVAL, "device slot out of range");
@@ -344,6 +346,7 @@ int wofdm_ber_run_shard(wofdm_handle h, const wofdm_sys_t* sys, const double* wi
                         const double* chan, int L, int C, const double* snr_db, int n_snr, int64_t ensemble,
                         uint64_t seed, uint32_t variant, int shard_index, int shard_count,
                         int64_t* bit_err, int64_t* bit_tot, int64_t* sym_err, int64_t* sym_tot) {
+    NvtxRange nvtx_("wofdm_ber_run_shard");
     if (!h) return WOFDM_EINVAL;
     if (!bit_err || !bit_tot || !sym_err || !sym_tot) return fail(h, WOFDM_EINVAL, "NULL output buffer");
     if (shard_count < 1 || shard_index < 0 || shard_index >= shard_count) return fail(h, WOFDM_EINVAL, "bad shard");
@@ -386,6 +389,7 @@ int wofdm_ber_verify(wofdm_handle h, const wofdm_sys_t* sys, const double* win_t
                      const double* chan, int L, int F, const double* snr_db,
                      const int32_t* sym_idx, const double* noise, int variant_kernel,
                      double* eq_out, int32_t* dec_idx, int64_t* bit_err, int64_t* sym_err) {
+    NvtxRange nvtx_("wofdm_ber_verify");
     if (!h) return WOFDM_EINVAL;
     int rc = validate_sys(h, sys, L);
     if (rc) return rc;
@@ -472,6 +476,7 @@ int wofdm_ber_verify(wofdm_handle h, const wofdm_sys_t* sys, const double* win_t
 
 int wofdm_ber_draws(wofdm_handle h, const wofdm_sys_t* sys, int L, uint64_t seed, uint32_t variant,
                     const int64_t* frame_ids, int F, int32_t* sym_idx, double* noise) {
+    NvtxRange nvtx_("wofdm_ber_draws");
     if (!h) return WOFDM_EINVAL;
     int rc = validate_sys(h, sys, L);
     if (rc) return rc;

@@ -127,6 +127,7 @@ int wofdm_channel_profile(const char* standard) {
 
 int wofdm_gen_channels(wofdm_handle h, int profile, int L, double doppler_freq, double sampling_rate, double frame_duration,
                        int no_frames, int n_sets, uint64_t seed, const double* phases, double* chan) {
+    NvtxRange nvtx_("wofdm_gen_channels");
     if (!h) return WOFDM_EINVAL;
     if (profile < 0 || profile > 3) return fail(h, WOFDM_EINVAL, "unknown ITU-R channel profile");
     if (L < 1 || no_frames < 1 || n_sets < 1 || !chan) return fail(h, WOFDM_EINVAL, "bad channel-generation arguments");

@@ -7,6 +7,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/wofdm.h"
 #include "ber_registry.h"
 
@@ -32,6 +34,14 @@ struct wofdm_ctx {
 };
 
 namespace wofdm {
+
+// NVTX range around a C-ABI entry point (header-only NVTX v3: a no-op unless a profiler is attached)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 inline int fail(wofdm_ctx* h, int code, const std::string& msg) {
     if (h) h->err = msg;

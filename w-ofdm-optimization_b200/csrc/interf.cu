@@ -284,6 +284,7 @@ int interf_upload(wofdm_ctx* h, const wofdm_sys_t* sys, const double* win_tx, co
 
 static int interf_run(wofdm_handle h, const wofdm_sys_t* sys, const double* win_tx, const double* win_rx,
                       const double* chan, int L, int C, int mode, int scalar, double* P) {
+    NvtxRange nvtx_("wofdm_interf_power");
     if (!h) return WOFDM_EINVAL;
     int rc = validate_sys(h, sys, L);
     if (rc) return rc;
@@ -364,6 +365,7 @@ __global__ void __launch_bounds__(256) gram_offdiag(const double* __restrict__ X
 }
 
 static int window_hessian_run(wofdm_handle h, const wofdm_sys_t* sys, const double* chan, int L, double* H_out, int* n_var_out) {
+    NvtxRange nvtx_("wofdm_window_hessian");
     if (!h) return WOFDM_EINVAL;
     int rc = validate_sys(h, sys, L);
     if (rc) return rc;
