@@ -48,6 +48,22 @@ def test_device_matches_golden_with_injected_phases(k):
 
 
 @pytest.mark.gpu
+def test_long_record_is_spread_over_blocks():
+    """no_frames beyond one CTA's share (two-pass energy): still the oracle's values, and the record's energy per path
+    is the profile power."""
+    import wofdm_b200 as W
+    rng = np.random.default_rng(3)
+    phases = rng.standard_normal((1, 6, 21, 2))
+    frames = 1700
+    with W.Handle([0]) as h:
+        got = h.gen_channels("vehicularA", 21, float(G["fd"]), float(G["fs"]), float(G["frame"]), no_frames=frames, n_sets=1,
+                             phases=phases)
+    ref = O.gen_chan("vehicularA", 21, float(G["fd"]), float(G["fs"]), float(G["frame"]), frames, phases[0])
+    assert got.shape == ref.shape == (21, frames)
+    assert np.abs(got - ref).max() <= REL * np.abs(ref).max()
+
+
+@pytest.mark.gpu
 def test_production_draws_and_driver_mirror(tmp_path):
     """On-device Philox phases: deterministic per seed, independent sets, and -- one frame per set, as the reference's
     driver stores channels -- every path has exactly its profile power with a uniform phase, so the mean tap energy

@@ -31,7 +31,11 @@ struct ChanGenParams {
     const double* phases_in;         // [set][path][osc][2] or NULL
     unsigned long long seed;
     double2* out;                    // [set][frame][L]
+    // long records (no_frames > CG_FRAMES_PER_BLOCK): a set is spread over n_blk CTAs, energies meet in `partial`
+    int n_blk;
+    double* partial;                 // [set][n_blk][CG_MAXP]
 };
+constexpr int CG_FRAMES_PER_BLOCK = 4 * CG_THREADS;
 
 __device__ __forceinline__ double2 chan_waveform(const ChanGenParams& p, const double* ph, int w, double t) {
     const double pi = 3.141592653589793;
@@ -50,6 +54,10 @@ __device__ __forceinline__ double2 chan_waveform(const ChanGenParams& p, const d
     return make_double2(sc * re, sc * im);
 }
 
+// PHASE 0: one CTA per set does everything (the reference's use: short sets).  Long records run twice over a grid of
+// (set, frame block): PHASE 1 leaves every block's path energies in p.partial, PHASE 2 adds them in block order
+// (every CTA of the set forms the same scale) and writes the block's taps.
+template <int PHASE>
 __global__ void __launch_bounds__(CG_THREADS) chan_gen_kernel(const ChanGenParams p) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     double* ph = reinterpret_cast<double*>(sm_raw);                       // [n_paths][21][2]
@@ -57,6 +65,8 @@ __global__ void __launch_bounds__(CG_THREADS) chan_gen_kernel(const ChanGenParam
     double* scale = red + CG_THREADS;                                     // [n_paths]
     const int tid = threadIdx.x;
     const long long set = blockIdx.x;
+    const int c_lo = PHASE == 0 ? 0 : blockIdx.y * CG_FRAMES_PER_BLOCK;
+    const int c_hi = PHASE == 0 ? p.no_frames : min(p.no_frames, c_lo + CG_FRAMES_PER_BLOCK);
     const int nph = p.n_paths * CG_OSC;
     for (int q = tid; q < nph; q += CG_THREADS) {
         if (p.phases_in) {
@@ -72,22 +82,35 @@ __global__ void __launch_bounds__(CG_THREADS) chan_gen_kernel(const ChanGenParam
     }
     __syncthreads();
     // energy of every path's waveform over the set's frames: per-thread partials in frame order, fixed-order tree
-    for (int w = 0; w < p.n_paths; ++w) {
-        double e = 0.0;
-        for (int c = tid; c < p.no_frames; c += CG_THREADS) {
-            const double2 v = chan_waveform(p, ph, w, (double)c / p.sampling_freq);
-            e += v.x * v.x + v.y * v.y;
-        }
-        red[tid] = e;
-        __syncthreads();
-        for (int s = CG_THREADS / 2; s > 0; s >>= 1) {
-            if (tid < s) red[tid] += red[tid + s];
+    if (PHASE != 2) {
+        for (int w = 0; w < p.n_paths; ++w) {
+            double e = 0.0;
+            for (int c = c_lo + tid; c < c_hi; c += CG_THREADS) {
+                const double2 v = chan_waveform(p, ph, w, (double)c / p.sampling_freq);
+                e += v.x * v.x + v.y * v.y;
+            }
+            red[tid] = e;
+            __syncthreads();
+            for (int s = CG_THREADS / 2; s > 0; s >>= 1) {
+                if (tid < s) red[tid] += red[tid + s];
+                __syncthreads();
+            }
+            if (tid == 0) {
+                if (PHASE == 0) scale[w] = sqrt(p.power_lin[w] / red[0]);
+                else p.partial[((size_t)set * p.n_blk + blockIdx.y) * CG_MAXP + w] = red[0];
+            }
             __syncthreads();
         }
-        if (tid == 0) scale[w] = sqrt(p.power_lin[w] / red[0]);
+        if (PHASE == 1) return;
+    } else {
+        if (tid < p.n_paths) {
+            double e = 0.0;
+            for (int b = 0; b < p.n_blk; ++b) e += p.partial[((size_t)set * p.n_blk + b) * CG_MAXP + tid];
+            scale[tid] = sqrt(p.power_lin[tid] / e);
+        }
         __syncthreads();
     }
-    for (int c = tid; c < p.no_frames; c += CG_THREADS) {
+    for (int c = c_lo + tid; c < c_hi; c += CG_THREADS) {
         double2 coef[CG_MAXP];
         for (int w = 0; w < p.n_paths; ++w) {
             const double2 v = chan_waveform(p, ph, w, (double)c / p.sampling_freq);
@@ -148,12 +171,15 @@ int wofdm_gen_channels(wofdm_handle h, int profile, int L, double doppler_freq, 
     }
     const size_t n_ph = phases ? (size_t)n_sets * pf.n * CG_OSC * 2 : 0;
     const size_t n_out = (size_t)n_sets * no_frames * L;
-    int rc = arena_reserve(h, d, sinc.size() * 8 + n_ph * 8 + n_out * 16);
+    const int n_blk = no_frames > CG_FRAMES_PER_BLOCK ? (no_frames + CG_FRAMES_PER_BLOCK - 1) / CG_FRAMES_PER_BLOCK : 1;
+    const size_t n_part = n_blk > 1 ? (size_t)n_sets * n_blk * CG_MAXP : 0;
+    int rc = arena_reserve(h, d, sinc.size() * 8 + n_ph * 8 + n_out * 16 + n_part * 8);
     if (rc) return rc;
     double* d_sinc = static_cast<double*>(arena_take(d, sinc.size() * 8));
     double* d_ph = n_ph ? static_cast<double*>(arena_take(d, n_ph * 8)) : nullptr;
     double2* d_out = static_cast<double2*>(arena_take(d, n_out * 16));
-    if (!d_sinc || !d_out || (n_ph && !d_ph)) return fail(h, WOFDM_ENOMEM, "arena exhausted");
+    double* d_part = n_part ? static_cast<double*>(arena_take(d, n_part * 8)) : nullptr;
+    if (!d_sinc || !d_out || (n_ph && !d_ph) || (n_part && !d_part)) return fail(h, WOFDM_ENOMEM, "arena exhausted");
     WOFDM_CUDA(h, cudaMemcpyAsync(d_sinc, sinc.data(), sinc.size() * 8, cudaMemcpyHostToDevice, d.stream));
     if (n_ph) WOFDM_CUDA(h, cudaMemcpyAsync(d_ph, phases, n_ph * 8, cudaMemcpyHostToDevice, d.stream));
     ChanGenParams p;
@@ -163,9 +189,16 @@ int wofdm_gen_channels(wofdm_handle h, int profile, int L, double doppler_freq, 
     for (int i = 0; i < pf.n; ++i) p.power_lin[i] = std::pow(10.0, pf.power_db[i] / 10.0);
     p.sinc = d_sinc; p.phases_in = d_ph; p.seed = seed; p.out = d_out;
     const size_t smem = (size_t)(CG_MAXP * CG_OSC * 2 + CG_THREADS + CG_MAXP) * sizeof(double);
-    chan_gen_kernel<<<n_sets, CG_THREADS, smem, d.stream>>>(p);
+    p.n_blk = n_blk; p.partial = d_part;
+    if (n_blk == 1) {
+        chan_gen_kernel<0><<<n_sets, CG_THREADS, smem, d.stream>>>(p);
+        h->launches += 1;
+    } else {
+        chan_gen_kernel<1><<<dim3(n_sets, n_blk), CG_THREADS, smem, d.stream>>>(p);
+        chan_gen_kernel<2><<<dim3(n_sets, n_blk), CG_THREADS, smem, d.stream>>>(p);
+        h->launches += 2;
+    }
     WOFDM_CUDA(h, cudaGetLastError());
-    h->launches += 1;
     // [set][frame][L] complex == L x (n_sets*no_frames) column-major
     WOFDM_CUDA(h, cudaMemcpyAsync(chan, d_out, n_out * 16, cudaMemcpyDeviceToHost, d.stream));
     WOFDM_CUDA(h, cudaStreamSynchronize(d.stream));
