@@ -34,7 +34,12 @@ def _worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     t = sharding.allreduce_counters(torch.from_numpy(counters_for((rank, world))))
     tot = sharding.allreduce_counters(torch.from_numpy(np.stack(sharding.totals(N_SNR, C, ENS, 256, 16, 4, (rank, world)))))
-    q.put((rank, t.numpy().copy(), tot.numpy().copy()))
+    # interference: contiguous channel blocks, one all-gather of the per-channel rows
+    Cc = 7
+    lo, hi = sharding.channel_block(Cc, rank, world)
+    P_local = np.arange(lo, hi, dtype=np.float64)[:, None] * np.ones((1, 4)) + 0.5
+    P = sharding.allgather_channel_rows(P_local, Cc)
+    q.put((rank, t.numpy().copy(), tot.numpy().copy(), P.numpy().copy()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -54,6 +59,17 @@ def test_two_rank_counter_allreduce():
         assert p.exitcode == 0
     want = counters_for((0, 1))
     want_tot = np.stack(sharding.totals(N_SNR, C, ENS, 256, 16, 4))
-    for _, t, tot in got:
+    for _, t, tot, P in got:
         assert np.array_equal(t, want)
         assert np.array_equal(tot, want_tot)
+        assert np.array_equal(P, np.arange(7, dtype=np.float64)[:, None] * np.ones((1, 4)) + 0.5)
+
+
+def test_channel_blocks_partition():
+    for C in (1, 7, 250, 10000):
+        for world in (1, 2, 3, 8):
+            blocks = [sharding.channel_block(C, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == C
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in blocks]
+            assert max(sizes) - min(sizes) <= 1

@@ -48,3 +48,29 @@ def allreduce_counters(counters, group=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return t
+
+
+# ---- interference power: channel realisations are independent, rank r takes a contiguous block (SURVEY 8e) ----------
+
+def channel_block(C: int, rank: int, world: int):
+    """[lo, hi) of the channel realisations rank `rank` evaluates: contiguous blocks, sizes differing by at most one."""
+    base, extra = divmod(int(C), int(world))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def allgather_channel_rows(P_local, C: int, group=None):
+    """Per-channel results of every rank, (C_rank, ...) rows in channel order -> (C, ...) on every rank: one
+    all-gather of the padded blocks (NCCL on GPUs, gloo on CPU).  Returns P_local unchanged outside a process group."""
+    import torch
+    import torch.distributed as dist
+    t = P_local if isinstance(P_local, torch.Tensor) else torch.as_tensor(np.asarray(P_local, dtype=np.float64))
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return t
+    world = dist.get_world_size(group)
+    rows = max(channel_block(C, r, world)[1] - channel_block(C, r, world)[0] for r in range(world))
+    pad = torch.zeros((rows,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    pad[: t.shape[0]] = t
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    return torch.cat([parts[r][: channel_block(C, r, world)[1] - channel_block(C, r, world)[0]] for r in range(world)])
