@@ -107,3 +107,18 @@ def test_tf32_split_tensor_path(handle, name):
     assert np.max(np.abs(P32[2] - want)) < tol
     S32 = handle.interf_power(to_sys(p), vt, vr, chans, mode=1, scalar=True)
     assert np.allclose(S32, P64.sum(axis=1), rtol=2e-5, atol=256 * 5e-8)
+
+
+@pytest.mark.parametrize("N,cp,ttx,trx,L", [(512, 32, 16, 20, 21), (1024, 64, 32, 40, 21), (512, 24, 8, 8, 90)])
+def test_tf32_split_other_sizes(handle, N, cp, ttx, trx, L):
+    """mode 1 for N = 512 / 1024 (several 256-column tiles per slice) and a channel long enough for more ISI rows."""
+    p = O.system_params("WOLA", N, cp, ttx, trx)
+    vt, vr, _, _ = O.perturbed_windows(p, seed=N)
+    chans = O.synth_channels(3, L, seed=N + 1)
+    P64 = handle.interf_power(to_sys(p), vt, vr, chans, mode=0)
+    P32 = handle.interf_power(to_sys(p), vt, vr, chans, mode=1)
+    tol = 2e-5 * np.max(P64) * (N / 256) + 5e-8 * (N / 256)
+    assert np.max(np.abs(P32 - P64)) < tol
+    with pytest.raises(W.WofdmError):
+        p2 = O.system_params("WOLA", 128, 16, 4, 4)
+        handle.interf_power(to_sys(p2), O.rc_window_tx(p2), O.rc_window_rx(p2), chans[:9], mode=1)

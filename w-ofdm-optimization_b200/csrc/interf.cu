@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(256) build_b(double* __restrict__ Bbig, const 
             tf32_split(b0 + i < n_rx ? acc[i].y : 0.0, hi.y, lo.y);
             tf32_split(b0 + i + 1 < n_rx ? acc[i + 1].x : 0.0, hi.z, lo.z);
             tf32_split(b0 + i + 1 < n_rx ? acc[i + 1].y : 0.0, hi.w, lo.w);
-            float* dst = bt + tf32_b_offset(s, nk, j, kk);
+            float* dst = bt + tf32_b_offset(s, nk, N, j, kk);
             *reinterpret_cast<float4*>(dst) = hi;
             *reinterpret_cast<float4*>(dst + (size_t)TF32_TN * TF32_KB) = lo;
         }
@@ -291,6 +291,7 @@ static int interf_run(wofdm_handle h, const wofdm_sys_t* sys, const double* win_
     if (!win_tx || !win_rx || !chan || !P || C < 1) return fail(h, WOFDM_EINVAL, "bad buffer");
     if (mode != 0 && mode != 1) return fail(h, WOFDM_EINVAL, "mode must be 0 (fp64) or 1 (TF32-split)");
     if (sys->N % 64) return fail(h, WOFDM_EUNSUPPORTED, "interference path needs N to be a multiple of 64");
+    if (mode == 1 && sys->N % TF32_TN) return fail(h, WOFDM_EUNSUPPORTED, "TF32-split interference path needs N to be a multiple of 256");
     DeviceCtx& d = h->devs[0];
     WOFDM_CUDA(h, cudaSetDevice(d.dev));
     InterfDev v;
@@ -306,7 +307,7 @@ static int interf_run(wofdm_handle h, const wofdm_sys_t* sys, const double* win_
         const int slices = nc * Ms;
         const dim3 bgrid((N + 255) / 256, (v.Kp / 2 + BB - 1) / BB, slices);
         const size_t bsm = (size_t)(L + 2 * BB) * sizeof(double2);
-        const bool tiled = mode == 1 && N == TF32_TN;         // the TF32 operand straight from the band product
+        const bool tiled = mode == 1;                         // the TF32 operand straight from the band product
         if (tiled)
             build_b<true><<<bgrid, 256, bsm, d.stream>>>(reinterpret_cast<double*>(interf_tf32_b_tiles(v, N)), v.T, v.chan, L, N,
                                                         v.n_tx, v.n_rx, v.N0, v.Kp, Ms, v.M, c0, scalar, k_isi);
@@ -320,7 +321,7 @@ static int interf_run(wofdm_handle h, const wofdm_sys_t* sys, const double* win_
             gemm_power_f64<false><<<dim3(N / BN, 2 * N / BM, slices), 256, smem, d.stream>>>(v.Rbig, v.Bbig, v.P, N, v.Kp, Ms, c0, scalar, k_isi);
             WOFDM_CUDA(h, cudaGetLastError());
         } else {
-            rc = interf_gemm_tf32(h, sys, v, Ms, c0, slices, scalar, k_isi, tiled);
+            rc = interf_gemm_tf32(h, sys, v, Ms, c0, slices, scalar, k_isi);
             if (rc) return rc;
         }
         h->launches += 2;

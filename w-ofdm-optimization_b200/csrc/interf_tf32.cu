@@ -76,7 +76,7 @@ __device__ __forceinline__ void cluster_sync_all() {
 
 // Persistent: grid = CLUSTER * min(tile pairs, resident clusters) CTAs of 192 threads; cluster q takes the tile pairs
 // q, q + clusters, ...; pair p = (slice p / (mtiles/2), row tiles 2*(p % (mtiles/2)) + rank).  Warps 0-3 = epilogue (TMEM lanes 32w..32w+31), warp 4 = producer, warp 5 = MMA issuer.
-// Rt: [2N/TM][nk][hi|lo][TM*KB] tiles, Bt: [slices][nk][hi|lo][TN*KB] tiles (see tile_split_* below)
+// Rt: [2N/TM][nk][hi|lo][TM*KB] tiles (tile_split_r below), Bt: [slices * N/TN][nk][hi|lo][TN*KB] tiles (build_b<true>, interf.cu)
 constexpr int NTHREADS = 192;
 template <int CLUSTER>
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_power_tf32(const float* __restrict__ Rt, const float* __restrict__ Bt,
@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_power_tf32(const float* __re
     uint32_t rank = 0;
     if (CLUSTER > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
     const int q0 = blockIdx.x / CLUSTER, nq = gridDim.x / CLUSTER, n_pairs = n_tiles / CLUSTER, ppairs = mtiles / CLUSTER;
+    const int ntile = N / TN;                                  // column tiles per slice: B tile sv = s * ntile + nt
 
     if (warp == 4) {   // both accumulators: all 512 columns (one CTA per SM: the stages take 192 KB of shared memory)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(2 * TN) : "memory");
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_power_tf32(const float* __re
             for (int p = q0; p < n_pairs; p += nq) {
                 const float* ra = Rt + (size_t)((p % ppairs) * CLUSTER + rank) * nk * (2 * TM * KB);
                 const float* rb = Bt + (size_t)(p / ppairs) * nk * (2 * TN * KB);
-                const int nk_t = ((p / ppairs) % Ms) == 0 ? nk : nk_isi;        // ISI slices: non-zero K prefix only
+                const int nk_t = ((p / ppairs / ntile) % Ms) == 0 ? nk : nk_isi; // ISI slices: non-zero K prefix only
                 for (int kb = 0; kb < nk_t; ++kb, ++it) {
                     const int st = it % NSTAGE;
                     if (it >= NSTAGE) mbar_wait(smem_u32(&empty_bar[st]), (uint32_t)(((it / NSTAGE) - 1) & 1));
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_power_tf32(const float* __re
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
                 const uint32_t tacc = tmem + (uint32_t)(buf * TN);
-                const int nk_t = ((p / ppairs) % Ms) == 0 ? nk : nk_isi;
+                const int nk_t = ((p / ppairs / ntile) % Ms) == 0 ? nk : nk_isi;
                 for (int kb = 0; kb < nk_t; ++kb, ++it) {
                     const int st = it % NSTAGE;
                     mbar_wait(smem_u32(&full_bar[st]), (uint32_t)((it / NSTAGE) & 1));
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_power_tf32(const float* __re
         int tl = 0;
         for (int p = q0; p < n_pairs; p += nq, ++tl) {
             const int buf = tl & 1;
-            const int m0 = ((p % ppairs) * CLUSTER + (int)rank) * TM, s = p / ppairs;
+            const int m0 = ((p % ppairs) * CLUSTER + (int)rank) * TM, sv = p / ppairs, s = sv / ntile, j0 = (sv % ntile) * TN;
             mbar_wait(smem_u32(&acc_full[buf]), (uint32_t)((tl >> 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int r = m0 + warp * 32 + lane, k = r % N;
@@ -200,7 +201,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_power_tf32(const float* __re
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     const float x = __uint_as_float(v[i]);
-                    if (!(ms == 0 && cc * 32 + i == k)) pw = fmaf(x, x, pw);
+                    if (!(ms == 0 && j0 + cc * 32 + i == k)) pw = fmaf(x, x, pw);
                 }
             }
             // this warp's quarter of the accumulator has been read: hand the buffer back to the MMA issuer
@@ -241,38 +242,13 @@ __global__ void tile_split_r(const double* __restrict__ Rbig, float* __restrict_
     }
 }
 
-// Bbig [slice][kk][j] fp64 -> Bt tiles [slice][kb][hi|lo][chunk][4]: 32 x 32 (kk x j) tiles through smem, each thread
-// writes the float4 of 4 consecutive kk for one row j; a warp writes 512 contiguous bytes
-__global__ void __launch_bounds__(256) tile_split_b(const double* __restrict__ Bbig, float* __restrict__ Bt, int N, int Kp,
-                                                    int Ms, int nk_isi) {
-    __shared__ double tile[32][33];
-    const int s = blockIdx.z, kb = blockIdx.y, j0 = blockIdx.x * 32, nk = Kp / KB;
-    if ((s % Ms) != 0 && kb >= nk_isi) return;               // K blocks an ISI slice does not have
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const double* src = Bbig + (size_t)s * Kp * N;
-    for (int i = ty; i < 32; i += 8) tile[i][tx] = src[(size_t)(kb * 32 + i) * N + j0 + tx];
-    __syncthreads();
-    const int t = threadIdx.x;
-    const int jl = (t & 7) | ((t >> 6) << 3), kc = (t >> 3) & 7;
-    float4 hi, lo;
-    split_hi_lo(tile[4 * kc + 0][jl], hi.x, lo.x);
-    split_hi_lo(tile[4 * kc + 1][jl], hi.y, lo.y);
-    split_hi_lo(tile[4 * kc + 2][jl], hi.z, lo.z);
-    split_hi_lo(tile[4 * kc + 3][jl], hi.w, lo.w);
-    const int j = j0 + jl;
-    const size_t c = (size_t)(j >> 3) * 64 + kc * 8 + (j & 7);
-    float* dst = Bt + ((size_t)s * nk + kb) * (2 * (size_t)TN * KB);
-    *reinterpret_cast<float4*>(dst + c * 4) = hi;
-    *reinterpret_cast<float4*>(dst + (size_t)TN * KB + c * 4) = lo;
-}
-
 float* interf_tf32_b_tiles(const InterfDev& v, int N) { return v.tf32_work + (size_t)2 * 2 * N * v.Kp; }
 
 int interf_gemm_tf32(wofdm_ctx* h, const wofdm_sys_t* sys, const InterfDev& v, int Ms, int c0, int slices, int scalar,
-                     int k_isi, bool b_tiled) {
+                     int k_isi) {
     DeviceCtx& d = h->devs[0];
     const int N = sys->N;
-    if (N != TN) return fail(h, WOFDM_EUNSUPPORTED, "TF32-split interference path is built for N = 256");
+    if (N % TN) return fail(h, WOFDM_EUNSUPPORTED, "TF32-split interference path needs N to be a multiple of 256");
     if (v.Kp % KB) return fail(h, WOFDM_EINVAL, "Kp must be a multiple of 32");
     const size_t nr = (size_t)2 * 2 * N * v.Kp;                      // Rt: hi + lo
     // fp32 work buffers live behind the fp64 B matrix of this batch (interf_upload reserved room for them)
@@ -280,10 +256,10 @@ int interf_gemm_tf32(wofdm_ctx* h, const wofdm_sys_t* sys, const InterfDev& v, i
     float* Bt = Rt + nr;
     tile_split_r<<<128, 256, 0, d.stream>>>(v.Rbig, Rt, 2 * N, v.Kp);
     const int nk_isi = k_isi / KB;
-    if (!b_tiled) tile_split_b<<<dim3(N / 32, v.Kp / KB, slices), 256, 0, d.stream>>>(v.Bbig, Bt, N, v.Kp, Ms, nk_isi);
+
     WOFDM_CUDA(h, cudaGetLastError());
     const size_t smem = (size_t)NSTAGE * STAGE_BYTES;
-    const int n_tiles = (2 * N / TM) * slices;
+    const int n_tiles = (2 * N / TM) * slices * (N / TN);
     const char* env = getenv("WOFDM_TF32_CLUSTER");
     const int cl = (env && atoi(env) == 1) ? 1 : 2;
     auto launch = [&](auto kern, int CL) -> int {
