@@ -341,3 +341,31 @@ def test_verify_and_replay_n512_tuned_kernel(handle, name):
     sym, nz = handle.ber_draws(s, 21, 31, 0, np.arange(4))
     want = sum(O.frame_chain_structured(p, vt, vr, h[:, f // 2], 20.0, sym[f].T, nz[f]).sym_err for f in range(4))
     assert abs(int(res["sym_err"][0]) - want) <= 3
+
+
+def test_device_draws_are_gaussian_and_uniform(handle):
+    """Quality of the on-device draws (Philox4x32-10 + Box-Muller on the MUFU approximations, exported with
+    wofdm_ber_draws): moments, Kolmogorov-Smirnov distance, independence of the two parts and of neighbours, uniform
+    constellation indices -- for the fp32 kernel's numbering (blocks of 17) and the fp64 one."""
+    from scipy import stats
+    s0 = W.params_from_name("wtx", 256, 16, 8, 0, bits=4, S=16)
+    for precision in (0, 1):
+        s = W.SysT(**{f: getattr(s0, f) for f, _ in s0._fields_})
+        s.precision = precision
+        sym, nz = handle.ber_draws(s, 21, 99, 0, np.arange(3000, 3024))
+        z = nz.ravel()
+        n = z.size                                            # ~1e5 complex samples
+        for part in (z.real, z.imag):
+            assert abs(part.mean()) < 4 / np.sqrt(n)
+            assert abs(part.var() - 1) < 4 * np.sqrt(2 / n)
+            assert abs(stats.kurtosis(part, fisher=False) - 3) < 4 * np.sqrt(24 / n)
+            assert abs(stats.skew(part)) < 4 * np.sqrt(6 / n)
+            assert stats.kstest(part, "norm").statistic < 1.95 / np.sqrt(n)      # 0.1 % level
+            assert abs(np.corrcoef(part[:-1], part[1:])[0, 1]) < 4 / np.sqrt(n)
+        assert abs(np.corrcoef(z.real, z.imag)[0, 1]) < 4 / np.sqrt(n)
+        assert np.abs(z).max() > 4.0                          # the tails are there (32-bit radius uniform)
+        counts = np.bincount(sym.ravel(), minlength=16)
+        assert stats.chisquare(counts).pvalue > 1e-4
+        # frames and variants are different streams
+        _, nz_b = handle.ber_draws(s, 21, 99, 1, np.arange(3000, 3002))
+        assert abs(np.corrcoef(nz[0].real, nz_b[0].real)[0, 1]) < 0.1 and not np.array_equal(nz[0], nz[1])
