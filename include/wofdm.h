@@ -57,6 +57,10 @@ typedef struct {
     int32_t constellation; /* 0 = python: natural-order un-normalised list (wofdm_simulation.py:179-182)
                               1 = matlab: qammod Gray, unit average power (main_BER_calculation.m:248) */
     int32_t precision;     /* 0 = fp32, 1 = fp64 */
+    int32_t guard;         /* null sub-carriers on EACH side of the centred spectrum (0 = all N carry data):
+                              matlab/main_channel_mask.m:55,388-391 (`offset`, zeros + ifftshift).  FFT bin k is
+                              active iff guard <= (k + N/2) mod N < N - guard; only active bins are counted.
+                              Needs bits < 8. */
 } wofdm_sys_t;
 
 /* ---- library / device ------------------------------------------------------------------- */

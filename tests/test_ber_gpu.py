@@ -25,7 +25,8 @@ def handle():
 
 def to_sys(p, precision):
     return W.SysT(N=p.N, cp=p.cp, cs=p.cs, tail_tx=p.tail_tx, tail_rx=p.tail_rx, rm=p.rm, shift=p.shift,
-                  bits=p.bits, S=p.S, noise_norm=p.noise_norm, constellation=p.constellation, precision=precision)
+                  bits=p.bits, S=p.S, noise_norm=p.noise_norm, constellation=p.constellation, precision=precision,
+                  guard=p.guard)
 
 
 def boundary_distance(eq_lattice, m):
@@ -58,12 +59,14 @@ def check_frames(handle, p, vt, vr, frames_in, precision, force_staged=False, di
             assert se[i] == ref.sym_err and be[i] == ref.bit_err, i
         else:
             safe = boundary_distance(ref.eq / sc, m) > 1e-3 * np.maximum(1.0, np.abs(ref.eq / sc))
+            safe |= ~p.active[:, None]          # null bins: exactly 0 + 0i on both sides, the tie rule decides
             assert np.array_equal(d[safe], ref.dec_idx[safe]), i
             assert (~safe).sum() <= max(3, 0.03 * safe.size)
             assert abs(int(se[i]) - ref.sym_err) <= int((~safe).sum())
-        # counters are consistent with the returned decisions
-        assert se[i] == np.count_nonzero(d != idx[:, 1:])
-        assert be[i] == O.bit_errors(idx[:, 1:], d)
+        # counters are consistent with the returned decisions (over the sub-carriers that carry data)
+        act = p.active
+        assert se[i] == np.count_nonzero(d[act] != idx[act, 1:])
+        assert be[i] == O.bit_errors(idx[act, 1:], d[act])
 
 
 @pytest.mark.parametrize("precision", [1, 0])
@@ -369,3 +372,37 @@ def test_device_draws_are_gaussian_and_uniform(handle):
         # frames and variants are different streams
         _, nz_b = handle.ber_draws(s, 21, 99, 1, np.arange(3000, 3002))
         assert abs(np.corrcoef(nz[0].real, nz_b[0].real)[0, 1]) < 0.1 and not np.array_equal(nz[0], nz[1])
+
+
+@pytest.mark.parametrize("precision", [1, 0])
+@pytest.mark.parametrize("name,N,cp,ttx,trx,bits,guard", [("wtx", 256, 16, 8, 0, 4, 64), ("CPW", 256, 22, 8, 10, 4, 64),
+                                                          ("WOLA", 256, 16, 8, 10, 6, 31), ("WOLA", 1024, 64, 32, 40, 6, 256),
+                                                          ("CP", 512, 32, 0, 0, 2, 128), ("wrx", 64, 8, 0, 4, 4, 16)])
+def test_guard_band(handle, name, N, cp, ttx, trx, bits, guard, precision):
+    """Null sub-carriers on both sides of the centred spectrum (matlab/main_channel_mask.m:55,388-391: offset = N/4,
+    zeros + ifftshift): verify mode against the oracle for every policy (exact fit, circular interior, cluster, N = 512,
+    staged), and a production replay; only the N - 2*guard active bins are counted."""
+    p = O.system_params(name, N, cp, ttx, trx, S=16, bits=bits, noise_norm=1, constellation=1, guard=guard)
+    vt, vr, _, _ = O.perturbed_windows(p, seed=guard)
+    rng = np.random.default_rng(guard + N)
+    h = O.synth_channels(2, 21, seed=guard)
+    n = O.noise_len(p, 21)
+    frames = [(h[:, k], 10.0 + 12 * k, rng.integers(0, 1 << bits, size=(N, 16)), rng.standard_normal(n) + 1j * rng.standard_normal(n))
+              for k in range(2)]
+    check_frames(handle, p, vt, vr, frames, precision)
+    if precision == 0:
+        check_frames(handle, p, vt, vr, frames, precision, direct=True)
+        check_frames(handle, p, vt, vr, frames, precision, force_staged=True)
+    s = to_sys(p, precision)
+    res = handle.ber_run(s, vt, vr, h, [18.0], 2, seed=guard)
+    assert res["sym_tot"][0] == 4 * (N - 2 * guard) * 15 and res["bit_tot"][0] == res["sym_tot"][0] * bits
+    sym, nz = handle.ber_draws(s, 21, guard, 0, np.arange(4))
+    want_s = want_b = 0
+    for f in range(4):
+        r = O.frame_chain_structured(p, vt, vr, h[:, f // 2], 18.0, sym[f].T, nz[f])
+        want_s += r.sym_err
+        want_b += r.bit_err
+    tol = 0 if precision == 1 else 3
+    assert abs(int(res["sym_err"][0]) - want_s) <= tol and abs(int(res["bit_err"][0]) - want_b) <= tol + 2
+    with pytest.raises(W.WofdmError):
+        handle.ber_run(W.params_from_name(name, N, cp, ttx, trx, bits=8, guard=guard), vt, vr, h, [18.0], 1)

@@ -28,7 +28,11 @@ class WofdmError(RuntimeError):
 class SysT(C.Structure):
     """wofdm_sys_t"""
     _fields_ = [(n, C.c_int32) for n in ("N", "cp", "cs", "tail_tx", "tail_rx", "rm", "shift", "bits", "S",
-                                         "noise_norm", "constellation", "precision")]
+                                         "noise_norm", "constellation", "precision", "guard")]
+
+    @property
+    def n_active(self):
+        return self.N - 2 * self.guard
 
     @property
     def n_tx(self):
@@ -120,8 +124,8 @@ def _ptr(a, t):
     return a.ctypes.data_as(t)
 
 
-def params_from_name(name, N, cp, tail_tx, tail_rx, bits=4, S=16, noise_norm=0, constellation=0, precision=0):
-    s = SysT(bits=bits, S=S, noise_norm=noise_norm, constellation=constellation, precision=precision)
+def params_from_name(name, N, cp, tail_tx, tail_rx, bits=4, S=16, noise_norm=0, constellation=0, precision=0, guard=0):
+    s = SysT(bits=bits, S=S, noise_norm=noise_norm, constellation=constellation, precision=precision, guard=guard)
     rc = load().wofdm_params_from_name(name.encode(), N, cp, tail_tx, tail_rx, C.byref(s))
     if rc:
         raise WofdmError(rc, f"unknown system {name!r}")
@@ -342,7 +346,7 @@ class BerPlan:
     def totals(self, ensemble, shard=(0, 1)):
         """(bit_tot, sym_tot) per SNR point for frames f = shard[0] mod shard[1]."""
         from .sharding import totals
-        return totals(self.n_snr, self.C, ensemble, self.sys.N, self.sys.S, self.sys.bits, shard)
+        return totals(self.n_snr, self.C, ensemble, self.sys.n_active, self.sys.S, self.sys.bits, shard)
 
     def close(self):
         if getattr(self, "_p", None):

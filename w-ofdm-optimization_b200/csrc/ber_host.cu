@@ -144,6 +144,7 @@ void fill_sys(BerParams& p, const wofdm_sys_t& s, int L) {
     p.stride = p.n_tx - s.tail_tx;
     p.L = L;
     p.noise_norm = s.noise_norm; p.constellation = s.constellation;
+    p.guard = s.guard;
     p.noise_len = noise_len(s, L);
     p.qscale = qam_scale(s);
 }
@@ -371,7 +372,7 @@ int wofdm_ber_run_shard(wofdm_handle h, const wofdm_sys_t* sys, const double* wi
             return x > shard_index ? (x - shard_index + shard_count - 1) / shard_count : 0;
         };
         const long long frames = count_upto(hi) - count_upto(lo);
-        sym_tot[i] = frames * (long long)sys->N * (sys->S - 1);
+        sym_tot[i] = frames * (long long)(sys->N - 2 * sys->guard) * (sys->S - 1);   // active sub-carriers only
         bit_tot[i] = sym_tot[i] * sys->bits;
     }
     return WOFDM_OK;

@@ -41,6 +41,7 @@ struct BerParams {
     int N, cp, cs, tail_tx, tail_rx, rm, shift, bits, S;
     int n_tx, stride, L;
     int noise_norm, constellation;
+    int guard;                 // null sub-carriers on each side of the centred spectrum (main_channel_mask.m:55,388-391)
     int chunk;                 // B: noise block = samples of the frame stream owned by one thread (regs policy);
                                // stream sample i uses draw (i/B)*(B+1) + i%B (B odd: blocks start on a Philox pair)
     int use_global;            // staged policy: frame buffers live in global scratch
@@ -107,6 +108,15 @@ __device__ __forceinline__ int slice_index(double2 e, int hb) {
     return (slice_level(e.x, m) << hb) | slice_level(e.y, m);
 }
 
+// Guard band (matlab/main_channel_mask.m:388-391: zeros on both sides of the centred spectrum, ifftshift): FFT bin k
+// carries data iff guard <= (k + N/2) mod N < N - guard.  A null bin takes constellation byte 255 on the Tx side
+// (qlut[255] = 0: nothing is sent there and the pilot's equaliser tap X0/Y0 is forced to 0) and the slicer's own
+// decision for 0 + 0i as its stored index, so it can never count as an error.
+template <int N> __device__ __forceinline__ bool bin_active(int k, int guard) {
+    const int c = (k + N / 2) & (N - 1);
+    return c >= guard && c < N - guard;
+}
+
 // 16 constellation indices (one byte each) of OFDM symbol s for thread t: sub-carriers t + q*TPF
 template <int N, bool VERIFY>
 __device__ __forceinline__ void load_sym_idx(const BerParams& prm, long long f, int s, int t, uint32_t (&w)[4]) {
@@ -164,7 +174,7 @@ struct BerSmem {
     int pad;        // zero samples in front of the frame stream (covers every negative tap index)
     int flen;       // frame-stream buffer elements incl. pad and tail slack (0: lives in global scratch)
     int xlen;       // second buffer elements: staged -> conv output / FFT exchange; regs -> noise / FFT exchange
-    int off_x, off_tw, off_geq, off_hf, off_taps, off_wtx, off_wrx, off_red, off_qlut, off_dlut, off_symw;   // byte offsets
+    int off_x, off_tw, off_geq, off_hf, off_taps, off_wtx, off_wrx, off_red, off_qlut, off_dlut, off_gmask, off_symw;   // byte offsets
     size_t bytes;
 };
 
@@ -202,7 +212,8 @@ __host__ __device__ inline BerSmem ber_smem_layout(int S, int stride, int tail_t
     o += ((N + tail_rx + 3) & ~3) * (int)sizeof(T);        m.off_red = o;
     o += 64 * (int)sizeof(T);                              m.off_qlut = o;
     o += 256 * E;                                          m.off_dlut = o;
-    o += 256;                                              m.off_symw = o;
+    o += 256;                                              m.off_gmask = o;
+    o += P::TPF * 32;                                      m.off_symw = o;     // guard band: two uint4 per thread of a transform
     o += S * P::TPF * 16;                                  // constellation-index words of every (symbol, thread)
     m.bytes = ((size_t)o + 15) & ~(size_t)15;
     return m;
@@ -302,6 +313,7 @@ ber_frame_kernel(const BerParams prm) {
     C2* qlut = reinterpret_cast<C2*>(smem_raw + lay.off_qlut);          // constellation index -> lattice point
     unsigned char* dlut = smem_raw + lay.off_dlut;                       // (re level)*m + (im level) -> index
     uint4* symw = reinterpret_cast<uint4*>(smem_raw + lay.off_symw);     // Tx -> Rx: the frame's constellation indices
+    uint4* gmask = reinterpret_cast<uint4*>(smem_raw + lay.off_gmask);   // guard band: [t][0] = 0xff in null bytes, [t][1] = stored index there
     C2* rbuf = xbuf;                            // staged: conv output; regs: the frame's noise (both alias the exchange)
     if (!REGS && prm.use_global) {
         C2* g = reinterpret_cast<C2*>(prm.scratch) + (size_t)blockIdx.x * 2 * prm.scratch_elems;
@@ -330,7 +342,19 @@ ber_frame_kernel(const BerParams prm) {
         qlut[i] = mk2<T>((T)(2 * a - (m - 1)), (T)(2 * c - (m - 1)));
         dlut[(a << hb) | c] = (unsigned char)i;
     }
+    if (tid == 0 && prm.bits < 8) qlut[255] = mk2<T>(0, 0);              // the null sub-carrier
     __syncthreads();
+    if (prm.guard > 0) {
+        const unsigned d0 = dlut[slice_index(mk2<T>(0, 0), hb)];          // what the slicer makes of a null bin
+        for (int tt = tid; tt < TPF; tt += NT) {
+            uint32_t ff[4] = {0, 0, 0, 0}, dd[4] = {0, 0, 0, 0};
+            for (int q = 0; q < 16; ++q)
+                if (!bin_active<N>(tt + q * TPF, prm.guard)) { ff[q >> 2] |= 0xffu << (8 * (q & 3)); dd[q >> 2] |= d0 << (8 * (q & 3)); }
+            gmask[2 * tt] = make_uint4(ff[0], ff[1], ff[2], ff[3]);
+            gmask[2 * tt + 1] = make_uint4(dd[0], dd[1], dd[2], dd[3]);
+        }
+        __syncthreads();
+    }
 
     C2 wk = mk2<T>(1, 0);                       // CIRC: exp(-2 pi i tid / N), the step of bin tid's DFT phasor
     if constexpr (CIRC) { float sn, cs_; sincospif(-2.0f * (float)tid / (float)N, &sn, &cs_); wk = mk2<T>((T)cs_, (T)sn); }
@@ -372,17 +396,25 @@ ber_frame_kernel(const BerParams prm) {
             const bool first = sb + se == 0;    // the frame's first symbol has no predecessor
             C2 v[16];
             {
-                uint32_t w[4];
+                uint32_t w[4], wq[4];             // stored indices (Rx compares against them) / Tx look-up indices
                 load_sym_idx<N, VERIFY>(prm, f, sb + se, t, w);
+#pragma unroll
+                for (int jw = 0; jw < 4; ++jw) wq[jw] = w[jw];
+                if (prm.guard > 0) {              // uniform: null bins send nothing and store the slicer's 0+0i decision
+                    const uint4 gf = gmask[2 * t], gd = gmask[2 * t + 1];
+                    const uint32_t ff[4] = {gf.x, gf.y, gf.z, gf.w}, dd[4] = {gd.x, gd.y, gd.z, gd.w};
+#pragma unroll
+                    for (int jw = 0; jw < 4; ++jw) { wq[jw] = w[jw] | ff[jw]; w[jw] = (w[jw] & ~ff[jw]) | dd[jw]; }
+                }
                 symw[se * TPF + t] = make_uint4(w[0], w[1], w[2], w[3]);
                 if constexpr (CIRC) {
                     // c = w_flat * (h circ x) = IFFT(H' o X)
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) cv[q] = cmul(qlut[sym_byte(w, q)], hf[t + q * TPF]);
+                    for (int q = 0; q < 16; ++q) cv[q] = cmul(qlut[sym_byte(wq, q)], hf[t + q * TPF]);
                     fft_regs<T, N, +1, FPP>(cv, t, xb, tw, slot);
                 }
 #pragma unroll
-                for (int q = 0; q < 16; ++q) v[q] = qlut[sym_byte(w, q)];
+                for (int q = 0; q < 16; ++q) v[q] = qlut[sym_byte(wq, q)];
             }
             fft_regs<T, N, +1, FPP>(v, t, xb, tw, slot);
             // CP/CS insertion + Tx window: sample i of symbol s is wtx[i] * x[(i - cp) mod N]
@@ -709,7 +741,8 @@ ber_frame_kernel(const BerParams prm) {
                     for (int k = tid; k < N; k += NT) {
                         const C2 y0 = geq[k];
                         const C2 x0 = qlut[pil[(k % TPF) * 16 + k / TPF]];
-                        const C2 gk = cscale(recip(y0.x * y0.x + y0.y * y0.y), cmulc(x0, y0));
+                        C2 gk = cscale(recip(y0.x * y0.x + y0.y * y0.y), cmulc(x0, y0));
+                        if (prm.guard > 0 && !bin_active<N>(k, prm.guard)) gk = mk2<T>(0, 0);   // null bin: equalised value 0 + 0i
                         geq[k] = gk;
                         if constexpr (CL > 1) {
 #pragma unroll

@@ -52,6 +52,8 @@ int validate_sys(wofdm_ctx* h, const wofdm_sys_t* s, int L) {
     if (s->noise_norm != 0 && s->noise_norm != 1) return fail(h, WOFDM_EINVAL, "noise_norm must be 0 or 1");
     if (s->constellation != 0 && s->constellation != 1) return fail(h, WOFDM_EINVAL, "constellation must be 0 or 1");
     if (s->precision != 0 && s->precision != 1) return fail(h, WOFDM_EINVAL, "precision must be 0 (fp32) or 1 (fp64)");
+    if (s->guard < 0 || 2 * s->guard >= s->N) return fail(h, WOFDM_EINVAL, "guard must lie in [0, N/2)");
+    if (s->guard > 0 && s->bits == 8) return fail(h, WOFDM_EUNSUPPORTED, "a guard band needs bits < 8 (constellation byte 255 marks a null sub-carrier)");
     if (L < 1 || L > 4096) return fail(h, WOFDM_EINVAL, "L must lie in [1, 4096]");
     return WOFDM_OK;
 }
