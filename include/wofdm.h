@@ -157,6 +157,17 @@ WOFDM_API int wofdm_interf_power(wofdm_handle h, const wofdm_sys_t* sys, const d
 WOFDM_API int wofdm_interf_power_scalar(wofdm_handle h, const wofdm_sys_t* sys, const double* win_tx,
                               const double* win_rx, const double* chan, int L, int C, int mode, double* P);
 
+/* ---- Channel-mask BER variant (next-row 8f-1) ----------------------------------------------------------------
+ * run_sim_mc of matlab/main_channel_mask.m:334-360 for the MASKED signal: the guard-band frame (sys->guard = offset)
+ * whose windowed symbols pass the DFT-domain raised-cosine mask of length 2 n_tx - 1 (dft_rc_filt, :398-417, roll_off
+ * as `rollOff`, 10 in the reference); the filter tail of each symbol is added to the next one.  Same arguments, draws
+ * (the symbol stream does not depend on `variant`) and counters as wofdm_ber_run, whose result with the same sys is
+ * the UNMASKED ber of that script.  fp32, N = 128 / 256 / 512, one device (the first of the handle). */
+WOFDM_API int wofdm_ber_run_masked(wofdm_handle h, const wofdm_sys_t* sys, const double* win_tx, const double* win_rx,
+                         const double* chan, int L, int C, const double* snr_db, int n_snr, int64_t ensemble,
+                         uint64_t seed, uint32_t variant, int roll_off,
+                         int64_t* bit_err, int64_t* bit_tot, int64_t* sym_err, int64_t* sym_tot);
+
 /* ---- Window-optimisation Hessian (next-row 8f-2) -------------------------------------------------------------
  * The quadratic form of the interference power in the reduced window variables: OptimizerTx / OptimizerRx /
  * OptimizerTxRx.gen_hessian (python/optimization_tools/optimizers.py:232-257, 387-410, 808-833) and

@@ -141,3 +141,39 @@ def test_production_ser_against_the_reference_itself(handle, name):
         mean, std = runs.mean(axis=0), runs.std(axis=0, ddof=1)
         z = (ref[w] - mean) / np.sqrt(std ** 2 * (1 + 1 / 24))
         assert np.all(np.abs(z) <= 3.5), (name, w, z, ref[w], mean)
+
+
+@pytest.mark.parametrize("name,cp,bits", [("wtx", 16, 4), ("WOLA", 22, 4), ("CP", 16, 2), ("CPW", 16, 6)])
+def test_channel_mask_variant_replay(handle, name, cp, bits):
+    """matlab/main_channel_mask.m: guard band N/4 + DFT-domain RC mask.  The production counters of the
+    masked chain, replayed through the oracle's line-by-line restatement (frame_chain_masked) from the exported draws;
+    the unmasked counters of the same symbols through frame_chain_structured.  (MATLAB-only path: parity unpinned.)"""
+    ttx = 8 if name in U.TX_SYSTEMS else 0
+    trx = 10 if name in U.RX_SYSTEMS else 0
+    p = O.system_params(name, 256, cp, ttx, trx, S=16, bits=bits, noise_norm=1, constellation=1, guard=64)
+    vt, vr, _, _ = O.perturbed_windows(p, seed=cp)
+    s = W.SysT(N=p.N, cp=p.cp, cs=p.cs, tail_tx=p.tail_tx, tail_rx=p.tail_rx, rm=p.rm, shift=p.shift, bits=bits, S=16,
+               noise_norm=1, constellation=1, precision=0, guard=64)
+    chans = O.synth_channels(2, 21, seed=cp)
+    snr = np.array([14.0, 32.0])
+    ens = 2
+    plain = handle.ber_run(s, vt, vr, chans, snr, ens, seed=5, variant=0)
+    masked = handle.ber_run_masked(s, vt, vr, chans, snr, ens, seed=5, variant=1, roll_off=10)
+    F = len(snr) * 2 * ens
+    sym, nz0 = handle.ber_draws(s, 21, 5, 0, np.arange(F))
+    _, nz1 = handle.ber_draws(s, 21, 5, 1, np.arange(F))
+    want = np.zeros((2, len(snr), 2), dtype=np.int64)
+    for f in range(F):
+        c, si = (f // ens) % 2, f // (ens * 2)
+        a = O.frame_chain_structured(p, vt, vr, chans[:, c], snr[si], sym[f].T, nz0[f])
+        b = O.frame_chain_masked(p, vt, vr, chans[:, c], snr[si], sym[f].T, nz1[f], roll_off=10)
+        want[0, si] += (a.sym_err, a.bit_err)
+        want[1, si] += (b.sym_err, b.bit_err)
+    assert np.all(masked["sym_tot"] == 2 * ens * 128 * 15) and np.all(masked["bit_tot"] == masked["sym_tot"] * bits)
+    for res, w in ((plain, want[0]), (masked, want[1])):
+        assert np.all(np.abs(res["sym_err"] - w[:, 0]) <= 3 + 0.003 * w[:, 0]), (res["sym_err"], w[:, 0])
+        assert np.all(np.abs(res["bit_err"] - w[:, 1]) <= 5 + 0.003 * w[:, 1]), (res["bit_err"], w[:, 1])
+    # the MATLAB-signature mirror returns [berMasked, ber]
+    bm, b0 = U.run_sim_mc(3, p.cp, p.cs, ttx, trx, np.diag(vt), np.diag(vr), chans[:, 0], 20.0, 64, p.rm, p.shift, 256, bits,
+                          16, 10, seed=1, handle=handle)
+    assert 0.0 <= b0 < 0.5 and 0.0 <= bm < 0.5

@@ -87,6 +87,8 @@ SIGNATURES = {
     "wofdm_ber_draws": (C.c_int, [C.c_void_p, _P(SysT), C.c_int, C.c_uint64, C.c_uint32, _i64p, C.c_int, _i32p, _dp]),
     "wofdm_interf_power": (C.c_int, [C.c_void_p, _P(SysT), _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, _dp]),
     "wofdm_interf_power_scalar": (C.c_int, [C.c_void_p, _P(SysT), _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, _dp]),
+    "wofdm_ber_run_masked": (C.c_int, [C.c_void_p, _P(SysT), _dp, _dp, _dp, C.c_int, C.c_int, _dp, C.c_int, C.c_int64, C.c_uint64,
+                                       C.c_uint32, C.c_int, _i64p, _i64p, _i64p, _i64p]),
     "wofdm_window_hessian": (C.c_int, [C.c_void_p, _P(SysT), _dp, C.c_int, _dp, _P(C.c_int)]),
     "wofdm_channel_profile": (C.c_int, [C.c_char_p]),
     "wofdm_gen_channels": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
@@ -232,6 +234,18 @@ class Handle:
         rc = load().wofdm_ber_run_shard(self._h, C.byref(s), _ptr(wt, _dp), _ptr(wr, _dp), _ptr(chf, _dp), L, Cn,
                                         _ptr(snr, _dp), n, int(ensemble), int(seed), int(variant),
                                         int(shard[0]), int(shard[1]), *[_ptr(o, _i64p) for o in out])
+        self._check(rc)
+        return dict(bit_err=out[0], bit_tot=out[1], sym_err=out[2], sym_tot=out[3])
+
+    def ber_run_masked(self, s, win_tx, win_rx, chan, snr_db, ensemble, seed=0, variant=0, roll_off=10):
+        """Channel-mask variant (wofdm_ber_run_masked): counters of the MASKED signal; ber_run with the same `s`
+        (s.guard = the script's offset) gives the unmasked ones on the same symbols."""
+        wt, wr, chf, L, Cn = self._win_chan(s, win_tx, win_rx, chan)
+        snr = _f64(np.ravel(snr_db))
+        out = [np.zeros(snr.size, dtype=np.int64) for _ in range(4)]
+        rc = load().wofdm_ber_run_masked(self._h, C.byref(s), _ptr(wt, _dp), _ptr(wr, _dp), _ptr(chf, _dp), L, Cn,
+                                         _ptr(snr, _dp), snr.size, int(ensemble), int(seed), int(variant), int(roll_off),
+                                         *[_ptr(o, _i64p) for o in out])
         self._check(rc)
         return dict(bit_err=out[0], bit_tot=out[1], sym_err=out[2], sym_tot=out[3])
 

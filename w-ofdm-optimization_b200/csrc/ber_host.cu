@@ -6,6 +6,7 @@
 #include <new>
 
 #include "host_common.h"
+#include "mask_kernel.cuh"
 
 using namespace wofdm;
 
@@ -523,6 +524,140 @@ int wofdm_ber_draws(wofdm_handle h, const wofdm_sys_t* sys, int L, uint64_t seed
     WOFDM_CUDA(h, cudaMemcpyAsync(sym_idx, d_sym, n_sym * 4, cudaMemcpyDeviceToHost, d.stream));
     WOFDM_CUDA(h, cudaMemcpyAsync(noise, d_noise, nlen * F * 16, cudaMemcpyDeviceToHost, d.stream));
     WOFDM_CUDA(h, cudaStreamSynchronize(d.stream));
+    return WOFDM_OK;
+}
+
+// Channel-mask variant (include/wofdm.h): frames in batches -- tx_mask_kernel writes the masked Tx streams of a batch
+// to HBM, the staged K1 kernel reads them (BerParams::tx_stream) and does channel, noise, Rx and counting as always.
+int wofdm_ber_run_masked(wofdm_handle h, const wofdm_sys_t* sys, const double* win_tx, const double* win_rx,
+                         const double* chan, int L, int C, const double* snr_db, int n_snr, int64_t ensemble,
+                         uint64_t seed, uint32_t variant, int roll_off,
+                         int64_t* bit_err, int64_t* bit_tot, int64_t* sym_err, int64_t* sym_tot) {
+    NvtxRange nvtx_("wofdm_ber_run_masked");
+    if (!h) return WOFDM_EINVAL;
+    int rc = validate_sys(h, sys, L);
+    if (rc) return rc;
+    if (!win_tx || !win_rx || !chan || !snr_db || !bit_err || !bit_tot || !sym_err || !sym_tot) return fail(h, WOFDM_EINVAL, "NULL buffer");
+    if (C < 1 || n_snr < 1 || ensemble < 1) return fail(h, WOFDM_EINVAL, "C, n_snr and ensemble must be >= 1");
+    if (sys->precision != 0) return fail(h, WOFDM_EUNSUPPORTED, "the channel-mask variant runs in fp32");
+    const int N = sys->N, n_tx = N + sys->cp + sys->cs, stride = n_tx - sys->tail_tx, M = 2 * n_tx - 1;
+    if (N != 128 && N != 256 && N != 512) return fail(h, WOFDM_EUNSUPPORTED, "the channel-mask variant is built for N = 128, 256, 512");
+    if (roll_off < 1 || M / 2 + 2 * roll_off > M) return fail(h, WOFDM_EINVAL, "roll_off does not fit the mask");
+    if (2 * n_tx > 3 * N + 1) return fail(h, WOFDM_EUNSUPPORTED, "cp + cs too long for the mask kernel (n_tx <= 1.5 N)");
+    DeviceCtx& d = h->devs[0];
+    WOFDM_CUDA(h, cudaSetDevice(d.dev));
+    Choice ch, prod;
+    rc = choose_variant(h, *sys, L, false, true, d.smem_optin, &ch);                // the staged kernel runs it
+    if (rc) return rc;
+    rc = choose_variant(h, *sys, L, false, false, d.smem_optin, &prod, win_tx);     // noise numbering of wofdm_ber_run / _draws
+    if (rc) return rc;
+    if (prod.var->CL > 1) return fail(h, WOFDM_EUNSUPPORTED, "no channel-mask variant for cluster kernels");
+    int nb = 0;
+    long long max_ctas = 0;
+    rc = prepare_kernel(h, *ch.var, ch.lay.bytes, d.sm_count, &nb, &max_ctas);
+    if (rc) return rc;
+    // g = IDFT_M(ifftshift(windowRC)), main_channel_mask.m:404-412, 477-493
+    std::vector<double> wrc(M, 0.0);
+    {
+        const int wl = M / 2, rest = M - wl - 2 * roll_off, zl = rest / 2;
+        for (int i = 0; i < roll_off; ++i) {
+            const double ax = -(roll_off + 1) / 2.0 + 1.0 + i;
+            const double v = std::sin(1.5707963267948966 * (0.5 + ax / roll_off));
+            wrc[zl + i] = v * v;
+            wrc[zl + roll_off + wl + (roll_off - 1 - i)] = v * v;
+        }
+        for (int i = 0; i < wl; ++i) wrc[zl + roll_off + i] = 1.0;
+    }
+    std::vector<float> g(2 * (size_t)M);
+    for (int n = 0; n < M; ++n) {
+        double re = 0.0, im = 0.0;
+        for (int k = 0; k < M; ++k) {                        // ifftshift: shifted[k] = wrc[(k + M/2) mod M] (odd M: floor)
+            const double w = wrc[(k + M / 2) % M];
+            if (w == 0.0) continue;
+            const double a = 6.283185307179586476925286766559 * (double)(((long long)k * n) % M) / (double)M;
+            re += w * std::cos(a); im += w * std::sin(a);
+        }
+        g[2 * n] = (float)(re / M); g[2 * n + 1] = (float)(im / M);
+    }
+    HostTables t;
+    build_tables(*sys, win_tx, win_rx, t);
+    std::vector<unsigned char> hchan, hsnr;
+    cast_chan(false, chan, (size_t)L * C, hchan);
+    std::vector<double> lin(n_snr);
+    for (int i = 0; i < n_snr; ++i) lin[i] = std::pow(10.0, -0.1 * snr_db[i]);
+    cast_any(false, lin, hsnr);
+    const long long total = (long long)n_snr * C * ensemble;
+    const size_t body = (size_t)sys->tail_tx + (size_t)sys->S * stride;
+    const long long batch = std::min<long long>(total, 8192);
+    const size_t scratch_elems = (size_t)ch.lay.pad + body + 64;
+    const int grid_ber = (int)std::min<long long>(batch, max_ctas);
+    const size_t scratch_bytes = ch.use_global ? (size_t)grid_ber * 2 * scratch_elems * sizeof(float2) : 0;
+    rc = arena_reserve(h, d, t.wtx.size() + t.wrx.size() + t.tw.size() + hchan.size() + hsnr.size() + g.size() * 4 +
+                                 (size_t)n_snr * 16 + (size_t)batch * body * sizeof(float2) + scratch_bytes);
+    if (rc) return rc;
+    auto put = [&](const void* src, size_t bytes, void** dst) -> cudaError_t {
+        *dst = arena_take(d, std::max<size_t>(bytes, 16));
+        if (!*dst) return cudaErrorMemoryAllocation;
+        return src ? cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, d.stream) : cudaSuccess;
+    };
+    void *d_wtx, *d_wrx, *d_tw, *d_chan, *d_snr, *d_g, *d_cnt, *d_stream, *d_scr = nullptr;
+    WOFDM_CUDA(h, put(t.wtx.data(), t.wtx.size(), &d_wtx));
+    WOFDM_CUDA(h, put(t.wrx.data(), t.wrx.size(), &d_wrx));
+    WOFDM_CUDA(h, put(t.tw.data(), t.tw.size(), &d_tw));
+    WOFDM_CUDA(h, put(hchan.data(), hchan.size(), &d_chan));
+    WOFDM_CUDA(h, put(hsnr.data(), hsnr.size(), &d_snr));
+    WOFDM_CUDA(h, put(g.data(), g.size() * 4, &d_g));
+    WOFDM_CUDA(h, put(nullptr, (size_t)n_snr * 16, &d_cnt));
+    WOFDM_CUDA(h, put(nullptr, (size_t)batch * body * sizeof(float2), &d_stream));
+    if (scratch_bytes) WOFDM_CUDA(h, put(nullptr, scratch_bytes, &d_scr));
+    WOFDM_CUDA(h, cudaMemsetAsync(d_cnt, 0, (size_t)n_snr * 16, d.stream));
+
+    MaskParams mp;
+    memset(&mp, 0, sizeof(mp));
+    mp.N = N; mp.cp = sys->cp; mp.cs = sys->cs; mp.tail_tx = sys->tail_tx; mp.bits = sys->bits; mp.S = sys->S;
+    mp.n_tx = n_tx; mp.stride = stride; mp.constellation = sys->constellation; mp.guard = sys->guard; mp.M = M;
+    mp.win_tx = static_cast<const float*>(d_wtx); mp.tw = static_cast<const float2*>(d_tw);
+    mp.g = static_cast<const float2*>(d_g); mp.seed = seed; mp.stream = static_cast<float2*>(d_stream);
+    BerParams prm;
+    fill_sys(prm, *sys, L);
+    prm.chunk = prod.chunk; prm.use_global = ch.use_global;
+    fill_split(prm, *ch.var);
+    prm.win_tx = d_wtx; prm.win_rx = d_wrx; prm.tw = d_tw; prm.chan = d_chan; prm.snr_lin = d_snr;
+    prm.C = C; prm.n_snr = n_snr; prm.ensemble = ensemble; prm.seed = seed; prm.variant = variant;
+    prm.counters = static_cast<unsigned long long*>(d_cnt);
+    prm.scratch = d_scr; prm.scratch_elems = (long long)scratch_elems;
+    prm.tx_stream = static_cast<const float2*>(d_stream);
+    size_t msm = 0;
+    for (long long f0 = 0; f0 < total; f0 += batch) {
+        const long long nf = std::min(batch, total - f0);
+        mp.frame_begin = f0; mp.frame_step = 1; mp.n_frames = nf;
+        const int mgrid = (int)std::min<long long>(nf, 2LL * d.sm_count);
+        cudaError_t e = cudaSuccess;
+        switch (N) {
+            case 128: msm = MaskSmem<128>::bytes(sys->S, n_tx, stride, sys->tail_tx, M);
+                      e = cudaFuncSetAttribute(tx_mask_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm);
+                      if (e == cudaSuccess) tx_mask_kernel<128><<<mgrid, 256, msm, d.stream>>>(mp); break;
+            case 256: msm = MaskSmem<256>::bytes(sys->S, n_tx, stride, sys->tail_tx, M);
+                      e = cudaFuncSetAttribute(tx_mask_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm);
+                      if (e == cudaSuccess) tx_mask_kernel<256><<<mgrid, 256, msm, d.stream>>>(mp); break;
+            default:  msm = MaskSmem<512>::bytes(sys->S, n_tx, stride, sys->tail_tx, M);
+                      e = cudaFuncSetAttribute(tx_mask_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm);
+                      if (e == cudaSuccess) tx_mask_kernel<512><<<mgrid, 256, msm, d.stream>>>(mp); break;
+        }
+        WOFDM_CUDA(h, e);
+        WOFDM_CUDA(h, cudaGetLastError());
+        prm.frame_begin = f0; prm.frame_step = 1; prm.n_frames = nf;
+        WOFDM_CUDA(h, ch.var->launch(prm, (int)std::min<long long>(nf, max_ctas), ch.lay.bytes, d.stream));
+        h->launches += 2;
+    }
+    std::vector<unsigned long long> cnt((size_t)n_snr * 2);
+    WOFDM_CUDA(h, cudaMemcpyAsync(cnt.data(), d_cnt, cnt.size() * 8, cudaMemcpyDeviceToHost, d.stream));
+    WOFDM_CUDA(h, cudaStreamSynchronize(d.stream));
+    for (int i = 0; i < n_snr; ++i) {
+        bit_err[i] = (int64_t)cnt[2 * i]; sym_err[i] = (int64_t)cnt[2 * i + 1];
+        sym_tot[i] = (int64_t)C * ensemble * (N - 2 * sys->guard) * (sys->S - 1);
+        bit_tot[i] = sym_tot[i] * sys->bits;
+    }
     return WOFDM_OK;
 }
 

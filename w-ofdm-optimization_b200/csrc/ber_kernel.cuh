@@ -42,6 +42,8 @@ struct BerParams {
     int n_tx, stride, L;
     int noise_norm, constellation;
     int guard;                 // null sub-carriers on each side of the centred spectrum (main_channel_mask.m:55,388-391)
+    const float2* tx_stream;   // staged policy only: the serialised Tx stream of local frame j at [j][tail_tx + S*stride],
+                               // produced by tx_mask_kernel (channel-mask variant); the Tx stage then only redraws the indices
     int chunk;                 // B: noise block = samples of the frame stream owned by one thread (regs policy);
                                // stream sample i uses draw (i/B)*(B+1) + i%B (B odd: blocks start on a Philox pair)
     int use_global;            // staged policy: frame buffers live in global scratch
@@ -389,7 +391,26 @@ ber_frame_kernel(const BerParams prm) {
 
         // =========================== transmitter ===========================
         C2 cv[16];                              // CIRC: interior of the channel output, c[t + q*TPF] (single Tx pass)
-        for (int s0 = 0; s0 < S; s0 += FPP) {
+        bool tx_done = false;
+        if constexpr (!REGS) {
+            if (prm.tx_stream != nullptr) {     // uniform: masked Tx stream from tx_mask_kernel (mask_kernel.cuh)
+                for (int e = tid; e < S * TPF; e += NT) {
+                    const int tt = e % TPF;
+                    uint32_t w[4];
+                    load_sym_idx<N, VERIFY>(prm, f, e / TPF, tt, w);
+                    if (prm.guard > 0) {
+                        const uint4 gf = gmask[2 * tt], gd = gmask[2 * tt + 1];
+                        w[0] = (w[0] & ~gf.x) | gd.x; w[1] = (w[1] & ~gf.y) | gd.y;
+                        w[2] = (w[2] & ~gf.z) | gd.z; w[3] = (w[3] & ~gf.w) | gd.w;
+                    }
+                    symw[e] = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+                const float2* src = prm.tx_stream + (size_t)j * body;
+                for (int i = tid; i < body; i += NT) ub[i] = mk2<T>((T)src[i].x, (T)src[i].y);
+                tx_done = true;
+            }
+        }
+        for (int s0 = 0; s0 < S && !tx_done; s0 += FPP) {
             const int s = s0 + slot;
             const bool act = s < S;
             const int se = act ? s : S - 1;     // idle slots shadow the last symbol (identical stores)

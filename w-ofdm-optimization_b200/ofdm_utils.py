@@ -148,6 +148,21 @@ def run_simulation(ensemble, symbolsPerTx, bitsPerSubcarrier, numSubcar, cpLengt
     return float(r["bit_err"][0] / r["bit_tot"][0])
 
 
+def run_sim_mc(ensemble, cpLength, csLength, tailTx, tailRx, windowTx, windowRx, channel, snr, offset,
+               prefixRemovalLength, circularShiftLength, numSubcar, bitsPerSubcar, symbolsPerTx, rollOff, seed=0, handle=None):
+    """[berMasked, ber] of one (window pair, channel, SNR) -- positional arguments of run_sim_mc,
+    matlab/main_channel_mask.m:334-337: numSubcar - 2*offset active sub-carriers, the same symbols with and without the
+    DFT-domain raised-cosine mask, independent noise.  Errors / bits over the whole ensemble."""
+    h = handle or default_handle()
+    s = capi.SysT(N=int(numSubcar), cp=int(cpLength), cs=int(csLength), tail_tx=int(tailTx), tail_rx=int(tailRx),
+                  rm=int(prefixRemovalLength), shift=int(circularShiftLength), bits=int(bitsPerSubcar),
+                  S=int(symbolsPerTx), noise_norm=1, constellation=1, precision=0, guard=int(offset))
+    wt, wr, ch = _diag(windowTx), _diag(windowRx), np.asarray(channel).ravel()
+    r = h.ber_run(s, wt, wr, ch, [float(snr)], int(ensemble), seed=seed, variant=0)
+    rm = h.ber_run_masked(s, wt, wr, ch, [float(snr)], int(ensemble), seed=seed, variant=1, roll_off=int(rollOff))
+    return float(rm["bit_err"][0] / rm["bit_tot"][0]), float(r["bit_err"][0] / r["bit_tot"][0])
+
+
 def calculate_interference(cpLength, typeOFDM, windowTx, windowRx, numSubcar, tailTx, tailRx, channels, mode=0,
                            handle=None):
     """Scalar interference power on the mean of `channels` (rows = realisations, as vehA200channel2 is stored),
