@@ -48,7 +48,7 @@ void fill_split(BerParams& prm, const BerVariant& v) {
 
 // win_tx (may be NULL): the circular-interior kernels need it flat between the tails; no_circ excludes them
 int choose_variant(wofdm_ctx* h, const wofdm_sys_t& s, int L, bool verify, bool force_staged, size_t smem_cap,
-                   Choice* out, const double* win_tx = nullptr, bool no_circ = false) {
+                   Choice* out, const double* win_tx = nullptr, bool no_circ = false, bool want_txs = false) {
     const int stride = s.N + s.cp + s.cs - s.tail_tx;
     const int sec = s.S * stride;
     const bool fp64 = s.precision == 1;
@@ -62,6 +62,7 @@ int choose_variant(wofdm_ctx* h, const wofdm_sys_t& s, int L, bool verify, bool 
     if (!fp64 && !force_staged) {
         for (const auto& v : h->variants) {
             if (v.TC == 0 || v.fp64 || v.verify != verify || v.N != s.N) continue;
+            if (v.txs != want_txs) continue;                 // the tx_stream instantiations serve the channel-mask variant only
             if (want && !strstr(v.name, want)) continue;
             // CL CTAs share a frame: S/CL consecutive symbols each, all of them in one pass of the CTA
             if (s.S % v.CL != 0 || (v.CL > 1 && s.S / v.CL > v.NT / (v.N / 16))) continue;
@@ -527,6 +528,27 @@ int wofdm_ber_draws(wofdm_handle h, const wofdm_sys_t* sys, int L, uint64_t seed
     return WOFDM_OK;
 }
 
+// in-place forward FFT of n = 2^k interleaved complex doubles (host; set-up of the mask response only)
+static void host_fft_pow2(std::vector<double>& a, int n) {
+    for (int i = 1, j = 0; i < n; ++i) {
+        int bit = n >> 1;
+        for (; j & bit; bit >>= 1) j ^= bit;
+        j ^= bit;
+        if (i < j) { std::swap(a[2 * i], a[2 * j]); std::swap(a[2 * i + 1], a[2 * j + 1]); }
+    }
+    for (int len = 2; len <= n; len <<= 1) {
+        const double ang = -6.283185307179586476925286766559 / len;
+        for (int i = 0; i < n; i += len)
+            for (int k = 0; k < len / 2; ++k) {
+                const double wr = std::cos(ang * k), wi = std::sin(ang * k);
+                const int u = i + k, v = i + k + len / 2;
+                const double xr = a[2 * v] * wr - a[2 * v + 1] * wi, xi = a[2 * v] * wi + a[2 * v + 1] * wr;
+                a[2 * v] = a[2 * u] - xr; a[2 * v + 1] = a[2 * u + 1] - xi;
+                a[2 * u] += xr; a[2 * u + 1] += xi;
+            }
+    }
+}
+
 // Channel-mask variant (include/wofdm.h): frames in batches -- tx_mask_kernel writes the masked Tx streams of a batch
 // to HBM, the staged K1 kernel reads them (BerParams::tx_stream) and does channel, noise, Rx and counting as always.
 int wofdm_ber_run_masked(wofdm_handle h, const wofdm_sys_t* sys, const double* win_tx, const double* win_rx,
@@ -547,8 +569,9 @@ int wofdm_ber_run_masked(wofdm_handle h, const wofdm_sys_t* sys, const double* w
     DeviceCtx& d = h->devs[0];
     WOFDM_CUDA(h, cudaSetDevice(d.dev));
     Choice ch, prod;
-    rc = choose_variant(h, *sys, L, false, true, d.smem_optin, &ch);                // the staged kernel runs it
+    rc = choose_variant(h, *sys, L, false, false, d.smem_optin, &ch, nullptr, true, true);   // a tx_stream kernel (tuned or staged) runs it
     if (rc) return rc;
+    if (ch.var->CL > 1) return fail(h, WOFDM_EUNSUPPORTED, "no channel-mask variant for cluster kernels");
     rc = choose_variant(h, *sys, L, false, false, d.smem_optin, &prod, win_tx);     // noise numbering of wofdm_ber_run / _draws
     if (rc) return rc;
     if (prod.var->CL > 1) return fail(h, WOFDM_EUNSUPPORTED, "no channel-mask variant for cluster kernels");
@@ -568,7 +591,7 @@ int wofdm_ber_run_masked(wofdm_handle h, const wofdm_sys_t* sys, const double* w
         }
         for (int i = 0; i < wl; ++i) wrc[zl + roll_off + i] = 1.0;
     }
-    std::vector<float> g(2 * (size_t)M);
+    std::vector<double> gd(2 * (size_t)M);
     for (int n = 0; n < M; ++n) {
         double re = 0.0, im = 0.0;
         for (int k = 0; k < M; ++k) {                        // ifftshift: shifted[k] = wrc[(k + M/2) mod M] (odd M: floor)
@@ -577,8 +600,21 @@ int wofdm_ber_run_masked(wofdm_handle h, const wofdm_sys_t* sys, const double* w
             const double a = 6.283185307179586476925286766559 * (double)(((long long)k * n) % M) / (double)M;
             re += w * std::cos(a); im += w * std::sin(a);
         }
-        g[2 * n] = (float)(re / M); g[2 * n + 1] = (float)(im / M);
+        gd[2 * n] = re / M; gd[2 * n + 1] = im / M;
     }
+    // the circular convolution (mod M) of an n_tx-sample symbol = a linear one with the periodic extension of g on
+    // [-(n_tx-1), M-1]: Gp = FFT_P of that sequence laid out circularly in P = 8N >= 4 n_tx - 3 points, times 1/P
+    const int P = 8 * N;
+    std::vector<double> gc(2 * (size_t)P, 0.0);
+    for (int mm = -(n_tx - 1); mm <= M - 1; ++mm) {
+        const int gi = ((mm % M) + M) % M, ci = ((mm % P) + P) % P;
+        gc[2 * ci] = gd[2 * gi]; gc[2 * ci + 1] = gd[2 * gi + 1];
+    }
+    host_fft_pow2(gc, P);
+    std::vector<float> g(2 * (size_t)P);
+    for (size_t i = 0; i < g.size(); ++i) g[i] = (float)(gc[i] / P);
+    std::vector<unsigned char> twp;
+    cast_any(false, build_twiddles(P), twp);
     HostTables t;
     build_tables(*sys, win_tx, win_rx, t);
     std::vector<unsigned char> hchan, hsnr;
@@ -592,7 +628,7 @@ int wofdm_ber_run_masked(wofdm_handle h, const wofdm_sys_t* sys, const double* w
     const size_t scratch_elems = (size_t)ch.lay.pad + body + 64;
     const int grid_ber = (int)std::min<long long>(batch, max_ctas);
     const size_t scratch_bytes = ch.use_global ? (size_t)grid_ber * 2 * scratch_elems * sizeof(float2) : 0;
-    rc = arena_reserve(h, d, t.wtx.size() + t.wrx.size() + t.tw.size() + hchan.size() + hsnr.size() + g.size() * 4 +
+    rc = arena_reserve(h, d, t.wtx.size() + t.wrx.size() + t.tw.size() + twp.size() + hchan.size() + hsnr.size() + g.size() * 4 +
                                  (size_t)n_snr * 16 + (size_t)batch * body * sizeof(float2) + scratch_bytes);
     if (rc) return rc;
     auto put = [&](const void* src, size_t bytes, void** dst) -> cudaError_t {
@@ -600,13 +636,14 @@ int wofdm_ber_run_masked(wofdm_handle h, const wofdm_sys_t* sys, const double* w
         if (!*dst) return cudaErrorMemoryAllocation;
         return src ? cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, d.stream) : cudaSuccess;
     };
-    void *d_wtx, *d_wrx, *d_tw, *d_chan, *d_snr, *d_g, *d_cnt, *d_stream, *d_scr = nullptr;
+    void *d_wtx, *d_wrx, *d_tw, *d_twp, *d_chan, *d_snr, *d_g, *d_cnt, *d_stream, *d_scr = nullptr;
     WOFDM_CUDA(h, put(t.wtx.data(), t.wtx.size(), &d_wtx));
     WOFDM_CUDA(h, put(t.wrx.data(), t.wrx.size(), &d_wrx));
     WOFDM_CUDA(h, put(t.tw.data(), t.tw.size(), &d_tw));
     WOFDM_CUDA(h, put(hchan.data(), hchan.size(), &d_chan));
     WOFDM_CUDA(h, put(hsnr.data(), hsnr.size(), &d_snr));
     WOFDM_CUDA(h, put(g.data(), g.size() * 4, &d_g));
+    WOFDM_CUDA(h, put(twp.data(), twp.size(), &d_twp));
     WOFDM_CUDA(h, put(nullptr, (size_t)n_snr * 16, &d_cnt));
     WOFDM_CUDA(h, put(nullptr, (size_t)batch * body * sizeof(float2), &d_stream));
     if (scratch_bytes) WOFDM_CUDA(h, put(nullptr, scratch_bytes, &d_scr));
@@ -617,10 +654,11 @@ int wofdm_ber_run_masked(wofdm_handle h, const wofdm_sys_t* sys, const double* w
     mp.N = N; mp.cp = sys->cp; mp.cs = sys->cs; mp.tail_tx = sys->tail_tx; mp.bits = sys->bits; mp.S = sys->S;
     mp.n_tx = n_tx; mp.stride = stride; mp.constellation = sys->constellation; mp.guard = sys->guard; mp.M = M;
     mp.win_tx = static_cast<const float*>(d_wtx); mp.tw = static_cast<const float2*>(d_tw);
-    mp.g = static_cast<const float2*>(d_g); mp.seed = seed; mp.stream = static_cast<float2*>(d_stream);
+    mp.Gp = static_cast<const float2*>(d_g); mp.twp = static_cast<const float2*>(d_twp);
+    mp.seed = seed; mp.stream = static_cast<float2*>(d_stream);
     BerParams prm;
     fill_sys(prm, *sys, L);
-    prm.chunk = prod.chunk; prm.use_global = ch.use_global;
+    prm.chunk = ch.var->TC > 0 ? ch.chunk : prod.chunk; prm.use_global = ch.use_global;
     fill_split(prm, *ch.var);
     prm.win_tx = d_wtx; prm.win_rx = d_wrx; prm.tw = d_tw; prm.chan = d_chan; prm.snr_lin = d_snr;
     prm.C = C; prm.n_snr = n_snr; prm.ensemble = ensemble; prm.seed = seed; prm.variant = variant;
@@ -631,16 +669,16 @@ int wofdm_ber_run_masked(wofdm_handle h, const wofdm_sys_t* sys, const double* w
     for (long long f0 = 0; f0 < total; f0 += batch) {
         const long long nf = std::min(batch, total - f0);
         mp.frame_begin = f0; mp.frame_step = 1; mp.n_frames = nf;
-        const int mgrid = (int)std::min<long long>(nf, 2LL * d.sm_count);
+        const int mgrid = (int)std::min<long long>(nf, (long long)d.sm_count);
         cudaError_t e = cudaSuccess;
         switch (N) {
-            case 128: msm = MaskSmem<128>::bytes(sys->S, n_tx, stride, sys->tail_tx, M);
+            case 128: msm = MaskSmem<128>::bytes(sys->S, stride, sys->tail_tx);
                       e = cudaFuncSetAttribute(tx_mask_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm);
                       if (e == cudaSuccess) tx_mask_kernel<128><<<mgrid, 256, msm, d.stream>>>(mp); break;
-            case 256: msm = MaskSmem<256>::bytes(sys->S, n_tx, stride, sys->tail_tx, M);
+            case 256: msm = MaskSmem<256>::bytes(sys->S, stride, sys->tail_tx);
                       e = cudaFuncSetAttribute(tx_mask_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm);
                       if (e == cudaSuccess) tx_mask_kernel<256><<<mgrid, 256, msm, d.stream>>>(mp); break;
-            default:  msm = MaskSmem<512>::bytes(sys->S, n_tx, stride, sys->tail_tx, M);
+            default:  msm = MaskSmem<512>::bytes(sys->S, stride, sys->tail_tx);
                       e = cudaFuncSetAttribute(tx_mask_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm);
                       if (e == cudaSuccess) tx_mask_kernel<512><<<mgrid, 256, msm, d.stream>>>(mp); break;
         }

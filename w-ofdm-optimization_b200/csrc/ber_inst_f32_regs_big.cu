@@ -2,6 +2,10 @@
 #include "ber_registry.h"
 namespace wofdm {
 void register_ber_f32_regs_big(std::vector<BerVariant>& out) {
+    // N = 256 with the Tx stream taken from HBM (channel-mask variant, matlab/main_channel_mask.m)
+    WOFDM_VARIANT_TXS(float, 256, 256, 17, 21, 2, true, "f32r")
+    WOFDM_VARIANT_TXS(float, 256, 256, 17, 21, 2, false, "f32r")
+    WOFDM_VARIANT_TXS(float, 256, 256, 19, 21, 2, false, "f32r")
     // N = 512: one CTA of 512 threads per frame (one per SM: stream + parked noise = 140 KB)
     WOFDM_VARIANT(float, 512, 512, 17, 21, 1, true, "f32r")
     WOFDM_VARIANT(float, 512, 512, 17, 21, 1, false, "f32r")

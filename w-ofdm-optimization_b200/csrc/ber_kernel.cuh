@@ -42,7 +42,7 @@ struct BerParams {
     int n_tx, stride, L;
     int noise_norm, constellation;
     int guard;                 // null sub-carriers on each side of the centred spectrum (main_channel_mask.m:55,388-391)
-    const float2* tx_stream;   // staged policy only: the serialised Tx stream of local frame j at [j][tail_tx + S*stride],
+    const float2* tx_stream;   // staged policy and TXS instantiations: the serialised Tx stream of local frame j at [j][tail_tx + S*stride],
                                // produced by tx_mask_kernel (channel-mask variant); the Tx stage then only redraws the indices
     int chunk;                 // B: noise block = samples of the frame stream owned by one thread (regs policy);
                                // stream sample i uses draw (i/B)*(B+1) + i%B (B odd: blocks start on a Philox pair)
@@ -271,7 +271,9 @@ template <int CL> __device__ __forceinline__ void frame_sync() {
     if constexpr (CL > 1) cooperative_groups::this_cluster().sync(); else __syncthreads();
 }
 
-template <typename T, int N, int NT, int TC, int LB, int MINB, bool FULL, bool VERIFY, int CL = 1, bool CIRC = false>
+// TXS: the Tx stage can take the frame's stream from HBM (BerParams::tx_stream, channel-mask variant).  Always possible in
+// the staged policy; the register-resident kernels get it as separate instantiations so that the main path keeps its code.
+template <typename T, int N, int NT, int TC, int LB, int MINB, bool FULL, bool VERIFY, int CL = 1, bool CIRC = false, bool TXS = false>
 __global__ void __launch_bounds__(NT, MINB)
 ber_frame_kernel(const BerParams prm) {
     using P = FftPlan<N>;
@@ -392,7 +394,8 @@ ber_frame_kernel(const BerParams prm) {
         // =========================== transmitter ===========================
         C2 cv[16];                              // CIRC: interior of the channel output, c[t + q*TPF] (single Tx pass)
         bool tx_done = false;
-        if constexpr (!REGS) {
+        if constexpr (TXS || TC == 0) {
+            static_assert(!(TXS && (CIRC || CL > 1)), "tx_stream: direct-form, one CTA per frame");
             if (prm.tx_stream != nullptr) {     // uniform: masked Tx stream from tx_mask_kernel (mask_kernel.cuh)
                 for (int e = tid; e < S * TPF; e += NT) {
                     const int tt = e % TPF;

@@ -11,6 +11,7 @@ struct BerVariant {
     int N, NT, TC, LB, MINB;
     int CL;                    // CTAs per frame (thread-block cluster size)
     bool circ;                 // interior of the channel output as a circular convolution (needs a flat Tx window)
+    bool txs;                  // accepts BerParams::tx_stream (channel-mask variant); the staged kernels always do
     bool full;                 // every register of every thread is a live stream sample (NT*TC == S*stride)
     bool fp64, verify;
     BerSmem (*layout)(int S, int stride, int tail_tx, int tail_rx, int L, int chunk, int use_global);
@@ -18,12 +19,12 @@ struct BerVariant {
     cudaError_t (*launch)(const BerParams& prm, int grid, size_t smem, cudaStream_t st);
 };
 
-template <typename T, int N, int NT, int TC, int LB, int MINB, bool FULL, bool V, int CL = 1, bool CIRC = false>
+template <typename T, int N, int NT, int TC, int LB, int MINB, bool FULL, bool V, int CL = 1, bool CIRC = false, bool TXS = false>
 struct BerVariantImpl {
     // grid = CTAs (a multiple of CL); CL > 1 launches thread-block clusters of CL CTAs
     static cudaError_t launch(const BerParams& prm, int grid, size_t smem, cudaStream_t st) {
         if constexpr (CL == 1) {
-            ber_frame_kernel<T, N, NT, TC, LB, MINB, FULL, V, 1, CIRC><<<grid, NT, smem, st>>>(prm);
+            ber_frame_kernel<T, N, NT, TC, LB, MINB, FULL, V, 1, CIRC, TXS><<<grid, NT, smem, st>>>(prm);
             return cudaGetLastError();
         } else {
             cudaLaunchConfig_t cfg = {};
@@ -32,15 +33,15 @@ struct BerVariantImpl {
             at[0].id = cudaLaunchAttributeClusterDimension;
             at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             cfg.attrs = at; cfg.numAttrs = 1;
-            return cudaLaunchKernelEx(&cfg, ber_frame_kernel<T, N, NT, TC, LB, MINB, FULL, V, CL, CIRC>, prm);
+            return cudaLaunchKernelEx(&cfg, ber_frame_kernel<T, N, NT, TC, LB, MINB, FULL, V, CL, CIRC, TXS>, prm);
         }
     }
     static BerVariant make(const char* name) {
         BerVariant v;
-        v.name = name; v.N = N; v.NT = NT; v.TC = TC; v.LB = LB; v.MINB = MINB; v.CL = CL; v.circ = CIRC; v.full = FULL;
+        v.name = name; v.N = N; v.NT = NT; v.TC = TC; v.LB = LB; v.MINB = MINB; v.CL = CL; v.circ = CIRC; v.txs = TXS || TC == 0; v.full = FULL;
         v.fp64 = sizeof(T) == 8; v.verify = V;
         v.layout = &ber_smem_layout<T, N, NT, TC, LB>;
-        v.fn = reinterpret_cast<const void*>(&ber_frame_kernel<T, N, NT, TC, LB, MINB, FULL, V, CL, CIRC>);
+        v.fn = reinterpret_cast<const void*>(&ber_frame_kernel<T, N, NT, TC, LB, MINB, FULL, V, CL, CIRC, TXS>);
         v.launch = &launch;
         return v;
     }
@@ -59,6 +60,10 @@ struct BerVariantImpl {
 #define WOFDM_VARIANT_CIRC(T, N, NT, TC, LB, MINB, FULL, tag)                                       \
     out.push_back(BerVariantImpl<T, N, NT, TC, LB, MINB, FULL, false, 1, true>::make("ber_" tag "_n" #N "_t" #NT "_c" #TC "_l" #LB "_b" #MINB "_f" #FULL "_circ")); \
     out.push_back(BerVariantImpl<T, N, NT, TC, LB, MINB, FULL, true, 1, true>::make("ber_" tag "_n" #N "_t" #NT "_c" #TC "_l" #LB "_b" #MINB "_f" #FULL "_circ_verify"));
+
+// register-resident kernels that can read the Tx stream from HBM (channel-mask variant); production only
+#define WOFDM_VARIANT_TXS(T, N, NT, TC, LB, MINB, FULL, tag)                                        \
+    out.push_back(BerVariantImpl<T, N, NT, TC, LB, MINB, FULL, false, 1, false, true>::make("ber_" tag "_n" #N "_t" #NT "_c" #TC "_l" #LB "_b" #MINB "_f" #FULL "_txs"));
 
 void register_ber_f32_staged(std::vector<BerVariant>& out);
 void register_ber_f64_staged(std::vector<BerVariant>& out);
