@@ -136,7 +136,8 @@ WOFDM_API int wofdm_ber_plan_destroy(wofdm_ber_plan plan);
  *   len = S*stride (noise_norm 0) or tail_tx + S*stride + L - 1 (noise_norm 1),
  *   eq_out: complex N x (S-1) x F, dec_idx: N x (S-1) x F, bit_err/sym_err: F.
  *   variant_kernel: 0 = the kernel wofdm_ber_run would pick, 1 = force the generic staged kernel,
- *   2 = exclude the circular-interior kernels (direct-form convolution over the whole frame). */
+ *   2 = the register-resident direct-form convolution over the whole frame (no tensor-core convolution, no
+ *   circular interior), 3 = exclude the tensor-core convolution kernels only. */
 WOFDM_API int wofdm_ber_verify(wofdm_handle h, const wofdm_sys_t* sys, const double* win_tx, const double* win_rx,
                      const double* chan, int L, int F, const double* snr_db,
                      const int32_t* sym_idx, const double* noise, int variant_kernel,

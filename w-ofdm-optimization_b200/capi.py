@@ -252,7 +252,7 @@ class Handle:
     def ber_plan(self, s, win_tx, win_rx, chan, snr_db):
         return BerPlan(self, s, win_tx, win_rx, chan, snr_db)
 
-    def ber_verify(self, s, win_tx, win_rx, chan, snr_db, sym_idx, noise, force_staged=False, direct=False):
+    def ber_verify(self, s, win_tx, win_rx, chan, snr_db, sym_idx, noise, force_staged=False, direct=False, no_tconv=False):
         """chan (L, F); snr_db (F,); sym_idx (F, S, N) ints; noise (F, noise_len) complex.
         Returns eq (F, S-1, N) complex, dec (F, S-1, N) int32, bit_err (F,), sym_err (F,)."""
         wt, wr, chf, L, F = self._win_chan(s, win_tx, win_rx, chan)
@@ -265,7 +265,7 @@ class Handle:
         dec = np.empty((F, s.S - 1, s.N), dtype=np.int32)
         be, se = np.zeros(F, dtype=np.int64), np.zeros(F, dtype=np.int64)
         rc = load().wofdm_ber_verify(self._h, C.byref(s), _ptr(wt, _dp), _ptr(wr, _dp), _ptr(chf, _dp), L, F,
-                                     _ptr(snr, _dp), _ptr(si, _i32p), _ptr(nz, _dp), 1 if force_staged else (2 if direct else 0),
+                                     _ptr(snr, _dp), _ptr(si, _i32p), _ptr(nz, _dp), 1 if force_staged else (2 if direct else (3 if no_tconv else 0)),
                                      _ptr(eq, _dp), _ptr(dec, _i32p), _ptr(be, _i64p), _ptr(se, _i64p))
         self._check(rc)
         return eq, dec, be, se

@@ -7,6 +7,7 @@
 
 #include "host_common.h"
 #include "mask_kernel.cuh"
+#include "ber_tconv.cuh"
 
 using namespace wofdm;
 
@@ -48,7 +49,8 @@ void fill_split(BerParams& prm, const BerVariant& v) {
 
 // win_tx (may be NULL): the circular-interior kernels need it flat between the tails; no_circ excludes them
 int choose_variant(wofdm_ctx* h, const wofdm_sys_t& s, int L, bool verify, bool force_staged, size_t smem_cap,
-                   Choice* out, const double* win_tx = nullptr, bool no_circ = false, bool want_txs = false) {
+                   Choice* out, const double* win_tx = nullptr, bool no_circ = false, bool want_txs = false,
+                   bool no_tconv = false) {
     const int stride = s.N + s.cp + s.cs - s.tail_tx;
     const int sec = s.S * stride;
     const bool fp64 = s.precision == 1;
@@ -59,11 +61,27 @@ int choose_variant(wofdm_ctx* h, const wofdm_sys_t& s, int L, bool verify, bool 
             if (win_tx[i] != win_tx[s.tail_tx]) { flat = false; break; }
     // WOFDM_VARIANT=<substring> restricts the tuned candidates (kernel tuning aid, e.g. "_b2")
     const char* want = getenv("WOFDM_VARIANT");
+    if (no_tconv || getenv("WOFDM_NO_TCONV")) no_tconv = true;
     if (!fp64 && !force_staged) {
         for (const auto& v : h->variants) {
             if (v.TC == 0 || v.fp64 || v.verify != verify || v.N != s.N) continue;
-            if (v.txs != want_txs) continue;                 // the tx_stream instantiations serve the channel-mask variant only
             if (want && !strstr(v.name, want)) continue;
+            if (v.ntile > 0) {
+                // channel convolution on the tensor cores (ber_tconv.cuh): first choice wherever it applies -- one Tx pass,
+                // L <= 21, prefix / suffix / tails inside the outer register rows, power sums and the zeros behind the
+                // stream inside the frame's tiles.  Noise numbering: draw = position (chunk 0).  Takes tx_stream too.
+                const int tpf = s.N / 16, body = s.tail_tx + sec;
+                if (no_tconv || s.S > v.NT / tpf || L > v.LB) continue;
+                if (s.cp > 2 * tpf || s.cs > 2 * tpf || s.tail_tx > 2 * tpf || s.tail_rx / 2 > tpf || s.shift > tpf) continue;
+                const int need = std::max(s.noise_norm == 1 ? body + L - 1 : sec, body + TCV_ZERO);
+                if (need > 512 * v.ntile) continue;
+                const BerSmem lay = v.layout(s.S, stride, s.tail_tx, s.tail_rx, L, 0, 0);
+                if (lay.bytes > smem_cap) continue;
+                if (!best.var || best.var->ntile == 0 || v.ntile < best.var->ntile) { best.var = &v; best.lay = lay; best.chunk = 0; }
+                continue;
+            }
+            if (best.var && best.var->ntile > 0) continue;
+            if (v.txs != want_txs) continue;                 // the tx_stream instantiations serve the channel-mask variant only
             // CL CTAs share a frame: S/CL consecutive symbols each, all of them in one pass of the CTA
             if (s.S % v.CL != 0 || (v.CL > 1 && s.S / v.CL > v.NT / (v.N / 16))) continue;
             const int S_cta = s.S / v.CL, sec_cta = sec / v.CL;
@@ -156,6 +174,21 @@ int prepare_kernel(wofdm_ctx* h, const BerVariant& v, size_t smem, int sm_count,
     WOFDM_CUDA(h, cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int nb = 0;
     WOFDM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, v.fn, v.NT, smem));
+    if (v.ntile > 0) {
+        // the occupancy calculator counts a kernel that allocates tensor memory as one CTA per SM; these kernels take
+        // 256 of the 512 columns, so registers, shared memory and tensor memory together decide
+        cudaFuncAttributes fa;
+        int dev = 0, smem_sm = 0, regs_sm = 0;
+        WOFDM_CUDA(h, cudaFuncGetAttributes(&fa, v.fn));
+        WOFDM_CUDA(h, cudaGetDevice(&dev));
+        WOFDM_CUDA(h, cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
+        WOFDM_CUDA(h, cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev));
+        const int by_smem = (int)((size_t)smem_sm / (smem + 1024)), by_regs = regs_sm / (((fa.numRegs + 7) & ~7) * v.NT);
+        const int by_tmem = 512 / (int)TCV_TMEM_COLS;
+        nb = std::max(nb, std::min(by_smem, std::min(by_regs, by_tmem)));
+    }
+    if (const char* f = getenv("WOFDM_FORCE_CTAS_PER_SM")) nb = std::max(1, atoi(f));    // tuning aid
+    if (getenv("WOFDM_DEBUG")) fprintf(stderr, "[wofdm] %s: smem %zu B, %d CTAs/SM\n", v.name, smem, nb);
     if (nb < 1) return fail(h, WOFDM_EUNSUPPORTED, "kernel variant cannot be resident on this device");
     *blocks_per_sm = nb;
     long long cap = (long long)nb * sm_count;
@@ -288,6 +321,7 @@ int wofdm_ber_plan_launch(wofdm_ber_plan p, int slot, int64_t ensemble, uint64_t
     prm.win_tx = pd.d_wtx; prm.win_rx = pd.d_wrx; prm.tw = pd.d_tw; prm.chan = pd.d_chan; prm.snr_lin = pd.d_snr;
     prm.C = p->C; prm.n_snr = p->n_snr; prm.ensemble = ensemble;
     prm.seed = seed; prm.variant = variant;
+    philox_round_keys(seed, prm.rk);
     prm.frame_begin = shard_index; prm.frame_step = shard_count; prm.n_frames = mine;
     prm.counters = pd.d_cnt;
     prm.scratch = pd.d_scratch;
@@ -408,7 +442,8 @@ int wofdm_ber_verify(wofdm_handle h, const wofdm_sys_t* sys, const double* win_t
     DeviceCtx& d = h->devs[0];
     WOFDM_CUDA(h, cudaSetDevice(d.dev));
     Choice ch;
-    rc = choose_variant(h, *sys, L, true, variant_kernel == 1, d.smem_optin, &ch, win_tx, variant_kernel == 2);
+    rc = choose_variant(h, *sys, L, true, variant_kernel == 1, d.smem_optin, &ch, win_tx, variant_kernel == 2, false,
+                        variant_kernel == 2 || variant_kernel == 3);
     if (rc) return rc;
     int nb = 0;
     long long max_ctas = 0;
@@ -498,6 +533,7 @@ int wofdm_ber_draws(wofdm_handle h, const wofdm_sys_t* sys, int L, uint64_t seed
     BerParams prm;
     fill_sys(prm, *sys, L);
     prm.seed = seed; prm.variant = variant;
+    philox_round_keys(seed, prm.rk);
     {   // the noise block B is a property of the kernel variant production mode dispatches to
         Choice ch;
         rc = choose_variant(h, *sys, L, false, false, d.smem_optin, &ch);
@@ -662,6 +698,7 @@ int wofdm_ber_run_masked(wofdm_handle h, const wofdm_sys_t* sys, const double* w
     fill_split(prm, *ch.var);
     prm.win_tx = d_wtx; prm.win_rx = d_wrx; prm.tw = d_tw; prm.chan = d_chan; prm.snr_lin = d_snr;
     prm.C = C; prm.n_snr = n_snr; prm.ensemble = ensemble; prm.seed = seed; prm.variant = variant;
+    philox_round_keys(seed, prm.rk);
     prm.counters = static_cast<unsigned long long*>(d_cnt);
     prm.scratch = d_scr; prm.scratch_elems = (long long)scratch_elems;
     prm.tx_stream = static_cast<const float2*>(d_stream);

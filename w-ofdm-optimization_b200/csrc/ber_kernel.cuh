@@ -45,7 +45,8 @@ struct BerParams {
     const float2* tx_stream;   // staged policy and TXS instantiations: the serialised Tx stream of local frame j at [j][tail_tx + S*stride],
                                // produced by tx_mask_kernel (channel-mask variant); the Tx stage then only redraws the indices
     int chunk;                 // B: noise block = samples of the frame stream owned by one thread (regs policy);
-                               // stream sample i uses draw (i/B)*(B+1) + i%B (B odd: blocks start on a Philox pair)
+                               // stream sample i uses draw (i/B)*(B+1) + i%B (B odd: blocks start on a Philox pair);
+                               // 0: stream sample i uses draw i (tensor-core convolution policy, ber_tconv.cuh)
     int use_global;            // staged policy: frame buffers live in global scratch
     int split, split_nt;       // CL > 1: stream samples per CTA and threads per CTA (noise block g = rank*NT + local/B); else 0
     // device tables, element type T / V2<T>
@@ -58,6 +59,7 @@ struct BerParams {
     long long ensemble;
     // production
     unsigned long long seed;
+    uint32_t rk[20];           // Philox round keys of `seed` (philox_round_keys; set together with seed)
     unsigned variant;
     long long frame_begin, frame_step, n_frames;   // frame ids f = frame_begin + j*frame_step, j < n_frames
     unsigned long long* counters;                  // [n_snr][2] = {bit_err, sym_err}
@@ -133,9 +135,8 @@ __device__ __forceinline__ void load_sym_idx(const BerParams& prm, long long f, 
             w[j] = x;
         }
     } else {
-        const uint4 r = philox4x32_10(make_uint4((uint32_t)f, (uint32_t)((unsigned long long)f >> 32),
-                                                 (uint32_t)(s * TPF + t), STREAM_SYM),
-                                      (uint32_t)prm.seed, (uint32_t)(prm.seed >> 32));
+        const uint4 r = philox4x32_10_rk(make_uint4((uint32_t)f, (uint32_t)((unsigned long long)f >> 32),
+                                                    (uint32_t)(s * TPF + t), STREAM_SYM), prm.rk);
         const uint32_t mask = ((1u << prm.bits) - 1u) * 0x01010101u;
         w[0] = r.x & mask; w[1] = r.y & mask; w[2] = r.z & mask; w[3] = r.w & mask;
     }
@@ -146,15 +147,19 @@ __device__ __forceinline__ int sym_byte(const uint32_t (&w)[4], int q) { return 
 // complex noise draws 2q and 2q+1 of frame f
 template <typename T>
 __device__ __forceinline__ void noise_pair(const BerParams& prm, long long f, uint32_t q, V2<T>& n0, V2<T>& n1) {
-    const uint4 r = philox4x32_10(make_uint4((uint32_t)f, (uint32_t)((unsigned long long)f >> 32), q,
-                                             STREAM_NOISE + prm.variant),
-                                  (uint32_t)prm.seed, (uint32_t)(prm.seed >> 32));
+    const uint4 r = philox4x32_10_rk(make_uint4((uint32_t)f, (uint32_t)((unsigned long long)f >> 32), q,
+                                                STREAM_NOISE + prm.variant), prm.rk);
     gauss_quad(r, n0, n1, T());
 }
 // noise of stream sample i (any policy): draw index (i/B)*(B+1) + i%B
 template <typename T>
 __device__ __forceinline__ V2<T> noise_at(const BerParams& prm, long long f, int i) {
     const int B = prm.chunk;
+    if (B == 0) {              // draw = position
+        V2<T> n0, n1;
+        noise_pair<T>(prm, f, (uint32_t)(i >> 1), n0, n1);
+        return (i & 1) ? n1 : n0;
+    }
     int k0 = 0;
     if (prm.split > 0) {       // frame shared by a cluster: blocks are numbered per CTA
         const int r = min(i / prm.split, prm.S * prm.stride / prm.split - 1);
@@ -177,6 +182,7 @@ struct BerSmem {
     int flen;       // frame-stream buffer elements incl. pad and tail slack (0: lives in global scratch)
     int xlen;       // second buffer elements: staged -> conv output / FFT exchange; regs -> noise / FFT exchange
     int off_x, off_tw, off_geq, off_hf, off_taps, off_wtx, off_wrx, off_red, off_qlut, off_dlut, off_gmask, off_symw;   // byte offsets
+    int off_lo, off_bt, off_bar;   // tensor-core convolution policy (ber_tconv.cuh): lo half of the split stream, taps operand, mbarrier
     size_t bytes;
 };
 

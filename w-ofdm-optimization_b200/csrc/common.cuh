@@ -84,6 +84,23 @@ __host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, ui
     return c;
 }
 
+// The same function with the ten round keys precomputed (they depend on the seed only): taken from a kernel parameter
+// they are constant-bank operands of the XORs, and the twenty key additions per call disappear.
+__host__ __device__ inline void philox_round_keys(unsigned long long seed, uint32_t (&rk)[20]) {
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int i = 0; i < 10; ++i) { rk[2 * i] = k0; rk[2 * i + 1] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+}
+__host__ __device__ __forceinline__ uint4 philox4x32_10_rk(uint4 c, const uint32_t (&rk)[20]) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        uint32_t lo0, hi0, lo1, hi1;
+        mul_wide32(0xD2511F53u, c.x, lo0, hi0);
+        mul_wide32(0xCD9E8D57u, c.z, lo1, hi1);
+        c = make_uint4(hi1 ^ c.y ^ rk[2 * i], lo1, hi0 ^ c.w ^ rk[2 * i + 1], lo0);
+    }
+    return c;
+}
+
 // Counter layout: (frame_lo, frame_hi, index, stream).
 //   stream 0            : constellation indices, index = s*(N/16) + t  -> 16 bytes = sub-carriers
 //                         t + q*(N/16), q = 0..15 of OFDM symbol s (low `bits` bits of byte q)

@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256) tx_mask_kernel(const MaskParams p) {
     }
     __syncthreads();
     BerParams draw = {};                                   // only what load_sym_idx reads
-    draw.seed = p.seed; draw.bits = p.bits; draw.S = S;
+    draw.seed = p.seed; philox_round_keys(p.seed, draw.rk); draw.bits = p.bits; draw.S = S;
     const int half = (S + FPPP - 1) / FPPP;                // symbols per big-transform slot: slot g takes g*half + pass
     for (long long j = blockIdx.x; j < p.n_frames; j += gridDim.x) {
         const long long f = p.frame_begin + j * p.frame_step;
