@@ -74,7 +74,7 @@ int choose_variant(wofdm_ctx* h, const wofdm_sys_t& s, int L, bool verify, bool 
                 if (no_tconv || s.S > v.NT / tpf || L > v.LB) continue;
                 if (s.cp > 2 * tpf || s.cs > 2 * tpf || s.tail_tx > 2 * tpf || s.tail_rx / 2 > tpf || s.shift > tpf) continue;
                 const int need = std::max(s.noise_norm == 1 ? body + L - 1 : sec, body + TCV_ZERO);
-                if (need > 512 * v.ntile) continue;
+                if (need > 512 * v.ntile || sec <= 512 * (v.ntile - 2)) continue;   // (the kernel range-checks its last two tiles only)
                 const BerSmem lay = v.layout(s.S, stride, s.tail_tx, s.tail_rx, L, 0, 0);
                 if (lay.bytes > smem_cap) continue;
                 if (!best.var || best.var->ntile == 0 || v.ntile < best.var->ntile) { best.var = &v; best.lay = lay; best.chunk = 0; }

@@ -359,8 +359,8 @@ ber_tconv_kernel(const BerParams prm) {
         // =========================== channel + AWGN ===========================
         // r = conv(h, u) (wofdm_simulation.py:206-209) on the tensor cores; y = r + sqrt(Pr*10^(-snr/10)/Pn) n with Pr, Pn
         // summed over the whole frame (:135-138; noise_norm 1: over the full convolution, main_BER_calculation.m:260-261,289-292)
-        // One elected lane issues the frame's MMAs, tile by tile between the noise draws of its own warp (6 MMAs = ~240
-        // cycles of tensor-core time per tile, less than the draws in between: the issue queue never blocks the warp);
+        // One elected lane issues the frame's MMAs, two tiles at a time between the first noise draws of its own warp (6 MMAs
+        // = ~240 cycles of tensor-core time per tile: the issue queue hardly ever blocks the warp);
         // the issuing warp rotates from frame to frame so that no scheduler carries it every time.
         const bool is_issuer = warp_u == (int)(issuer & (NW - 1));   // warp-uniform
         ++issuer;
@@ -372,28 +372,31 @@ ber_tconv_kernel(const BerParams prm) {
 #pragma unroll
         for (int tt = 0; tt < NTILE; ++tt) {
             const int p = 512 * tt + 4 * row + 2 * wg;
-            if (is_issuer) {
+            if (is_issuer && 2 * tt < NTILE) {           // two tiles per step: every MMA is in flight before the draws are half done
                 if (tcv_elect_one()) {
-                    const uint32_t tacc = tmem + (uint32_t)(16 * tt);
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        tcv_mma(tacc, tcv_desc(a_hi + tt * 2048 + k * 32, 16, 128), tcv_desc(b0 + k * 256, 128, 768), k != 0);
-                        tcv_mma(tacc, tcv_desc(a_lo + tt * 2048 + k * 32, 16, 128), tcv_desc(b0 + k * 256, 128, 1536), 1u);
+                    for (int ti = 2 * tt; ti < 2 * tt + 2 && ti < NTILE; ++ti) {
+                        const uint32_t tacc = tmem + (uint32_t)(16 * ti);
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            tcv_mma(tacc, tcv_desc(a_hi + ti * 2048 + k * 32, 16, 128), tcv_desc(b0 + k * 256, 128, 768), k != 0);
+                            tcv_mma(tacc, tcv_desc(a_lo + ti * 2048 + k * 32, 16, 128), tcv_desc(b0 + k * 256, 128, 1536), 1u);
+                        }
+                        if (ti == NTILE - 1)
+                            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(tcv_smem_u32(bar)) : "memory");
                     }
-                    if (tt == NTILE - 1)
-                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(tcv_smem_u32(bar)) : "memory");
                 }
                 __syncwarp();
             }
             C2 n0 = mk2<T>(0, 0), n1 = mk2<T>(0, 0);
-            if (512 * tt + 128 * (warp & 3) < npow) {          // warp-uniform
+            if (tt < NTILE - 2 || 512 * tt + 128 * (warp & 3) < npow) {   // warp-uniform; every tile but the last two lies inside the sums
                 if constexpr (VERIFY) {
                     const double2* nin = prm.noise_in + (size_t)f * prm.noise_len;
                     if (p < npow) n0 = to_v2<T>(nin[p]);
                     if (p + 1 < npow) n1 = to_v2<T>(nin[p + 1]);
                 } else {
                     noise_pair<T>(prm, f, (uint32_t)(p >> 1), n0, n1);
-                    if (512 * (tt + 1) > npow) {               // uniform: only the last tile(s) hold samples past the sums
+                    if (tt >= NTILE - 2 && 512 * (tt + 1) > npow) {   // uniform: only the last tiles hold samples past the sums
                         if (p >= npow) n0 = mk2<T>(0, 0);
                         if (p + 1 >= npow) n1 = mk2<T>(0, 0);
                     }
@@ -424,7 +427,7 @@ ber_tconv_kernel(const BerParams prm) {
                 if (t0 + u < NTILE) {
                     const int tt = t0 + u, p = 512 * tt + 4 * row + 2 * wg;
                     C2 r0 = cadd(a0[u], b0[u]), r1 = cadd(a1[u], b1[u]);
-                    if (512 * (tt + 1) > npow) {
+                    if (tt >= NTILE - 2 && 512 * (tt + 1) > npow) {
                         if (p >= npow) r0 = mk2<T>(0, 0);
                         if (p + 1 >= npow) r1 = mk2<T>(0, 0);
                     }
@@ -440,7 +443,7 @@ ber_tconv_kernel(const BerParams prm) {
 #pragma unroll
         for (int tt = 0; tt < NTILE; ++tt) {
             const int p = 512 * tt + 4 * row + 2 * wg;
-            if (512 * tt + 128 * (warp & 3) < sec) {           // warp-uniform
+            if (tt < NTILE - 2 || 512 * tt + 128 * (warp & 3) < sec) {   // warp-uniform
                 C2 a0, a1, b0, b1;
                 tcv_ld4(tlane + (uint32_t)(16 * tt), a0, a1);
                 tcv_ld4(tlane + (uint32_t)(16 * tt + 8), b0, b1);
