@@ -198,8 +198,8 @@ ber_tconv_kernel(const BerParams prm) {
 
     // this thread's operand row inside every tile (TMEM lane) and its half of the row's four outputs
     const int wg = warp >> 2, row = (warp & 3) * 32 + lane;
-    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
-    const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(4 * wg);
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);      // the warp index as a value the compiler knows to be warp-uniform
+    const uint32_t tlane = tmem + ((uint32_t)((warp_u & 3) * 32) << 16) + (uint32_t)(4 * (warp_u >> 2));
     uint32_t phase = 0, issuer = blockIdx.x;
 
     const long long fslot = blockIdx.x, nslots = gridDim.x;
@@ -441,16 +441,24 @@ ber_tconv_kernel(const BerParams prm) {
         __syncthreads();                           // also: every thread has seen the MMAs complete -- the split stream is dead
         const T g = noise_gain(block_total<NW>(red), snr_lin, block_total<NW>(red + 32));
 #pragma unroll
-        for (int tt = 0; tt < NTILE; ++tt) {
-            const int p = 512 * tt + 4 * row + 2 * wg;
-            if (tt < NTILE - 2 || 512 * tt + 128 * (warp & 3) < sec) {   // warp-uniform
-                C2 a0, a1, b0, b1;
-                tcv_ld4(tlane + (uint32_t)(16 * tt), a0, a1);
-                tcv_ld4(tlane + (uint32_t)(16 * tt + 8), b0, b1);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                const C2 y0 = caxpy(g, nz[tt][0], cadd(a0, b0)), y1 = caxpy(g, nz[tt][1], cadd(a1, b1));
-                if (p + 1 < sec) *reinterpret_cast<float4*>(yb + p) = make_float4(y0.x, y0.y, y1.x, y1.y);
-                else if (p < sec) yb[p] = y0;
+        for (int t0 = 0; t0 < NTILE; t0 += GT) {
+            C2 a0[GT], a1[GT], b0[GT], b1[GT];
+#pragma unroll
+            for (int u = 0; u < GT; ++u) {
+                if (t0 + u < NTILE) {
+                    tcv_ld4(tlane + (uint32_t)(16 * (t0 + u)), a0[u], a1[u]);
+                    tcv_ld4(tlane + (uint32_t)(16 * (t0 + u) + 8), b0[u], b1[u]);
+                }
+            }
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int u = 0; u < GT; ++u) {
+                if (t0 + u < NTILE) {
+                    const int tt = t0 + u, p = 512 * tt + 4 * row + 2 * wg;
+                    const C2 y0 = caxpy(g, nz[tt][0], cadd(a0[u], b0[u])), y1 = caxpy(g, nz[tt][1], cadd(a1[u], b1[u]));
+                    if (tt < NTILE - 2 || p + 1 < sec) *reinterpret_cast<float4*>(yb + p) = make_float4(y0.x, y0.y, y1.x, y1.y);
+                    else if (p < sec) yb[p] = y0;
+                }
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
