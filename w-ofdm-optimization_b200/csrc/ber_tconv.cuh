@@ -37,6 +37,10 @@ constexpr float TCV_XSCALE = 64.0f;   // stream and taps are scaled by powers of
 constexpr float TCV_HSCALE = 16.0f;   // everything behind the channel is scale-invariant (measured powers, pilot equaliser)
 constexpr uint32_t TCV_IDESC = (1u << 4) | ((16u >> 3) << 17) | ((128u >> 4) << 24);   // D f32, A = B = f16, K-major, N 16, M 128
 constexpr uint32_t TCV_TMEM_COLS = 256;
+#ifndef TCV_TPS
+#define TCV_TPS 16                    // tiles whose MMAs are issued in front of one noise draw of the issuing warp (16: the whole
+                                      // frame at once -- measured 6.80 ms against 6.90 (2 per draw) and 6.95 (3 per draw))
+#endif
 
 __host__ __device__ constexpr int tconv_alen(int ntile) { return TCV_PAD + ntile * 512 + TCV_SLACK; }
 
@@ -359,8 +363,9 @@ ber_tconv_kernel(const BerParams prm) {
         // =========================== channel + AWGN ===========================
         // r = conv(h, u) (wofdm_simulation.py:206-209) on the tensor cores; y = r + sqrt(Pr*10^(-snr/10)/Pn) n with Pr, Pn
         // summed over the whole frame (:135-138; noise_norm 1: over the full convolution, main_BER_calculation.m:260-261,289-292)
-        // One elected lane issues the frame's MMAs, two tiles at a time between the first noise draws of its own warp (6 MMAs
-        // = ~240 cycles of tensor-core time per tile: the issue queue hardly ever blocks the warp);
+        // One elected lane issues the frame's MMAs (uniform datapath: 6 UTCHMMA per tile back to back) in front of its warp's
+        // noise draws; the tensor core then works through them (~40 cycles each, bound by its shared-memory reads) while
+        // every warp draws noise;
         // the issuing warp rotates from frame to frame so that no scheduler carries it every time.
         const bool is_issuer = warp_u == (int)(issuer & (NW - 1));   // warp-uniform
         ++issuer;
@@ -372,10 +377,10 @@ ber_tconv_kernel(const BerParams prm) {
 #pragma unroll
         for (int tt = 0; tt < NTILE; ++tt) {
             const int p = 512 * tt + 4 * row + 2 * wg;
-            if (is_issuer && 2 * tt < NTILE) {           // two tiles per step: every MMA is in flight before the draws are half done
+            if (is_issuer && TCV_TPS * tt < NTILE) {           // two tiles per step: every MMA is in flight before the draws are half done
                 if (tcv_elect_one()) {
 #pragma unroll
-                    for (int ti = 2 * tt; ti < 2 * tt + 2 && ti < NTILE; ++ti) {
+                    for (int ti = TCV_TPS * tt; ti < TCV_TPS * tt + TCV_TPS && ti < NTILE; ++ti) {
                         const uint32_t tacc = tmem + (uint32_t)(16 * ti);
 #pragma unroll
                         for (int k = 0; k < 3; ++k) {
