@@ -37,7 +37,7 @@ def boundary_distance(eq_lattice, m):
     return np.minimum(ax(eq_lattice.real), ax(eq_lattice.imag))
 
 
-def check_frames(handle, p, vt, vr, frames_in, precision, force_staged=False, direct=False):
+def check_frames(handle, p, vt, vr, frames_in, precision, force_staged=False, direct=False, no_tconv=False):
     """frames_in: list of (chan, snr, sym_idx (N,S), noise)"""
     s = to_sys(p, precision)
     F = len(frames_in)
@@ -45,7 +45,7 @@ def check_frames(handle, p, vt, vr, frames_in, precision, force_staged=False, di
     snr = np.array([f[1] for f in frames_in])
     sym = np.stack([f[2].T for f in frames_in])                      # (F, S, N)
     nz = np.stack([f[3] for f in frames_in])
-    eq, dec, be, se = handle.ber_verify(s, vt, vr, chan, snr, sym, nz, force_staged=force_staged, direct=direct)
+    eq, dec, be, se = handle.ber_verify(s, vt, vr, chan, snr, sym, nz, force_staged=force_staged, direct=direct, no_tconv=no_tconv)
     m = O.qam_levels(p.bits)
     sc = O.qam_scale(p.bits, p.constellation)
     for i, (h, snr_i, idx, noise) in enumerate(frames_in):
@@ -109,11 +109,18 @@ def test_verify_shapes_and_conventions(handle, N, S, bits, conv, nn, precision):
         check_frames(handle, p, vt, vr, frames, precision, force_staged=True)
         if precision == 0:
             check_frames(handle, p, vt, vr, frames, precision, direct=True)      # direct-form convolution over the whole frame
+            check_frames(handle, p, vt, vr, frames, precision, no_tconv=True)    # register policies incl. the circular interior
 
 
-def test_production_replay_matches_oracle(handle):
+@pytest.mark.parametrize("policy", ["tconv", "regs"])
+def test_production_replay_matches_oracle(handle, policy, monkeypatch):
     """Production mode: export the on-device Philox draws of some frames, replay them through the
-    oracle and require the same error counts (fp64 exact; fp32 up to boundary flips)."""
+    oracle and require the same error counts (fp64 exact; fp32 up to boundary flips).  fp32 runs the tensor-core
+    convolution kernel (draw = stream position) or, with WOFDM_NO_TCONV, the register policies (blocks of 17)."""
+    if policy == "regs":
+        monkeypatch.setenv("WOFDM_NO_TCONV", "1")
+    else:
+        monkeypatch.delenv("WOFDM_NO_TCONV", raising=False)
     g = load_ser_golden("WOLA")
     chans = np.concatenate([g["A_channels"], g["B_channels"]], axis=1)      # (21, 3)
     snr = np.array([6.0, 18.0])
@@ -123,6 +130,9 @@ def test_production_replay_matches_oracle(handle):
             p = golden_params(g, 16, constellation=conv, noise_norm=nn)
             vt, vr = golden_windows(g, p)[0]
             s = to_sys(p, precision)
+            if precision == 0:
+                plan = handle.ber_plan(s, vt, vr, chans, snr)
+                assert ("f32t" in plan.kernel) == (policy == "tconv"), plan.kernel
             res = handle.ber_run(s, vt, vr, chans, snr, ens, seed=1234, variant=1)
             F = len(snr) * chans.shape[1] * ens
             ids = np.arange(F)
@@ -190,16 +200,22 @@ def test_production_is_deterministic_and_grid_independent(handle, name, N, cp, t
     chans = O.synth_channels(7, 21, seed=2)
     snr = np.array([3.0, 14.0, 27.0])
     ens = 40 if N == 256 else 12
-    ref = handle.ber_run(s, vt, vr, chans, snr, ens, seed=4242)
-    assert ref["sym_err"][0] > ref["sym_err"][2] > 0
-    for lim in ("", "1", ""):
-        if lim:
-            monkeypatch.setenv("WOFDM_MAX_CTAS_PER_SM", lim)
+    for no_tconv in ((False, True) if N == 256 else (False,)):   # N = 256: tensor-core convolution, then the register policies
+        if no_tconv:
+            monkeypatch.setenv("WOFDM_NO_TCONV", "1")
         else:
-            monkeypatch.delenv("WOFDM_MAX_CTAS_PER_SM", raising=False)
-        again = handle.ber_run(s, vt, vr, chans, snr, ens, seed=4242)
-        for k in ref:
-            assert np.array_equal(ref[k], again[k]), (k, lim)
+            monkeypatch.delenv("WOFDM_NO_TCONV", raising=False)
+        ref = handle.ber_run(s, vt, vr, chans, snr, ens, seed=4242)
+        assert ref["sym_err"][0] > ref["sym_err"][2] > 0
+        for lim in ("", "1", ""):
+            if lim:
+                monkeypatch.setenv("WOFDM_MAX_CTAS_PER_SM", lim)
+            else:
+                monkeypatch.delenv("WOFDM_MAX_CTAS_PER_SM", raising=False)
+            again = handle.ber_run(s, vt, vr, chans, snr, ens, seed=4242)
+            for k in ref:
+                assert np.array_equal(ref[k], again[k]), (k, lim, no_tconv)
+    monkeypatch.delenv("WOFDM_NO_TCONV", raising=False)
 
 
 def test_sharding_is_exact(handle):
@@ -286,6 +302,34 @@ def test_full_size_properties_configs1(handle):
     assert np.all(full["sym_err"] <= full["bit_err"]) and np.all(full["bit_err"] <= 4 * full["sym_err"])
 
 
+def test_tensor_core_convolution_is_fp32_grade(handle):
+    """The tensor-core convolution (split fp16 stream x split fp16 taps, fp32 accumulation) against the register
+    direct form on the same injected draws: the equalised symbols of the two fp32 kernels differ by rounding only
+    (both sit ~1e-6 from the fp64 oracle), decisions identical away from decision boundaries; BASELINE configs[1]
+    dispatches to it."""
+    p = O.system_params("wtx", 256, 16, 8, 0, S=16, bits=4, noise_norm=1, constellation=1)
+    vt, vr, _, _ = O.perturbed_windows(p, seed=3)
+    s = to_sys(p, 0)
+    rng = np.random.default_rng(3)
+    F = 6
+    chan = O.synth_channels(F, 21, seed=9)
+    n = O.noise_len(p, 21)
+    snr = np.linspace(0.0, 50.0, F)
+    sym = rng.integers(0, 16, size=(F, 16, 256))
+    nz = rng.standard_normal((F, n)) + 1j * rng.standard_normal((F, n))
+    plan = handle.ber_plan(s, vt, vr, chan, snr)
+    assert "f32t" in plan.kernel, plan.kernel
+    eq_t, dec_t, _, _ = handle.ber_verify(s, vt, vr, chan, snr, sym, nz)
+    eq_d, dec_d, _, _ = handle.ber_verify(s, vt, vr, chan, snr, sym, nz, direct=True)
+    for f in range(F):
+        ref = O.frame_chain_structured(p, vt, vr, chan[:, f], snr[f], sym[f].T, nz[f]).eq.T
+        e_t = np.linalg.norm(eq_t[f] - ref) / np.linalg.norm(ref)
+        e_d = np.linalg.norm(eq_d[f] - ref) / np.linalg.norm(ref)
+        assert e_t < 1e-5 and e_d < 1e-5, (f, e_t, e_d)            # north star: 1e-4 for fp32
+        assert e_t < 4 * e_d + 1e-6, (f, e_t, e_d)
+    assert np.mean(dec_t != dec_d) < 2e-3
+
+
 @pytest.mark.parametrize("cp", [10, 22, 32])
 @pytest.mark.parametrize("name", O.SYSTEMS)
 def test_verify_every_system_over_the_cp_range(handle, name, cp):
@@ -302,8 +346,9 @@ def test_verify_every_system_over_the_cp_range(handle, name, cp):
         h = O.synth_channels(1, 21, seed=cp + k)[:, 0]
         n = O.noise_len(p, 21)
         frames.append((h, 8.0 + 15 * k, rng.integers(0, 16, size=(256, 16)), rng.standard_normal(n) + 1j * rng.standard_normal(n)))
-    check_frames(handle, p, vt, vr, frames, 0)
+    check_frames(handle, p, vt, vr, frames, 0)                       # tensor-core convolution (the production choice)
     check_frames(handle, p, vt, vr, frames, 0, direct=True)
+    check_frames(handle, p, vt, vr, frames, 0, no_tconv=True)
 
 
 @pytest.mark.parametrize("name,cp", [("WOLA", 40), ("CPW", 128), ("CPwtx", 96), ("wrx", 72), ("CP", 128)])
@@ -346,13 +391,18 @@ def test_verify_and_replay_n512_tuned_kernel(handle, name):
     assert abs(int(res["sym_err"][0]) - want) <= 3
 
 
-def test_device_draws_are_gaussian_and_uniform(handle):
+@pytest.mark.parametrize("policy", ["tconv", "regs"])
+def test_device_draws_are_gaussian_and_uniform(handle, policy, monkeypatch):
     """Quality of the on-device draws (Philox4x32-10 + Box-Muller on the MUFU approximations, exported with
     wofdm_ber_draws): moments, Kolmogorov-Smirnov distance, independence of the two parts and of neighbours, uniform
-    constellation indices -- for the fp32 kernel's numbering (blocks of 17) and the fp64 one."""
+    constellation indices -- for the fp32 kernels' numberings (draw = position / blocks of 17) and the fp64 one."""
     from scipy import stats
+    if policy == "regs":
+        monkeypatch.setenv("WOFDM_NO_TCONV", "1")
+    else:
+        monkeypatch.delenv("WOFDM_NO_TCONV", raising=False)
     s0 = W.params_from_name("wtx", 256, 16, 8, 0, bits=4, S=16)
-    for precision in (0, 1):
+    for precision in ((0, 1) if policy == "tconv" else (0,)):
         s = W.SysT(**{f: getattr(s0, f) for f, _ in s0._fields_})
         s.precision = precision
         sym, nz = handle.ber_draws(s, 21, 99, 0, np.arange(3000, 3024))
@@ -392,6 +442,7 @@ def test_guard_band(handle, name, N, cp, ttx, trx, bits, guard, precision):
     check_frames(handle, p, vt, vr, frames, precision)
     if precision == 0:
         check_frames(handle, p, vt, vr, frames, precision, direct=True)
+        check_frames(handle, p, vt, vr, frames, precision, no_tconv=True)
         check_frames(handle, p, vt, vr, frames, precision, force_staged=True)
     s = to_sys(p, precision)
     res = handle.ber_run(s, vt, vr, h, [18.0], 2, seed=guard)
