@@ -303,7 +303,12 @@ def main():
                          "bound_note": "on-chip bound: the denominator is the FP32 FMA peak the north star names; the kernel's real "
                                        "limits are the math dispatch port (FFMA2/IMAD/LOP3 = 2 cycles per warp instruction, no "
                                        "co-issue of integer work with packed FP32) and shared-memory wavefronts -- DESIGN.md section 3, "
-                                       "tools/ubench/pipes*.cu"},
+                                       "tools/ubench/pipes*.cu",
+                         "tensor_note": ("kernel ber_f32t_*: the 'conv' share of the algorithmic flops (the L-tap channel convolution) "
+                                         "runs on the tensor pipe (tcgen05 kind::f16, 3-term fp16 split = fp32-grade, DESIGN.md section 3) "
+                                         "to relieve the FP32 dispatch port; FFTs, windows, noise, equaliser and slicer stay on the FP32 pipe; "
+                                         "the figure is still algorithmic flops / time against the FP32 FMA peak"
+                                         if "f32t" in plan.kernel else "all arithmetic on the FP32 pipe")},
             "ber_check": {"snr_db": [float(snr[k]) for k in (0, 10, 15, 20, 29)],
                           "ber": [float(be[k] / max(bt[k], 1)) if world == 1 else float(be[k] / (bt[k])) for k in (0, 10, 15, 20, 29)]},
         }
