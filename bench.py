@@ -173,8 +173,9 @@ def main():
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
 
-    if os.environ.get("NCCL_DEBUG"):                             # NCCL logs to stdout by default: ONE JSON line there
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # NCCL logs to stdout by default (also when the level comes from an nccl.conf rather than NCCL_DEBUG, as seen on an
+    # 8-GPU box: "NCCL version ..."): stdout carries ONE JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
     import wofdm_b200 as W
