@@ -195,6 +195,19 @@ WOFDM_API int wofdm_gen_channels(wofdm_handle h, int profile, int L, double dopp
                        double frame_duration, int no_frames, int n_sets, uint64_t seed, const double* phases,
                        double* chan);
 
+/* Next row 8f-3: PSD / out-of-band-radiation estimate of the windowed Tx signal.  Replaces the signal construction of
+ * wOFDMSystem.estimate_obr and __psd_estimate (python/ofdm_utils/timefreq_simulation.py:104-123, 216-253; MATLAB twin
+ * matlab/main_OOB_figures.m:121-159): records of n_sym OFDM symbols on the sub-carrier allocation of :223-232 (DC and the
+ * 2*guard_band - 1 centre bins null, N - 2*guard_band data rows), IDFT, CP/CS, Tx window win_tx (N + cp + cs values),
+ * overlap-add of the tails (tail_tx = 0: plain serialisation, as the reference does for the un-windowed signals), cut
+ * into slices of 8N samples (the last, partial one zero padded), |fftshift(FFT)|^2 averaged over slices and records.
+ *   sym_idx: int32 [records][n_sym][N - 2*guard_band] injected constellation indices (records = 1 reproduces the
+ *   reference's estimator for its draw), or NULL: on-device Philox draws keyed by (seed, record, symbol).
+ *   psd: 8N doubles, the reference's X_est (fftshifted).  N = 256. */
+WOFDM_API int wofdm_psd_estimate(wofdm_handle h, int N, int cp, int cs, int tail_tx, int bits, int constellation,
+                       const double* win_tx, int guard_band, int n_sym, int64_t records, uint64_t seed,
+                       const int32_t* sym_idx, double* psd);
+
 #ifdef __cplusplus
 }
 #endif

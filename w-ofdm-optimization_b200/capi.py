@@ -93,6 +93,8 @@ SIGNATURES = {
     "wofdm_channel_profile": (C.c_int, [C.c_char_p]),
     "wofdm_gen_channels": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
                                      C.c_uint64, _dp, _dp]),
+    "wofdm_psd_estimate": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_int, C.c_int,
+                                     C.c_int64, C.c_uint64, _i32p, _dp]),
 }
 
 _lib = None
@@ -248,6 +250,24 @@ class Handle:
                                          *[_ptr(o, _i64p) for o in out])
         self._check(rc)
         return dict(bit_err=out[0], bit_tot=out[1], sym_err=out[2], sym_tot=out[3])
+
+    def psd_estimate(self, N, cp, cs, tail_tx, win_tx, guard_band=48, n_sym=256, records=1, seed=0, sym_idx=None,
+                     bits=4, constellation=0):
+        """X_est of timefreq_simulation.py:104-123 for the Tx signal of window win_tx (8N doubles, fftshifted), averaged
+        over `records` records; sym_idx (records, n_sym, N - 2*guard_band) injects the constellation indices."""
+        w = _f64(np.ravel(win_tx))
+        if w.size != N + cp + cs:
+            raise WofdmError(EINVAL, "psd_estimate: win_tx must have N + cp + cs entries")
+        si = None
+        if sym_idx is not None:
+            si = np.ascontiguousarray(sym_idx, dtype=np.int32)
+            if si.shape != (records, n_sym, N - 2 * guard_band):
+                raise WofdmError(EINVAL, "psd_estimate: sym_idx must be (records, n_sym, N - 2*guard_band)")
+        out = np.empty(8 * N, dtype=np.float64)
+        rc = load().wofdm_psd_estimate(self._h, N, cp, cs, tail_tx, bits, constellation, _ptr(w, _dp), guard_band, n_sym,
+                                       records, seed, _ptr(si, _i32p) if si is not None else None, _ptr(out, _dp))
+        self._check(rc)
+        return out
 
     def ber_plan(self, s, win_tx, win_rx, chan, snr_db):
         return BerPlan(self, s, win_tx, win_rx, chan, snr_db)
