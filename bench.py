@@ -153,7 +153,20 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_JSON_FD = None
+
+
+def emit(line):
+    """The one JSON line of the contract, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, data)
 
 
 def main():
@@ -173,9 +186,14 @@ def main():
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
 
-    # NCCL logs to stdout by default (also when the level comes from an nccl.conf rather than NCCL_DEBUG, as seen on an
-    # 8-GPU box: "NCCL version ..."): stdout carries ONE JSON line
+    # stdout carries ONE JSON line: NCCL writes its log lines to stdout by default ("NCCL version ..." was seen on the
+    # multi-GPU boxes, where NCCL_DEBUG=VERSION ignores NCCL_DEBUG_FILE), so every other writer of file descriptor 1 --
+    # C libraries included -- is sent to stderr and the JSON line goes out through the saved descriptor
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     import wofdm_b200 as W
@@ -317,7 +335,7 @@ def main():
             v, sample, rate1 = cpu_port_throughput(12.0, os.cpu_count() or 1)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": sample,
                                     "single_core": rate1}
-        print(json.dumps(line), flush=True)
+        emit(line)
     plan.close()
     h.close()
     if world > 1:
