@@ -64,7 +64,7 @@ __host__ __device__ inline BerSmem tconv_smem_layout(int S, int stride, int tail
     o += ((N + tail_rx + 3) & ~3) * 4;        m.off_red = o;
     o += 64 * 4;                              m.off_qlut = o;
     o += 256 * 8;                             m.off_dlut = o;
-    o += 256;                                 m.off_gmask = o;
+    o += 4 * 256 * 4;                         m.off_gmask = o;      // decision tables, one per byte lane of a packed word
     o += P::TPF * 32;                         m.off_symw = o;
     o += S * P::TPF * 16;                     m.off_bar = o;
     o += 16;
@@ -157,7 +157,7 @@ ber_tconv_kernel(const BerParams prm) {
     T* wrx = reinterpret_cast<T*>(smem_raw + lay.off_wrx);
     T* red = reinterpret_cast<T*>(smem_raw + lay.off_red);
     C2* qlut = reinterpret_cast<C2*>(smem_raw + lay.off_qlut);
-    unsigned char* dlut = smem_raw + lay.off_dlut;
+    uint32_t* dlut4 = reinterpret_cast<uint32_t*>(smem_raw + lay.off_dlut);   // [b][(re level << hb) | im level] = index << 8b
     uint4* gmask = reinterpret_cast<uint4*>(smem_raw + lay.off_gmask);
     uint4* symw = reinterpret_cast<uint4*>(smem_raw + lay.off_symw);
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw + lay.off_bar);
@@ -181,7 +181,8 @@ ber_tconv_kernel(const BerParams prm) {
         int a, c;
         idx_to_levels(i, hb, m, prm.constellation, a, c);
         qlut[i] = mk2<T>((T)(2 * a - (m - 1)), (T)(2 * c - (m - 1)));
-        dlut[(a << hb) | c] = (unsigned char)i;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) dlut4[b * 256 + ((a << hb) | c)] = (uint32_t)i << (8 * b);
     }
     if (tid == 0 && prm.bits < 8) qlut[255] = mk2<T>(0, 0);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -189,7 +190,7 @@ ber_tconv_kernel(const BerParams prm) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
     if (prm.guard > 0) {
-        const unsigned d0 = dlut[slice_index(mk2<T>(0, 0), hb)];
+        const unsigned d0 = dlut4[slice_index(mk2<T>(0, 0), hb)];
         for (int tt = tid; tt < TPF; tt += NT) {
             uint32_t ff[4] = {0, 0, 0, 0}, dd[4] = {0, 0, 0, 0};
             for (int q = 0; q < 16; ++q)
@@ -518,19 +519,26 @@ ber_tconv_kernel(const BerParams prm) {
             }
             __syncthreads();
             if (act && s > 0) {
+                // decisions of four sub-carriers packed like the stored Tx indices (byte q & 3 of word q >> 2): one XOR,
+                // one population count for the bit errors and one (of the non-zero bytes) for the symbol errors per word
 #pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                    const int k = t + q * TPF;
-                    const C2 e = cmul(v[q], geq[k]);                                       // :231
-                    const int dec = dlut[slice_index(e, hb)];                              // :233
-                    const int txi = sym_byte(w, q);
-                    sym_cnt += (dec != txi);                                               // :235
-                    bit_cnt += __popc(dec ^ txi);
-                    if constexpr (VERIFY) {
-                        const size_t o = ((size_t)f * (prm.S - 1) + (s - 1)) * N + k;
-                        prm.eq_out[o] = make_double2((double)e.x * prm.qscale, (double)e.y * prm.qscale);
-                        prm.dec_out[o] = dec;
+                for (int gq = 0; gq < 4; ++gq) {
+                    uint32_t d4 = 0;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int q = 4 * gq + b, k = t + q * TPF;
+                        const C2 e = cmul(v[q], geq[k]);                                   // :231
+                        const uint32_t dq = dlut4[b * 256 + slice_index(e, hb)];           // :233
+                        d4 |= dq;
+                        if constexpr (VERIFY) {
+                            const size_t o = ((size_t)f * (prm.S - 1) + (s - 1)) * N + k;
+                            prm.eq_out[o] = make_double2((double)e.x * prm.qscale, (double)e.y * prm.qscale);
+                            prm.dec_out[o] = (int32_t)(dq >> (8 * b));
+                        }
                     }
+                    const uint32_t x = d4 ^ w[gq];
+                    bit_cnt += __popc(x);                                                  // :235 (bits) ...
+                    sym_cnt += __popc((((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u);   // ... and symbols: bytes that differ
                 }
             }
         }
