@@ -330,6 +330,25 @@ def test_tensor_core_convolution_is_fp32_grade(handle):
     assert np.mean(dec_t != dec_d) < 2e-3
 
 
+@pytest.mark.parametrize("name,cp", [("WOLA", 16), ("CPwtx", 22), ("CPW", 10)])
+def test_tensor_core_kernel_with_windows_that_are_not_flat(handle, name, cp):
+    """The tensor-core kernel folds a flat Tx window into its constellation table and divides a flat Rx window out
+    (every window the reference produces is flat between its tails); arbitrary windows take its general path."""
+    ttx = 8 if name in ("CPW", "WOLA", "CPwtx", "wtx") else 0
+    trx = 10 if name in ("CPW", "WOLA", "CPwrx", "wrx") else 0
+    p = O.system_params(name, 256, cp, ttx, trx, S=16, bits=6, noise_norm=1, constellation=1)
+    rng = np.random.default_rng(cp)
+    vt = rng.uniform(0.5, 1.0, p.n_tx)
+    vr = rng.uniform(0.5, 1.0, p.N + p.tail_rx)
+    frames = []
+    for k in range(2):
+        h = O.synth_channels(1, 21, seed=30 + k)[:, 0]
+        n = O.noise_len(p, 21)
+        frames.append((h, 14.0 + 20 * k, rng.integers(0, 64, size=(256, 16)), rng.standard_normal(n) + 1j * rng.standard_normal(n)))
+    check_frames(handle, p, vt, vr, frames, 0)
+    check_frames(handle, p, vt, vr, frames, 0, direct=True)
+
+
 @pytest.mark.parametrize("cp", [10, 22, 32])
 @pytest.mark.parametrize("name", O.SYSTEMS)
 def test_verify_every_system_over_the_cp_range(handle, name, cp):

@@ -29,6 +29,7 @@ struct wofdm_ber_plan_s {
     const BerVariant* var = nullptr;
     BerSmem lay{};
     int chunk = 0, use_global = 0;
+    int flat_tx = 0, flat_rx = 0;
     bool transient = false;    // buffers live in the devices' arenas (one-shot plan of wofdm_ber_run*): nothing to free
     std::vector<PlanDev> devs;
 };
@@ -40,6 +41,17 @@ struct Choice {
     BerSmem lay{};
     int chunk = 0, use_global = 0;
 };
+
+// tensor-core kernel: windows that are one value between their tails (BerParams::flat_tx / flat_rx)
+void fill_flat(BerParams& prm, const wofdm_sys_t& s, const double* win_tx, const double* win_rx) {
+    const int n_tx = s.N + s.cp + s.cs;
+    bool ft = s.cp >= s.tail_tx && s.cs >= s.tail_tx && win_tx[s.tail_tx] != 0.0;
+    for (int i = s.tail_tx; ft && i < n_tx - s.tail_tx; ++i) ft = win_tx[i] == win_tx[s.tail_tx];
+    bool fr = win_rx[s.tail_rx] != 0.0;
+    for (int i = s.tail_rx; fr && i < s.N; ++i) fr = win_rx[i] == win_rx[s.tail_rx];
+    prm.flat_tx = ft ? 1 : 0;
+    prm.flat_rx = fr ? 1 : 0;
+}
 
 // noise numbering of a frame shared by a cluster (BerParams::split)
 void fill_split(BerParams& prm, const BerVariant& v) {
@@ -236,6 +248,11 @@ static int plan_create_impl(wofdm_handle h, const wofdm_sys_t* sys, const double
     rc = choose_variant(h, *sys, L, false, false, cap, &ch, win_tx);
     if (rc) { delete p; return rc; }
     p->var = ch.var; p->lay = ch.lay; p->chunk = ch.chunk; p->use_global = ch.use_global;
+    {
+        BerParams fp;
+        fill_flat(fp, *sys, win_tx, win_rx);
+        p->flat_tx = fp.flat_tx; p->flat_rx = fp.flat_rx;
+    }
 
     HostTables t;
     build_tables(*sys, win_tx, win_rx, t);
@@ -317,6 +334,7 @@ int wofdm_ber_plan_launch(wofdm_ber_plan p, int slot, int64_t ensemble, uint64_t
     BerParams prm;
     fill_sys(prm, p->sys, p->L);
     prm.chunk = p->chunk; prm.use_global = p->use_global;
+    prm.flat_tx = p->flat_tx; prm.flat_rx = p->flat_rx;
     fill_split(prm, *p->var);
     prm.win_tx = pd.d_wtx; prm.win_rx = pd.d_wrx; prm.tw = pd.d_tw; prm.chan = pd.d_chan; prm.snr_lin = pd.d_snr;
     prm.C = p->C; prm.n_snr = p->n_snr; prm.ensemble = ensemble;
@@ -491,6 +509,7 @@ int wofdm_ber_verify(wofdm_handle h, const wofdm_sys_t* sys, const double* win_t
     BerParams prm;
     fill_sys(prm, *sys, L);
     prm.chunk = ch.chunk; prm.use_global = ch.use_global;
+    fill_flat(prm, *sys, win_tx, win_rx);
     fill_split(prm, *ch.var);
     prm.win_tx = d_wtx; prm.win_rx = d_wrx; prm.tw = d_tw; prm.chan = d_chan; prm.snr_lin = d_snr;
     prm.C = F; prm.n_snr = F; prm.ensemble = 1;
@@ -695,6 +714,8 @@ int wofdm_ber_run_masked(wofdm_handle h, const wofdm_sys_t* sys, const double* w
     BerParams prm;
     fill_sys(prm, *sys, L);
     prm.chunk = ch.var->TC > 0 ? ch.chunk : prod.chunk; prm.use_global = ch.use_global;
+    fill_flat(prm, *sys, win_tx, win_rx);
+    prm.flat_tx = 0;                       // (the Tx stream comes from tx_mask_kernel)
     fill_split(prm, *ch.var);
     prm.win_tx = d_wtx; prm.win_rx = d_wrx; prm.tw = d_tw; prm.chan = d_chan; prm.snr_lin = d_snr;
     prm.C = C; prm.n_snr = n_snr; prm.ensemble = ensemble; prm.seed = seed; prm.variant = variant;

@@ -41,6 +41,8 @@ struct BerParams {
     int N, cp, cs, tail_tx, tail_rx, rm, shift, bits, S;
     int n_tx, stride, L;
     int noise_norm, constellation;
+    int flat_tx, flat_rx;      // tensor-core kernel (ber_tconv.cuh): the window is one value between its tails (and cp, cs >= tail_tx
+                               // for Tx): that value moves into the constellation table / is divided out, the flat rows skip the product
     int guard;                 // null sub-carriers on each side of the centred spectrum (main_channel_mask.m:55,388-391)
     const float2* tx_stream;   // staged policy and TXS instantiations: the serialised Tx stream of local frame j at [j][tail_tx + S*stride],
                                // produced by tx_mask_kernel (channel-mask variant); the Tx stage then only redraws the indices

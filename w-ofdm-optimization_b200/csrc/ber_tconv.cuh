@@ -63,7 +63,7 @@ __host__ __device__ inline BerSmem tconv_smem_layout(int S, int stride, int tail
     o += ((stride + tail_tx + 3) & ~3) * 4;   m.off_wrx = o;
     o += ((N + tail_rx + 3) & ~3) * 4;        m.off_red = o;
     o += 64 * 4;                              m.off_qlut = o;
-    o += 256 * 8;                             m.off_dlut = o;
+    o += 2 * 256 * 8;                         m.off_dlut = o;       // lattice points: Rx (pilot) copy, Tx copy (carries the flat window value)
     o += 4 * 256 * 4;                         m.off_gmask = o;      // decision tables, one per byte lane of a packed word
     o += P::TPF * 32;                         m.off_symw = o;
     o += S * P::TPF * 16;                     m.off_bar = o;
@@ -157,6 +157,7 @@ ber_tconv_kernel(const BerParams prm) {
     T* wrx = reinterpret_cast<T*>(smem_raw + lay.off_wrx);
     T* red = reinterpret_cast<T*>(smem_raw + lay.off_red);
     C2* qlut = reinterpret_cast<C2*>(smem_raw + lay.off_qlut);
+    C2* qtx = qlut + 256;
     uint32_t* dlut4 = reinterpret_cast<uint32_t*>(smem_raw + lay.off_dlut);   // [b][(re level << hb) | im level] = index << 8b
     uint4* gmask = reinterpret_cast<uint4*>(smem_raw + lay.off_gmask);
     uint4* symw = reinterpret_cast<uint4*>(smem_raw + lay.off_symw);
@@ -174,17 +175,25 @@ ber_tconv_kernel(const BerParams prm) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < P::NTW; i += NT) tw[i] = reinterpret_cast<const C2*>(prm.tw)[i];
-    for (int i = tid; i < n_tx; i += NT) wtx[i] = reinterpret_cast<const T*>(prm.win_tx)[i] * TCV_XSCALE;
-    for (int i = tid; i < N + prm.tail_rx; i += NT) wrx[i] = reinterpret_cast<const T*>(prm.win_rx)[i];
+    // flat windows (host-checked): the Tx window's flat value rides on the constellation table and wtx holds the ratio to it
+    // (1 on every body row: no product there); the Rx window is divided by its flat value (a common factor of the
+    // received signal cancels in the pilot equaliser) and rows 1..13 of the Rx gather skip the product
+    const bool flat_tx = prm.flat_tx != 0, flat_rx = prm.flat_rx != 0;
+    const T wflat = flat_tx ? reinterpret_cast<const T*>(prm.win_tx)[beta] : (T)1;
+    const T rflat = flat_rx ? reinterpret_cast<const T*>(prm.win_rx)[prm.tail_rx] : (T)1;
+    for (int i = tid; i < n_tx; i += NT)
+        wtx[i] = flat_tx ? reinterpret_cast<const T*>(prm.win_tx)[i] / wflat : reinterpret_cast<const T*>(prm.win_tx)[i] * TCV_XSCALE;
+    for (int i = tid; i < N + prm.tail_rx; i += NT) wrx[i] = reinterpret_cast<const T*>(prm.win_rx)[i] / rflat;
     for (int i = tid; i < TCV_PAD; i += NT) ahi[i] = 0u;
     for (int i = tid; i < (1 << prm.bits); i += NT) {
         int a, c;
         idx_to_levels(i, hb, m, prm.constellation, a, c);
         qlut[i] = mk2<T>((T)(2 * a - (m - 1)), (T)(2 * c - (m - 1)));
+        qtx[i] = flat_tx ? cscale(wflat * TCV_XSCALE, qlut[i]) : qlut[i];
 #pragma unroll
         for (int b = 0; b < 4; ++b) dlut4[b * 256 + ((a << hb) | c)] = (uint32_t)i << (8 * b);
     }
-    if (tid == 0 && prm.bits < 8) qlut[255] = mk2<T>(0, 0);
+    if (tid == 0 && prm.bits < 8) { qlut[255] = mk2<T>(0, 0); qtx[255] = mk2<T>(0, 0); }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -280,14 +289,21 @@ ber_tconv_kernel(const BerParams prm) {
                 }
                 symw[se * TPF + t] = make_uint4(w[0], w[1], w[2], w[3]);
 #pragma unroll
-                for (int q = 0; q < 16; ++q) v[q] = qlut[sym_byte(wq, q)];
+                for (int q = 0; q < 16; ++q) v[q] = qtx[sym_byte(wq, q)];
             }
             fft_regs<T, N, +1, FPP>(v, t, xb, tw, slot);
             // CP/CS insertion + Tx window (transmitter.py:13-35, 61-87); heads i < tail_tx overlap the previous symbol's
             // falling tail (wofdm_simulation.py:190-203) and are added after the barrier
             uint32_t* const sh = uh + se * stride;
             uint32_t* const sl = ul + se * stride;
-            if (cp >= beta) {
+            if (flat_tx) {                        // uniform (implies cp, cs >= tail_tx: the body lies in the flat part)
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    uint32_t hi, lo;
+                    split_h2(v[q], hi, lo);
+                    sh[t + q * TPF + cp] = hi; sl[t + q * TPF + cp] = lo;
+                }
+            } else if (cp >= beta) {
                 T wv[16];
 #pragma unroll
                 for (int q = 0; q < 16; ++q) wv[q] = wtx[t + q * TPF + cp];
@@ -484,9 +500,9 @@ ber_tconv_kernel(const BerParams prm) {
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
                 if (q >= 1 && q <= 13) {
-                    // tail_rx/2, shift <= TPF: rows 1..13 neither wrap nor touch the overlap-add margins
+                    // tail_rx/2, shift <= TPF: rows 1..13 neither wrap nor touch the overlap-add margins (nor the window tails)
                     const int n = t + q * TPF + prm.shift;
-                    v[q] = cscale(wr[n], ys[n]);
+                    v[q] = flat_rx ? ys[n] : cscale(wr[n], ys[n]);
                     continue;
                 }
                 const int a0 = (q * TPF + prm.shift) & (N - 1);
