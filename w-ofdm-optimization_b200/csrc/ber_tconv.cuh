@@ -57,9 +57,9 @@ __host__ __device__ inline BerSmem tconv_smem_layout(int S, int stride, int tail
     o += m.flen * 4;                                      // alo (the received stream y lies over ahi | alo from byte 80)
     o = (o + 15) & ~15;              m.off_x = o;
     o += m.xlen * 8;                 m.off_tw = o;
-    o += P::NTW * 8;                 m.off_geq = o;       // equaliser taps (Rx stage) lie over the taps operand (channel stage)
-    m.off_bt = o;
-    o += (N * 8 > 3 * 768 ? N * 8 : 3 * 768);   m.off_wtx = o;   // [T_hi | T_lo | zeros], 8 rows x 48 halves each
+    o += P::NTW * 8;                 m.off_geq = o;
+    o += N * 8;                      m.off_bt = o;
+    o += 3 * 768;                    m.off_wtx = o;       // [T_hi | T_lo | zeros], 8 rows x 48 halves each
     o += ((stride + tail_tx + 3) & ~3) * 4;   m.off_wrx = o;
     o += ((N + tail_rx + 3) & ~3) * 4;        m.off_red = o;
     o += 64 * 4;                              m.off_qlut = o;
@@ -185,6 +185,7 @@ ber_tconv_kernel(const BerParams prm) {
         wtx[i] = flat_tx ? reinterpret_cast<const T*>(prm.win_tx)[i] / wflat : reinterpret_cast<const T*>(prm.win_tx)[i] * TCV_XSCALE;
     for (int i = tid; i < N + prm.tail_rx; i += NT) wrx[i] = reinterpret_cast<const T*>(prm.win_rx)[i] / rflat;
     for (int i = tid; i < TCV_PAD; i += NT) ahi[i] = 0u;
+    for (int i = tid; i < 768 / 4; i += NT) reinterpret_cast<uint32_t*>(bt + 1536)[i] = 0u;
     for (int i = tid; i < (1 << prm.bits); i += NT) {
         int a, c;
         idx_to_levels(i, hb, m, prm.constellation, a, c);
@@ -243,7 +244,6 @@ ber_tconv_kernel(const BerParams prm) {
             const int off = (jj >> 2) * 128 + n * 16 + (jj & 3) * 4;
             *reinterpret_cast<uint32_t*>(bt + off) = hi;
             *reinterpret_cast<uint32_t*>(bt + 768 + off) = lo;
-            *reinterpret_cast<uint32_t*>(bt + 1536 + off) = 0u;                  // (the equaliser taps of the previous frame lay over it)
         } else if (tid < 8 * 24 + TCV_PAD) {
             alo[tid - 8 * 24] = 0u;                                              // (y of the previous frame lay over it)
         } else if (tid - (8 * 24 + TCV_PAD) < TCV_ZERO) {
@@ -569,7 +569,9 @@ ber_tconv_kernel(const BerParams prm) {
                 atomicAdd(prm.counters + 2 * si + 1, (unsigned long long)sym_cnt);
             }
         }
-        __syncthreads();   // stream / geq / taps operand are rewritten by the next frame
+        // No barrier here: what the next frame's Tx stage overwrites (the split stream over y, the symbol words, the taps
+        // operand, the exchange buffers) was last read before the pilot barriers above by every thread; geq, red and the
+        // tensor-memory accumulators are rewritten only behind the next frame's own barriers.
         f += df;
         if constexpr (!VERIFY) {
             fe += de;
