@@ -37,6 +37,9 @@ constexpr float TCV_XSCALE = 64.0f;   // stream and taps are scaled by powers of
 constexpr float TCV_HSCALE = 16.0f;   // everything behind the channel is scale-invariant (measured powers, pilot equaliser)
 constexpr uint32_t TCV_IDESC = (1u << 4) | ((16u >> 3) << 17) | ((128u >> 4) << 24);   // D f32, A = B = f16, K-major, N 16, M 128
 constexpr uint32_t TCV_TMEM_COLS = 256;
+#ifndef TCV_NISSUE
+#define TCV_NISSUE 4                   // warps that issue a frame's MMAs (one elected lane each)
+#endif
 #ifndef TCV_TPS
 #define TCV_TPS 16                    // tiles whose MMAs are issued in front of one noise draw of the issuing warp (16: the whole
                                       // frame at once -- measured 6.80 ms against 6.90 (2 per draw) and 6.95 (3 per draw))
@@ -171,7 +174,7 @@ ber_tconv_kernel(const BerParams prm) {
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(tcv_smem_u32(bar)), "r"(1) : "memory");   // one commit per frame
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(tcv_smem_u32(bar)), "r"(TCV_NISSUE) : "memory");   // one commit per issuing warp and frame
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < P::NTW; i += NT) tw[i] = reinterpret_cast<const C2*>(prm.tw)[i];
@@ -384,7 +387,8 @@ ber_tconv_kernel(const BerParams prm) {
         // noise draws; the tensor core then works through them (~40 cycles each, bound by its shared-memory reads) while
         // every warp draws noise;
         // the issuing warp rotates from frame to frame so that no scheduler carries it every time.
-        const bool is_issuer = warp_u == (int)(issuer & (NW - 1));   // warp-uniform
+        const int irank = (warp_u - (int)issuer) & (NW - 1);          // warp-uniform: issuing warps have irank < TCV_NISSUE
+        const bool is_issuer = irank < TCV_NISSUE;
         ++issuer;
         if (is_issuer) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t a_hi = tcv_smem_u32(ahi), a_lo = tcv_smem_u32(alo), b0 = tcv_smem_u32(bt);
@@ -398,15 +402,16 @@ ber_tconv_kernel(const BerParams prm) {
                 if (tcv_elect_one()) {
 #pragma unroll
                     for (int ti = TCV_TPS * tt; ti < TCV_TPS * tt + TCV_TPS && ti < NTILE; ++ti) {
+                        if (ti % TCV_NISSUE != irank) continue;          // the issuing warps share the tiles round-robin
                         const uint32_t tacc = tmem + (uint32_t)(16 * ti);
 #pragma unroll
                         for (int k = 0; k < 3; ++k) {
                             tcv_mma(tacc, tcv_desc(a_hi + ti * 2048 + k * 32, 16, 128), tcv_desc(b0 + k * 256, 128, 768), k != 0);
                             tcv_mma(tacc, tcv_desc(a_lo + ti * 2048 + k * 32, 16, 128), tcv_desc(b0 + k * 256, 128, 1536), 1u);
                         }
-                        if (ti == NTILE - 1)
-                            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(tcv_smem_u32(bar)) : "memory");
                     }
+                    if (TCV_TPS * tt + TCV_TPS >= NTILE)                 // after this warp's last tile: completes when all of its MMAs have
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(tcv_smem_u32(bar)) : "memory");
                 }
                 __syncwarp();
             }
