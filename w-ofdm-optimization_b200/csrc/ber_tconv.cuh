@@ -15,14 +15,19 @@
 //   * B (16 x 48, K-major) holds the taps, rebuilt per frame: output column 2o / 2o+1 = Re / Im of r[4 row + o], o < 4, from
 //     T_hi; columns 8 + (2o, 2o+1) the same from T_lo.  r = hi.[T_hi | T_lo] + lo.[T_hi | 0]: two 128 x 16 x 16 MMAs per
 //     (tile of 512 samples, K step of 8 samples), fp32 accumulation in tensor memory (16 columns per tile);
-//   * the MMAs of a frame (6 per tile, issued by one lane of each warp) run while all threads draw the frame's noise
-//     (Philox + Box-Muller, kept in registers: nothing is parked in shared memory); the accumulators are read with
-//     tcgen05.ld once for the frame-wide signal power and once more for y = r + g n, which is written as plain fp32
-//     over the (dead) split stream for the Rx stage.
+//   * the MMAs of a frame (6 per tile; one elected lane of each of TCV_NISSUE warps issues them on the uniform datapath and
+//     commits them to an mbarrier) run while all threads draw the frame's noise (Philox + Box-Muller, kept in registers:
+//     nothing is parked in shared memory); the accumulators are read with tcgen05.ld once for the frame-wide signal
+//     power and once more for y = r + g n, which is written as plain fp32 over the (dead) split stream for the Rx stage.
 // Outputs past the kept samples (MATLAB's full-length noise normalisation) are more rows of the same product: the
 // stream is followed by zeros.  Noise numbering: stream sample i uses draw i (BerParams::chunk == 0), thread-independent.
-// fp32, one CTA of 256 threads per frame, S <= 16 symbols in one Tx pass, L <= 21, prefix / suffix / tails within the
-// outer register rows (the host checks, ber_host.cu:choose_variant).
+// Around the convolution: a Tx window that is one value between its tails rides on the constellation table, an Rx window
+// of that kind is divided out (BerParams::flat_tx / flat_rx, host-checked; arbitrary windows take the general path); the
+// slicer packs the decisions of four sub-carriers into a word and counts bit and symbol errors per word; six CTA
+// barriers per frame (none at its end: see the comment there).
+// fp32, one CTA of 256 threads per frame, two CTAs per SM (256 of the 512 tensor-memory columns each), S <= 16 symbols in
+// one Tx pass, L <= 21, prefix / suffix / tails within the outer register rows (the host checks,
+// ber_host.cu:choose_variant).
 #pragma once
 #include <cuda_fp16.h>
 #include "ber_kernel.cuh"
@@ -38,7 +43,8 @@ constexpr float TCV_HSCALE = 16.0f;   // everything behind the channel is scale-
 constexpr uint32_t TCV_IDESC = (1u << 4) | ((16u >> 3) << 17) | ((128u >> 4) << 24);   // D f32, A = B = f16, K-major, N 16, M 128
 constexpr uint32_t TCV_TMEM_COLS = 256;
 #ifndef TCV_NISSUE
-#define TCV_NISSUE 4                   // warps that issue a frame's MMAs (one elected lane each)
+#define TCV_NISSUE 4                   // warps that issue a frame's MMAs (one elected lane each, tiles round-robin); measured on
+                                      // the quick bench: 1 -> 6.42 ms, 2 -> 6.47, 4 -> 6.34, 8 -> 6.51
 #endif
 #ifndef TCV_TPS
 #define TCV_TPS 16                    // tiles whose MMAs are issued in front of one noise draw of the issuing warp (16: the whole
@@ -383,10 +389,10 @@ ber_tconv_kernel(const BerParams prm) {
         // =========================== channel + AWGN ===========================
         // r = conv(h, u) (wofdm_simulation.py:206-209) on the tensor cores; y = r + sqrt(Pr*10^(-snr/10)/Pn) n with Pr, Pn
         // summed over the whole frame (:135-138; noise_norm 1: over the full convolution, main_BER_calculation.m:260-261,289-292)
-        // One elected lane issues the frame's MMAs (uniform datapath: 6 UTCHMMA per tile back to back) in front of its warp's
-        // noise draws; the tensor core then works through them (~40 cycles each, bound by its shared-memory reads) while
-        // every warp draws noise;
-        // the issuing warp rotates from frame to frame so that no scheduler carries it every time.
+        // One elected lane of each of TCV_NISSUE warps issues its share of the frame's MMAs (uniform datapath: 6 UTCHMMA per
+        // tile back to back) in front of the warp's noise draws; the tensor core then works through them (~40 cycles each,
+        // bound by its shared-memory reads) while every warp draws noise.  The issuing warps rotate from frame to frame
+        // so that no scheduler carries them every time.
         const int irank = (warp_u - (int)issuer) & (NW - 1);          // warp-uniform: issuing warps have irank < TCV_NISSUE
         const bool is_issuer = irank < TCV_NISSUE;
         ++issuer;
@@ -398,7 +404,7 @@ ber_tconv_kernel(const BerParams prm) {
 #pragma unroll
         for (int tt = 0; tt < NTILE; ++tt) {
             const int p = 512 * tt + 4 * row + 2 * wg;
-            if (is_issuer && TCV_TPS * tt < NTILE) {           // two tiles per step: every MMA is in flight before the draws are half done
+            if (is_issuer && TCV_TPS * tt < NTILE) {           // (TCV_TPS = 16: everything in front of the first draw)
                 if (tcv_elect_one()) {
 #pragma unroll
                     for (int ti = TCV_TPS * tt; ti < TCV_TPS * tt + TCV_TPS && ti < NTILE; ++ti) {
