@@ -812,7 +812,11 @@ ber_frame_kernel(const BerParams prm) {
                 atomicAdd(prm.counters + 2 * si + 1, (unsigned long long)sym_cnt);
             }
         }
-        __syncthreads();   // taps / stream / geq are rewritten by the next frame
+        // the register policy with one CTA per frame needs no barrier here: taps were copied to registers before the power
+        // barrier, the stream and the symbol words were last read before the pilot barriers, the parked noise before the
+        // receiver's; geq and red are rewritten only behind the next frame's own barriers (CIRC recomputes hf from taps
+        // behind its own barriers but reads them late; clusters and the staged policy keep the barrier)
+        if (!(REGS && CL == 1 && !CIRC && !VERIFY)) __syncthreads();   // taps / stream / geq are rewritten by the next frame
         f += df;
         if constexpr (!VERIFY) {
             fe += de;
