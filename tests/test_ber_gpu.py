@@ -388,9 +388,15 @@ def test_verify_cluster_kernel_over_shapes(handle, name, cp):
     plan.close()
 
 
+@pytest.mark.parametrize("policy", ["tconv", "regs"])
 @pytest.mark.parametrize("name", ["WOLA", "CPW", "CP"])
-def test_verify_and_replay_n512_tuned_kernel(handle, name):
-    """N = 512: one 512-thread CTA per frame (register-resident policy), verify mode and a production replay."""
+def test_verify_and_replay_n512_tuned_kernel(handle, name, policy, monkeypatch):
+    """N = 512: one 512-thread CTA per frame (tensor-core convolution; register-resident policy with WOFDM_NO_TCONV),
+    verify mode and a production replay."""
+    if policy == "regs":
+        monkeypatch.setenv("WOFDM_NO_TCONV", "1")
+    else:
+        monkeypatch.delenv("WOFDM_NO_TCONV", raising=False)
     ttx, trx = (0, 0) if name == "CP" else (16, 20)
     p = O.system_params(name, 512, 32, ttx, trx, S=16, bits=4, noise_norm=1, constellation=1)
     vt, vr, _, _ = O.perturbed_windows(p, seed=3)
@@ -399,10 +405,10 @@ def test_verify_and_replay_n512_tuned_kernel(handle, name):
     n = O.noise_len(p, 21)
     frames = [(h[:, k], 12.0 + 10 * k, rng.integers(0, 16, size=(512, 16)), rng.standard_normal(n) + 1j * rng.standard_normal(n))
               for k in range(2)]
-    check_frames(handle, p, vt, vr, frames, 0)
+    check_frames(handle, p, vt, vr, frames, 0, no_tconv=(policy == "regs"))
     s = to_sys(p, 0)
     plan = handle.ber_plan(s, vt, vr, h, [20.0])
-    assert "n512_t512" in plan.kernel, plan.kernel
+    assert "n512_t512" in plan.kernel and ("f32t" in plan.kernel) == (policy == "tconv"), plan.kernel
     plan.close()
     res = handle.ber_run(s, vt, vr, h, [20.0], 2, seed=31)
     sym, nz = handle.ber_draws(s, 21, 31, 0, np.arange(4))

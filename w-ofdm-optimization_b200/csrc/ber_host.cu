@@ -188,7 +188,7 @@ int prepare_kernel(wofdm_ctx* h, const BerVariant& v, size_t smem, int sm_count,
     WOFDM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, v.fn, v.NT, smem));
     if (v.ntile > 0) {
         // the occupancy calculator counts a kernel that allocates tensor memory as one CTA per SM; these kernels take
-        // 256 of the 512 columns, so registers, shared memory and tensor memory together decide
+        // 256 of the 512 columns (N = 256; all of them at N = 512), so registers, shared memory and tensor memory together decide
         cudaFuncAttributes fa;
         int dev = 0, smem_sm = 0, regs_sm = 0;
         WOFDM_CUDA(h, cudaFuncGetAttributes(&fa, v.fn));
@@ -196,7 +196,7 @@ int prepare_kernel(wofdm_ctx* h, const BerVariant& v, size_t smem, int sm_count,
         WOFDM_CUDA(h, cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
         WOFDM_CUDA(h, cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev));
         const int by_smem = (int)((size_t)smem_sm / (smem + 1024)), by_regs = regs_sm / (((fa.numRegs + 7) & ~7) * v.NT);
-        const int by_tmem = 512 / (int)TCV_TMEM_COLS;
+        const int by_tmem = 512 / (int)tconv_tmem_cols(v.ntile);
         nb = std::max(nb, std::min(by_smem, std::min(by_regs, by_tmem)));
     }
     if (const char* f = getenv("WOFDM_FORCE_CTAS_PER_SM")) nb = std::max(1, atoi(f));    // tuning aid

@@ -1,5 +1,6 @@
 // fp32 instantiations of K1 with the channel convolution on the tensor cores (ber_tconv.cuh): N = 256, one CTA of 256
-// threads per frame, two CTAs per SM; NTILE = tiles of 512 stream samples (tensor-memory accumulators) per frame.
+// threads per frame, two CTAs per SM; N = 512, one CTA of 512 threads per frame and SM; NTILE = tiles of 512 stream samples
+// (tensor-memory accumulators) per frame.
 #include "ber_registry.h"
 #include "ber_tconv.cuh"
 namespace wofdm {
@@ -28,5 +29,8 @@ struct TconvVariantImpl {
 void register_ber_f32_tconv(std::vector<BerVariant>& out) {
     WOFDM_VARIANT_TCONV(256, 256, 9, 2)
     WOFDM_VARIANT_TCONV(256, 256, 10, 2)
+    // N = 512: one CTA of 512 threads per frame and SM, all 512 tensor-memory columns
+    WOFDM_VARIANT_TCONV(512, 512, 18, 1)
+    WOFDM_VARIANT_TCONV(512, 512, 19, 1)
 }
 }  // namespace wofdm

@@ -25,8 +25,9 @@
 // of that kind is divided out (BerParams::flat_tx / flat_rx, host-checked; arbitrary windows take the general path); the
 // slicer packs the decisions of four sub-carriers into a word and counts bit and symbol errors per word; six CTA
 // barriers per frame (none at its end: see the comment there).
-// fp32, one CTA of 256 threads per frame, two CTAs per SM (256 of the 512 tensor-memory columns each), S <= 16 symbols in
-// one Tx pass, L <= 21, prefix / suffix / tails within the outer register rows (the host checks,
+// fp32; N = 256: one CTA of 256 threads per frame, two CTAs per SM (256 of the 512 tensor-memory columns each); N = 512:
+// one CTA of 512 threads per frame and SM (all 512 columns; the two sets of eight warps take the even / odd tiles);
+// S <= 16 symbols in one Tx pass, L <= 21, prefix / suffix / tails within the outer register rows (the host checks,
 // ber_host.cu:choose_variant).
 #pragma once
 #include <cuda_fp16.h>
@@ -41,14 +42,11 @@ constexpr int TCV_ZERO = 24;          // zero samples written behind the stream 
 constexpr float TCV_XSCALE = 64.0f;   // stream and taps are scaled by powers of two into the comfortable fp16 range;
 constexpr float TCV_HSCALE = 16.0f;   // everything behind the channel is scale-invariant (measured powers, pilot equaliser)
 constexpr uint32_t TCV_IDESC = (1u << 4) | ((16u >> 3) << 17) | ((128u >> 4) << 24);   // D f32, A = B = f16, K-major, N 16, M 128
-constexpr uint32_t TCV_TMEM_COLS = 256;
+// tensor-memory columns a CTA allocates: 16 per tile, a power of two (two CTAs per SM when 256 are enough)
+__host__ __device__ constexpr uint32_t tconv_tmem_cols(int ntile) { return 16 * ntile <= 256 ? 256u : 512u; }
 #ifndef TCV_NISSUE
 #define TCV_NISSUE 4                   // warps that issue a frame's MMAs (one elected lane each, tiles round-robin); measured on
                                       // the quick bench: 1 -> 6.42 ms, 2 -> 6.47, 4 -> 6.34, 8 -> 6.51
-#endif
-#ifndef TCV_TPS
-#define TCV_TPS 16                    // tiles whose MMAs are issued in front of one noise draw of the issuing warp (16: the whole
-                                      // frame at once -- measured 6.80 ms against 6.90 (2 per draw) and 6.95 (3 per draw))
 #endif
 
 __host__ __device__ constexpr int tconv_alen(int ntile) { return TCV_PAD + ntile * 512 + TCV_SLACK; }
@@ -136,8 +134,12 @@ ber_tconv_kernel(const BerParams prm) {
     using C2 = float2;
     using P = FftPlan<N>;
     constexpr int TPF = P::TPF, FPP = NT / TPF, ER = 2, NW = NT / 32;
-    static_assert(NT == 256, "two warpgroups share the four outputs of an operand row");
-    static_assert(16 * NTILE <= (int)TCV_TMEM_COLS, "accumulators of a frame must fit the tensor-memory allocation");
+    // 256 threads: warps 0-3 / 4-7 take outputs 0,1 / 2,3 of their rows in every tile.  512 threads (N = 512): a second
+    // set of eight warps, and the two sets take the even / the odd tiles.
+    static_assert(NT == 256 || NT == 512, "eight warps read a tile's accumulators");
+    constexpr int TG = NT / 256, NTH = (NTILE + TG - 1) / TG;             // tile sets; tiles per thread
+    constexpr uint32_t TMEM_COLS = tconv_tmem_cols(NTILE);
+    static_assert(16 * NTILE <= (int)TMEM_COLS, "accumulators of a frame must fit tensor memory");
 
     extern __shared__ __align__(128) unsigned char tcv_smem[];
     unsigned char* const smem_raw = tcv_smem;
@@ -176,7 +178,7 @@ ber_tconv_kernel(const BerParams prm) {
 
     // ---- one-time: tensor memory, barrier, tables ----
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tcv_smem_u32(tmem_slot)), "r"(TCV_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tcv_smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
@@ -221,9 +223,10 @@ ber_tconv_kernel(const BerParams prm) {
     }
 
     // this thread's operand row inside every tile (TMEM lane) and its half of the row's four outputs
-    const int wg = warp >> 2, row = (warp & 3) * 32 + lane;
+    const int wg = (warp >> 2) & 1, row = (warp & 3) * 32 + lane;
     const int warp_u = __shfl_sync(0xffffffffu, warp, 0);      // the warp index as a value the compiler knows to be warp-uniform
-    const uint32_t tlane = tmem + ((uint32_t)((warp_u & 3) * 32) << 16) + (uint32_t)(4 * (warp_u >> 2));
+    const int tp = TG == 1 ? 0 : (warp_u >> 3);                // this warp's tile set: tiles tp, tp + TG, ...
+    const uint32_t tlane = tmem + ((uint32_t)((warp_u & 3) * 32) << 16) + (uint32_t)(4 * ((warp_u >> 2) & 1));
     uint32_t phase = 0, issuer = blockIdx.x;
 
     const long long fslot = blockIdx.x, nslots = gridDim.x;
@@ -398,31 +401,32 @@ ber_tconv_kernel(const BerParams prm) {
         ++issuer;
         if (is_issuer) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t a_hi = tcv_smem_u32(ahi), a_lo = tcv_smem_u32(alo), b0 = tcv_smem_u32(bt);
-        // ---- noise of this thread's samples p, p+1 of every tile, p = 512 tile + 4 row + 2 wg (draw = position), |n|^2 partial
-        C2 nz[NTILE][2];
+        if (is_issuer) {
+            if (tcv_elect_one()) {
+#pragma unroll
+                for (int ti = 0; ti < NTILE; ++ti) {
+                    if (ti % TCV_NISSUE != irank) continue;              // the issuing warps share the tiles round-robin
+                    const uint32_t tacc = tmem + (uint32_t)(16 * ti);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        tcv_mma(tacc, tcv_desc(a_hi + ti * 2048 + k * 32, 16, 128), tcv_desc(b0 + k * 256, 128, 768), k != 0);
+                        tcv_mma(tacc, tcv_desc(a_lo + ti * 2048 + k * 32, 16, 128), tcv_desc(b0 + k * 256, 128, 1536), 1u);
+                    }
+                }
+                // completes when all of this warp's MMAs have
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(tcv_smem_u32(bar)) : "memory");
+            }
+            __syncwarp();
+        }
+        // ---- noise of this thread's samples p, p+1 of its tiles, p = 512 tile + 4 row + 2 wg (draw = position), |n|^2 partial
+        C2 nz[NTH][2];
         C2 pr2 = mk2<T>(0, 0), pn2 = mk2<T>(0, 0);
 #pragma unroll
-        for (int tt = 0; tt < NTILE; ++tt) {
+        for (int kt = 0; kt < NTH; ++kt) {
+            const int tt = TG * kt + tp;
             const int p = 512 * tt + 4 * row + 2 * wg;
-            if (is_issuer && TCV_TPS * tt < NTILE) {           // (TCV_TPS = 16: everything in front of the first draw)
-                if (tcv_elect_one()) {
-#pragma unroll
-                    for (int ti = TCV_TPS * tt; ti < TCV_TPS * tt + TCV_TPS && ti < NTILE; ++ti) {
-                        if (ti % TCV_NISSUE != irank) continue;          // the issuing warps share the tiles round-robin
-                        const uint32_t tacc = tmem + (uint32_t)(16 * ti);
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) {
-                            tcv_mma(tacc, tcv_desc(a_hi + ti * 2048 + k * 32, 16, 128), tcv_desc(b0 + k * 256, 128, 768), k != 0);
-                            tcv_mma(tacc, tcv_desc(a_lo + ti * 2048 + k * 32, 16, 128), tcv_desc(b0 + k * 256, 128, 1536), 1u);
-                        }
-                    }
-                    if (TCV_TPS * tt + TCV_TPS >= NTILE)                 // after this warp's last tile: completes when all of its MMAs have
-                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(tcv_smem_u32(bar)) : "memory");
-                }
-                __syncwarp();
-            }
             C2 n0 = mk2<T>(0, 0), n1 = mk2<T>(0, 0);
-            if (tt < NTILE - 2 || 512 * tt + 128 * (warp & 3) < npow) {   // warp-uniform; every tile but the last two lies inside the sums
+            if (tt < NTILE - 2 || (tt < NTILE && 512 * tt + 128 * (warp & 3) < npow)) {   // warp-uniform; every tile but the last two lies inside the sums
                 if constexpr (VERIFY) {
                     const double2* nin = prm.noise_in + (size_t)f * prm.noise_len;
                     if (p < npow) n0 = to_v2<T>(nin[p]);
@@ -435,7 +439,7 @@ ber_tconv_kernel(const BerParams prm) {
                     }
                 }
             }
-            nz[tt][0] = n0; nz[tt][1] = n1;
+            nz[kt][0] = n0; nz[kt][1] = n1;
             pn2 = csq_acc(n0, pn2);
             pn2 = csq_acc(n1, pn2);
         }
@@ -445,20 +449,21 @@ ber_tconv_kernel(const BerParams prm) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         constexpr int GT = 3;                      // tiles per batch of accumulator loads (one wait per batch)
 #pragma unroll
-        for (int t0 = 0; t0 < NTILE; t0 += GT) {
+        for (int t0 = 0; t0 < NTH; t0 += GT) {
             C2 a0[GT], a1[GT], b0[GT], b1[GT];
 #pragma unroll
             for (int u = 0; u < GT; ++u) {
-                if (t0 + u < NTILE) {
-                    tcv_ld4(tlane + (uint32_t)(16 * (t0 + u)), a0[u], a1[u]);
-                    tcv_ld4(tlane + (uint32_t)(16 * (t0 + u) + 8), b0[u], b1[u]);
+                if (t0 + u < NTH) {
+                    const int tt = min(TG * (t0 + u) + tp, NTILE - 1);      // (a set's tile past the frame: result masked below)
+                    tcv_ld4(tlane + (uint32_t)(16 * tt), a0[u], a1[u]);
+                    tcv_ld4(tlane + (uint32_t)(16 * tt + 8), b0[u], b1[u]);
                 }
             }
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
             for (int u = 0; u < GT; ++u) {
-                if (t0 + u < NTILE) {
-                    const int tt = t0 + u, p = 512 * tt + 4 * row + 2 * wg;
+                if (t0 + u < NTH) {
+                    const int tt = TG * (t0 + u) + tp, p = 512 * tt + 4 * row + 2 * wg;
                     C2 r0 = cadd(a0[u], b0[u]), r1 = cadd(a1[u], b1[u]);
                     if (tt >= NTILE - 2 && 512 * (tt + 1) > npow) {
                         if (p >= npow) r0 = mk2<T>(0, 0);
@@ -474,21 +479,22 @@ ber_tconv_kernel(const BerParams prm) {
         __syncthreads();                           // also: every thread has seen the MMAs complete -- the split stream is dead
         const T g = noise_gain(block_total<NW>(red), snr_lin, block_total<NW>(red + 32));
 #pragma unroll
-        for (int t0 = 0; t0 < NTILE; t0 += GT) {
+        for (int t0 = 0; t0 < NTH; t0 += GT) {
             C2 a0[GT], a1[GT], b0[GT], b1[GT];
 #pragma unroll
             for (int u = 0; u < GT; ++u) {
-                if (t0 + u < NTILE) {
-                    tcv_ld4(tlane + (uint32_t)(16 * (t0 + u)), a0[u], a1[u]);
-                    tcv_ld4(tlane + (uint32_t)(16 * (t0 + u) + 8), b0[u], b1[u]);
+                if (t0 + u < NTH) {
+                    const int tt = min(TG * (t0 + u) + tp, NTILE - 1);
+                    tcv_ld4(tlane + (uint32_t)(16 * tt), a0[u], a1[u]);
+                    tcv_ld4(tlane + (uint32_t)(16 * tt + 8), b0[u], b1[u]);
                 }
             }
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
             for (int u = 0; u < GT; ++u) {
-                if (t0 + u < NTILE) {
-                    const int tt = t0 + u, p = 512 * tt + 4 * row + 2 * wg;
-                    const C2 y0 = caxpy(g, nz[tt][0], cadd(a0[u], b0[u])), y1 = caxpy(g, nz[tt][1], cadd(a1[u], b1[u]));
+                if (t0 + u < NTH) {
+                    const int tt = TG * (t0 + u) + tp, p = 512 * tt + 4 * row + 2 * wg;
+                    const C2 y0 = caxpy(g, nz[t0 + u][0], cadd(a0[u], b0[u])), y1 = caxpy(g, nz[t0 + u][1], cadd(a1[u], b1[u]));
                     if (tt < NTILE - 2 || p + 1 < sec) *reinterpret_cast<float4*>(yb + p) = make_float4(y0.x, y0.y, y1.x, y1.y);
                     else if (p < sec) yb[p] = y0;
                 }
@@ -594,7 +600,7 @@ ber_tconv_kernel(const BerParams prm) {
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(TCV_TMEM_COLS) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(TMEM_COLS) : "memory");
 }
 
 }  // namespace wofdm
