@@ -34,6 +34,22 @@ def test_oracle_reproduces_the_reference_estimate():
             assert np.max(np.abs(est - ref)) < 1e-12 * np.max(ref), (name, key)
 
 
+def test_analytical_psd_of_the_mirror_matches_the_reference():
+    """The closed-form curves S_opt / S_rc / S_cp are host code (no GPU needed): the mirror's analytical_psd against the
+    reference's own outputs, and the allocation of estimate_obr (DC and 95 centre bins null, 160 data rows)."""
+    from wofdm_b200 import timefreq
+    bins = O.psd_data_bins(256, 48)
+    assert bins.size == 160 and bins[0] == 1 and bins[79] == 80 and bins[80] == 176 and bins[-1] == 255
+    for k, g, name, p, sig in cases():
+        ttx, trx = int(g[f"c{k}_ttx"]), int(g[f"c{k}_trx"])
+        m = timefreq.wOFDMSystem(name, 256, p.cp, ttx, trx, "/tmp")
+        assert m.cs_len == p.cs
+        S = m.analytical_psd(200e-9, np.diag(g[f"c{k}_win_tx"]), 48, 2048)
+        for got, key in zip(S, ("opt", "rc", "cp")):
+            ref = g[f"c{k}_S_{key}"]
+            assert np.allclose(got, ref, rtol=1e-9, atol=1e-12 * np.max(ref)), (name, key)
+
+
 @pytest.fixture(scope="module")
 def handle():
     h = W.Handle([0])
