@@ -120,10 +120,13 @@ WOFDM_API int wofdm_ber_plan_create(wofdm_handle h, const wofdm_sys_t* sys, cons
                           wofdm_ber_plan* plan);
 /* Zeroes the plan's device counters and launches the shard on device slot `slot` of the handle,
  * on `stream` (a cudaStream_t; NULL = the plan's own stream).  Returns without synchronising.
+ * One launch per slot and read: a second launch on the same slot before wofdm_ber_plan_read REPLACES the
+ * first launch's counts (it waits for the first one if that ran on a different stream).
  * d_counters (optional out) = device pointer to int64[n_snr][2] = {bit_err, sym_err}. */
 WOFDM_API int wofdm_ber_plan_launch(wofdm_ber_plan plan, int slot, int64_t ensemble, uint64_t seed, uint32_t variant,
                           int shard_index, int shard_count, void* stream, void** d_counters);
-/* Waits for the launches and adds the counters of every slot launched since the last read. */
+/* Waits for the launches and adds up the counters of the slots (devices) launched since the last read:
+ * each slot contributes its most recent launch. */
 WOFDM_API int wofdm_ber_plan_read(wofdm_ber_plan plan, int64_t* bit_err, int64_t* sym_err);
 /* Name of the kernel variant the plan dispatches to (for logs / profiles). */
 WOFDM_API const char* wofdm_ber_plan_kernel(wofdm_ber_plan plan);

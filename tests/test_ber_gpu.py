@@ -330,6 +330,69 @@ def test_tensor_core_convolution_is_fp32_grade(handle):
     assert np.mean(dec_t != dec_d) < 2e-3
 
 
+@pytest.mark.parametrize("hscale,wscale", [(1e-6, 1.0), (1e4, 1.0), (1.0, 3e4), (3e-7, 1e-5)])
+def test_tensor_core_kernel_is_scale_invariant(handle, hscale, wscale):
+    """The tensor-core kernels stage the stream and the taps as fp16 pairs behind fixed scales; the host gives them a
+    known range (unit-peak Tx window and taps, ber_host.cu: build_tables / cast_chan), which the chain allows: a common
+    factor of the Tx signal or of a channel's taps cancels in the measured-power noise gain and the pilot equaliser.
+    Channels in path-loss units or an un-normalised window must give the oracle's answer."""
+    p = O.system_params("WOLA", 256, 16, 8, 10, S=16, bits=4, noise_norm=0, constellation=0)
+    vt, vr, _, _ = O.perturbed_windows(p, seed=5)
+    rng = np.random.default_rng(17)
+    frames = []
+    for k in range(3):
+        h = O.synth_channels(1, 21, seed=40 + k)[:, 0] * hscale * (1.0 + k)
+        n = O.noise_len(p, 21)
+        frames.append((h, 10.0 + 15 * k, rng.integers(0, 16, size=(256, 16)), rng.standard_normal(n) + 1j * rng.standard_normal(n)))
+    s = to_sys(p, 0)
+    plan = handle.ber_plan(s, vt * wscale, vr, np.stack([f[0] for f in frames], axis=1), [10.0])
+    assert "f32t" in plan.kernel, plan.kernel
+    plan.close()
+    check_frames(handle, p, vt * wscale, vr, frames, 0)
+    # production mode: same counters as the well-scaled job, up to boundary flips (fp32 rounding differs with the scale)
+    chan = O.synth_channels(4, 21, seed=50)
+    snr = np.array([5.0, 25.0])
+    a = handle.ber_run(s, vt, vr, chan, snr, 3, seed=9)
+    b = handle.ber_run(s, vt * wscale, vr, chan * hscale, snr, 3, seed=9)
+    assert np.all(np.abs(a["sym_err"] - b["sym_err"]) <= 3 + 0.002 * a["sym_err"]), (a["sym_err"], b["sym_err"])
+
+
+def test_production_replay_frame_received_in_two_passes(handle):
+    """S = 17 > 16 transforms per CTA: the register kernels receive the frame in two passes and the second one reads the
+    stream after the pilot barriers, so the frame keeps its closing barrier (WOLA, cp = 16 has rm = 6 <
+    tail_tx = 8, where a missing barrier lets the next frame's first Tx tail land in the samples pass 2 still reads).
+    Production counters of a job with several frames per CTA must equal the verify-mode kernel's (which always had the
+    barrier) on the exported draws of every frame, exactly: same arithmetic, same code."""
+    g = load_ser_golden("WOLA")
+    chans = np.concatenate([g["A_channels"], g["B_channels"]], axis=1)
+    snr = np.array([8.0, 30.0])
+    ens = 200                                  # 1200 frames on <= 296 resident CTAs
+    p = golden_params(g, 17, constellation=0, noise_norm=0)
+    vt, vr = golden_windows(g, p)[0]
+    s = to_sys(p, 0)
+    plan = handle.ber_plan(s, vt, vr, chans, snr)
+    assert "f32t" not in plan.kernel and "_c" in plan.kernel, plan.kernel       # a register-policy kernel
+    plan.close()
+    res = handle.ber_run(s, vt, vr, chans, snr, ens, seed=77)
+    C = chans.shape[1]
+    F = len(snr) * C * ens
+    ids = np.arange(F)
+    want_s, want_b = np.zeros(len(snr), dtype=np.int64), np.zeros(len(snr), dtype=np.int64)
+    for lo in range(0, F, 300):
+        part = ids[lo:lo + 300]
+        sym, nz = handle.ber_draws(s, chans.shape[0], 77, 0, part)
+        _, _, be, se = handle.ber_verify(s, vt, vr, chans[:, (part // ens) % C], snr[part // (ens * C)], sym, nz)
+        np.add.at(want_s, part // (ens * C), se)
+        np.add.at(want_b, part // (ens * C), be)
+    assert np.array_equal(res["sym_err"], want_s) and np.array_equal(res["bit_err"], want_b)
+    # and the oracle on a sample of the frames
+    sym, nz = handle.ber_draws(s, chans.shape[0], 77, 0, ids[::97])
+    _, _, _, se = handle.ber_verify(s, vt, vr, chans[:, (ids[::97] // ens) % C], snr[ids[::97] // (ens * C)], sym, nz)
+    tot = sum(O.frame_chain_structured(p, vt, vr, chans[:, (f // ens) % C], snr[f // (ens * C)], sym[k].T, nz[k]).sym_err
+              for k, f in enumerate(ids[::97]))
+    assert abs(int(se.sum()) - tot) <= 3 + 0.002 * tot
+
+
 @pytest.mark.parametrize("name,cp", [("WOLA", 16), ("CPwtx", 22), ("CPW", 10)])
 def test_tensor_core_kernel_with_windows_that_are_not_flat(handle, name, cp):
     """The tensor-core kernel folds a flat Tx window into its constellation table and divides a flat Rx window out

@@ -7,6 +7,7 @@ creating a handle without a CUDA device raises ``WofdmError``.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 import os
 
 import numpy as np
@@ -188,9 +189,12 @@ class Handle:
         if rc:
             self._h = None
             raise WofdmError(rc, "wofdm_create failed (no CUDA device? this library has no CPU path)")
+        self._plans = weakref.WeakSet()         # live BerPlan objects: a plan's native side points into this context
 
     def close(self):
         if getattr(self, "_h", None):
+            for p in list(getattr(self, "_plans", ())):     # plans first: wofdm_ber_plan_destroy reads the context
+                p.close()
             load().wofdm_destroy(self._h)
             self._h = None
 
@@ -359,6 +363,7 @@ class BerPlan:
         rc = load().wofdm_ber_plan_create(handle._h, C.byref(s), _ptr(wt, _dp), _ptr(wr, _dp), _ptr(chf, _dp), L, Cn,
                                           _ptr(snr, _dp), snr.size, C.byref(self._p))
         handle._check(rc)
+        handle._plans.add(self)
 
     @property
     def kernel(self):

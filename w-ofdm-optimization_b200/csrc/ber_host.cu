@@ -7,7 +7,7 @@
 
 #include "host_common.h"
 #include "mask_kernel.cuh"
-#include "ber_tconv.cuh"
+#include "ber_tconv2.cuh"
 
 using namespace wofdm;
 
@@ -57,6 +57,7 @@ void fill_flat(BerParams& prm, const wofdm_sys_t& s, const double* win_tx, const
 void fill_split(BerParams& prm, const BerVariant& v) {
     prm.split = v.CL > 1 ? prm.S * prm.stride / v.CL : 0;
     prm.split_nt = v.CL > 1 ? v.NT : 0;
+    prm.n48 = v.gen == 2 ? 1 : 0;      // 48-bit noise draws in receiver layout (ber_kernel.cuh: noise_draw48)
 }
 
 // win_tx (may be NULL): the circular-interior kernels need it flat between the tails; no_circ excludes them
@@ -74,6 +75,7 @@ int choose_variant(wofdm_ctx* h, const wofdm_sys_t& s, int L, bool verify, bool 
     // WOFDM_VARIANT=<substring> restricts the tuned candidates (kernel tuning aid, e.g. "_b2")
     const char* want = getenv("WOFDM_VARIANT");
     if (no_tconv || getenv("WOFDM_NO_TCONV")) no_tconv = true;
+    const int tconv_gen = getenv("WOFDM_TCONV_GEN") ? atoi(getenv("WOFDM_TCONV_GEN")) : 2;   // 1: ber_tconv.cuh, 2: ber_tconv2.cuh
     if (!fp64 && !force_staged) {
         for (const auto& v : h->variants) {
             if (v.TC == 0 || v.fp64 || v.verify != verify || v.N != s.N) continue;
@@ -84,6 +86,9 @@ int choose_variant(wofdm_ctx* h, const wofdm_sys_t& s, int L, bool verify, bool 
                 // stream inside the frame's tiles.  Noise numbering: draw = position (chunk 0).  Takes tx_stream too.
                 const int tpf = s.N / 16, body = s.tail_tx + sec;
                 if (no_tconv || s.S > v.NT / tpf || L > v.LB) continue;
+                if (v.gen != tconv_gen) continue;
+                // second generation: a receiver thread holds at most N48_MAXLEV noise samples besides its 16 FFT rows
+                if (v.gen == 2 && (stride - s.N + (s.noise_norm == 1 ? s.tail_tx + L - 1 : 0) + tpf - 1) / tpf > N48_MAXLEV) continue;
                 if (s.cp > 2 * tpf || s.cs > 2 * tpf || s.tail_tx > 2 * tpf || s.tail_rx / 2 > tpf || s.shift > tpf) continue;
                 const int need = std::max(s.noise_norm == 1 ? body + L - 1 : sec, body + TCV_ZERO);
                 if (need > 512 * v.ntile || sec <= 512 * (v.ntile - 2)) continue;   // (the kernel range-checks its last two tiles only)
@@ -150,10 +155,19 @@ struct HostTables {
     std::vector<unsigned char> wtx, wrx, tw;
 };
 
-void build_tables(const wofdm_sys_t& s, const double* win_tx, const double* win_rx, HostTables& t) {
+// unit_peak (tensor-core kernels): the Tx window is divided by its largest magnitude.  Those kernels stage the stream and
+// the taps as fp16 pairs behind fixed power-of-two scales (ber_tconv.cuh: TCV_XSCALE, TCV_HSCALE), so their inputs must
+// have a known range; the chain itself does not care -- a common factor of the Tx signal or of a channel's taps scales
+// r, the noise follows the measured signal power (wofdm_simulation.py:135-138) and the pilot equaliser divides it out (:223-232).
+void build_tables(const wofdm_sys_t& s, const double* win_tx, const double* win_rx, HostTables& t, bool unit_peak = false) {
     const bool fp64 = s.precision == 1;
     const int n_tx = s.N + s.cp + s.cs;
-    const double k = qam_scale(s) / (double)s.N;   // IDFT 1/N (transmitter.py:58) and constellation scale
+    double k = qam_scale(s) / (double)s.N;   // IDFT 1/N (transmitter.py:58) and constellation scale
+    if (unit_peak) {
+        double mx = 0.0;
+        for (int i = 0; i < n_tx; ++i) mx = std::max(mx, std::fabs(win_tx[i]));
+        if (mx > 0.0 && std::isfinite(mx)) k /= mx;
+    }
     std::vector<double> a(n_tx), b(s.N + s.tail_rx);
     for (int i = 0; i < n_tx; ++i) a[i] = win_tx[i] * k;
     for (int i = 0; i < s.N + s.tail_rx; ++i) b[i] = win_rx[i];
@@ -162,9 +176,20 @@ void build_tables(const wofdm_sys_t& s, const double* win_tx, const double* win_
     cast_any(fp64, build_twiddles(s.N), t.tw);
 }
 
-// channel matrix L x C column-major complex double -> [C][L] V2<T> (same memory order, cast only)
-void cast_chan(bool fp64, const double* chan, size_t n_complex, std::vector<unsigned char>& dst) {
+// channel matrix L x C column-major complex double -> [C][L] V2<T> (same memory order, cast only).  unit_peak (tensor-core
+// kernels, see build_tables): every channel's taps are divided by their largest component magnitude.
+void cast_chan(bool fp64, const double* chan, size_t n_complex, std::vector<unsigned char>& dst, int L = 0, bool unit_peak = false) {
     std::vector<double> v(chan, chan + 2 * n_complex);
+    if (unit_peak && L > 0) {
+        for (size_t c = 0; c + (size_t)L <= n_complex; c += (size_t)L) {
+            double mx = 0.0;
+            for (int i = 0; i < 2 * L; ++i) mx = std::max(mx, std::fabs(v[2 * c + i]));
+            if (mx > 0.0 && std::isfinite(mx)) {
+                const double inv = 1.0 / mx;
+                for (int i = 0; i < 2 * L; ++i) v[2 * c + i] *= inv;
+            }
+        }
+    }
     cast_any(fp64, v, dst);
 }
 
@@ -255,9 +280,10 @@ static int plan_create_impl(wofdm_handle h, const wofdm_sys_t* sys, const double
     }
 
     HostTables t;
-    build_tables(*sys, win_tx, win_rx, t);
+    const bool unit_peak = p->var->ntile > 0;
+    build_tables(*sys, win_tx, win_rx, t, unit_peak);
     std::vector<unsigned char> hchan, hsnr;
-    cast_chan(fp64, chan, (size_t)L * C, hchan);
+    cast_chan(fp64, chan, (size_t)L * C, hchan, L, unit_peak);
     std::vector<double> lin(n_snr);
     for (int i = 0; i < n_snr; ++i) lin[i] = std::pow(10.0, -0.1 * snr_db[i]);   // wofdm_simulation.py:138
     cast_any(fp64, lin, hsnr);
@@ -279,7 +305,7 @@ static int plan_create_impl(wofdm_handle h, const wofdm_sys_t* sys, const double
         cudaError_t e = cudaSetDevice(d.dev);
         if (e == cudaSuccess) {
             rc = prepare_kernel(h, *p->var, p->lay.bytes, d.sm_count, &pd.blocks_per_sm, &pd.max_ctas);
-            if (rc) { delete p; return rc; }
+            if (rc) { const std::string msg = h->err; wofdm_ber_plan_destroy(p); h->err = msg; return rc; }
         }
         // staged policy with frame buffers in global memory: two of them per resident CTA
         const size_t scratch_elems = (size_t)p->lay.pad + sys->tail_tx + (size_t)sys->S * (sys->N + sys->cp + sys->cs - sys->tail_tx) + 64;
@@ -287,7 +313,7 @@ static int plan_create_impl(wofdm_handle h, const wofdm_sys_t* sys, const double
         if (e == cudaSuccess && transient) {
             rc = arena_reserve(h, d, t.wtx.size() + t.wrx.size() + t.tw.size() + hchan.size() + hsnr.size() +
                                          (size_t)n_snr * 16 + pd.scratch_bytes);
-            if (rc) { delete p; return rc; }
+            if (rc) { const std::string msg = h->err; wofdm_ber_plan_destroy(p); h->err = msg; return rc; }
         }
         if (e == cudaSuccess) e = up(&pd.d_wtx, t.wtx);
         if (e == cudaSuccess) e = up(&pd.d_wrx, t.wrx);
@@ -345,6 +371,8 @@ int wofdm_ber_plan_launch(wofdm_ber_plan p, int slot, int64_t ensemble, uint64_t
     prm.scratch = pd.d_scratch;
     prm.scratch_elems = p->use_global ? (long long)(pd.scratch_bytes / ((size_t)pd.blocks_per_sm * d.sm_count * 2 * elem_bytes(p->sys))) : 0;
 
+    // a launch owns its slot's counters: one that is still pending on ANOTHER stream must finish before they are zeroed
+    if (pd.pending && pd.last_stream != st) WOFDM_CUDA(h, cudaStreamSynchronize(pd.last_stream));
     WOFDM_CUDA(h, cudaMemsetAsync(pd.d_cnt, 0, (size_t)p->n_snr * 2 * sizeof(unsigned long long), st));
     if (mine > 0) {
         long long cap = pd.max_ctas;
@@ -470,9 +498,9 @@ int wofdm_ber_verify(wofdm_handle h, const wofdm_sys_t* sys, const double* win_t
     const int grid = (int)std::min<long long>(F, std::max<long long>(max_ctas / ch.var->CL, 1)) * ch.var->CL;
 
     HostTables t;
-    build_tables(*sys, win_tx, win_rx, t);
+    build_tables(*sys, win_tx, win_rx, t, ch.var->ntile > 0);
     std::vector<unsigned char> hchan, hsnr;
-    cast_chan(fp64, chan, (size_t)L * F, hchan);
+    cast_chan(fp64, chan, (size_t)L * F, hchan, L, ch.var->ntile > 0);
     std::vector<double> lin(F);
     for (int i = 0; i < F; ++i) lin[i] = std::pow(10.0, -0.1 * snr_db[i]);
     cast_any(fp64, lin, hsnr);
@@ -671,9 +699,9 @@ int wofdm_ber_run_masked(wofdm_handle h, const wofdm_sys_t* sys, const double* w
     std::vector<unsigned char> twp;
     cast_any(false, build_twiddles(P), twp);
     HostTables t;
-    build_tables(*sys, win_tx, win_rx, t);
+    build_tables(*sys, win_tx, win_rx, t, ch.var->ntile > 0);   // (tx_mask_kernel shares the table: a common factor of its stream)
     std::vector<unsigned char> hchan, hsnr;
-    cast_chan(false, chan, (size_t)L * C, hchan);
+    cast_chan(false, chan, (size_t)L * C, hchan, L, ch.var->ntile > 0);
     std::vector<double> lin(n_snr);
     for (int i = 0; i < n_snr; ++i) lin[i] = std::pow(10.0, -0.1 * snr_db[i]);
     cast_any(false, lin, hsnr);
@@ -717,6 +745,11 @@ int wofdm_ber_run_masked(wofdm_handle h, const wofdm_sys_t* sys, const double* w
     fill_flat(prm, *sys, win_tx, win_rx);
     prm.flat_tx = 0;                       // (the Tx stream comes from tx_mask_kernel)
     fill_split(prm, *ch.var);
+    if (ch.var->TC == 0) {                 // staged kernel: the noise numbering of wofdm_ber_run / _draws (noise_at follows it)
+        BerParams tmp = prm;
+        fill_split(tmp, *prod.var);
+        prm.n48 = tmp.n48;
+    }
     prm.win_tx = d_wtx; prm.win_rx = d_wrx; prm.tw = d_tw; prm.chan = d_chan; prm.snr_lin = d_snr;
     prm.C = C; prm.n_snr = n_snr; prm.ensemble = ensemble; prm.seed = seed; prm.variant = variant;
     philox_round_keys(seed, prm.rk);

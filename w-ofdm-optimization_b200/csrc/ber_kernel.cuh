@@ -51,6 +51,7 @@ struct BerParams {
                                // 0: stream sample i uses draw i (tensor-core convolution policy, ber_tconv.cuh)
     int use_global;            // staged policy: frame buffers live in global scratch
     int split, split_nt;       // CL > 1: stream samples per CTA and threads per CTA (noise block g = rank*NT + local/B); else 0
+    int n48;                   // 1: 48-bit noise draws in receiver layout (ber_tconv2.cuh): noise_draw48
     // device tables, element type T / V2<T>
     const void* win_tx;        // [n_tx]   v_tx * qam_scale / N
     const void* win_rx;        // [N + tail_rx]
@@ -123,17 +124,38 @@ template <int N> __device__ __forceinline__ bool bin_active(int k, int guard) {
     return c >= guard && c < N - guard;
 }
 
-// 16 constellation indices (one byte each) of OFDM symbol s for thread t: sub-carriers t + q*TPF
+// Symbols travel through the kernels as LEVEL CODES, one byte per sub-carrier: (re level << hb) | im level, levels
+// 0..m-1 <-> lattice points 2*level - (m-1).  A production draw IS a level code (uniform over the alphabet either way);
+// the constellation index of the convention (python natural order / MATLAB Gray) is levels_to_idx(code) and only exists
+// at the boundary: verify mode converts the injected indices on load and the decisions on store, wofdm_ber_draws exports
+// indices.  In code space the slicer's output needs no table, a symbol error is a non-zero byte of (decided ^ sent), and
+// the bit errors are popc(x ^ ((x >> 1) & gray_mask)): both conventions' bit maps are GF(2)-linear in the level bits
+// (natural: identity; Gray per axis: v ^ (v >> 1), and MATLAB's inverted imaginary axis m-1-c = c ^ (m-1) cancels in the XOR).
+__host__ __device__ __forceinline__ uint32_t gray_xor_mask(int bits, int constellation) {
+    const int hb = bits >> 1;
+    if (constellation == 0 || hb < 2) return 0u;
+    const uint32_t fm = (1u << (hb - 1)) - 1u;           // v >> 1 stays inside its own field
+    return (fm | (fm << hb)) * 0x01010101u;
+}
+// bit errors of four packed level codes (x = decided ^ sent)
+__device__ __forceinline__ unsigned code_bit_errors(uint32_t x, uint32_t gmask) { return __popc(x ^ ((x >> 1) & gmask)); }
+
+// 16 level codes (one byte each) of OFDM symbol s for thread t: sub-carriers t + q*TPF
 template <int N, bool VERIFY>
 __device__ __forceinline__ void load_sym_idx(const BerParams& prm, long long f, int s, int t, uint32_t (&w)[4]) {
     constexpr int TPF = N / 16;
     if constexpr (VERIFY) {
         const int32_t* src = prm.sym_idx + ((size_t)f * prm.S + s) * N;
+        const int hb = prm.bits >> 1, m = 1 << hb;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             uint32_t x = 0;
 #pragma unroll
-            for (int b = 0; b < 4; ++b) x |= ((uint32_t)src[t + (4 * j + b) * TPF] & 0xffu) << (8 * b);
+            for (int b = 0; b < 4; ++b) {
+                int a, c;
+                idx_to_levels(src[t + (4 * j + b) * TPF] & 0xff, hb, m, prm.constellation, a, c);
+                x |= (uint32_t)((a << hb) | c) << (8 * b);
+            }
             w[j] = x;
         }
     } else {
@@ -153,10 +175,92 @@ __device__ __forceinline__ void noise_pair(const BerParams& prm, long long f, ui
                                                 STREAM_NOISE + prm.variant), prm.rk);
     gauss_quad(r, n0, n1, T());
 }
+// ---- 48-bit noise draws in receiver layout (ber_tconv2.cuh) --------------------------------------------------------
+// The tensor-core kernels draw the noise of a frame where the receiver uses it: thread t (of N/16 = TPF) of symbol s's
+// transform holds, in registers, the noise of the 16 samples its FFT rows gather -- block offsets n = (t + q TPF + shift)
+// mod N, q = 0..15, stream position s stride + rm + hh + n -- plus its share of the symbol's other stride - N samples,
+// the "extras" x = 0 .. XA-1 laid along the ring of threads (thread (base + x) mod TPF, level x / TPF):
+//   x < hh            head of the Rx window's overlap-add, block index k = x          (added to n = N - hh + x)
+//   hh <= x < 2 hh    its tail,                            k = N + x                  (added to n = x - hh)
+//   2 hh <= x < XA    the rm samples in front of the block that the receiver drops (they count in the noise power only)
+//   x >= XA           last symbol, noise_norm = 1: the tail_tx + L - 1 samples behind the frame (full-convolution sums)
+// base = (N - hh - shift) mod TPF puts every overlap-add sample into the thread that needs it.
+// 48 random bits per complex sample: a 32-bit radius word and a 16-bit angle (65 536 phases).  Philox calls of (s, t):
+// counter index ((s TPF + t) 9 + c); c = 3 g + {0, 1, 2} serve the main samples q = 8 g + e: radius = word e of (call 3g,
+// call 3g+1), angle = half e & 1 of word e >> 1 of call 3g+2; c = 6, 7, 8 give the words V[0..9) of the extras: levels
+// 2 j, 2 j + 1 take their angles from the halves of V[3 j] and their radii from V[3 j + 1], V[3 j + 2].
+constexpr int N48_MAXLEV = 6;
+__device__ __forceinline__ uint4 noise48_call(const BerParams& prm, long long f, uint32_t q) {
+    return philox4x32_10_rk(make_uint4((uint32_t)f, (uint32_t)((unsigned long long)f >> 32), q, STREAM_NOISE + prm.variant), prm.rk);
+}
+// two complex samples: radius words u0, u1, angles = low / high half of aw.  Same arithmetic as gauss_quad.
+__device__ __forceinline__ void gauss_quad48(uint32_t u0, uint32_t u1, uint32_t aw, float2& n0, float2& n1) {
+    const float2 u = fma2(make_float2(__uint2float_rn(u0), __uint2float_rn(u1)),
+                          make_float2(2.3283064365386963e-10f, 2.3283064365386963e-10f),
+                          make_float2(1.1641532182693481e-10f, 1.1641532182693481e-10f));
+    float2 lg, rr;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg.x) : "f"(u.x));
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg.y) : "f"(u.y));
+    const float2 t = mul2(lg, make_float2(-1.3862943611198906f, -1.3862943611198906f));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rr.x) : "f"(t.x));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rr.y) : "f"(t.y));
+    // theta = 2 pi a / 65536, a the signed 16-bit half: in [-pi, pi)
+    const float2 th = mul2(make_float2(__int2float_rn((int32_t)(aw << 16)), __int2float_rn((int32_t)(aw & 0xffff0000u))),
+                           make_float2(1.4629180792671596e-09f, 1.4629180792671596e-09f));
+    float s0, c0, s1, c1;
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s0) : "f"(th.x));
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c0) : "f"(th.x));
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s1) : "f"(th.y));
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c1) : "f"(th.y));
+    n0 = mul2(make_float2(c0, s0), make_float2(rr.x, rr.x));
+    n1 = mul2(make_float2(c1, s1), make_float2(rr.y, rr.y));
+}
+__device__ __forceinline__ uint32_t u4_word(const uint4& v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
+// geometry of the extras of a frame (host and device)
+struct N48Geom { int tpf, hh, xa, tailx, base; };
+__host__ __device__ __forceinline__ N48Geom n48_geom(const BerParams& prm) {
+    N48Geom g;
+    g.tpf = prm.N / 16; g.hh = prm.tail_rx >> 1; g.xa = prm.stride - prm.N;
+    g.tailx = prm.noise_norm == 1 ? prm.tail_tx + prm.L - 1 : 0;
+    g.base = (prm.N - g.hh - prm.shift) & (g.tpf - 1);
+    return g;
+}
+// frame offset (relative to the symbol's first stream sample) of extra x
+__host__ __device__ __forceinline__ int n48_extra_offset(const BerParams& prm, const N48Geom& g, int x) {
+    return x < g.hh ? prm.rm + x : x < 2 * g.hh ? prm.rm + prm.N + x : x < g.xa ? x - 2 * g.hh : prm.stride + (x - g.xa);
+}
+// noise of stream sample p (export path, wofdm_ber_draws / noise_at)
+__device__ __forceinline__ float2 noise_draw48(const BerParams& prm, long long f, int p) {
+    const N48Geom g = n48_geom(prm);
+    const int s = min(p / prm.stride, prm.S - 1), o = p - s * prm.stride;
+    int t, wr, wa, half, cr, ca;            // thread; radius word / angle word (call, index)
+    if (o >= prm.rm + g.hh && o < prm.rm + g.hh + prm.N) {
+        const int tp = (o - prm.rm - g.hh - prm.shift) & (prm.N - 1);
+        t = tp & (g.tpf - 1);
+        const int q = tp / g.tpf, gq = q >> 3, e = q & 7;
+        cr = 3 * gq + (e >> 2); wr = e & 3; ca = 3 * gq + 2; wa = e >> 1; half = e & 1;
+    } else {
+        const int x = o < prm.rm ? 2 * g.hh + o : o < prm.rm + g.hh ? o - prm.rm : o < prm.stride ? o - prm.rm - prm.N : g.xa + o - prm.stride;
+        t = (g.base + x) & (g.tpf - 1);
+        const int lev = x / g.tpf, j = lev >> 1;
+        const int ia = 3 * j, ir = 3 * j + 1 + (lev & 1);
+        cr = 6 + (ir >> 2); wr = ir & 3; ca = 6 + (ia >> 2); wa = ia & 3; half = lev & 1;
+    }
+    const uint32_t q0 = (uint32_t)(s * g.tpf + t) * 9u;
+    const uint32_t uw = u4_word(noise48_call(prm, f, q0 + (uint32_t)cr), wr), aw = u4_word(noise48_call(prm, f, q0 + (uint32_t)ca), wa);
+    float2 n0, n1;
+    gauss_quad48(uw, uw, aw, n0, n1);
+    return half ? n1 : n0;
+}
+
 // noise of stream sample i (any policy): draw index (i/B)*(B+1) + i%B
 template <typename T>
 __device__ __forceinline__ V2<T> noise_at(const BerParams& prm, long long f, int i) {
     const int B = prm.chunk;
+    if (prm.n48) {             // (fp32 kernels only)
+        const float2 z = noise_draw48(prm, f, i);
+        return mk2<T>((T)z.x, (T)z.y);
+    }
     if (B == 0) {              // draw = position
         V2<T> n0, n1;
         noise_pair<T>(prm, f, (uint32_t)(i >> 1), n0, n1);
@@ -322,8 +426,7 @@ ber_frame_kernel(const BerParams prm) {
     T* wtx = reinterpret_cast<T*>(smem_raw + lay.off_wtx);
     T* wrx = reinterpret_cast<T*>(smem_raw + lay.off_wrx);
     T* red = reinterpret_cast<T*>(smem_raw + lay.off_red);
-    C2* qlut = reinterpret_cast<C2*>(smem_raw + lay.off_qlut);          // constellation index -> lattice point
-    unsigned char* dlut = smem_raw + lay.off_dlut;                       // (re level)*m + (im level) -> index
+    C2* qlut = reinterpret_cast<C2*>(smem_raw + lay.off_qlut);          // level code -> lattice point
     uint4* symw = reinterpret_cast<uint4*>(smem_raw + lay.off_symw);     // Tx -> Rx: the frame's constellation indices
     uint4* gmask = reinterpret_cast<uint4*>(smem_raw + lay.off_gmask);   // guard band: [t][0] = 0xff in null bytes, [t][1] = stored index there
     C2* rbuf = xbuf;                            // staged: conv output; regs: the frame's noise (both alias the exchange)
@@ -348,16 +451,13 @@ ber_frame_kernel(const BerParams prm) {
     for (int i = tid; i < n_tx; i += NT) wtx[i] = reinterpret_cast<const T*>(prm.win_tx)[i];
     for (int i = tid; i < N + prm.tail_rx; i += NT) wrx[i] = reinterpret_cast<const T*>(prm.win_rx)[i];
     for (int i = tid; i < lay.pad; i += NT) fbuf[i] = mk2<T>(0, 0);
-    for (int i = tid; i < (1 << prm.bits); i += NT) {
-        int a, c;
-        idx_to_levels(i, hb, m, prm.constellation, a, c);
-        qlut[i] = mk2<T>((T)(2 * a - (m - 1)), (T)(2 * c - (m - 1)));
-        dlut[(a << hb) | c] = (unsigned char)i;
-    }
+    for (int i = tid; i < (1 << prm.bits); i += NT)                      // level code -> lattice point
+        qlut[i] = mk2<T>((T)(2 * (i >> hb) - (m - 1)), (T)(2 * (i & (m - 1)) - (m - 1)));
     if (tid == 0 && prm.bits < 8) qlut[255] = mk2<T>(0, 0);              // the null sub-carrier
+    const uint32_t gxm = gray_xor_mask(prm.bits, prm.constellation);
     __syncthreads();
     if (prm.guard > 0) {
-        const unsigned d0 = dlut[slice_index(mk2<T>(0, 0), hb)];          // what the slicer makes of a null bin
+        const unsigned d0 = slice_index(mk2<T>(0, 0), hb);                // what the slicer makes of a null bin
         for (int tt = tid; tt < TPF; tt += NT) {
             uint32_t ff[4] = {0, 0, 0, 0}, dd[4] = {0, 0, 0, 0};
             for (int q = 0; q < 16; ++q)
@@ -789,14 +889,14 @@ ber_frame_kernel(const BerParams prm) {
                 for (int q = 0; q < 16; ++q) {
                     const int k = t + q * TPF;
                     const C2 e = cmul(v[q], geq[k]);                                       // :231
-                    const int dec = dlut[slice_index(e, hb)];                              // :233
+                    const int dec = slice_index(e, hb);                                    // :233 (level code)
                     const int txi = sym_byte(w, q);
                     sym_cnt += (dec != txi);                                               // :235
-                    bit_cnt += __popc(dec ^ txi);
+                    bit_cnt += code_bit_errors((uint32_t)(dec ^ txi), gxm);
                     if constexpr (VERIFY) {
                         const size_t o = ((size_t)f * (prm.S - 1) + (sb + s - 1)) * N + k;
                         prm.eq_out[o] = make_double2((double)e.x * prm.qscale, (double)e.y * prm.qscale);
-                        prm.dec_out[o] = dec;
+                        prm.dec_out[o] = levels_to_idx(dec >> hb, dec & (m - 1), hb, m, prm.constellation);
                     }
                 }
             }
@@ -816,7 +916,8 @@ ber_frame_kernel(const BerParams prm) {
         // barrier, the stream and the symbol words were last read before the pilot barriers, the parked noise before the
         // receiver's; geq and red are rewritten only behind the next frame's own barriers (CIRC recomputes hf from taps
         // behind its own barriers but reads them late; clusters and the staged policy keep the barrier)
-        if (!(REGS && CL == 1 && !CIRC && !VERIFY)) __syncthreads();   // taps / stream / geq are rewritten by the next frame
+        // (a frame received in more than one pass, S > FPP, reads the stream after the pilot barriers: it keeps the barrier too)
+        if (!(REGS && CL == 1 && !CIRC && !VERIFY) || S > FPP) __syncthreads();   // taps / stream / geq are rewritten by the next frame
         f += df;
         if constexpr (!VERIFY) {
             fe += de;
@@ -838,7 +939,11 @@ __global__ void draws_sym_kernel(BerParams prm, const long long* frame_ids, int3
     for (int t = threadIdx.x; t < TPF; t += blockDim.x) {
         uint32_t w[4];
         load_sym_idx<N, false>(prm, f, s, t, w);
-        for (int q = 0; q < 16; ++q) out[((size_t)blockIdx.y * prm.S + s) * N + t + q * TPF] = sym_byte(w, q);
+        const int hb = prm.bits >> 1, m = 1 << hb;
+        for (int q = 0; q < 16; ++q) {
+            const int code = sym_byte(w, q);
+            out[((size_t)blockIdx.y * prm.S + s) * N + t + q * TPF] = levels_to_idx(code >> hb, code & (m - 1), hb, m, prm.constellation);
+        }
     }
 }
 template <typename T>

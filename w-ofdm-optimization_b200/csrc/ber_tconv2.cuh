@@ -1,0 +1,566 @@
+// ber_tconv2.cuh -- K1, second generation of the tensor-core-convolution frame kernel (tcgen05, sm_100a).
+//
+// Same chain as ber_frame_kernel (ber_kernel.cuh; reference loop body python/ofdm_utils/wofdm_simulation.py:171-240,
+// matlab/main_BER_calculation.m:245-273) and the same Hankel-operand convolution as ber_tconv.cuh (the frame stream,
+// split in two fp16 halves, IS the K-major A operand; the frame's taps are B; fp32 accumulators in tensor memory).
+// What is new is everything around the convolution -- the first generation spent 65 % of its issue slots there:
+//
+//   * ONE pass over the accumulators, and the noise where the receiver needs it.  Every receiver thread draws, into
+//     registers and while the MMAs run, the noise of exactly the samples its FFT rows will gather (plus its share of the
+//     symbol's other samples, which only count in the noise power; ber_kernel.cuh: noise_draw48 is the numbering).  When
+//     the MMAs have completed, tcgen05.ld reads r = conv(h, u) once: |r|^2 goes into the frame-wide sum and r itself, as
+//     plain fp32, over the dead split stream (two interleaved halves: conflict-free stores, base + immediate loads).  The
+//     exact-SNR gain g = sqrt(Pr 10^(-snr/10) / Pn) (wofdm_simulation.py:135-138) is applied where the receiver gathers
+//     its block: y = r + g n.  The first generation's second tcgen05.ld pass, its y store and one CTA barrier per frame
+//     are gone.
+//   * Symbols are level codes (ber_kernel.cuh: load_sym_idx): the slicer's packed decisions are compared with the sent
+//     codes directly, no decision table, bit errors by the GF(2)-linear Gray map of the XOR.
+//   * 48 random bits per complex noise sample instead of 64: a 32-bit radius word and a 16-bit angle (65 536 phases),
+//     three Philox4x32-10 calls per eight samples.
+//   * Only the warps that issue the MMAs wait for the whole stream to be written (bar.sync); all others announce their
+//     part (bar.arrive) and start drawing noise.  MMA descriptors advance by one addition.
+//
+// fp32; N = 256: one CTA of 256 threads per frame, two CTAs per SM (256 of the 512 tensor-memory columns each);
+// N = 512: one CTA of 512 threads per frame and SM.  S <= 16 symbols in one Tx pass, L <= TCV_LB, prefix / suffix /
+// tails within the outer register rows (ber_host.cu:choose_variant checks).
+#pragma once
+#include <cuda_fp16.h>
+#include "ber_kernel.cuh"
+#include "ber_tconv.cuh"
+
+namespace wofdm {
+
+#ifndef TCV2_NISSUE
+#define TCV2_NISSUE 4
+#endif
+constexpr int TCV2_BAR_STREAM = 14;      // named barrier: "the split stream of this frame is complete"
+
+template <int N, int NT, int NTILE>
+__host__ __device__ inline BerSmem tconv2_smem_layout(int S, int stride, int tail_tx, int tail_rx, int L, int chunk, int use_global) {
+    using P = FftPlan<N>;
+    constexpr int FPP = NT / P::TPF;
+    BerSmem m;
+    m.pad = TCV_PAD;
+    m.flen = tconv_alen(NTILE);
+    m.xlen = FPP * P::XLEN;
+    int o = 0;
+    o += m.flen * 4;                 m.off_lo = o;        // ahi
+    o += m.flen * 4;                                      // alo (r lies over ahi | alo from byte 4 * TCV_PAD, two halves of
+    o += 64;                                              //      128 NTILE + 4 chunks of 16 bytes)
+    o = (o + 15) & ~15;              m.off_x = o;
+    o += m.xlen * 8;                 m.off_tw = o;
+    o += P::NTW * 8;                 m.off_geq = o;
+    o += N * 8;                      m.off_bt = o;
+    o += 3 * 768;                    m.off_wtx = o;       // [T_hi | T_lo | zeros], 8 rows x 48 halves each
+    o += ((stride + tail_tx + 3) & ~3) * 4;   m.off_wrx = o;
+    o += ((N + tail_rx + 3) & ~3) * 4;        m.off_red = o;
+    o += 64 * 4;                              m.off_qlut = o;
+    o += 2 * 256 * 8;                         m.off_gmask = o;      // lattice points: Rx (pilot) copy, Tx copy (carries the flat window value)
+    o += P::TPF * 32;                         m.off_symw = o;
+    o += S * P::TPF * 16;                     m.off_bar = o;
+    o += 16;
+    m.off_hf = m.off_taps = m.off_dlut = 0;
+    m.bytes = ((size_t)o + 15) & ~(size_t)15;
+    (void)L; (void)chunk; (void)use_global;
+    return m;
+}
+
+template <int N, int NT, int NTILE, int MINB, bool VERIFY>
+__global__ void __launch_bounds__(NT, MINB)
+ber_tconv2_kernel(const BerParams prm) {
+    using T = float;
+    using C2 = float2;
+    using P = FftPlan<N>;
+    constexpr int TPF = P::TPF, FPP = NT / TPF, ER = 2, NW = NT / 32;
+    static_assert(NT == 256 || NT == 512, "eight warps read a tile's accumulators");
+    constexpr int TG = NT / 256, NTH = (NTILE + TG - 1) / TG;             // tile sets; tiles per thread
+    constexpr uint32_t TMEM_COLS = tconv_tmem_cols(NTILE);
+    static_assert(16 * NTILE <= (int)TMEM_COLS, "accumulators of a frame must fit tensor memory");
+
+    extern __shared__ __align__(128) unsigned char tcv_smem[];
+    unsigned char* const smem_raw = tcv_smem;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int slot = tid / TPF, t = tid % TPF;
+    const int S = prm.S, stride = prm.stride, n_tx = prm.n_tx, beta = prm.tail_tx, L = prm.L;
+    const int cp = prm.cp, cs = prm.cs;
+    const int hh = prm.tail_rx >> 1;
+    const int hb = prm.bits >> 1, m = 1 << hb;
+    const int sec = S * stride;                 // samples kept after the channel
+    const int body = beta + sec;                // serialised Tx stream length
+    const int npow = prm.noise_norm == 1 ? body + L - 1 : sec;   // samples inside the frame-wide power sums
+
+    const BerSmem lay = tconv2_smem_layout<N, NT, NTILE>(S, stride, beta, prm.tail_rx, L, 0, 0);
+    uint32_t* const ahi = reinterpret_cast<uint32_t*>(smem_raw);
+    uint32_t* const alo = reinterpret_cast<uint32_t*>(smem_raw + lay.off_lo);
+    uint32_t* const uh = ahi + TCV_PAD;         // uh[i], ul[i]: split stream sample i
+    uint32_t* const ul = alo + TCV_PAD;
+    C2* const rb = reinterpret_cast<C2*>(smem_raw + TCV_PAD * 4);   // channel output r[i], over the dead split stream (keeps ahi's zero pad)
+    static_assert((TCV_PAD * 4) % 16 == 0, "r is stored in 16-byte pairs");
+    C2* const xbuf = reinterpret_cast<C2*>(smem_raw + lay.off_x);  // FFT exchange, one region per transform group
+    C2* tw = reinterpret_cast<C2*>(smem_raw + lay.off_tw);
+    C2* geq = reinterpret_cast<C2*>(smem_raw + lay.off_geq);
+    unsigned char* bt = smem_raw + lay.off_bt;
+    T* wtx = reinterpret_cast<T*>(smem_raw + lay.off_wtx);
+    T* wrx = reinterpret_cast<T*>(smem_raw + lay.off_wrx);
+    T* red = reinterpret_cast<T*>(smem_raw + lay.off_red);
+    C2* qlut = reinterpret_cast<C2*>(smem_raw + lay.off_qlut);     // level code -> lattice point
+    C2* qtx = qlut + 256;                                           // ... times the flat Tx window value
+    uint4* gmask = reinterpret_cast<uint4*>(smem_raw + lay.off_gmask);
+    uint4* symw = reinterpret_cast<uint4*>(smem_raw + lay.off_symw);
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw + lay.off_bar);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + lay.off_bar + 8);
+    C2* const xb = xbuf + slot * P::XLEN;
+
+    // ---- one-time: tensor memory, barrier, tables ----
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tcv_smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(tcv_smem_u32(bar)), "r"(TCV2_NISSUE) : "memory");   // one commit per issuing warp and frame
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < P::NTW; i += NT) tw[i] = reinterpret_cast<const C2*>(prm.tw)[i];
+    // flat windows (host-checked): the Tx window's flat value rides on the constellation table and wtx holds the ratio to it
+    // (1 on every body row: no product there); the Rx window is divided by its flat value (a common factor of the
+    // received signal cancels in the pilot equaliser) and rows 1..13 of the Rx gather skip the product
+    const bool flat_tx = prm.flat_tx != 0, flat_rx = prm.flat_rx != 0;
+    const T wflat = flat_tx ? reinterpret_cast<const T*>(prm.win_tx)[beta] : (T)1;
+    const T rflat = flat_rx ? reinterpret_cast<const T*>(prm.win_rx)[prm.tail_rx] : (T)1;
+    for (int i = tid; i < n_tx; i += NT)
+        wtx[i] = flat_tx ? reinterpret_cast<const T*>(prm.win_tx)[i] / wflat : reinterpret_cast<const T*>(prm.win_tx)[i] * TCV_XSCALE;
+    for (int i = tid; i < N + prm.tail_rx; i += NT) wrx[i] = reinterpret_cast<const T*>(prm.win_rx)[i] / rflat;
+    for (int i = tid; i < TCV_PAD; i += NT) ahi[i] = 0u;
+    for (int i = tid; i < 768 / 4; i += NT) reinterpret_cast<uint32_t*>(bt + 1536)[i] = 0u;
+    for (int i = tid; i < (1 << prm.bits); i += NT) {
+        qlut[i] = mk2<T>((T)(2 * (i >> hb) - (m - 1)), (T)(2 * (i & (m - 1)) - (m - 1)));
+        qtx[i] = flat_tx ? cscale(wflat * TCV_XSCALE, qlut[i]) : qlut[i];
+    }
+    if (tid == 0 && prm.bits < 8) { qlut[255] = mk2<T>(0, 0); qtx[255] = mk2<T>(0, 0); }
+    const uint32_t gxm = gray_xor_mask(prm.bits, prm.constellation);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+    if (prm.guard > 0) {
+        const unsigned d0 = slice_index(mk2<T>(0, 0), hb);
+        for (int tt = tid; tt < TPF; tt += NT) {
+            uint32_t ff[4] = {0, 0, 0, 0}, dd[4] = {0, 0, 0, 0};
+            for (int q = 0; q < 16; ++q)
+                if (!bin_active<N>(tt + q * TPF, prm.guard)) { ff[q >> 2] |= 0xffu << (8 * (q & 3)); dd[q >> 2] |= d0 << (8 * (q & 3)); }
+            gmask[2 * tt] = make_uint4(ff[0], ff[1], ff[2], ff[3]);
+            gmask[2 * tt + 1] = make_uint4(dd[0], dd[1], dd[2], dd[3]);
+        }
+        __syncthreads();
+    }
+
+    // this thread's operand row inside every tile (TMEM lane) and its half of the row's four outputs
+    const int wg = (warp >> 2) & 1, row = (warp & 3) * 32 + lane;
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);      // the warp index as a value the compiler knows to be warp-uniform
+    const int tp = TG == 1 ? 0 : (warp_u >> 3);                // this warp's tile set: tiles tp, tp + TG, ...
+    const uint32_t tlane = tmem + ((uint32_t)((warp_u & 3) * 32) << 16) + (uint32_t)(4 * ((warp_u >> 2) & 1));
+    uint32_t phase = 0, issuer = blockIdx.x;
+    // MMA descriptors of tile 0, K step 0 (tile: +2048 B = +128 in the address field, K step: +32 B = +2; B operand: +256 B = +16)
+    const uint64_t d_ahi = tcv_desc(tcv_smem_u32(ahi), 16, 128), d_alo = tcv_desc(tcv_smem_u32(alo), 16, 128);
+    const uint64_t d_bhl = tcv_desc(tcv_smem_u32(bt), 128, 768), d_bh0 = tcv_desc(tcv_smem_u32(bt), 128, 1536);
+    // channel output r, parked over the dead split stream in two halves: R[wg] holds outputs 2 wg, 2 wg + 1 of every operand
+    // row as one 16-byte chunk per row -- consecutive lanes store consecutive chunks (no bank conflicts) and a receiver
+    // thread's samples i = i0 + q TPF all have the same i mod 4, i.e. the same half and chunk slot: base + immediate
+    const int RCH = NTILE * 128 + 4;            // chunks per half (+4: the halves sit 64 bytes apart modulo 128)
+    // extras of the noise draws (ber_kernel.cuh: noise_draw48)
+    const N48Geom ng = n48_geom(prm);
+    const int xt = (t - ng.base) & (TPF - 1);   // this thread's extras: x = xt + lev * TPF
+
+    const long long fslot = blockIdx.x, nslots = gridDim.x;
+    long long f = prm.frame_begin + fslot * prm.frame_step;
+    const long long df = nslots * prm.frame_step;
+    long long fe = 0, de = 0;
+    int ci = 0, si = 0, dc = 0, ds = 0;
+    if constexpr (!VERIFY) {
+        const long long q = f / prm.ensemble, dq = df / prm.ensemble;
+        fe = f - q * prm.ensemble;   de = df - dq * prm.ensemble;
+        si = (int)(q / prm.C);       ci = (int)(q - (long long)si * prm.C);
+        ds = (int)(dq / prm.C);      dc = (int)(dq - (long long)ds * prm.C);
+    }
+    for (long long j = fslot; j < prm.n_frames; j += nslots) {
+        if constexpr (VERIFY) { ci = (int)f; si = (int)f; }
+        const T snr_lin = reinterpret_cast<const T*>(prm.snr_lin)[si];
+        // ---- taps operand of this frame: n = 2o + comp (o < 4), K pair jj = sample offset in the row, tap l = LB-1 + o - jj
+        if (tid < 8 * 24) {
+            const int n = tid / 24, jj = tid % 24;
+            const int o = n >> 1, l = TCV_LB - 1 + o - jj;
+            C2 tpv = mk2<T>(0, 0);
+            if (l >= 0 && l < L) tpv = reinterpret_cast<const C2*>(prm.chan)[(size_t)ci * L + l];
+            tpv = cscale(TCV_HSCALE, tpv);
+            const C2 v = (n & 1) ? mk2<T>(tpv.y, tpv.x) : mk2<T>(tpv.x, -tpv.y);     // multiplies (Re u, Im u)
+            uint32_t hi, lo;
+            split_h2(v, hi, lo);
+            const int off = (jj >> 2) * 128 + n * 16 + (jj & 3) * 4;
+            *reinterpret_cast<uint32_t*>(bt + off) = hi;
+            *reinterpret_cast<uint32_t*>(bt + 768 + off) = lo;
+        } else if (tid < 8 * 24 + TCV_PAD) {
+            alo[tid - 8 * 24] = 0u;                                              // (r of the previous frame lay over it)
+        } else if (tid - (8 * 24 + TCV_PAD) < TCV_ZERO) {
+            const int i = body + tid - (8 * 24 + TCV_PAD);                       // the linear convolution sees zeros behind the stream
+            uh[i] = 0u; ul[i] = 0u;
+        }
+
+        // =========================== transmitter ===========================
+        if (prm.tx_stream != nullptr) {          // uniform: masked Tx stream from tx_mask_kernel (mask_kernel.cuh)
+            for (int e = tid; e < S * TPF; e += NT) {
+                const int tt = e % TPF;
+                uint32_t w[4];
+                load_sym_idx<N, VERIFY>(prm, f, e / TPF, tt, w);
+                if (prm.guard > 0) {
+                    const uint4 gf = gmask[2 * tt], gd = gmask[2 * tt + 1];
+                    w[0] = (w[0] & ~gf.x) | gd.x; w[1] = (w[1] & ~gf.y) | gd.y;
+                    w[2] = (w[2] & ~gf.z) | gd.z; w[3] = (w[3] & ~gf.w) | gd.w;
+                }
+                symw[e] = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            const float2* src = prm.tx_stream + (size_t)j * body;
+            for (int i = tid; i < body; i += NT) {
+                uint32_t hi, lo;
+                split_h2(cscale(TCV_XSCALE, src[i]), hi, lo);
+                uh[i] = hi; ul[i] = lo;
+            }
+            __syncthreads();
+        } else {
+            const int s = slot;
+            const bool act = s < S;
+            const int se = act ? s : S - 1;     // idle slots shadow the last symbol (identical stores)
+            const bool first = se == 0;         // the frame's first symbol has no predecessor
+            C2 v[16];
+            {
+                uint32_t w[4], wq[4];
+                load_sym_idx<N, VERIFY>(prm, f, se, t, w);
+#pragma unroll
+                for (int jw = 0; jw < 4; ++jw) wq[jw] = w[jw];
+                if (prm.guard > 0) {
+                    const uint4 gf = gmask[2 * t], gd = gmask[2 * t + 1];
+                    const uint32_t ff[4] = {gf.x, gf.y, gf.z, gf.w}, dd[4] = {gd.x, gd.y, gd.z, gd.w};
+#pragma unroll
+                    for (int jw = 0; jw < 4; ++jw) { wq[jw] = w[jw] | ff[jw]; w[jw] = (w[jw] & ~ff[jw]) | dd[jw]; }
+                }
+                symw[se * TPF + t] = make_uint4(w[0], w[1], w[2], w[3]);
+#pragma unroll
+                for (int q = 0; q < 16; ++q) v[q] = qtx[sym_byte(wq, q)];
+            }
+            fft_regs<T, N, +1, FPP>(v, t, xb, tw, slot);
+            // CP/CS insertion + Tx window (transmitter.py:13-35, 61-87); heads i < tail_tx overlap the previous symbol's
+            // falling tail (wofdm_simulation.py:190-203) and are added after the barrier
+            uint32_t* const sh = uh + se * stride;
+            uint32_t* const sl = ul + se * stride;
+            if (flat_tx) {                        // uniform (implies cp, cs >= tail_tx: the body lies in the flat part)
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    uint32_t hi, lo;
+                    split_h2(v[q], hi, lo);
+                    sh[t + q * TPF + cp] = hi; sl[t + q * TPF + cp] = lo;
+                }
+            } else if (cp >= beta) {
+                T wv[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) wv[q] = wtx[t + q * TPF + cp];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    uint32_t hi, lo;
+                    split_h2(cscale(wv[q], v[q]), hi, lo);
+                    sh[t + q * TPF + cp] = hi; sl[t + q * TPF + cp] = lo;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const int i = t + q * TPF + cp;
+                    if (q >= ER || i >= beta || first) {
+                        uint32_t hi, lo;
+                        split_h2(cscale(wtx[i], v[q]), hi, lo);
+                        sh[i] = hi; sl[i] = lo;
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 16 - ER; q < 16; ++q) {
+                if (q * TPF + TPF > N - cp) {             // uniform: this register row reaches the prefix
+                    const int i = t + q * TPF - (N - cp);
+                    if (i >= 0 && (i >= beta || first)) {
+                        uint32_t hi, lo;
+                        split_h2(cscale(wtx[i], v[q]), hi, lo);
+                        sh[i] = hi; sl[i] = lo;
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < ER; ++q) {
+                if (q * TPF < cs) {                        // uniform: ... the suffix
+                    const int i = t + q * TPF + cp + N;
+                    if (i < n_tx) {
+                        uint32_t hi, lo;
+                        split_h2(cscale(wtx[i], v[q]), hi, lo);
+                        sh[i] = hi; sl[i] = lo;
+                    }
+                }
+            }
+            __syncthreads();                    // (also: every transform group is done with its exchange region)
+            if (beta > 0 && act && !first) {
+#pragma unroll
+                for (int q = 16 - ER; q < 16; ++q) {
+                    if (q * TPF + TPF > N - cp) {
+                        const int i = t + q * TPF - (N - cp);
+                        if (i >= 0 && i < beta) {
+                            uint32_t hi, lo;
+                            split_h2(caxpy(wtx[i], v[q], join_h2(sh[i], sl[i])), hi, lo);
+                            sh[i] = hi; sl[i] = lo;
+                        }
+                    }
+                }
+                if (cp < beta) {
+#pragma unroll
+                    for (int q = 0; q < ER; ++q) {
+                        const int i = t + q * TPF + cp;
+                        if (i < beta) {
+                            uint32_t hi, lo;
+                            split_h2(caxpy(wtx[i], v[q], join_h2(sh[i], sl[i])), hi, lo);
+                            sh[i] = hi; sl[i] = lo;
+                        }
+                    }
+                }
+            }
+        }
+        // the tensor core reads shared memory through the async proxy
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+
+        // =========================== channel + AWGN ===========================
+        // r = conv(h, u) (wofdm_simulation.py:206-209) on the tensor cores; y = r + sqrt(Pr*10^(-snr/10)/Pn) n with Pr, Pn
+        // summed over the whole frame (:135-138; noise_norm 1: over the full convolution, main_BER_calculation.m:260-261,289-292)
+        // One elected lane of each of TCV2_NISSUE warps (rotating from frame to frame) waits for the whole stream and issues
+        // its share of the frame's MMAs; every other warp only announces its stores and goes on to the noise draws.
+        const int irank = (warp_u - (int)issuer) & (NW - 1);          // warp-uniform: issuing warps have irank < TCV2_NISSUE
+        const bool is_issuer = irank < TCV2_NISSUE;
+        ++issuer;
+        if (is_issuer) {
+            asm volatile("bar.sync %0, %1;" :: "n"(TCV2_BAR_STREAM), "n"(NT) : "memory");
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (tcv_elect_one()) {
+#pragma unroll
+                for (int ti = 0; ti < NTILE; ++ti) {
+                    if (ti % TCV2_NISSUE != irank) continue;              // the issuing warps share the tiles round-robin
+                    const uint32_t tacc = tmem + (uint32_t)(16 * ti);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        tcv_mma(tacc, d_ahi + (uint64_t)(ti * 128 + k * 2), d_bhl + (uint64_t)(k * 16), k != 0);
+                        tcv_mma(tacc, d_alo + (uint64_t)(ti * 128 + k * 2), d_bh0 + (uint64_t)(k * 16), 1u);
+                    }
+                }
+                // completes when all of this warp's MMAs have
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(tcv_smem_u32(bar)) : "memory");
+            }
+            __syncwarp();
+        } else {
+            asm volatile("bar.arrive %0, %1;" :: "n"(TCV2_BAR_STREAM), "n"(NT) : "memory");
+        }
+        // ---- noise, in receiver layout and in registers (ber_kernel.cuh: noise_draw48): the 16 samples this thread's FFT
+        //      rows gather, and its extras; |n|^2 partial
+        C2 nz[16], nx[N48_MAXLEV];
+        C2 pr2 = mk2<T>(0, 0), pn2 = mk2<T>(0, 0);
+        {
+            const bool act = slot < S;
+            const int se = act ? slot : S - 1;
+            const int xas = ng.xa + (se == S - 1 ? ng.tailx : 0);        // extras of this symbol (uniform per transform group)
+            const int nlev = (xas + TPF - 1) / TPF;
+            const int pbase = se * stride;
+            if constexpr (VERIFY) {
+                const double2* nin = prm.noise_in + (size_t)f * prm.noise_len + pbase;
+#pragma unroll
+                for (int q = 0; q < 16; ++q) nz[q] = to_v2<T>(nin[prm.rm + hh + ((t + q * TPF + prm.shift) & (N - 1))]);
+#pragma unroll
+                for (int lev = 0; lev < N48_MAXLEV; ++lev) {
+                    const int x = xt + lev * TPF;
+                    nx[lev] = x < xas ? to_v2<T>(nin[n48_extra_offset(prm, ng, x)]) : mk2<T>(0, 0);
+                }
+            } else {
+                const uint32_t q0 = (uint32_t)(se * TPF + t) * 9u;
+#pragma unroll
+                for (int gq = 0; gq < 2; ++gq) {
+                    const uint4 ca = noise48_call(prm, f, q0 + 3 * gq), cb = noise48_call(prm, f, q0 + 3 * gq + 1);
+                    const uint4 cc = noise48_call(prm, f, q0 + 3 * gq + 2);
+                    gauss_quad48(ca.x, ca.y, cc.x, nz[8 * gq + 0], nz[8 * gq + 1]);
+                    gauss_quad48(ca.z, ca.w, cc.y, nz[8 * gq + 2], nz[8 * gq + 3]);
+                    gauss_quad48(cb.x, cb.y, cc.z, nz[8 * gq + 4], nz[8 * gq + 5]);
+                    gauss_quad48(cb.z, cb.w, cc.w, nz[8 * gq + 6], nz[8 * gq + 7]);
+                }
+#pragma unroll
+                for (int lev = 0; lev < N48_MAXLEV; ++lev) nx[lev] = mk2<T>(0, 0);
+                if (nlev > 0) {                                          // uniform per transform group
+                    const uint4 c6 = noise48_call(prm, f, q0 + 6);
+                    gauss_quad48(c6.y, c6.z, c6.x, nx[0], nx[1]);
+                    if (nlev > 2) {
+                        const uint4 c7 = noise48_call(prm, f, q0 + 7);
+                        gauss_quad48(c7.x, c7.y, c6.w, nx[2], nx[3]);
+                        if (nlev > 4) {
+                            const uint4 c8 = noise48_call(prm, f, q0 + 8);
+                            gauss_quad48(c7.w, c8.x, c7.z, nx[4], nx[5]);
+                        }
+                    }
+#pragma unroll
+                    for (int lev = 0; lev < N48_MAXLEV; ++lev)
+                        if (xt + lev * TPF >= xas) nx[lev] = mk2<T>(0, 0);
+                }
+            }
+            if (act) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) pn2 = csq_acc(nz[q], pn2);
+#pragma unroll
+                for (int lev = 0; lev < N48_MAXLEV; ++lev) pn2 = csq_acc(nx[lev], pn2);
+            }
+        }
+        // ---- the channel output, once: frame-wide signal power, r parked over the dead split stream
+        tcv_mbar_wait(tcv_smem_u32(bar), phase);
+        phase ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        constexpr int GT = 3;                      // tiles per batch of accumulator loads (one wait per batch)
+        float4* const rst = reinterpret_cast<float4*>(rb) + wg * RCH + row;
+#pragma unroll
+        for (int t0 = 0; t0 < NTH; t0 += GT) {
+            C2 a0[GT], a1[GT], b0[GT], b1[GT];
+#pragma unroll
+            for (int u = 0; u < GT; ++u) {
+                if (t0 + u < NTH) {
+                    const int tt = min(TG * (t0 + u) + tp, NTILE - 1);      // (a set's tile past the frame: result masked below)
+                    tcv_ld4(tlane + (uint32_t)(16 * tt), a0[u], a1[u]);
+                    tcv_ld4(tlane + (uint32_t)(16 * tt + 8), b0[u], b1[u]);
+                }
+            }
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int u = 0; u < GT; ++u) {
+                if (t0 + u < NTH) {
+                    const int tt = TG * (t0 + u) + tp, p = 512 * tt + 4 * row + 2 * wg;
+                    const C2 r0 = cadd(a0[u], b0[u]), r1 = cadd(a1[u], b1[u]);
+                    if (tt < NTILE - 2) {
+                        pr2 = csq_acc(r0, pr2);
+                        pr2 = csq_acc(r1, pr2);
+                        rst[128 * tt] = make_float4(r0.x, r0.y, r1.x, r1.y);
+                    } else if (tt < NTILE) {
+                        if (p < npow) pr2 = csq_acc(r0, pr2);
+                        if (p + 1 < npow) pr2 = csq_acc(r1, pr2);
+                        if (p < sec) rst[128 * tt] = make_float4(r0.x, r0.y, r1.x, r1.y);   // (a sample past the frame is never gathered)
+                    }
+                }
+            }
+        }
+        T pr = warp_sum(pr2.x + pr2.y), pn = warp_sum(pn2.x + pn2.y);
+        if (lane == 0) { red[warp] = pr; red[32 + warp] = pn; }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();                           // r and the power partials are complete
+        const T g = noise_gain(block_total<NW>(red), snr_lin, block_total<NW>(red + 32));
+
+        // =========================== receiver ===========================
+        // block s: y = r + g n; z[k] = wrx[k]*y[s*stride + rm + k]; o[n] = sum_{k = n + hh (mod N)} z[k];
+        // q[n] = o[(n + shift) mod N]; Y = DFT(q)   (receiver.py:13-133)
+        unsigned bit_cnt = 0, sym_cnt = 0;
+        {
+            const int s = slot;
+            const bool act = s < S;
+            const int se = act ? s : S - 1;
+            C2 v[16];
+            // r of stream sample i: half (i >> 1) & 1, chunk i >> 2, element i & 1 -- constant i mod 4 for all of this thread's samples
+            const int ib = se * stride + prm.rm + hh;                    // stream position of block offset n = 0
+            const int i0 = ib + t + prm.shift;
+            const C2* const rsel = rb + ((i0 >> 1) & 1) * (2 * RCH) + (i0 & 1);
+            const C2* const rrow = rsel + (i0 >> 2) * 2;                     // row q: sample i0 + q TPF
+            auto r_at = [&](int i) -> C2 { return rsel[(i >> 2) * 2]; };     // i = i0 (mod 4)
+            const T* wr = wrx + hh;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                if (q >= 1 && q <= 13) {
+                    // tail_rx/2, shift <= TPF: rows 1..13 neither wrap nor touch the overlap-add margins (nor the window tails)
+                    const int n = t + q * TPF + prm.shift;
+                    const C2 y = caxpy(g, nz[q], rrow[q * (TPF / 2)]);
+                    v[q] = flat_rx ? y : cscale(wr[n], y);
+                    continue;
+                }
+                const int a0 = (q * TPF + prm.shift) & (N - 1);
+                const int n = (t + q * TPF + prm.shift) & (N - 1);
+                C2 o = cscale(wr[n], caxpy(g, nz[q], r_at(ib + n)));
+                if (hh > 0) {
+                    const bool wraps = a0 + TPF > N;
+                    // overlap-add: the window's tail n + N (extra x = n + hh) and its head n - N (extra x = n - (N - hh))
+                    if (wraps || a0 < hh) { if (n < hh) o = caxpy(wr[n + N], caxpy(g, (n + hh >= TPF) ? nx[1] : nx[0], r_at(ib + n + N)), o); }
+                    if (wraps || a0 + TPF > N - hh) { if (n >= N - hh) o = caxpy(wr[n - N], caxpy(g, nx[0], r_at(ib + n - N)), o); }
+                }
+                v[q] = o;
+            }
+            fft_regs<T, N, -1, FPP>(v, t, xb, tw, slot);
+            const uint4 wv = symw[se * TPF + t];
+            const uint32_t w[4] = {wv.x, wv.y, wv.z, wv.w};
+            // pilot (wofdm_simulation.py:223): the pilot's threads publish Y0, then every thread turns one bin into the
+            // equaliser tap G[k] = X0[k] / Y0[k] (lattice units)
+            if (se == 0) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) geq[t + q * TPF] = v[q];
+            }
+            __syncthreads();
+            const unsigned char* pil = reinterpret_cast<const unsigned char*>(symw);
+            for (int k = tid; k < N; k += NT) {
+                const C2 y0 = geq[k];
+                const C2 x0 = qlut[pil[(k % TPF) * 16 + k / TPF]];
+                C2 gk = cscale(recip(y0.x * y0.x + y0.y * y0.y), cmulc(x0, y0));
+                if (prm.guard > 0 && !bin_active<N>(k, prm.guard)) gk = mk2<T>(0, 0);
+                geq[k] = gk;
+            }
+            __syncthreads();
+            if (act && s > 0) {
+                // decisions of four sub-carriers packed like the sent level codes (byte q & 3 of word q >> 2): one XOR per
+                // word, the bit errors through the Gray map of the XOR, the symbol errors as its non-zero bytes
+#pragma unroll
+                for (int gq = 0; gq < 4; ++gq) {
+                    uint32_t d4 = 0;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int q = 4 * gq + b, k = t + q * TPF;
+                        const C2 e = cmul(v[q], geq[k]);                                   // :231
+                        const uint32_t dq = (uint32_t)slice_index(e, hb);                  // :233
+                        d4 |= dq << (8 * b);
+                        if constexpr (VERIFY) {
+                            const size_t o = ((size_t)f * (prm.S - 1) + (s - 1)) * N + k;
+                            prm.eq_out[o] = make_double2((double)e.x * prm.qscale, (double)e.y * prm.qscale);
+                            prm.dec_out[o] = levels_to_idx((int)(dq >> hb), (int)(dq & (m - 1)), hb, m, prm.constellation);
+                        }
+                    }
+                    const uint32_t x = d4 ^ w[gq];
+                    bit_cnt += code_bit_errors(x, gxm);                                    // :235 (bits) ...
+                    sym_cnt += __popc((((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u);   // ... and symbols: bytes that differ
+                }
+            }
+        }
+        bit_cnt = warp_sum(bit_cnt);
+        sym_cnt = warp_sum(sym_cnt);
+        if (lane == 0) {
+            if constexpr (VERIFY) {
+                atomicAdd(reinterpret_cast<unsigned long long*>(prm.bit_err_f) + f, (unsigned long long)bit_cnt);
+                atomicAdd(reinterpret_cast<unsigned long long*>(prm.sym_err_f) + f, (unsigned long long)sym_cnt);
+            } else {
+                atomicAdd(prm.counters + 2 * si, (unsigned long long)bit_cnt);
+                atomicAdd(prm.counters + 2 * si + 1, (unsigned long long)sym_cnt);
+            }
+        }
+        // No barrier here: what the next frame's prologue and Tx stage overwrite (the split stream over r, the symbol words,
+        // the taps operand, the exchange regions over the parked noise) was last read before the pilot barriers above by
+        // every thread; geq, red and the tensor-memory accumulators are rewritten only behind the next frame's own barriers.
+        f += df;
+        if constexpr (!VERIFY) {
+            fe += de;
+            if (fe >= prm.ensemble) { fe -= prm.ensemble; ++ci; }
+            ci += dc;
+            if (ci >= prm.C) { ci -= prm.C; ++si; }
+            si += ds;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(TMEM_COLS) : "memory");
+}
+
+}  // namespace wofdm

@@ -61,11 +61,8 @@ __global__ void __launch_bounds__(256) tx_mask_kernel(const MaskParams p) {
     for (int i = tid; i < PP::NTW; i += NT) twp[i] = p.twp[i];
     for (int i = tid; i < 256; i += NT) {
         float2 v = make_float2(0.f, 0.f);
-        if (i < (1 << p.bits)) {
-            int a, c;
-            idx_to_levels(i, hb, m, p.constellation, a, c);
-            v = make_float2((float)(2 * a - (m - 1)), (float)(2 * c - (m - 1)));
-        }
+        if (i < (1 << p.bits))                             // level code -> lattice point (ber_kernel.cuh: load_sym_idx)
+            v = make_float2((float)(2 * (i >> hb) - (m - 1)), (float)(2 * (i & (m - 1)) - (m - 1)));
         qlut[i] = v;
     }
     __syncthreads();

@@ -132,6 +132,7 @@ int wofdm_create_on(wofdm_handle* out, const int* device_ids, int n) {
         h->devs.push_back(d);
     }
     register_ber_f32_tconv(h->variants);
+    register_ber_f32_tconv2(h->variants);
     register_ber_f32_regs(h->variants);
     register_ber_f32_staged(h->variants);
     register_ber_f64_staged(h->variants);

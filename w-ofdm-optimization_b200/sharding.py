@@ -46,6 +46,8 @@ def allreduce_counters(counters, group=None):
     import torch.distributed as dist
     t = counters if isinstance(counters, torch.Tensor) else torch.as_tensor(np.asarray(counters, dtype=np.int64))
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        if dist.get_backend(group) == "nccl" and not t.is_cuda:      # NCCL reduces device tensors only
+            t = t.cuda()
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return t
 
@@ -67,6 +69,8 @@ def allgather_channel_rows(P_local, C: int, group=None):
     t = P_local if isinstance(P_local, torch.Tensor) else torch.as_tensor(np.asarray(P_local, dtype=np.float64))
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return t
+    if dist.get_backend(group) == "nccl" and not t.is_cuda:
+        t = t.cuda()
     world = dist.get_world_size(group)
     rows = max(channel_block(C, r, world)[1] - channel_block(C, r, world)[0] for r in range(world))
     pad = torch.zeros((rows,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
