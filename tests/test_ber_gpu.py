@@ -157,10 +157,16 @@ def test_production_replay_matches_oracle(handle, policy, monkeypatch):
                 assert np.all(np.abs(res["bit_err"] - want_bit) <= 4 + 0.002 * want_bit)
 
 
+@pytest.mark.parametrize("policy", ["tconv", "regs"])
 @pytest.mark.parametrize("name,nn", [("WOLA", 0), ("CPW", 1), ("CP", 1)])
-def test_production_replay_cluster_kernel(handle, name, nn):
+def test_production_replay_cluster_kernel(handle, name, nn, policy, monkeypatch):
     """N = 1024 (one frame per 2-CTA cluster): the exported Philox draws, replayed through the oracle, give the
-    production counters -- pins the per-CTA noise numbering, the DSMEM tail / halo and the cluster-wide sums."""
+    production counters -- pins the noise numbering, the DSMEM tail / halo and the cluster-wide sums of both cluster
+    kernels (tensor-core convolution; register policy behind WOFDM_NO_TCONV)."""
+    if policy == "regs":
+        monkeypatch.setenv("WOFDM_NO_TCONV", "1")
+    else:
+        monkeypatch.delenv("WOFDM_NO_TCONV", raising=False)
     N, S, bits = 1024, 16, 6
     a, b = (0, 0) if name == "CP" else (32, 40)
     p = O.system_params(name, N, 64, a, b, S=S, bits=bits, noise_norm=nn, constellation=1)
@@ -433,9 +439,15 @@ def test_verify_every_system_over_the_cp_range(handle, name, cp):
     check_frames(handle, p, vt, vr, frames, 0, no_tconv=True)
 
 
+@pytest.mark.parametrize("policy", ["tconv", "regs"])
 @pytest.mark.parametrize("name,cp", [("WOLA", 40), ("CPW", 128), ("CPwtx", 96), ("wrx", 72), ("CP", 128)])
-def test_verify_cluster_kernel_over_shapes(handle, name, cp):
-    """N = 1024 (2-CTA cluster kernel), 4x scaled tails, other CP lengths than the stress configuration's 64."""
+def test_verify_cluster_kernel_over_shapes(handle, name, cp, policy, monkeypatch):
+    """N = 1024 (2-CTA cluster kernels: tensor-core convolution, and the register policy behind WOFDM_NO_TCONV), 4x scaled
+    tails, other CP lengths than the stress configuration's 64."""
+    if policy == "regs":
+        monkeypatch.setenv("WOFDM_NO_TCONV", "1")
+    else:
+        monkeypatch.delenv("WOFDM_NO_TCONV", raising=False)
     ttx = 32 if name in ("CPW", "WOLA", "CPwtx", "wtx") else 0
     trx = 40 if name in ("CPW", "WOLA", "CPwrx", "wrx") else 0
     p = O.system_params(name, 1024, cp, ttx, trx, S=16, bits=6, noise_norm=1, constellation=1)
@@ -447,7 +459,7 @@ def test_verify_cluster_kernel_over_shapes(handle, name, cp):
     check_frames(handle, p, vt, vr, frames, 0)
     s = to_sys(p, 0)
     plan = handle.ber_plan(s, vt, vr, h[:, None], [22.0])
-    assert "_cl2" in plan.kernel, plan.kernel
+    assert "_cl" in plan.kernel and ("f32t" in plan.kernel) == (policy == "tconv"), plan.kernel
     plan.close()
 
 

@@ -21,7 +21,9 @@ torch.cuda.set_stream(stream)
 st = stream.cuda_stream
 cases = [("wtx", 16, 0, 0), ("wtx", 16, 1, 1), ("WOLA", 16, 0, 0), ("CPW", 16, 0, 0), ("CP", 16, 0, 0), ("CPwtx", 10, 0, 0), ("wrx", 22, 0, 0)]
 if N != 256:
-    cases = [("WOLA", 32 * scale // 2, 0, 0), ("CPW", 16 * scale, 0, 0)]
+    cases = [("WOLA", 16 * scale, 0, 0), ("CPW", 16 * scale, 0, 0), ("WOLA", 16 * scale, 1, 1)]
+if os.environ.get("K1AB_CASES"):
+    cases = [cases[int(i)] for i in os.environ["K1AB_CASES"].split(",")]
 for name, cp, nn, conv in cases:
     ttx, trx = 8 * scale, 10 * scale
     if name in ("CP", "wrx", "CPwrx"): ttx = 0

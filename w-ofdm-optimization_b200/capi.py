@@ -105,10 +105,11 @@ def load():
     """dlopen libwofdm.so (built by ``__graft_entry__.build()`` / ``make -C csrc``)."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            raise WofdmError(ENODEV, f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
+        path = os.environ.get("WOFDM_LIB", LIB_PATH)       # development aid: an alternative build of the same library
+        if not os.path.exists(path):
+            raise WofdmError(ENODEV, f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; "
                                      f"g.build()'` (nvcc, sm_100a). There is no CPU fallback.")
-        lib = C.CDLL(LIB_PATH)
+        lib = C.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args

@@ -84,15 +84,18 @@ int choose_variant(wofdm_ctx* h, const wofdm_sys_t& s, int L, bool verify, bool 
                 // channel convolution on the tensor cores (ber_tconv.cuh): first choice wherever it applies -- one Tx pass,
                 // L <= 21, prefix / suffix / tails inside the outer register rows, power sums and the zeros behind the
                 // stream inside the frame's tiles.  Noise numbering: draw = position (chunk 0).  Takes tx_stream too.
-                const int tpf = s.N / 16, body = s.tail_tx + sec;
-                if (no_tconv || s.S > v.NT / tpf || L > v.LB) continue;
+                // CL CTAs share a frame: S/CL consecutive symbols each, in one Tx pass of the CTA
+                if (s.S % v.CL != 0) continue;
+                const int tpf = s.N / 16, S_cta = s.S / v.CL, sec_cta = sec / v.CL, body = s.tail_tx + sec_cta;
+                if (no_tconv || S_cta > v.NT / tpf || L > v.LB) continue;
                 if (v.gen != tconv_gen) continue;
+                if (v.CL > 1 && want_txs) continue;                  // (the masked Tx stream is a one-CTA-per-frame feature)
                 // second generation: a receiver thread holds at most N48_MAXLEV noise samples besides its 16 FFT rows
                 if (v.gen == 2 && (stride - s.N + (s.noise_norm == 1 ? s.tail_tx + L - 1 : 0) + tpf - 1) / tpf > N48_MAXLEV) continue;
                 if (s.cp > 2 * tpf || s.cs > 2 * tpf || s.tail_tx > 2 * tpf || s.tail_rx / 2 > tpf || s.shift > tpf) continue;
-                const int need = std::max(s.noise_norm == 1 ? body + L - 1 : sec, body + TCV_ZERO);
-                if (need > 512 * v.ntile || sec <= 512 * (v.ntile - 2)) continue;   // (the kernel range-checks its last two tiles only)
-                const BerSmem lay = v.layout(s.S, stride, s.tail_tx, s.tail_rx, L, 0, 0);
+                const int need = std::max(s.noise_norm == 1 ? body + L - 1 : sec_cta, body + TCV_ZERO);
+                if (need > 512 * v.ntile || sec_cta <= 512 * (v.ntile - 2)) continue;   // (the kernel range-checks its last two tiles only)
+                const BerSmem lay = v.layout(S_cta, stride, s.tail_tx, s.tail_rx, L, 0, 0);
                 if (lay.bytes > smem_cap) continue;
                 if (!best.var || best.var->ntile == 0 || v.ntile < best.var->ntile) { best.var = &v; best.lay = lay; best.chunk = 0; }
                 continue;
@@ -239,7 +242,9 @@ int prepare_kernel(wofdm_ctx* h, const BerVariant& v, size_t smem, int sm_count,
         int ncl = 0;
         WOFDM_CUDA(h, cudaOccupancyMaxActiveClusters(&ncl, v.fn, &cfg));
         if (ncl < 1) return fail(h, WOFDM_EUNSUPPORTED, "no thread-block cluster of this variant fits the device");
-        cap = (long long)ncl * v.CL;
+        // (tensor-memory kernels: the cluster occupancy query, too, counts one CTA per SM; nb above is the real residency.
+        //  A grid larger than what is resident is still correct -- frames are taken round-robin by cluster index.)
+        cap = std::max<long long>((long long)ncl * v.CL, v.ntile > 0 ? ((long long)nb * sm_count / v.CL) * v.CL : 0);
     }
     if (max_ctas) *max_ctas = cap;
     return WOFDM_OK;

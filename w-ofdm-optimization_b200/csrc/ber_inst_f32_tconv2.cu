@@ -5,19 +5,30 @@
 #include "ber_tconv2.cuh"
 namespace wofdm {
 namespace {
-template <int N, int NT, int NTILE, int MINB, bool V>
+template <int N, int NT, int NTILE, int MINB, bool V, int CL = 1>
 struct Tconv2VariantImpl {
+    // grid = CTAs (a multiple of CL); CL > 1 launches thread-block clusters of CL CTAs
     static cudaError_t launch(const BerParams& prm, int grid, size_t smem, cudaStream_t st) {
-        ber_tconv2_kernel<N, NT, NTILE, MINB, V><<<grid, NT, smem, st>>>(prm);
-        return cudaGetLastError();
+        if constexpr (CL == 1) {
+            ber_tconv2_kernel<N, NT, NTILE, MINB, V><<<grid, NT, smem, st>>>(prm);
+            return cudaGetLastError();
+        } else {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            return cudaLaunchKernelEx(&cfg, ber_tconv2_kernel<N, NT, NTILE, MINB, V, CL>, prm);
+        }
     }
     static BerVariant make(const char* name) {
         BerVariant v;
-        v.name = name; v.N = N; v.NT = NT; v.TC = 2 * NTILE; v.LB = TCV_LB; v.MINB = MINB; v.CL = 1; v.circ = false; v.txs = true; v.full = false;
+        v.name = name; v.N = N; v.NT = NT; v.TC = 2 * NTILE; v.LB = TCV_LB; v.MINB = MINB; v.CL = CL; v.circ = false; v.txs = true; v.full = false;
         v.ntile = NTILE; v.gen = 2;
         v.fp64 = false; v.verify = V;
         v.layout = &tconv2_smem_layout<N, NT, NTILE>;
-        v.fn = reinterpret_cast<const void*>(&ber_tconv2_kernel<N, NT, NTILE, MINB, V>);
+        v.fn = reinterpret_cast<const void*>(&ber_tconv2_kernel<N, NT, NTILE, MINB, V, CL>);
         v.launch = &launch;
         return v;
     }
@@ -26,10 +37,19 @@ struct Tconv2VariantImpl {
 #define WOFDM_VARIANT_TCONV2(N, NT, NTILE, MINB)                                                              \
     out.push_back(Tconv2VariantImpl<N, NT, NTILE, MINB, false>::make("ber_f32t2_n" #N "_t" #NT "_tiles" #NTILE "_b" #MINB)); \
     out.push_back(Tconv2VariantImpl<N, NT, NTILE, MINB, true>::make("ber_f32t2_n" #N "_t" #NT "_tiles" #NTILE "_b" #MINB "_verify"));
+// CL CTAs per frame (thread-block cluster): NTILE tiles per CTA
+#define WOFDM_VARIANT_TCONV2_CL(N, NT, NTILE, MINB, CL)                                                       \
+    out.push_back(Tconv2VariantImpl<N, NT, NTILE, MINB, false, CL>::make("ber_f32t2_n" #N "_t" #NT "_tiles" #NTILE "_b" #MINB "_cl" #CL)); \
+    out.push_back(Tconv2VariantImpl<N, NT, NTILE, MINB, true, CL>::make("ber_f32t2_n" #N "_t" #NT "_tiles" #NTILE "_b" #MINB "_cl" #CL "_verify"));
 void register_ber_f32_tconv2(std::vector<BerVariant>& out) {
     WOFDM_VARIANT_TCONV2(256, 256, 9, 2)
     WOFDM_VARIANT_TCONV2(256, 256, 10, 2)
     WOFDM_VARIANT_TCONV2(512, 512, 18, 1)
     WOFDM_VARIANT_TCONV2(512, 512, 19, 1)
+    // N = 1024: a cluster of two CTAs of 512 threads per frame, 8 OFDM symbols and 17..19 tiles per CTA, one CTA per SM
+    WOFDM_VARIANT_TCONV2_CL(1024, 512, 18, 1, 2)
+    WOFDM_VARIANT_TCONV2_CL(1024, 512, 19, 1, 2)
+    // (measured and not kept: the same frames on clusters of 256-thread CTAs, two CTAs of different frames per SM --
+    //  N = 512 as 2 x 256 threads: 1.98e8 OFDM symbols/s against 2.06e8; N = 1024 as 4 x 256: 5.5e7 against 8.4e7)
 }
 }  // namespace wofdm

@@ -65,7 +65,12 @@ __host__ __device__ inline BerSmem tconv2_smem_layout(int S, int stride, int tai
     return m;
 }
 
-template <int N, int NT, int NTILE, int MINB, bool VERIFY>
+// CL = 2: a thread-block cluster of two CTAs shares one frame, S/2 consecutive OFDM symbols and their part of the frame
+// stream per CTA (N = 1024: stream and exchange buffers of a whole frame are 278 KB, more than one SM holds).  The CTAs meet
+// three times per frame through distributed shared memory: the second CTA takes the first one's last Tx tail and the
+// L - 1 samples of convolution history (PULLED, a few dozen words), the per-warp power partials and the pilot's equaliser
+// taps are PUSHED into both CTAs, so every read is local.
+template <int N, int NT, int NTILE, int MINB, bool VERIFY, int CL = 1>
 __global__ void __launch_bounds__(NT, MINB)
 ber_tconv2_kernel(const BerParams prm) {
     using T = float;
@@ -76,18 +81,23 @@ ber_tconv2_kernel(const BerParams prm) {
     constexpr int TG = NT / 256, NTH = (NTILE + TG - 1) / TG;             // tile sets; tiles per thread
     constexpr uint32_t TMEM_COLS = tconv_tmem_cols(NTILE);
     static_assert(16 * NTILE <= (int)TMEM_COLS, "accumulators of a frame must fit tensor memory");
+    static_assert(CL * NW <= 32, "per-warp power partials of all CTAs must fit the reduction scratch");
 
     extern __shared__ __align__(128) unsigned char tcv_smem[];
     unsigned char* const smem_raw = tcv_smem;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int slot = tid / TPF, t = tid % TPF;
-    const int S = prm.S, stride = prm.stride, n_tx = prm.n_tx, beta = prm.tail_tx, L = prm.L;
+    int rank = 0;
+    if constexpr (CL > 1) rank = (int)cooperative_groups::this_cluster().block_rank();
+    const bool last_rank = rank == CL - 1;
+    const int S = prm.S / CL, sb = rank * S;    // this CTA's symbols: sb .. sb + S - 1 (the whole frame when CL == 1)
+    const int stride = prm.stride, n_tx = prm.n_tx, beta = prm.tail_tx, L = prm.L;
     const int cp = prm.cp, cs = prm.cs;
     const int hh = prm.tail_rx >> 1;
     const int hb = prm.bits >> 1, m = 1 << hb;
-    const int sec = S * stride;                 // samples kept after the channel
+    const int sec = S * stride;                 // samples kept after the channel (this CTA's)
     const int body = beta + sec;                // serialised Tx stream length
-    const int npow = prm.noise_norm == 1 ? body + L - 1 : sec;   // samples inside the frame-wide power sums
+    const int npow = (prm.noise_norm == 1 && last_rank) ? body + L - 1 : sec;   // samples inside the frame-wide power sums
 
     const BerSmem lay = tconv2_smem_layout<N, NT, NTILE>(S, stride, beta, prm.tail_rx, L, 0, 0);
     uint32_t* const ahi = reinterpret_cast<uint32_t*>(smem_raw);
@@ -171,7 +181,16 @@ ber_tconv2_kernel(const BerParams prm) {
     const N48Geom ng = n48_geom(prm);
     const int xt = (t - ng.base) & (TPF - 1);   // this thread's extras: x = xt + lev * TPF
 
-    const long long fslot = blockIdx.x, nslots = gridDim.x;
+    // distributed shared memory: the previous CTA's split stream (its last Tx tail and the convolution history)
+    const uint32_t* prev_uh = uh;
+    const uint32_t* prev_ul = ul;
+    if constexpr (CL > 1) {
+        if (rank > 0) {
+            prev_uh = cooperative_groups::this_cluster().map_shared_rank(uh, rank - 1);
+            prev_ul = cooperative_groups::this_cluster().map_shared_rank(ul, rank - 1);
+        }
+    }
+    const long long fslot = blockIdx.x / CL, nslots = gridDim.x / CL;   // frames in flight on the grid
     long long f = prm.frame_begin + fslot * prm.frame_step;
     const long long df = nslots * prm.frame_step;
     long long fe = 0, de = 0;
@@ -210,7 +229,7 @@ ber_tconv2_kernel(const BerParams prm) {
             for (int e = tid; e < S * TPF; e += NT) {
                 const int tt = e % TPF;
                 uint32_t w[4];
-                load_sym_idx<N, VERIFY>(prm, f, e / TPF, tt, w);
+                load_sym_idx<N, VERIFY>(prm, f, sb + e / TPF, tt, w);
                 if (prm.guard > 0) {
                     const uint4 gf = gmask[2 * tt], gd = gmask[2 * tt + 1];
                     w[0] = (w[0] & ~gf.x) | gd.x; w[1] = (w[1] & ~gf.y) | gd.y;
@@ -224,16 +243,16 @@ ber_tconv2_kernel(const BerParams prm) {
                 split_h2(cscale(TCV_XSCALE, src[i]), hi, lo);
                 uh[i] = hi; ul[i] = lo;
             }
-            __syncthreads();
+            frame_sync<CL>();
         } else {
             const int s = slot;
             const bool act = s < S;
             const int se = act ? s : S - 1;     // idle slots shadow the last symbol (identical stores)
-            const bool first = se == 0;         // the frame's first symbol has no predecessor
+            const bool first = sb + se == 0;    // the frame's first symbol has no predecessor
             C2 v[16];
             {
                 uint32_t w[4], wq[4];
-                load_sym_idx<N, VERIFY>(prm, f, se, t, w);
+                load_sym_idx<N, VERIFY>(prm, f, sb + se, t, w);
 #pragma unroll
                 for (int jw = 0; jw < 4; ++jw) wq[jw] = w[jw];
                 if (prm.guard > 0) {
@@ -301,7 +320,10 @@ ber_tconv2_kernel(const BerParams prm) {
                     }
                 }
             }
-            __syncthreads();                    // (also: every transform group is done with its exchange region)
+            frame_sync<CL>();                   // every symbol's tail is in place
+            // the falling tail of the previous symbol: same buffer, or the previous CTA's (behind its kept samples)
+            const uint32_t* const th = (CL > 1 && se == 0) ? prev_uh + sec : sh;
+            const uint32_t* const tl = (CL > 1 && se == 0) ? prev_ul + sec : sl;
             if (beta > 0 && act && !first) {
 #pragma unroll
                 for (int q = 16 - ER; q < 16; ++q) {
@@ -309,7 +331,7 @@ ber_tconv2_kernel(const BerParams prm) {
                         const int i = t + q * TPF - (N - cp);
                         if (i >= 0 && i < beta) {
                             uint32_t hi, lo;
-                            split_h2(caxpy(wtx[i], v[q], join_h2(sh[i], sl[i])), hi, lo);
+                            split_h2(caxpy(wtx[i], v[q], join_h2(th[i], tl[i])), hi, lo);
                             sh[i] = hi; sl[i] = lo;
                         }
                     }
@@ -320,12 +342,18 @@ ber_tconv2_kernel(const BerParams prm) {
                         const int i = t + q * TPF + cp;
                         if (i < beta) {
                             uint32_t hi, lo;
-                            split_h2(caxpy(wtx[i], v[q], join_h2(sh[i], sl[i])), hi, lo);
+                            split_h2(caxpy(wtx[i], v[q], join_h2(th[i], tl[i])), hi, lo);
                             sh[i] = hi; sl[i] = lo;
                         }
                     }
                 }
             }
+        }
+        if constexpr (CL > 1) {
+            // convolution history: the last TCV_PAD stream samples of the previous CTA (none of them is a head)
+            if (rank > 0 && tid < TCV_PAD) { ahi[tid] = prev_uh[sec - TCV_PAD + tid]; alo[tid] = prev_ul[sec - TCV_PAD + tid]; }
+            // "I have taken what I need from my neighbour's stream": awaited before anybody parks r over a stream
+            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
         }
         // the tensor core reads shared memory through the async proxy
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -367,9 +395,10 @@ ber_tconv2_kernel(const BerParams prm) {
         {
             const bool act = slot < S;
             const int se = act ? slot : S - 1;
-            const int xas = ng.xa + (se == S - 1 ? ng.tailx : 0);        // extras of this symbol (uniform per transform group)
+            const int sg = sb + se;                                      // symbol index in the frame
+            const int xas = ng.xa + (sg == prm.S - 1 ? ng.tailx : 0);    // extras of this symbol (uniform per transform group)
             const int nlev = (xas + TPF - 1) / TPF;
-            const int pbase = se * stride;
+            const int pbase = sg * stride;
             if constexpr (VERIFY) {
                 const double2* nin = prm.noise_in + (size_t)f * prm.noise_len + pbase;
 #pragma unroll
@@ -380,7 +409,7 @@ ber_tconv2_kernel(const BerParams prm) {
                     nx[lev] = x < xas ? to_v2<T>(nin[n48_extra_offset(prm, ng, x)]) : mk2<T>(0, 0);
                 }
             } else {
-                const uint32_t q0 = (uint32_t)(se * TPF + t) * 9u;
+                const uint32_t q0 = (uint32_t)(sg * TPF + t) * 9u;
 #pragma unroll
                 for (int gq = 0; gq < 2; ++gq) {
                     const uint4 ca = noise48_call(prm, f, q0 + 3 * gq), cb = noise48_call(prm, f, q0 + 3 * gq + 1);
@@ -419,6 +448,7 @@ ber_tconv2_kernel(const BerParams prm) {
         tcv_mbar_wait(tcv_smem_u32(bar), phase);
         phase ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if constexpr (CL > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
         constexpr int GT = 3;                      // tiles per batch of accumulator loads (one wait per batch)
         float4* const rst = reinterpret_cast<float4*>(rb) + wg * RCH + row;
 #pragma unroll
@@ -451,10 +481,18 @@ ber_tconv2_kernel(const BerParams prm) {
             }
         }
         T pr = warp_sum(pr2.x + pr2.y), pn = warp_sum(pn2.x + pn2.y);
-        if (lane == 0) { red[warp] = pr; red[32 + warp] = pn; }
+        if (lane == 0) {
+            // warp partials go to slot rank*NW + warp of EVERY CTA of the frame: same order, same gain everywhere
+#pragma unroll
+            for (int r = 0; r < CL; ++r) {
+                T* rr = red;
+                if constexpr (CL > 1) rr = cooperative_groups::this_cluster().map_shared_rank(red, r);
+                rr[rank * NW + warp] = pr; rr[32 + rank * NW + warp] = pn;
+            }
+        }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();                           // r and the power partials are complete
-        const T g = noise_gain(block_total<NW>(red), snr_lin, block_total<NW>(red + 32));
+        frame_sync<CL>();                          // r and the power partials are complete
+        const T g = noise_gain(block_total<CL * NW>(red), snr_lin, block_total<CL * NW>(red + 32));
 
         // =========================== receiver ===========================
         // block s: y = r + g n; z[k] = wrx[k]*y[s*stride + rm + k]; o[n] = sum_{k = n + hh (mod N)} z[k];
@@ -497,21 +535,27 @@ ber_tconv2_kernel(const BerParams prm) {
             const uint32_t w[4] = {wv.x, wv.y, wv.z, wv.w};
             // pilot (wofdm_simulation.py:223): the pilot's threads publish Y0, then every thread turns one bin into the
             // equaliser tap G[k] = X0[k] / Y0[k] (lattice units)
-            if (se == 0) {
+            if (rank == 0) {
+                if (se == 0) {
 #pragma unroll
-                for (int q = 0; q < 16; ++q) geq[t + q * TPF] = v[q];
+                    for (int q = 0; q < 16; ++q) geq[t + q * TPF] = v[q];
+                }
+                __syncthreads();
+                const unsigned char* pil = reinterpret_cast<const unsigned char*>(symw);
+                for (int k = tid; k < N; k += NT) {
+                    const C2 y0 = geq[k];
+                    const C2 x0 = qlut[pil[(k % TPF) * 16 + k / TPF]];
+                    C2 gk = cscale(recip(y0.x * y0.x + y0.y * y0.y), cmulc(x0, y0));
+                    if (prm.guard > 0 && !bin_active<N>(k, prm.guard)) gk = mk2<T>(0, 0);
+                    geq[k] = gk;
+                    if constexpr (CL > 1) {
+#pragma unroll
+                        for (int r = 1; r < CL; ++r) cooperative_groups::this_cluster().map_shared_rank(geq, r)[k] = gk;
+                    }
+                }
             }
-            __syncthreads();
-            const unsigned char* pil = reinterpret_cast<const unsigned char*>(symw);
-            for (int k = tid; k < N; k += NT) {
-                const C2 y0 = geq[k];
-                const C2 x0 = qlut[pil[(k % TPF) * 16 + k / TPF]];
-                C2 gk = cscale(recip(y0.x * y0.x + y0.y * y0.y), cmulc(x0, y0));
-                if (prm.guard > 0 && !bin_active<N>(k, prm.guard)) gk = mk2<T>(0, 0);
-                geq[k] = gk;
-            }
-            __syncthreads();
-            if (act && s > 0) {
+            frame_sync<CL>();
+            if (act && sb + s > 0) {
                 // decisions of four sub-carriers packed like the sent level codes (byte q & 3 of word q >> 2): one XOR per
                 // word, the bit errors through the Gray map of the XOR, the symbol errors as its non-zero bytes
 #pragma unroll
@@ -524,7 +568,7 @@ ber_tconv2_kernel(const BerParams prm) {
                         const uint32_t dq = (uint32_t)slice_index(e, hb);                  // :233
                         d4 |= dq << (8 * b);
                         if constexpr (VERIFY) {
-                            const size_t o = ((size_t)f * (prm.S - 1) + (s - 1)) * N + k;
+                            const size_t o = ((size_t)f * (prm.S - 1) + (sb + s - 1)) * N + k;
                             prm.eq_out[o] = make_double2((double)e.x * prm.qscale, (double)e.y * prm.qscale);
                             prm.dec_out[o] = levels_to_idx((int)(dq >> hb), (int)(dq & (m - 1)), hb, m, prm.constellation);
                         }
@@ -559,7 +603,7 @@ ber_tconv2_kernel(const BerParams prm) {
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    frame_sync<CL>();                              // (nobody leaves while a peer may still read its shared memory)
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(TMEM_COLS) : "memory");
 }
 
