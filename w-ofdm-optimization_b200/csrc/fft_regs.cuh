@@ -138,8 +138,11 @@ __device__ __forceinline__ void fft_regs(V2<T> (&v)[16], const int t, V2<T>* __r
 #pragma unroll
             for (int m = 1; m < 16; ++m) w[m - 1] = tw[tw_off + m * Ns + k];
             fft_group_sync<TPF, NB>(group);
+            {   // fft_pad(t + m TPF) = fft_pad(t) + m (TPF + TPF/16): one address, immediate offsets
+                const V2<T>* const xr = xb + fft_pad(t);
 #pragma unroll
-            for (int m = 0; m < 16; ++m) v[m] = xb[fft_pad(t + m * TPF)];
+                for (int m = 0; m < 16; ++m) v[m] = xr[m * (TPF + TPF / 16)];
+            }
 #pragma unroll
             for (int m = 1; m < 16; ++m) v[m] = tw_apply<T, DIR>(v[m], w[m - 1]);
             tw_off += 16 * Ns;
@@ -149,15 +152,25 @@ __device__ __forceinline__ void fft_regs(V2<T> (&v)[16], const int t, V2<T>* __r
         if (!(last && P::r == 1)) {
             fft_group_sync<TPF, NB>(group);        // the group has finished reading the previous layout (also of an earlier call)
             const int base = (t - k) * 16 + k;
+            {   // base = 16 Ns j + k, k < Ns: fft_pad(base + m Ns) = fft_pad(base) + m (Ns = 1) or + m (Ns + Ns/16)
+                V2<T>* const xw = xb + fft_pad(base);
+                const int step = Ns == 1 ? 1 : Ns + Ns / 16;
 #pragma unroll
-            for (int m = 0; m < 16; ++m) xb[fft_pad(base + m * Ns)] = v[m];
+                for (int m = 0; m < 16; ++m) xw[m * step] = v[m];
+            }
         }
     }
     if constexpr (P::r > 1) {
         constexpr int r = P::r, G = 16 / r;   // G butterflies of radix r per thread
         fft_group_sync<TPF, NB>(group);
+        if constexpr (TPF % 16 == 0) {
+            const V2<T>* const xr = xb + fft_pad(t);
 #pragma unroll
-        for (int q = 0; q < 16; ++q) v[q] = xb[fft_pad(t + q * TPF)];
+            for (int q = 0; q < 16; ++q) v[q] = xr[q * (TPF + TPF / 16)];
+        } else {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[q] = xb[fft_pad(t + q * TPF)];
+        }
 #pragma unroll
         for (int b = 0; b < G; ++b) {
             const int jb = t + b * TPF;
