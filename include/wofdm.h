@@ -114,10 +114,31 @@ WOFDM_API int wofdm_ber_run_shard(wofdm_handle h, const wofdm_sys_t* sys, const 
                         uint64_t seed, uint32_t variant, int shard_index, int shard_count,
                         int64_t* bit_err, int64_t* bit_tot, int64_t* sym_err, int64_t* sym_tot);
 
+/* Several window pairs on the SAME symbols in one call -- what the reference's loops do per frame: optimised and RC
+ * windows on one signal_digmod with independent noise (python/ofdm_utils/wofdm_simulation.py:183-236), the RC window
+ * and the six CaseA/CaseB steps of WOLA / CPW (matlab/main_BER_calculation.m:118-198).
+ *   win_tx: n_var x n_tx doubles (pair v at win_tx + v*n_tx), win_rx: n_var x (N+tail_rx), n_var <= WOFDM_MAX_VARIANTS.
+ *   bit_err / sym_err: n_var x n_snr (pair v at + v*n_snr); bit_tot / sym_tot: n_snr (the same for every pair).
+ * Pair v gets exactly the counters of wofdm_ber_run_shard(..., variant + v, ...) with its windows: symbols depend on
+ * (seed, frame), pair v's noise on (seed, frame, variant + v).  Where the tensor-core kernel applies, all pairs of a frame
+ * are evaluated by ONE launch (symbols drawn once, tables of all pairs resident); otherwise one launch per pair. */
+#define WOFDM_MAX_VARIANTS 8
+WOFDM_API int wofdm_ber_run_multi(wofdm_handle h, const wofdm_sys_t* sys, const double* win_tx, const double* win_rx, int n_var,
+                        const double* chan, int L, int C, const double* snr_db, int n_snr, int64_t ensemble,
+                        uint64_t seed, uint32_t variant, int shard_index, int shard_count,
+                        int64_t* bit_err, int64_t* bit_tot, int64_t* sym_err, int64_t* sym_tot);
+
 /* Device-resident form: inputs are uploaded once, launches are asynchronous. */
 WOFDM_API int wofdm_ber_plan_create(wofdm_handle h, const wofdm_sys_t* sys, const double* win_tx, const double* win_rx,
                           const double* chan, int L, int C, const double* snr_db, int n_snr,
                           wofdm_ber_plan* plan);
+/* The same for n_var window pairs (layout as in wofdm_ber_run_multi): counters are int64[n_var][n_snr][2] and
+ * wofdm_ber_plan_read fills n_var x n_snr entries.  wofdm_ber_plan_variants returns n_var; *fused (optional) = 1 if one
+ * launch evaluates all pairs. */
+WOFDM_API int wofdm_ber_plan_create_multi(wofdm_handle h, const wofdm_sys_t* sys, const double* win_tx, const double* win_rx,
+                                int n_var, const double* chan, int L, int C, const double* snr_db, int n_snr,
+                                wofdm_ber_plan* plan);
+WOFDM_API int wofdm_ber_plan_variants(wofdm_ber_plan plan, int* fused);
 /* Zeroes the plan's device counters and launches the shard on device slot `slot` of the handle,
  * on `stream` (a cudaStream_t; NULL = the plan's own stream).  Returns without synchronising.
  * One launch per slot and read: a second launch on the same slot before wofdm_ber_plan_read REPLACES the

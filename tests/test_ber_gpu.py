@@ -157,6 +157,49 @@ def test_production_replay_matches_oracle(handle, policy, monkeypatch):
                 assert np.all(np.abs(res["bit_err"] - want_bit) <= 4 + 0.002 * want_bit)
 
 
+@pytest.mark.parametrize("name,N,cp,bits,nv,precision", [("WOLA", 256, 16, 4, 7, 0), ("wtx", 256, 22, 4, 2, 0), ("CPW", 512, 32, 6, 3, 0),
+                                                        ("WOLA", 1024, 64, 6, 2, 0), ("WOLA", 256, 16, 4, 3, 1), ("wrx", 64, 8, 2, 2, 0)])
+def test_window_variants_in_one_launch(handle, name, N, cp, bits, nv, precision):
+    """The reference evaluates several window pairs on every frame's symbols (optimised + RC, wofdm_simulation.py:183-236;
+    RC + six optimisation steps for WOLA / CPW, main_BER_calculation.m:118-198).  wofdm_ber_run_multi does that in one
+    call -- one launch where the tensor-core kernel applies (fp32, N >= 256), one launch per pair otherwise -- and pair v
+    must get EXACTLY the counters of a single-pair run with variant v."""
+    sc = N // 256 if N >= 256 else 1
+    ttx = (8 * sc if N >= 256 else 2) if name in ("CPW", "WOLA", "CPwtx", "wtx") else 0
+    trx = (10 * sc if N >= 256 else 2) if name in ("CPW", "WOLA", "CPwrx", "wrx") else 0
+    p = O.system_params(name, N, cp, ttx, trx, S=16, bits=bits, noise_norm=1, constellation=1)
+    s = to_sys(p, precision)
+    wins = []
+    for v in range(nv):
+        if v == 1:
+            wins.append((O.rc_window_tx(p), O.rc_window_rx(p)))                    # flat windows
+        elif v == 4:
+            rng = np.random.default_rng(v)                                           # windows that are not flat
+            wins.append((rng.uniform(0.5, 1.0, p.n_tx), rng.uniform(0.5, 1.0, p.N + p.tail_rx)))
+        else:
+            vt, vr, _, _ = O.perturbed_windows(p, seed=10 + v)
+            wins.append((vt * (0.9 + 0.05 * v), vr))
+    chan = O.synth_channels(3, 21 if N >= 64 else 5, seed=3)
+    snr = np.array([4.0, 16.0, 28.0])
+    ens = 5 if N <= 256 else 2
+    multi = handle.ber_run_multi(s, [w[0] for w in wins], [w[1] for w in wins], chan, snr, ens, seed=99, variant=2)
+    plan = handle.ber_plan_multi(s, [w[0] for w in wins], [w[1] for w in wins], chan, snr)
+    assert plan.fused == (precision == 0 and N >= 256), plan.kernel
+    plan.launch(ens, seed=99, variant=2)
+    be, se = plan.read()
+    plan.close()
+    assert np.array_equal(be, multi["bit_err"]) and np.array_equal(se, multi["sym_err"])
+    for v, (vt, vr) in enumerate(wins):
+        one = handle.ber_run(s, vt, vr, chan, snr, ens, seed=99, variant=2 + v)
+        assert np.array_equal(one["bit_err"], multi["bit_err"][v]) and np.array_equal(one["sym_err"], multi["sym_err"][v]), v
+        assert np.array_equal(one["bit_tot"], multi["bit_tot"]) and np.array_equal(one["sym_tot"], multi["sym_tot"])
+    # different windows, different counters; same symbols: shards add up
+    assert not np.array_equal(multi["bit_err"][0], multi["bit_err"][1])
+    parts = [handle.ber_run_multi(s, [w[0] for w in wins], [w[1] for w in wins], chan, snr, ens, seed=99, variant=2, shard=(i, 3))
+             for i in range(3)]
+    assert np.array_equal(sum(q["bit_err"] for q in parts), multi["bit_err"])
+
+
 @pytest.mark.parametrize("policy", ["tconv", "regs"])
 @pytest.mark.parametrize("name,nn", [("WOLA", 0), ("CPW", 1), ("CP", 1)])
 def test_production_replay_cluster_kernel(handle, name, nn, policy, monkeypatch):

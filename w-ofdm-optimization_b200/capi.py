@@ -76,6 +76,11 @@ SIGNATURES = {
                                 C.c_uint64, C.c_uint32, _i64p, _i64p, _i64p, _i64p]),
     "wofdm_ber_run_shard": (C.c_int, [C.c_void_p, _P(SysT), _dp, _dp, _dp, C.c_int, C.c_int, _dp, C.c_int, C.c_int64,
                                       C.c_uint64, C.c_uint32, C.c_int, C.c_int, _i64p, _i64p, _i64p, _i64p]),
+    "wofdm_ber_run_multi": (C.c_int, [C.c_void_p, _P(SysT), _dp, _dp, C.c_int, _dp, C.c_int, C.c_int, _dp, C.c_int, C.c_int64,
+                                      C.c_uint64, C.c_uint32, C.c_int, C.c_int, _i64p, _i64p, _i64p, _i64p]),
+    "wofdm_ber_plan_create_multi": (C.c_int, [C.c_void_p, _P(SysT), _dp, _dp, C.c_int, _dp, C.c_int, C.c_int, _dp, C.c_int,
+                                              _P(C.c_void_p)]),
+    "wofdm_ber_plan_variants": (C.c_int, [C.c_void_p, _P(C.c_int)]),
     "wofdm_ber_plan_create": (C.c_int, [C.c_void_p, _P(SysT), _dp, _dp, _dp, C.c_int, C.c_int, _dp, C.c_int,
                                         _P(C.c_void_p)]),
     "wofdm_ber_plan_launch": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_uint32, C.c_int, C.c_int,
@@ -244,6 +249,29 @@ class Handle:
         self._check(rc)
         return dict(bit_err=out[0], bit_tot=out[1], sym_err=out[2], sym_tot=out[3])
 
+    def _win_multi(self, s, wins_tx, wins_rx):
+        """(n_var, n_tx), (n_var, N+tail_rx) contiguous doubles from lists / 2-D arrays of windows."""
+        wt = _f64(np.atleast_2d(np.asarray(wins_tx, dtype=np.float64)))
+        wr = _f64(np.atleast_2d(np.asarray(wins_rx, dtype=np.float64)))
+        if wt.ndim != 2 or wr.ndim != 2 or wt.shape[0] != wr.shape[0] or wt.shape[1] != s.n_tx or wr.shape[1] != s.N + s.tail_rx:
+            raise WofdmError(EINVAL, f"windows must be (n_var, n_tx={s.n_tx}) and (n_var, N+tail_rx={s.N + s.tail_rx})")
+        return wt, wr
+
+    def ber_run_multi(self, s, wins_tx, wins_rx, chan, snr_db, ensemble, seed=0, variant=0, shard=(0, 1)):
+        """n_var window pairs on the same symbols (wofdm_ber_run_multi).  bit_err / sym_err: (n_var, n_snr);
+        pair v = ber_run(..., variant=variant + v) with its windows."""
+        wt, wr = self._win_multi(s, wins_tx, wins_rx)
+        _, _, chf, L, Cn = self._win_chan(s, wt[0], wr[0], chan)
+        snr = _f64(np.ravel(snr_db))
+        n, nv = snr.size, wt.shape[0]
+        be, se = np.zeros((nv, n), dtype=np.int64), np.zeros((nv, n), dtype=np.int64)
+        bt, st = np.zeros(n, dtype=np.int64), np.zeros(n, dtype=np.int64)
+        rc = load().wofdm_ber_run_multi(self._h, C.byref(s), _ptr(wt, _dp), _ptr(wr, _dp), nv, _ptr(chf, _dp), L, Cn,
+                                        _ptr(snr, _dp), n, int(ensemble), int(seed), int(variant), int(shard[0]), int(shard[1]),
+                                        _ptr(be, _i64p), _ptr(bt, _i64p), _ptr(se, _i64p), _ptr(st, _i64p))
+        self._check(rc)
+        return dict(bit_err=be, bit_tot=bt, sym_err=se, sym_tot=st)
+
     def ber_run_masked(self, s, win_tx, win_rx, chan, snr_db, ensemble, seed=0, variant=0, roll_off=10):
         """Channel-mask variant (wofdm_ber_run_masked): counters of the MASKED signal; ber_run with the same `s`
         (s.guard = the script's offset) gives the unmasked ones on the same symbols."""
@@ -273,6 +301,10 @@ class Handle:
                                        records, seed, _ptr(si, _i32p) if si is not None else None, _ptr(out, _dp))
         self._check(rc)
         return out
+
+    def ber_plan_multi(self, s, wins_tx, wins_rx, chan, snr_db):
+        """Device-resident plan of n_var window pairs (wofdm_ber_plan_create_multi)."""
+        return BerPlan(self, s, wins_tx, wins_rx, chan, snr_db, multi=True)
 
     def ber_plan(self, s, win_tx, win_rx, chan, snr_db):
         return BerPlan(self, s, win_tx, win_rx, chan, snr_db)
@@ -355,14 +387,22 @@ class Handle:
 class BerPlan:
     """Device-resident inputs of one (system, windows, channel set, SNR grid); asynchronous launches."""
 
-    def __init__(self, handle, s, win_tx, win_rx, chan, snr_db):
+    def __init__(self, handle, s, win_tx, win_rx, chan, snr_db, multi=False):
         self.handle, self.sys = handle, s
-        wt, wr, chf, L, Cn = handle._win_chan(s, win_tx, win_rx, chan)
         snr = _f64(np.ravel(snr_db))
-        self.n_snr, self.L, self.C = snr.size, L, Cn
         self._p = C.c_void_p()
-        rc = load().wofdm_ber_plan_create(handle._h, C.byref(s), _ptr(wt, _dp), _ptr(wr, _dp), _ptr(chf, _dp), L, Cn,
-                                          _ptr(snr, _dp), snr.size, C.byref(self._p))
+        if multi:
+            wt, wr = handle._win_multi(s, win_tx, win_rx)
+            _, _, chf, L, Cn = handle._win_chan(s, wt[0], wr[0], chan)
+            self.n_var = wt.shape[0]
+            rc = load().wofdm_ber_plan_create_multi(handle._h, C.byref(s), _ptr(wt, _dp), _ptr(wr, _dp), self.n_var, _ptr(chf, _dp),
+                                                    L, Cn, _ptr(snr, _dp), snr.size, C.byref(self._p))
+        else:
+            wt, wr, chf, L, Cn = handle._win_chan(s, win_tx, win_rx, chan)
+            self.n_var = 1
+            rc = load().wofdm_ber_plan_create(handle._h, C.byref(s), _ptr(wt, _dp), _ptr(wr, _dp), _ptr(chf, _dp), L, Cn,
+                                              _ptr(snr, _dp), snr.size, C.byref(self._p))
+        self.n_snr, self.L, self.C = snr.size, L, Cn
         handle._check(rc)
         handle._plans.add(self)
 
@@ -378,8 +418,17 @@ class BerPlan:
         self.handle._check(rc)
         return d.value
 
+    @property
+    def fused(self):
+        """True if one launch evaluates all window pairs of the plan."""
+        f = C.c_int(0)
+        load().wofdm_ber_plan_variants(self._p, C.byref(f))
+        return bool(f.value)
+
     def read(self):
-        be, se = np.zeros(self.n_snr, dtype=np.int64), np.zeros(self.n_snr, dtype=np.int64)
+        """(bit_err, sym_err): (n_snr,) each, or (n_var, n_snr) for a multi-variant plan."""
+        shape = (self.n_var, self.n_snr) if self.n_var > 1 else (self.n_snr,)
+        be, se = np.zeros(shape, dtype=np.int64), np.zeros(shape, dtype=np.int64)
         self.handle._check(load().wofdm_ber_plan_read(self._p, _ptr(be, _i64p), _ptr(se, _i64p)))
         return be, se
 

@@ -29,7 +29,9 @@ struct wofdm_ber_plan_s {
     const BerVariant* var = nullptr;
     BerSmem lay{};
     int chunk = 0, use_global = 0;
-    int flat_tx = 0, flat_rx = 0;
+    int flat_tx = 0, flat_rx = 0;  // bit v = window pair v
+    int n_var = 1;                 // window pairs of the plan
+    bool fused = false;            // all of them in ONE launch (second-generation tensor-core kernel); else one launch each
     bool transient = false;    // buffers live in the devices' arenas (one-shot plan of wofdm_ber_run*): nothing to free
     std::vector<PlanDev> devs;
 };
@@ -43,14 +45,20 @@ struct Choice {
 };
 
 // tensor-core kernel: windows that are one value between their tails (BerParams::flat_tx / flat_rx)
-void fill_flat(BerParams& prm, const wofdm_sys_t& s, const double* win_tx, const double* win_rx) {
-    const int n_tx = s.N + s.cp + s.cs;
-    bool ft = s.cp >= s.tail_tx && s.cs >= s.tail_tx && win_tx[s.tail_tx] != 0.0;
-    for (int i = s.tail_tx; ft && i < n_tx - s.tail_tx; ++i) ft = win_tx[i] == win_tx[s.tail_tx];
-    bool fr = win_rx[s.tail_rx] != 0.0;
-    for (int i = s.tail_rx; fr && i < s.N; ++i) fr = win_rx[i] == win_rx[s.tail_rx];
-    prm.flat_tx = ft ? 1 : 0;
-    prm.flat_rx = fr ? 1 : 0;
+// (n_var window pairs back to back: bit v of flat_tx / flat_rx = pair v)
+void fill_flat(BerParams& prm, const wofdm_sys_t& s, const double* win_tx, const double* win_rx, int n_var = 1) {
+    const int n_tx = s.N + s.cp + s.cs, n_wr = s.N + s.tail_rx;
+    prm.flat_tx = prm.flat_rx = 0;
+    for (int v = 0; v < n_var; ++v) {
+        const double* wt = win_tx + (size_t)v * n_tx;
+        const double* wr = win_rx + (size_t)v * n_wr;
+        bool ft = s.cp >= s.tail_tx && s.cs >= s.tail_tx && wt[s.tail_tx] != 0.0;
+        for (int i = s.tail_tx; ft && i < n_tx - s.tail_tx; ++i) ft = wt[i] == wt[s.tail_tx];
+        bool fr = wr[s.tail_rx] != 0.0;
+        for (int i = s.tail_rx; fr && i < s.N; ++i) fr = wr[i] == wr[s.tail_rx];
+        prm.flat_tx |= (ft ? 1 : 0) << v;
+        prm.flat_rx |= (fr ? 1 : 0) << v;
+    }
 }
 
 // noise numbering of a frame shared by a cluster (BerParams::split)
@@ -63,7 +71,7 @@ void fill_split(BerParams& prm, const BerVariant& v) {
 // win_tx (may be NULL): the circular-interior kernels need it flat between the tails; no_circ excludes them
 int choose_variant(wofdm_ctx* h, const wofdm_sys_t& s, int L, bool verify, bool force_staged, size_t smem_cap,
                    Choice* out, const double* win_tx = nullptr, bool no_circ = false, bool want_txs = false,
-                   bool no_tconv = false) {
+                   bool no_tconv = false, int nvar = 1) {
     const int stride = s.N + s.cp + s.cs - s.tail_tx;
     const int sec = s.S * stride;
     const bool fp64 = s.precision == 1;
@@ -95,7 +103,8 @@ int choose_variant(wofdm_ctx* h, const wofdm_sys_t& s, int L, bool verify, bool 
                 if (s.cp > 2 * tpf || s.cs > 2 * tpf || s.tail_tx > 2 * tpf || s.tail_rx / 2 > tpf || s.shift > tpf) continue;
                 const int need = std::max(s.noise_norm == 1 ? body + L - 1 : sec_cta, body + TCV_ZERO);
                 if (need > 512 * v.ntile || sec_cta <= 512 * (v.ntile - 2)) continue;   // (the kernel range-checks its last two tiles only)
-                const BerSmem lay = v.layout(S_cta, stride, s.tail_tx, s.tail_rx, L, 0, 0);
+                if (nvar > 1 && v.gen != 2) continue;                // (several window pairs per launch: ber_tconv2.cuh only)
+                const BerSmem lay = v.layout(S_cta, stride, s.tail_tx, s.tail_rx, L, v.gen == 2 ? nvar : 0, 0);
                 if (lay.bytes > smem_cap) continue;
                 if (!best.var || best.var->ntile == 0 || v.ntile < best.var->ntile) { best.var = &v; best.lay = lay; best.chunk = 0; }
                 continue;
@@ -256,7 +265,7 @@ size_t elem_bytes(const wofdm_sys_t& s) { return s.precision == 1 ? sizeof(doubl
 
 // transient = true: device buffers come out of the per-device arena (no cudaMalloc / cudaFree per call); such a plan
 // must be destroyed before the arena is used again (wofdm_ber_run_shard does exactly that)
-static int plan_create_impl(wofdm_handle h, const wofdm_sys_t* sys, const double* win_tx, const double* win_rx,
+static int plan_create_impl(wofdm_handle h, const wofdm_sys_t* sys, const double* win_tx, const double* win_rx, int n_var,
                             const double* chan, int L, int C, const double* snr_db, int n_snr,
                             wofdm_ber_plan* out, bool transient) {
     NvtxRange nvtx_("wofdm_ber_plan_create");
@@ -267,26 +276,38 @@ static int plan_create_impl(wofdm_handle h, const wofdm_sys_t* sys, const double
     if (rc) return rc;
     if (!win_tx || !win_rx || !chan || !snr_db) return fail(h, WOFDM_EINVAL, "NULL input buffer");
     if (C < 1 || n_snr < 1) return fail(h, WOFDM_EINVAL, "C and n_snr must be >= 1");
+    if (n_var < 1 || n_var > WOFDM_MAX_VARIANTS) return fail(h, WOFDM_EINVAL, "n_var must be in [1, WOFDM_MAX_VARIANTS]");
     const bool fp64 = sys->precision == 1;
 
     wofdm_ber_plan_s* p = new (std::nothrow) wofdm_ber_plan_s();
     if (!p) return fail(h, WOFDM_ENOMEM, "host allocation failed");
-    p->ctx = h; p->sys = *sys; p->L = L; p->C = C; p->n_snr = n_snr; p->transient = transient;
+    p->ctx = h; p->sys = *sys; p->L = L; p->C = C; p->n_snr = n_snr; p->transient = transient; p->n_var = n_var;
     Choice ch;
     size_t cap = h->devs[0].smem_optin;
     for (auto& d : h->devs) cap = std::min(cap, d.smem_optin);
-    rc = choose_variant(h, *sys, L, false, false, cap, &ch, win_tx);
+    // several window pairs: one launch for all of them where the second-generation tensor-core kernel applies and holds
+    // their tables; otherwise the pairs are launched one after the other on the same draws (same counters either way)
+    rc = choose_variant(h, *sys, L, false, false, cap, &ch, win_tx, false, false, false, n_var);
+    p->fused = rc == WOFDM_OK && n_var > 1 && ch.var->gen == 2;
+    if (n_var > 1 && !p->fused) rc = choose_variant(h, *sys, L, false, false, cap, &ch, win_tx, /*no_circ=*/true);
     if (rc) { delete p; return rc; }
     p->var = ch.var; p->lay = ch.lay; p->chunk = ch.chunk; p->use_global = ch.use_global;
     {
         BerParams fp;
-        fill_flat(fp, *sys, win_tx, win_rx);
+        fill_flat(fp, *sys, win_tx, win_rx, n_var);
         p->flat_tx = fp.flat_tx; p->flat_rx = fp.flat_rx;
     }
 
     HostTables t;
     const bool unit_peak = p->var->ntile > 0;
-    build_tables(*sys, win_tx, win_rx, t, unit_peak);
+    const int n_tx = sys->N + sys->cp + sys->cs, n_wr = sys->N + sys->tail_rx;
+    for (int v = 0; v < n_var; ++v) {              // tables of the window pairs back to back
+        HostTables tv;
+        build_tables(*sys, win_tx + (size_t)v * n_tx, win_rx + (size_t)v * n_wr, tv, unit_peak);
+        t.wtx.insert(t.wtx.end(), tv.wtx.begin(), tv.wtx.end());
+        t.wrx.insert(t.wrx.end(), tv.wrx.begin(), tv.wrx.end());
+        if (v == 0) t.tw = tv.tw;
+    }
     std::vector<unsigned char> hchan, hsnr;
     cast_chan(fp64, chan, (size_t)L * C, hchan, L, unit_peak);
     std::vector<double> lin(n_snr);
@@ -317,7 +338,7 @@ static int plan_create_impl(wofdm_handle h, const wofdm_sys_t* sys, const double
         pd.scratch_bytes = p->use_global ? (size_t)pd.blocks_per_sm * d.sm_count * 2 * scratch_elems * elem_bytes(*sys) : 0;
         if (e == cudaSuccess && transient) {
             rc = arena_reserve(h, d, t.wtx.size() + t.wrx.size() + t.tw.size() + hchan.size() + hsnr.size() +
-                                         (size_t)n_snr * 16 + pd.scratch_bytes);
+                                         (size_t)n_var * n_snr * 16 + pd.scratch_bytes);
             if (rc) { const std::string msg = h->err; wofdm_ber_plan_destroy(p); h->err = msg; return rc; }
         }
         if (e == cudaSuccess) e = up(&pd.d_wtx, t.wtx);
@@ -325,7 +346,7 @@ static int plan_create_impl(wofdm_handle h, const wofdm_sys_t* sys, const double
         if (e == cudaSuccess) e = up(&pd.d_tw, t.tw);
         if (e == cudaSuccess) e = up(&pd.d_chan, hchan);
         if (e == cudaSuccess) e = up(&pd.d_snr, hsnr);
-        if (e == cudaSuccess) e = dev_alloc(reinterpret_cast<void**>(&pd.d_cnt), (size_t)n_snr * 2 * sizeof(unsigned long long));
+        if (e == cudaSuccess) e = dev_alloc(reinterpret_cast<void**>(&pd.d_cnt), (size_t)n_var * n_snr * 2 * sizeof(unsigned long long));
         if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);   // host vectors go out of scope
         if (e == cudaSuccess && p->use_global) e = dev_alloc(&pd.d_scratch, pd.scratch_bytes);
         if (e != cudaSuccess) {
@@ -343,7 +364,18 @@ extern "C" {
 int wofdm_ber_plan_create(wofdm_handle h, const wofdm_sys_t* sys, const double* win_tx, const double* win_rx,
                           const double* chan, int L, int C, const double* snr_db, int n_snr,
                           wofdm_ber_plan* out) {
-    return plan_create_impl(h, sys, win_tx, win_rx, chan, L, C, snr_db, n_snr, out, false);
+    return plan_create_impl(h, sys, win_tx, win_rx, 1, chan, L, C, snr_db, n_snr, out, false);
+}
+
+int wofdm_ber_plan_create_multi(wofdm_handle h, const wofdm_sys_t* sys, const double* win_tx, const double* win_rx, int n_var,
+                                const double* chan, int L, int C, const double* snr_db, int n_snr, wofdm_ber_plan* out) {
+    return plan_create_impl(h, sys, win_tx, win_rx, n_var, chan, L, C, snr_db, n_snr, out, false);
+}
+
+int wofdm_ber_plan_variants(wofdm_ber_plan p, int* fused) {
+    if (!p) return WOFDM_EINVAL;
+    if (fused) *fused = p->fused ? 1 : 0;
+    return p->n_var;
 }
 
 int wofdm_ber_plan_launch(wofdm_ber_plan p, int slot, int64_t ensemble, uint64_t seed, uint32_t variant,
@@ -354,7 +386,7 @@ int wofdm_ber_plan_launch(wofdm_ber_plan p, int slot, int64_t ensemble, uint64_t
     if (slot < 0 || slot >= (int)p->devs.size()) return fail(h, WOFDM_EINVAL, "device slot out of range");
     if (ensemble < 1) return fail(h, WOFDM_EINVAL, "ensemble must be >= 1");
     if (shard_count < 1 || shard_index < 0 || shard_index >= shard_count) return fail(h, WOFDM_EINVAL, "bad shard");
-    if (variant > 0xfffffff0u) return fail(h, WOFDM_EINVAL, "variant too large");
+    if (variant > 0xfffffff0u - WOFDM_MAX_VARIANTS) return fail(h, WOFDM_EINVAL, "variant too large");
     DeviceCtx& d = h->devs[slot];
     PlanDev& pd = p->devs[slot];
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : d.stream;
@@ -378,15 +410,33 @@ int wofdm_ber_plan_launch(wofdm_ber_plan p, int slot, int64_t ensemble, uint64_t
 
     // a launch owns its slot's counters: one that is still pending on ANOTHER stream must finish before they are zeroed
     if (pd.pending && pd.last_stream != st) WOFDM_CUDA(h, cudaStreamSynchronize(pd.last_stream));
-    WOFDM_CUDA(h, cudaMemsetAsync(pd.d_cnt, 0, (size_t)p->n_snr * 2 * sizeof(unsigned long long), st));
+    WOFDM_CUDA(h, cudaMemsetAsync(pd.d_cnt, 0, (size_t)p->n_var * p->n_snr * 2 * sizeof(unsigned long long), st));
     if (mine > 0) {
         long long cap = pd.max_ctas;
         if (const char* lim = getenv("WOFDM_MAX_CTAS_PER_SM"))            // tuning aid: occupancy sensitivity
             cap = std::min<long long>(cap, (long long)std::max(1, atoi(lim)) * d.sm_count);
         const int cl = p->var->CL;
         const int grid = (int)std::min<long long>(mine, std::max<long long>(cap / cl, 1)) * cl;   // CTAs = frames in flight x cluster size
-        WOFDM_CUDA(h, p->var->launch(prm, grid, p->lay.bytes, st));
-        h->launches += 1;
+        if (p->fused || p->n_var == 1) {
+            prm.nvar = p->n_var;
+            WOFDM_CUDA(h, p->var->launch(prm, grid, p->lay.bytes, st));
+            h->launches += 1;
+        } else {
+            // one launch per window pair: pair v = a single-pair launch with variant + v on tables / counters v
+            const size_t eb = p->sys.precision == 1 ? sizeof(double) : sizeof(float);
+            const int n_tx = p->sys.N + p->sys.cp + p->sys.cs, n_wr = p->sys.N + p->sys.tail_rx;
+            for (int v = 0; v < p->n_var; ++v) {
+                BerParams pv = prm;
+                pv.nvar = 1;
+                pv.win_tx = static_cast<const char*>(pd.d_wtx) + (size_t)v * n_tx * eb;
+                pv.win_rx = static_cast<const char*>(pd.d_wrx) + (size_t)v * n_wr * eb;
+                pv.flat_tx = (p->flat_tx >> v) & 1; pv.flat_rx = (p->flat_rx >> v) & 1;
+                pv.variant = variant + (uint32_t)v;
+                pv.counters = pd.d_cnt + (size_t)v * p->n_snr * 2;
+                WOFDM_CUDA(h, p->var->launch(pv, grid, p->lay.bytes, st));
+                h->launches += 1;
+            }
+        }
     }
     pd.pending = true;
     pd.last_stream = st;
@@ -398,8 +448,9 @@ int wofdm_ber_plan_read(wofdm_ber_plan p, int64_t* bit_err, int64_t* sym_err) {
     if (!p) return WOFDM_EINVAL;
     wofdm_ctx* h = p->ctx;
     if (!bit_err || !sym_err) return fail(h, WOFDM_EINVAL, "NULL output buffer");
-    for (int i = 0; i < p->n_snr; ++i) { bit_err[i] = 0; sym_err[i] = 0; }
-    std::vector<unsigned long long> tmp((size_t)p->n_snr * 2);
+    const int n_out = p->n_var * p->n_snr;       // [n_var][n_snr]
+    for (int i = 0; i < n_out; ++i) { bit_err[i] = 0; sym_err[i] = 0; }
+    std::vector<unsigned long long> tmp((size_t)n_out * 2);
     for (size_t s = 0; s < p->devs.size(); ++s) {
         PlanDev& pd = p->devs[s];
         if (!pd.pending) continue;
@@ -407,7 +458,7 @@ int wofdm_ber_plan_read(wofdm_ber_plan p, int64_t* bit_err, int64_t* sym_err) {
         WOFDM_CUDA(h, cudaMemcpyAsync(tmp.data(), pd.d_cnt, tmp.size() * sizeof(unsigned long long),
                                       cudaMemcpyDeviceToHost, pd.last_stream));
         WOFDM_CUDA(h, cudaStreamSynchronize(pd.last_stream));
-        for (int i = 0; i < p->n_snr; ++i) { bit_err[i] += (int64_t)tmp[2 * i]; sym_err[i] += (int64_t)tmp[2 * i + 1]; }
+        for (int i = 0; i < n_out; ++i) { bit_err[i] += (int64_t)tmp[2 * i]; sym_err[i] += (int64_t)tmp[2 * i + 1]; }
         pd.pending = false;
     }
     return WOFDM_OK;
@@ -434,13 +485,21 @@ int wofdm_ber_run_shard(wofdm_handle h, const wofdm_sys_t* sys, const double* wi
                         const double* chan, int L, int C, const double* snr_db, int n_snr, int64_t ensemble,
                         uint64_t seed, uint32_t variant, int shard_index, int shard_count,
                         int64_t* bit_err, int64_t* bit_tot, int64_t* sym_err, int64_t* sym_tot) {
-    NvtxRange nvtx_("wofdm_ber_run_shard");
+    return wofdm_ber_run_multi(h, sys, win_tx, win_rx, 1, chan, L, C, snr_db, n_snr, ensemble, seed, variant, shard_index,
+                               shard_count, bit_err, bit_tot, sym_err, sym_tot);
+}
+
+int wofdm_ber_run_multi(wofdm_handle h, const wofdm_sys_t* sys, const double* win_tx, const double* win_rx, int n_var,
+                        const double* chan, int L, int C, const double* snr_db, int n_snr, int64_t ensemble,
+                        uint64_t seed, uint32_t variant, int shard_index, int shard_count,
+                        int64_t* bit_err, int64_t* bit_tot, int64_t* sym_err, int64_t* sym_tot) {
+    NvtxRange nvtx_("wofdm_ber_run_multi");
     if (!h) return WOFDM_EINVAL;
     if (!bit_err || !bit_tot || !sym_err || !sym_tot) return fail(h, WOFDM_EINVAL, "NULL output buffer");
     if (shard_count < 1 || shard_index < 0 || shard_index >= shard_count) return fail(h, WOFDM_EINVAL, "bad shard");
     if (ensemble < 1) return fail(h, WOFDM_EINVAL, "ensemble must be >= 1");
     wofdm_ber_plan p = nullptr;
-    int rc = plan_create_impl(h, sys, win_tx, win_rx, chan, L, C, snr_db, n_snr, &p, true);
+    int rc = plan_create_impl(h, sys, win_tx, win_rx, n_var, chan, L, C, snr_db, n_snr, &p, true);
     if (rc) return rc;
     // the handle's devices split this shard's frames between them: device i takes the sub-shard
     // shard_index + shard_count*i of shard_count*ndev, so results do not depend on the GPU count

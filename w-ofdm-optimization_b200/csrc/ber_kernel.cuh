@@ -43,6 +43,9 @@ struct BerParams {
     int noise_norm, constellation;
     int flat_tx, flat_rx;      // tensor-core kernel (ber_tconv.cuh): the window is one value between its tails (and cp, cs >= tail_tx
                                // for Tx): that value moves into the constellation table / is divided out, the flat rows skip the product
+                               // (bit v = window pair v of a multi-variant plan)
+    int nvar;                  // ber_tconv2.cuh: window pairs evaluated on every frame's symbols in one launch (<= 1: one);
+                               // win_tx / win_rx hold nvar tables back to back, counters are [nvar][n_snr][2]
     int guard;                 // null sub-carriers on each side of the centred spectrum (main_channel_mask.m:55,388-391)
     const float2* tx_stream;   // staged policy and TXS instantiations: the serialised Tx stream of local frame j at [j][tail_tx + S*stride],
                                // produced by tx_mask_kernel (channel-mask variant); the Tx stage then only redraws the indices
@@ -190,8 +193,9 @@ __device__ __forceinline__ void noise_pair(const BerParams& prm, long long f, ui
 // call 3g+1), angle = half e & 1 of word e >> 1 of call 3g+2; c = 6, 7, 8 give the words V[0..9) of the extras: levels
 // 2 j, 2 j + 1 take their angles from the halves of V[3 j] and their radii from V[3 j + 1], V[3 j + 2].
 constexpr int N48_MAXLEV = 6;
-__device__ __forceinline__ uint4 noise48_call(const BerParams& prm, long long f, uint32_t q) {
-    return philox4x32_10_rk(make_uint4((uint32_t)f, (uint32_t)((unsigned long long)f >> 32), q, STREAM_NOISE + prm.variant), prm.rk);
+// (var: window pair of a multi-variant launch; its noise stream is that of a single launch with variant + var)
+__device__ __forceinline__ uint4 noise48_call(const BerParams& prm, long long f, uint32_t q, int var = 0) {
+    return philox4x32_10_rk(make_uint4((uint32_t)f, (uint32_t)((unsigned long long)f >> 32), q, STREAM_NOISE + prm.variant + (uint32_t)var), prm.rk);
 }
 // two complex samples: radius words u0, u1, angles = low / high half of aw.  Same arithmetic as gauss_quad.
 __device__ __forceinline__ void gauss_quad48(uint32_t u0, uint32_t u1, uint32_t aw, float2& n0, float2& n1) {

@@ -35,8 +35,11 @@ namespace wofdm {
 #endif
 constexpr int TCV2_BAR_STREAM = 14;      // named barrier: "the split stream of this frame is complete"
 
+__host__ __device__ constexpr int tconv2_wtx_len(int stride, int tail_tx) { return (stride + tail_tx + 3) & ~3; }
+__host__ __device__ constexpr int tconv2_wrx_len(int N, int tail_rx) { return (N + tail_rx + 3) & ~3; }
+
 template <int N, int NT, int NTILE>
-__host__ __device__ inline BerSmem tconv2_smem_layout(int S, int stride, int tail_tx, int tail_rx, int L, int chunk, int use_global) {
+__host__ __device__ inline BerSmem tconv2_smem_layout(int S, int stride, int tail_tx, int tail_rx, int L, int nvar, int use_global) {
     using P = FftPlan<N>;
     constexpr int FPP = NT / P::TPF;
     BerSmem m;
@@ -52,8 +55,9 @@ __host__ __device__ inline BerSmem tconv2_smem_layout(int S, int stride, int tai
     o += P::NTW * 8;                 m.off_geq = o;
     o += N * 8;                      m.off_bt = o;
     o += 3 * 768;                    m.off_wtx = o;       // [T_hi | T_lo | zeros], 8 rows x 48 halves each
-    o += ((stride + tail_tx + 3) & ~3) * 4;   m.off_wrx = o;
-    o += ((N + tail_rx + 3) & ~3) * 4;        m.off_red = o;
+    const int nv = nvar > 1 ? nvar : 1;                   // window pairs evaluated per frame (BerParams::nvar)
+    o += nv * tconv2_wtx_len(stride, tail_tx) * 4;   m.off_wrx = o;
+    o += nv * tconv2_wrx_len(N, tail_rx) * 4;        m.off_red = o;
     o += 64 * 4;                              m.off_qlut = o;
     o += 2 * 256 * 8;                         m.off_gmask = o;      // lattice points: Rx (pilot) copy, Tx copy (carries the flat window value)
     o += P::TPF * 32;                         m.off_symw = o;
@@ -61,7 +65,7 @@ __host__ __device__ inline BerSmem tconv2_smem_layout(int S, int stride, int tai
     o += 16;
     m.off_hf = m.off_taps = m.off_dlut = 0;
     m.bytes = ((size_t)o + 15) & ~(size_t)15;
-    (void)L; (void)chunk; (void)use_global;
+    (void)L; (void)use_global;
     return m;
 }
 
@@ -99,7 +103,8 @@ ber_tconv2_kernel(const BerParams prm) {
     const int body = beta + sec;                // serialised Tx stream length
     const int npow = (prm.noise_norm == 1 && last_rank) ? body + L - 1 : sec;   // samples inside the frame-wide power sums
 
-    const BerSmem lay = tconv2_smem_layout<N, NT, NTILE>(S, stride, beta, prm.tail_rx, L, 0, 0);
+    const int nvar = (!VERIFY && prm.nvar > 1) ? prm.nvar : 1;     // window pairs evaluated on every frame's symbols
+    const BerSmem lay = tconv2_smem_layout<N, NT, NTILE>(S, stride, beta, prm.tail_rx, L, nvar, 0);
     uint32_t* const ahi = reinterpret_cast<uint32_t*>(smem_raw);
     uint32_t* const alo = reinterpret_cast<uint32_t*>(smem_raw + lay.off_lo);
     uint32_t* const uh = ahi + TCV_PAD;         // uh[i], ul[i]: split stream sample i
@@ -110,8 +115,9 @@ ber_tconv2_kernel(const BerParams prm) {
     C2* tw = reinterpret_cast<C2*>(smem_raw + lay.off_tw);
     C2* geq = reinterpret_cast<C2*>(smem_raw + lay.off_geq);
     unsigned char* bt = smem_raw + lay.off_bt;
-    T* wtx = reinterpret_cast<T*>(smem_raw + lay.off_wtx);
-    T* wrx = reinterpret_cast<T*>(smem_raw + lay.off_wrx);
+    T* const wtx_all = reinterpret_cast<T*>(smem_raw + lay.off_wtx);   // [nvar][WTXL]
+    T* const wrx_all = reinterpret_cast<T*>(smem_raw + lay.off_wrx);   // [nvar][WRXL]
+    const int WTXL = tconv2_wtx_len(stride, beta), WRXL = tconv2_wrx_len(N, prm.tail_rx);
     T* red = reinterpret_cast<T*>(smem_raw + lay.off_red);
     C2* qlut = reinterpret_cast<C2*>(smem_raw + lay.off_qlut);     // level code -> lattice point
     C2* qtx = qlut + 256;                                           // ... times the flat Tx window value
@@ -134,18 +140,28 @@ ber_tconv2_kernel(const BerParams prm) {
     // flat windows (host-checked): the Tx window's flat value rides on the constellation table and wtx holds the ratio to it
     // (1 on every body row: no product there); the Rx window is divided by its flat value (a common factor of the
     // received signal cancels in the pilot equaliser) and rows 1..13 of the Rx gather skip the product
-    const bool flat_tx = prm.flat_tx != 0, flat_rx = prm.flat_rx != 0;
-    const T wflat = flat_tx ? reinterpret_cast<const T*>(prm.win_tx)[beta] : (T)1;
-    const T rflat = flat_rx ? reinterpret_cast<const T*>(prm.win_rx)[prm.tail_rx] : (T)1;
-    for (int i = tid; i < n_tx; i += NT)
-        wtx[i] = flat_tx ? reinterpret_cast<const T*>(prm.win_tx)[i] / wflat : reinterpret_cast<const T*>(prm.win_tx)[i] * TCV_XSCALE;
-    for (int i = tid; i < N + prm.tail_rx; i += NT) wrx[i] = reinterpret_cast<const T*>(prm.win_rx)[i] / rflat;
+    // (BerParams::flat_tx / flat_rx: bit v = window pair v)
+    for (int vv = 0; vv < nvar; ++vv) {
+        const T* gw = reinterpret_cast<const T*>(prm.win_tx) + (size_t)vv * n_tx;
+        const T* gr = reinterpret_cast<const T*>(prm.win_rx) + (size_t)vv * (N + prm.tail_rx);
+        const bool ft = (prm.flat_tx >> vv) & 1, fr = (prm.flat_rx >> vv) & 1;
+        const T wflat = ft ? gw[beta] : (T)1, rflat = fr ? gr[prm.tail_rx] : (T)1;
+        for (int i = tid; i < n_tx; i += NT) wtx_all[vv * WTXL + i] = ft ? gw[i] / wflat : gw[i] * TCV_XSCALE;
+        for (int i = tid; i < N + prm.tail_rx; i += NT) wrx_all[vv * WRXL + i] = gr[i] / rflat;
+    }
+    // constellation table of window pair vv for the Tx stage
+    auto build_qtx = [&](int vv) {
+        const bool ft = (prm.flat_tx >> vv) & 1;
+        const T wflat = ft ? reinterpret_cast<const T*>(prm.win_tx)[(size_t)vv * n_tx + beta] : (T)1;
+        for (int i = tid; i < (1 << prm.bits); i += NT) {
+            const C2 q = mk2<T>((T)(2 * (i >> hb) - (m - 1)), (T)(2 * (i & (m - 1)) - (m - 1)));
+            qtx[i] = ft ? cscale(wflat * TCV_XSCALE, q) : q;
+        }
+    };
     for (int i = tid; i < TCV_PAD; i += NT) ahi[i] = 0u;
     for (int i = tid; i < 768 / 4; i += NT) reinterpret_cast<uint32_t*>(bt + 1536)[i] = 0u;
-    for (int i = tid; i < (1 << prm.bits); i += NT) {
-        qlut[i] = mk2<T>((T)(2 * (i >> hb) - (m - 1)), (T)(2 * (i & (m - 1)) - (m - 1)));
-        qtx[i] = flat_tx ? cscale(wflat * TCV_XSCALE, qlut[i]) : qlut[i];
-    }
+    for (int i = tid; i < (1 << prm.bits); i += NT) qlut[i] = mk2<T>((T)(2 * (i >> hb) - (m - 1)), (T)(2 * (i & (m - 1)) - (m - 1)));
+    build_qtx(0);
     if (tid == 0 && prm.bits < 8) { qlut[255] = mk2<T>(0, 0); qtx[255] = mk2<T>(0, 0); }
     const uint32_t gxm = gray_xor_mask(prm.bits, prm.constellation);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -204,8 +220,15 @@ ber_tconv2_kernel(const BerParams prm) {
     for (long long j = fslot; j < prm.n_frames; j += nslots) {
         if constexpr (VERIFY) { ci = (int)f; si = (int)f; }
         const T snr_lin = reinterpret_cast<const T*>(prm.snr_lin)[si];
+      // every window pair of the plan on this frame's symbols (drawn once), each with its own noise stream
+      // (wofdm_simulation.py:183-236: optimised and RC windows on one signal_digmod; main_BER_calculation.m:118-198)
+      for (int var = 0; var < nvar; ++var) {
+        const bool flat_tx = (prm.flat_tx >> var) & 1, flat_rx = (prm.flat_rx >> var) & 1;
+        const T* const wtx = wtx_all + var * WTXL;
+        const T* const wrx = wrx_all + var * WRXL;
         // ---- taps operand of this frame: n = 2o + comp (o < 4), K pair jj = sample offset in the row, tap l = LB-1 + o - jj
         if (tid < 8 * 24) {
+          if (var == 0) {
             const int n = tid / 24, jj = tid % 24;
             const int o = n >> 1, l = TCV_LB - 1 + o - jj;
             C2 tpv = mk2<T>(0, 0);
@@ -217,6 +240,7 @@ ber_tconv2_kernel(const BerParams prm) {
             const int off = (jj >> 2) * 128 + n * 16 + (jj & 3) * 4;
             *reinterpret_cast<uint32_t*>(bt + off) = hi;
             *reinterpret_cast<uint32_t*>(bt + 768 + off) = lo;
+          }
         } else if (tid < 8 * 24 + TCV_PAD) {
             alo[tid - 8 * 24] = 0u;                                              // (r of the previous frame lay over it)
         } else if (tid - (8 * 24 + TCV_PAD) < TCV_ZERO) {
@@ -252,7 +276,12 @@ ber_tconv2_kernel(const BerParams prm) {
             C2 v[16];
             {
                 uint32_t w[4], wq[4];
-                load_sym_idx<N, VERIFY>(prm, f, sb + se, t, w);
+                if (var == 0) {
+                    load_sym_idx<N, VERIFY>(prm, f, sb + se, t, w);
+                } else {                           // the symbols of the frame, as stored by the first window pair
+                    const uint4 ws = symw[se * TPF + t];
+                    w[0] = ws.x; w[1] = ws.y; w[2] = ws.z; w[3] = ws.w;
+                }
 #pragma unroll
                 for (int jw = 0; jw < 4; ++jw) wq[jw] = w[jw];
                 if (prm.guard > 0) {
@@ -261,7 +290,7 @@ ber_tconv2_kernel(const BerParams prm) {
 #pragma unroll
                     for (int jw = 0; jw < 4; ++jw) { wq[jw] = w[jw] | ff[jw]; w[jw] = (w[jw] & ~ff[jw]) | dd[jw]; }
                 }
-                symw[se * TPF + t] = make_uint4(w[0], w[1], w[2], w[3]);
+                if (var == 0) symw[se * TPF + t] = make_uint4(w[0], w[1], w[2], w[3]);
 #pragma unroll
                 for (int q = 0; q < 16; ++q) v[q] = qtx[sym_byte(wq, q)];
             }
@@ -412,8 +441,8 @@ ber_tconv2_kernel(const BerParams prm) {
                 const uint32_t q0 = (uint32_t)(sg * TPF + t) * 9u;
 #pragma unroll
                 for (int gq = 0; gq < 2; ++gq) {
-                    const uint4 ca = noise48_call(prm, f, q0 + 3 * gq), cb = noise48_call(prm, f, q0 + 3 * gq + 1);
-                    const uint4 cc = noise48_call(prm, f, q0 + 3 * gq + 2);
+                    const uint4 ca = noise48_call(prm, f, q0 + 3 * gq, var), cb = noise48_call(prm, f, q0 + 3 * gq + 1, var);
+                    const uint4 cc = noise48_call(prm, f, q0 + 3 * gq + 2, var);
                     gauss_quad48(ca.x, ca.y, cc.x, nz[8 * gq + 0], nz[8 * gq + 1]);
                     gauss_quad48(ca.z, ca.w, cc.y, nz[8 * gq + 2], nz[8 * gq + 3]);
                     gauss_quad48(cb.x, cb.y, cc.z, nz[8 * gq + 4], nz[8 * gq + 5]);
@@ -422,13 +451,13 @@ ber_tconv2_kernel(const BerParams prm) {
 #pragma unroll
                 for (int lev = 0; lev < N48_MAXLEV; ++lev) nx[lev] = mk2<T>(0, 0);
                 if (nlev > 0) {                                          // uniform per transform group
-                    const uint4 c6 = noise48_call(prm, f, q0 + 6);
+                    const uint4 c6 = noise48_call(prm, f, q0 + 6, var);
                     gauss_quad48(c6.y, c6.z, c6.x, nx[0], nx[1]);
                     if (nlev > 2) {
-                        const uint4 c7 = noise48_call(prm, f, q0 + 7);
+                        const uint4 c7 = noise48_call(prm, f, q0 + 7, var);
                         gauss_quad48(c7.x, c7.y, c6.w, nx[2], nx[3]);
                         if (nlev > 4) {
-                            const uint4 c8 = noise48_call(prm, f, q0 + 8);
+                            const uint4 c8 = noise48_call(prm, f, q0 + 8, var);
                             gauss_quad48(c7.w, c8.x, c7.z, nx[4], nx[5]);
                         }
                     }
@@ -554,6 +583,7 @@ ber_tconv2_kernel(const BerParams prm) {
                     }
                 }
             }
+            if (nvar > 1) build_qtx(var + 1 < nvar ? var + 1 : 0);   // (the Tx stage's table of the next window pair)
             frame_sync<CL>();
             if (act && sb + s > 0) {
                 // decisions of four sub-carriers packed like the sent level codes (byte q & 3 of word q >> 2): one XOR per
@@ -586,13 +616,14 @@ ber_tconv2_kernel(const BerParams prm) {
                 atomicAdd(reinterpret_cast<unsigned long long*>(prm.bit_err_f) + f, (unsigned long long)bit_cnt);
                 atomicAdd(reinterpret_cast<unsigned long long*>(prm.sym_err_f) + f, (unsigned long long)sym_cnt);
             } else {
-                atomicAdd(prm.counters + 2 * si, (unsigned long long)bit_cnt);
-                atomicAdd(prm.counters + 2 * si + 1, (unsigned long long)sym_cnt);
+                atomicAdd(prm.counters + 2 * (var * prm.n_snr + si), (unsigned long long)bit_cnt);
+                atomicAdd(prm.counters + 2 * (var * prm.n_snr + si) + 1, (unsigned long long)sym_cnt);
             }
         }
         // No barrier here: what the next frame's prologue and Tx stage overwrite (the split stream over r, the symbol words,
         // the taps operand, the exchange regions over the parked noise) was last read before the pilot barriers above by
         // every thread; geq, red and the tensor-memory accumulators are rewritten only behind the next frame's own barriers.
+      }   // window pairs
         f += df;
         if constexpr (!VERIFY) {
             fe += de;

@@ -76,10 +76,10 @@ class wOFDMSystem:
             ser = r["sym_err"] / r["sym_tot"]
             np.save(os.path.join(path_to_ser, f"CP_{self.cp_len}.npy"), ser)
             return ser
-        r_opt = h.ber_run(s, _diag(window_tx), _diag(window_rx), channel_models, snr, ensemble, seed=self.seed, variant=0)
-        r_rc = h.ber_run(s, capi.rc_window_tx(s), capi.rc_window_rx(s), channel_models, snr, ensemble, seed=self.seed,
-                         variant=1)
-        ser_opt, ser_rc = r_opt["sym_err"] / r_opt["sym_tot"], r_rc["sym_err"] / r_rc["sym_tot"]
+        # ONE call (one launch where the tensor-core kernel applies): both window pairs on every frame's symbols
+        r = h.ber_run_multi(s, [_diag(window_tx), capi.rc_window_tx(s)], [_diag(window_rx), capi.rc_window_rx(s)],
+                            channel_models, snr, ensemble, seed=self.seed, variant=0)
+        ser_opt, ser_rc = r["sym_err"][0] / r["sym_tot"], r["sym_err"][1] / r["sym_tot"]
         np.save(os.path.join(path_to_ser, f"opt_{self.name}_{self.cp_len}.npy"), ser_opt)
         np.save(os.path.join(path_to_ser, f"rc_{self.name}_{self.cp_len}.npy"), ser_rc)
         return ser_opt, ser_rc
@@ -146,6 +146,21 @@ def run_simulation(ensemble, symbolsPerTx, bitsPerSubcarrier, numSubcar, cpLengt
                   S=int(symbolsPerTx), noise_norm=1, constellation=1, precision=0)
     r = h.ber_run(s, _diag(windowTx), _diag(windowRx), np.asarray(channel).ravel(), [float(snr)], int(ensemble), seed=seed)
     return float(r["bit_err"][0] / r["bit_tot"][0])
+
+
+def run_simulation_multi(ensemble, symbolsPerTx, bitsPerSubcarrier, numSubcar, cpLength, csLength, windowsTx, channel, snr,
+                         tailTx, tailRx, windowsRx, prefixRemovalLength, circularShiftLength, seed=0, handle=None):
+    """The window variants main_BER_calculation.m evaluates per (channel, SNR) -- {optimised, RC} for wtx / wrx (:66-117),
+    RC + CaseA steps 1-3 + CaseB steps 1-3 for WOLA / CPW (:118-198) -- in ONE call on the same bits: windowsTx / windowsRx
+    are lists of n_var diagonal matrices (or vectors); returns n_var BERs, variant v with the noise stream of
+    run_simulation(..., seed) called with variant v."""
+    h = handle or default_handle()
+    s = capi.SysT(N=int(numSubcar), cp=int(cpLength), cs=int(csLength), tail_tx=int(tailTx), tail_rx=int(tailRx),
+                  rm=int(prefixRemovalLength), shift=int(circularShiftLength), bits=int(bitsPerSubcarrier),
+                  S=int(symbolsPerTx), noise_norm=1, constellation=1, precision=0)
+    r = h.ber_run_multi(s, [_diag(w) for w in windowsTx], [_diag(w) for w in windowsRx], np.asarray(channel).ravel(),
+                        [float(snr)], int(ensemble), seed=seed)
+    return r["bit_err"][:, 0] / r["bit_tot"][0]
 
 
 def run_sim_mc(ensemble, cpLength, csLength, tailTx, tailRx, windowTx, windowRx, channel, snr, offset,
