@@ -291,9 +291,8 @@ def k2_section(torch, dist, W, capi, h, world, rank):
     n_rx, n_tx, N = s.stride, s.n_tx, s.N
     M = 1 + -(-(21 - 1 + s.tail_tx) // n_rx)
     dense = (8 * N * n_rx * n_tx + 8 * N * n_tx * N) * chan.shape[1] * M          # per (channel, slice)
-    gemm = 8 * N * n_rx * N * chan.shape[1] * M                                 # the tensor-core GEMM actually executed
     out = {"shapes": f"WOLA N=256 cp=16: Rx_mat {N}x{n_rx}, H {n_rx}x{n_tx}, Tx_mat {n_tx}x{N}, {chan.shape[1]} channels x {M} slices",
-           "dense_gflop_per_call": dense / 1e9, "executed_gemm_gflop_per_call": gemm / 1e9,
+           "dense_gflop_per_call": dense / 1e9,
            "api": "wofdm_interf_power (ctypes, host buffers in, per-channel rows out)"}
     for mode, key in ((0, "fp64"), (1, "tf32")):
         for _ in range(3):
@@ -316,8 +315,14 @@ def k2_section(torch, dist, W, capi, h, world, rank):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             assert allP.shape[0] == chan.shape[1]
         dt = float(t.item())
+        tm = h.interf_last_timing()
+        # executed tensor-core GEMM: slice 0 contracts all K rows, an ISI slice only its non-zero prefix
+        gemm = 2 * (2 * N) * (tm["k_slice0"] + (M - 1) * tm["k_isi"]) * N * mine.shape[1]
         out[key + "_ms"] = dt * 1e3
+        out[key + "_device_ms"], out[key + "_band_product_ms"], out[key + "_gemm_ms"] = tm["total_ms"], tm["band_ms"], tm["gemm_ms"]
         out[key + "_dense_tflops"] = dense / dt / 1e12
+        out[key + "_executed_gflop_per_rank"] = gemm / 1e9
+        out[key + "_gemm_kernel_tflops"] = gemm / (tm["gemm_ms"] * 1e-3) / 1e12 if tm["gemm_ms"] > 0 else None
         out[key + "_executed_tflops"] = gemm / dt / 1e12
         if world > 1:
             out[key + "_allgather_ms"] = t_g / reps * 1e3
@@ -494,11 +499,15 @@ def main():
         if rank == 0:
             pk = gemm_peaks(torch)
             k2.update(pk)
-            k2["frac_fp64"] = k2["fp64_executed_tflops"] / pk["fp64_tflops"]
-            k2["frac_tf32"] = 3.0 * k2["tf32_executed_tflops"] / pk["tf32_tflops"]
-            k2["frac_note"] = ("executed tensor-core GEMM flops per second of the whole host-buffer call (builders, band product, "
-                               "copies included) over the cuBLAS GEMM rate measured in this process (DGEMM 4096^3; TF32 8192^3); "
-                               "the TF32 path executes 3 products per fp64 one (3xTF32 split), hence the factor 3")
+            k2["frac_fp64"] = k2["fp64_gemm_kernel_tflops"] / pk["fp64_tflops"]
+            k2["frac_tf32"] = 3.0 * k2["tf32_gemm_kernel_tflops"] / pk["tf32_tflops"]
+            k2["frac_fp64_whole_call"] = k2["fp64_executed_tflops"] * world / pk["fp64_tflops"]
+            k2["frac_tf32_whole_call"] = 3.0 * k2["tf32_executed_tflops"] * world / pk["tf32_tflops"]
+            k2["frac_note"] = ("frac_*: executed tensor-core GEMM flops (slice 0: all K rows; ISI slices: their non-zero K prefix) over "
+                               "the contraction kernel's device time (CUDA events inside the library, wofdm_interf_last_timing), against "
+                               "the cuBLAS GEMM rate measured in this process (DGEMM 4096^3; TF32 8192^3); the TF32 path executes 3 "
+                               "products per fp64 one (3xTF32 split), hence the factor 3.  frac_*_whole_call: the same flops over the "
+                               "wall time of the host-buffer call (uploads, matrix builders, band product, download included)")
             tp = os.path.join(REPO, "profiles", "k2_traffic.json")
             if os.path.exists(tp):
                 with open(tp) as fh:

@@ -182,6 +182,13 @@ WOFDM_API int wofdm_interf_power(wofdm_handle h, const wofdm_sys_t* sys, const d
 WOFDM_API int wofdm_interf_power_scalar(wofdm_handle h, const wofdm_sys_t* sys, const double* win_tx,
                               const double* win_rx, const double* chan, int L, int C, int mode, double* P);
 
+/* Device times of the handle's last wofdm_interf_power* call, from CUDA events on its stream (ms; -1 = not taken:
+ * kernel times exist for calls whose channels fit one batch): the whole call on the device (uploads, matrix builders,
+ * band product, contraction, download), the band product B = H.Tx_mat alone, the tensor-core contraction alone.
+ * k_slice0 / k_isi: rows of the real-form K dimension contracted for slice 0 / for every ISI slice (only the non-zero
+ * prefix of an ISI slice exists), i.e. the executed GEMM is 2 * 2N * k * N flop per (channel, slice).  Any may be NULL. */
+WOFDM_API int wofdm_interf_last_timing(wofdm_handle h, double* total_ms, double* band_ms, double* gemm_ms, int* k_slice0, int* k_isi);
+
 /* ---- Channel-mask BER variant (next-row 8f-1) ----------------------------------------------------------------
  * run_sim_mc of matlab/main_channel_mask.m:334-360 for the MASKED signal: the guard-band frame (sys->guard = offset)
  * whose windowed symbols pass the DFT-domain raised-cosine mask of length 2 n_tx - 1 (dft_rc_filt, :398-417, roll_off

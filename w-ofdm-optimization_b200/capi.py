@@ -93,6 +93,7 @@ SIGNATURES = {
     "wofdm_ber_draws": (C.c_int, [C.c_void_p, _P(SysT), C.c_int, C.c_uint64, C.c_uint32, _i64p, C.c_int, _i32p, _dp]),
     "wofdm_interf_power": (C.c_int, [C.c_void_p, _P(SysT), _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, _dp]),
     "wofdm_interf_power_scalar": (C.c_int, [C.c_void_p, _P(SysT), _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, _dp]),
+    "wofdm_interf_last_timing": (C.c_int, [C.c_void_p, _dp, _dp, _dp, _P(C.c_int), _P(C.c_int)]),
     "wofdm_ber_run_masked": (C.c_int, [C.c_void_p, _P(SysT), _dp, _dp, _dp, C.c_int, C.c_int, _dp, C.c_int, C.c_int64, C.c_uint64,
                                        C.c_uint32, C.c_int, _i64p, _i64p, _i64p, _i64p]),
     "wofdm_window_hessian": (C.c_int, [C.c_void_p, _P(SysT), _dp, C.c_int, _dp, _P(C.c_int)]),
@@ -351,6 +352,13 @@ class Handle:
         self._check(rc)
         return P
 
+
+    def interf_last_timing(self):
+        """dict(total_ms, band_ms, gemm_ms, k_slice0, k_isi) of the last interf_power call (wofdm_interf_last_timing)."""
+        t, b, g = C.c_double(), C.c_double(), C.c_double()
+        k0, ki = C.c_int(), C.c_int()
+        self._check(load().wofdm_interf_last_timing(self._h, C.byref(t), C.byref(b), C.byref(g), C.byref(k0), C.byref(ki)))
+        return dict(total_ms=t.value, band_ms=b.value, gemm_ms=g.value, k_slice0=k0.value, k_isi=ki.value)
 
     def window_hessian(self, s, chan):
         """Hessian of the interference power in the reduced window variables (wofdm_window_hessian) for ONE impulse

@@ -31,6 +31,11 @@ struct wofdm_ctx {
     std::vector<wofdm::BerVariant> variants;
     std::string err;
     int64_t launches = 0;
+    // device time of the last wofdm_interf_power* call (CUDA events on the handle's stream): whole call on the device
+    // (uploads, builders, band product, contraction, download), the band product and the contraction alone; -1 = not taken
+    cudaEvent_t interf_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    double interf_ms[3] = {-1.0, -1.0, -1.0};
+    double interf_k_isi = 0.0, interf_kp = 0.0;      // K rows contracted per ISI slice / per slice 0
 };
 
 namespace wofdm {

@@ -15,6 +15,7 @@
 //       dimension, with the off-diagonal mask and the row-wise sum of |.|^2 fused into the epilogue.
 // The TF32-split tensor path (mode 1) lives in interf_tf32.cu.
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
 #include "host_common.h"
@@ -24,13 +25,16 @@ namespace wofdm {
 
 // ---- K3: matrix builders ----------------------------------------------------------------------
 // Tx_mat[i][k] = vtx[i]/N * exp(+2 pi i k n / N), n = (i - cp) mod N      (transmitter.py:13-58)
-__global__ void build_tx_matrix(double2* __restrict__ T, const double* __restrict__ vtx, int N, int cp, int n_tx) {
+// (T32, optional: the same matrix rounded to fp32 for the TF32 path's band product)
+__global__ void build_tx_matrix(double2* __restrict__ T, const double* __restrict__ vtx, int N, int cp, int n_tx,
+                                float2* __restrict__ T32 = nullptr) {
     const int i = blockIdx.x, n = ((i - cp) % N + N) % N;
     for (int k = threadIdx.x; k < N; k += blockDim.x) {
         double s, c;
         sincospi(2.0 * (double)(((long long)k * n) % N) / (double)N, &s, &c);
         const double w = vtx[i] / (double)N;
         T[(size_t)i * N + k] = make_double2(w * c, w * s);
+        if (T32) T32[(size_t)i * N + k] = make_float2((float)(w * c), (float)(w * s));
     }
 }
 
@@ -66,7 +70,8 @@ __global__ void build_rx_matrix(double* __restrict__ Rbig, const double* __restr
 // has isi_rows = L - 1 + tail_tx non-zero rows at most, a PREFIX of K in this layout.  Only round_up(2 isi_rows, 64)
 // rows of such a slice are written here and read by the contraction kernels (interf_isi_k).
 // Each thread forms BB consecutive rows b of one column j from the BB + L - 1 rows of Tx_mat they share.
-constexpr int BB = 8;
+constexpr int BB = 8;       // fp64 path
+constexpr int BBT = 16;     // TF32 path: more rows per thread = fewer re-reads of Tx_mat (it is L2 bandwidth that bounds the kernel)
 __host__ __device__ inline int interf_isi_k(int L, int tail_tx, int n_rx, int Kp) {
     const int rows = L - 1 + tail_tx < n_rx ? L - 1 + tail_tx : n_rx;
     const int k = rows > 0 ? ((2 * rows + 63) / 64) * 64 : 64;   // never empty: the contraction initialises its accumulators
@@ -76,10 +81,12 @@ __host__ __device__ inline int interf_isi_k(int L, int tail_tx, int n_rx, int Kp
 // then the float work buffer and the fp64 B matrix never exists.  That path is fp32-grade by contract (3xTF32), so
 // its band product runs in packed FP32 (taps and Tx_mat rounded to fp32, fp32 accumulation: ~1e-7 relative, far
 // inside the stated bound) instead of FP64 FMAs, which bound the fp64 variant of this kernel.
+// T: Tx_mat as double2 (fp64 path) or float2 (TILED: rounded once by tile_tx_f32, half the bytes per re-read)
 template <bool TILED>
-__global__ void __launch_bounds__(256) build_b(double* __restrict__ Bbig, const double2* __restrict__ T,
+__global__ void __launch_bounds__(256) build_b(double* __restrict__ Bbig, const void* __restrict__ Tv,
                                                const double2* __restrict__ chan, int L, int N, int n_tx, int n_rx,
                                                int N0, int Kp, int Ms, int M, int c0, int sum_isi, int k_isi) {
+    constexpr int BB = TILED ? BBT : wofdm::BB;
     // taps of this slice's channel in shared memory, zero-padded by BB on both sides: the inner loop needs no
     // range checks and reads them as broadcasts
     extern __shared__ __align__(16) double2 hs_raw[];
@@ -108,9 +115,7 @@ __global__ void __launch_bounds__(256) build_b(double* __restrict__ Bbig, const 
             for (int rr = 0; rr < BB + L - 1; ++rr) {
                 const int row = r_lo + rr;
                 if (row < 0 || row >= n_tx) continue;
-                const double2 xd = T[(size_t)row * N + j];
-                A2 x;
-                x.x = xd.x; x.y = xd.y;
+                const A2 x = reinterpret_cast<const A2*>(Tv)[(size_t)row * N + j];
                 const A2* hw = h + (L - 1) - rr;              // tap of output i: hw[i] (zero outside [0, L))
 #pragma unroll
                 for (int i = 0; i < BB; ++i) cmac(acc[i], hw[i], x);
@@ -256,11 +261,17 @@ int interf_upload(wofdm_ctx* h, const wofdm_sys_t* sys, const double* win_tx, co
     v.M = 1 + (L - 1 + sys->tail_tx + n_rx - 1) / n_rx;     // channel.py:42
     const size_t bytes = (size_t)(n_tx + N + sys->tail_rx) * 8 + (size_t)L * C * 16 + (size_t)n_tx * N * 16 +
                          (size_t)2 * N * v.Kp * 8;
-    // batch of channels whose B matrices fit the staging budget (1 GiB of the arena)
+    // batch of channels whose B matrices fit the staging budget (1 GiB of the arena).  Measured and not kept: batches small
+    // enough for the staging buffer to stay inside the 126 MB L2 (so that the operand never travels to HBM and back: one
+    // 250-channel call moves 331 MB) -- 1.70 -> 2.31 ms (fp64) and 0.43 -> 0.74 ms (TF32) at 48 MB: the call is bound by its
+    // kernels, not by that traffic, and short batches quantise badly over 148 SMs.  WOFDM_K2_BATCH_MB repeats the experiment.
     const size_t per_chan = (size_t)v.M * v.Kp * N * 8;
-    v.batch = (int)std::max<size_t>(1, std::min<size_t>((size_t)C, ((size_t)1 << 30) / per_chan));   // <= 1 GiB of B per batch
+    size_t budget = (size_t)1 << 30;
+    if (const char* e = getenv("WOFDM_K2_BATCH_MB")) budget = (size_t)std::max(1, atoi(e)) << 20;     // tuning aid
+    v.batch = (int)std::max<size_t>(1, std::min<size_t>((size_t)C, budget / per_chan));
     const size_t tf32_bytes = mode == 1 ? ((size_t)2 * 2 * N * v.Kp + (size_t)2 * v.batch * v.M * N * v.Kp) * 4 : 0;
-    int rc = arena_reserve(h, d, bytes + (size_t)v.batch * per_chan + (size_t)C * N * 8 + tf32_bytes);
+    const size_t t32_bytes = mode == 1 ? (size_t)n_tx * N * 8 : 0;
+    int rc = arena_reserve(h, d, bytes + (size_t)v.batch * per_chan + (size_t)C * N * 8 + tf32_bytes + t32_bytes + 256);
     if (rc) return rc;
     v.vtx = static_cast<double*>(arena_take(d, (size_t)n_tx * 8));
     v.vrx = static_cast<double*>(arena_take(d, (size_t)(N + sys->tail_rx) * 8));
@@ -270,11 +281,13 @@ int interf_upload(wofdm_ctx* h, const wofdm_sys_t* sys, const double* win_tx, co
     v.Bbig = static_cast<double*>(arena_take(d, (size_t)v.batch * per_chan));
     v.P = static_cast<double*>(arena_take(d, (size_t)C * N * 8));
     v.tf32_work = tf32_bytes ? static_cast<float*>(arena_take(d, tf32_bytes)) : nullptr;
+    v.T32 = t32_bytes ? static_cast<float2*>(arena_take(d, t32_bytes)) : nullptr;
+    if (t32_bytes && !v.T32) return fail(h, WOFDM_ENOMEM, "arena exhausted");
     if ((tf32_bytes && !v.tf32_work) || !v.vtx || !v.vrx || !v.chan || !v.T || !v.Rbig || !v.Bbig || !v.P) return fail(h, WOFDM_ENOMEM, "arena exhausted");
     WOFDM_CUDA(h, cudaMemcpyAsync(v.vtx, win_tx, (size_t)n_tx * 8, cudaMemcpyHostToDevice, d.stream));
     WOFDM_CUDA(h, cudaMemcpyAsync(v.vrx, win_rx, (size_t)(N + sys->tail_rx) * 8, cudaMemcpyHostToDevice, d.stream));
     WOFDM_CUDA(h, cudaMemcpyAsync(v.chan, chan, (size_t)L * C * 16, cudaMemcpyHostToDevice, d.stream));
-    build_tx_matrix<<<n_tx, 256, 0, d.stream>>>(v.T, v.vtx, N, sys->cp, n_tx);
+    build_tx_matrix<<<n_tx, 256, 0, d.stream>>>(v.T, v.vtx, N, sys->cp, n_tx, v.T32);
     build_rx_matrix<<<N, 256, 0, d.stream>>>(v.Rbig, v.vrx, N, sys->tail_rx, sys->rm, sys->shift, n_rx, v.Kp);
     WOFDM_CUDA(h, cudaGetLastError());
     h->launches += 2;
@@ -294,9 +307,13 @@ static int interf_run(wofdm_handle h, const wofdm_sys_t* sys, const double* win_
     if (mode == 1 && sys->N % TF32_TN) return fail(h, WOFDM_EUNSUPPORTED, "TF32-split interference path needs N to be a multiple of 256");
     DeviceCtx& d = h->devs[0];
     WOFDM_CUDA(h, cudaSetDevice(d.dev));
+    for (auto& e : h->interf_ev)
+        if (!e) WOFDM_CUDA(h, cudaEventCreate(&e));
+    WOFDM_CUDA(h, cudaEventRecord(h->interf_ev[0], d.stream));
     InterfDev v;
     rc = interf_upload(h, sys, win_tx, win_rx, chan, L, C, mode, &v);
     if (rc) return rc;
+    const bool one_batch = v.batch >= C;             // (the kernel times are taken for single-batch calls)
     const int N = sys->N;
     const size_t pbytes = scalar ? (size_t)C * 8 : (size_t)C * N * 8;
     WOFDM_CUDA(h, cudaMemsetAsync(v.P, 0, pbytes, d.stream));
@@ -305,16 +322,19 @@ static int interf_run(wofdm_handle h, const wofdm_sys_t* sys, const double* win_
     for (int c0 = 0; c0 < C; c0 += v.batch) {
         const int nc = std::min(v.batch, C - c0);
         const int slices = nc * Ms;
-        const dim3 bgrid((N + 255) / 256, (v.Kp / 2 + BB - 1) / BB, slices);
-        const size_t bsm = (size_t)(L + 2 * BB) * sizeof(double2);
         const bool tiled = mode == 1;                         // the TF32 operand straight from the band product
+        const int bb = tiled ? BBT : BB;
+        if (one_batch) WOFDM_CUDA(h, cudaEventRecord(h->interf_ev[1], d.stream));
+        const dim3 bgrid((N + 255) / 256, (v.Kp / 2 + bb - 1) / bb, slices);
+        const size_t bsm = (size_t)(L + 2 * bb) * sizeof(double2);
         if (tiled)
-            build_b<true><<<bgrid, 256, bsm, d.stream>>>(reinterpret_cast<double*>(interf_tf32_b_tiles(v, N)), v.T, v.chan, L, N,
+            build_b<true><<<bgrid, 256, bsm, d.stream>>>(reinterpret_cast<double*>(interf_tf32_b_tiles(v, N)), v.T32, v.chan, L, N,
                                                         v.n_tx, v.n_rx, v.N0, v.Kp, Ms, v.M, c0, scalar, k_isi);
         else
             build_b<false><<<bgrid, 256, bsm, d.stream>>>(v.Bbig, v.T, v.chan, L, N, v.n_tx, v.n_rx, v.N0, v.Kp, Ms, v.M, c0,
                                                          scalar, k_isi);
         WOFDM_CUDA(h, cudaGetLastError());
+        if (one_batch) WOFDM_CUDA(h, cudaEventRecord(h->interf_ev[2], d.stream));
         if (mode == 0) {
             constexpr size_t smem = (size_t)(2 * BM * AS + 2 * BK * BS) * sizeof(double);
             WOFDM_CUDA(h, cudaFuncSetAttribute(gemm_power_f64<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -324,10 +344,20 @@ static int interf_run(wofdm_handle h, const wofdm_sys_t* sys, const double* win_
             rc = interf_gemm_tf32(h, sys, v, Ms, c0, slices, scalar, k_isi);
             if (rc) return rc;
         }
+        if (one_batch) WOFDM_CUDA(h, cudaEventRecord(h->interf_ev[3], d.stream));
         h->launches += 2;
     }
     WOFDM_CUDA(h, cudaMemcpyAsync(P, v.P, pbytes, cudaMemcpyDeviceToHost, d.stream));
+    WOFDM_CUDA(h, cudaEventRecord(h->interf_ev[4], d.stream));
     WOFDM_CUDA(h, cudaStreamSynchronize(d.stream));
+    float ms = 0.f;
+    h->interf_ms[0] = h->interf_ms[1] = h->interf_ms[2] = -1.0;
+    if (cudaEventElapsedTime(&ms, h->interf_ev[0], h->interf_ev[4]) == cudaSuccess) h->interf_ms[0] = ms;
+    if (one_batch) {
+        if (cudaEventElapsedTime(&ms, h->interf_ev[1], h->interf_ev[2]) == cudaSuccess) h->interf_ms[1] = ms;
+        if (cudaEventElapsedTime(&ms, h->interf_ev[2], h->interf_ev[3]) == cudaSuccess) h->interf_ms[2] = ms;
+    }
+    h->interf_k_isi = k_isi; h->interf_kp = v.Kp;
     return WOFDM_OK;
 }
 
@@ -448,6 +478,16 @@ int wofdm_interf_power(wofdm_handle h, const wofdm_sys_t* sys, const double* win
 int wofdm_interf_power_scalar(wofdm_handle h, const wofdm_sys_t* sys, const double* win_tx, const double* win_rx,
                               const double* chan, int L, int C, int mode, double* P) {
     return interf_run(h, sys, win_tx, win_rx, chan, L, C, mode, 1, P);
+}
+
+int wofdm_interf_last_timing(wofdm_handle h, double* total_ms, double* band_ms, double* gemm_ms, int* k_slice0, int* k_isi) {
+    if (!h) return WOFDM_EINVAL;
+    if (total_ms) *total_ms = h->interf_ms[0];
+    if (band_ms) *band_ms = h->interf_ms[1];
+    if (gemm_ms) *gemm_ms = h->interf_ms[2];
+    if (k_slice0) *k_slice0 = (int)h->interf_kp;
+    if (k_isi) *k_isi = (int)h->interf_k_isi;
+    return WOFDM_OK;
 }
 
 int wofdm_window_hessian(wofdm_handle h, const wofdm_sys_t* sys, const double* chan, int L, double* H, int* n_var) {

@@ -9,6 +9,7 @@ struct InterfDev {
     double *vtx, *vrx;     // windows
     double2* chan;         // [C][L]
     double2* T;            // Tx_mat [n_tx][N]
+    float2* T32;           // mode 1: the same, rounded to fp32 (band product of the TF32 path)
     double* Rbig;          // [2N][Kp], real form of Rx_mat, K interleaved (Re, Im) like Bbig's rows
     double* Bbig;          // [batch*Ms][Kp][N], rows 2b / 2b+1 = Re / Im B[b] per slice
     double* P;             // [C][N] (or [C] in scalar mode)

@@ -158,6 +158,9 @@ int wofdm_destroy(wofdm_handle h) {
         if (d.stream) { cudaStreamSynchronize(d.stream); cudaStreamDestroy(d.stream); }
         if (d.arena) cudaFree(d.arena);
     }
+    if (!h->devs.empty()) cudaSetDevice(h->devs[0].dev);
+    for (auto& e : h->interf_ev)
+        if (e) cudaEventDestroy(e);
     delete h;
     return WOFDM_OK;
 }
