@@ -15,6 +15,24 @@ from helpers import golden_params, golden_windows, load_ser_golden, replay_frame
 pytestmark = pytest.mark.gpu
 
 TOL = {0: 1e-4, 1: 1e-9}
+# fp32: largest deviation of ONE equalised symbol, relative to the frame's largest symbol (lattice units).  Observed over the
+# whole suite on a B200: 4.7e-5 (a deep-fade bin; printed by test_zz_report_observed_fp32_slack), at most 1 decision per
+# frame close enough to a boundary to differ legitimately, production counters equal to the oracle's in every replay.
+# The north star allows 1e-4 on the frame norm; the per-symbol budget is the same number.
+FP32_SYM_TOL = 1e-4
+OBSERVED = {"unsafe": 0, "dev": 0.0, "prod": 0.0}
+
+
+def flip_budget(p, eqs, tol=1e-4):
+    """How many decisions fp32 rounding may flip: symbols whose oracle value lies within `tol` (relative to max(1, |x|),
+    lattice units -- the north star's fp32 tolerance) of a decision boundary."""
+    m = O.qam_levels(p.bits)
+    sc = O.qam_scale(p.bits, p.constellation)
+    n = 0
+    for eq in eqs:
+        x = eq[p.active] / sc
+        n += int(np.count_nonzero(boundary_distance(x, m) <= tol * np.maximum(1.0, np.abs(x))))
+    return n
 
 
 @pytest.fixture(scope="module")
@@ -58,11 +76,16 @@ def check_frames(handle, p, vt, vr, frames_in, precision, force_staged=False, di
             assert np.array_equal(d, ref.dec_idx), i
             assert se[i] == ref.sym_err and be[i] == ref.bit_err, i
         else:
-            safe = boundary_distance(ref.eq / sc, m) > 1e-3 * np.maximum(1.0, np.abs(ref.eq / sc))
+            # a decision may differ from the oracle's only where the device's OWN deviation (twice it, for the rounding of
+            # the slicer's input) reaches a decision boundary; the deviation itself is bounded per symbol
+            dev = np.abs(got - ref.eq) / sc
+            assert dev.max() <= FP32_SYM_TOL * max(1.0, np.abs(ref.eq / sc).max()), (i, dev.max())
+            safe = boundary_distance(ref.eq / sc, m) > 2.0 * dev + 1e-7
             safe |= ~p.active[:, None]          # null bins: exactly 0 + 0i on both sides, the tie rule decides
             assert np.array_equal(d[safe], ref.dec_idx[safe]), i
-            assert (~safe).sum() <= max(3, 0.03 * safe.size)
             assert abs(int(se[i]) - ref.sym_err) <= int((~safe).sum())
+            OBSERVED["unsafe"] = max(OBSERVED["unsafe"], int((~safe).sum()))
+            OBSERVED["dev"] = max(OBSERVED["dev"], float(dev.max() / max(1.0, np.abs(ref.eq / sc).max())))
         # counters are consistent with the returned decisions (over the sub-carriers that carry data)
         act = p.active
         assert se[i] == np.count_nonzero(d[act] != idx[act, 1:])
@@ -141,6 +164,7 @@ def test_production_replay_matches_oracle(handle, policy, monkeypatch):
             assert abs(np.mean(np.abs(nz) ** 2) - 2.0) < 0.05
             want_sym = np.zeros(len(snr), dtype=np.int64)
             want_bit = np.zeros(len(snr), dtype=np.int64)
+            slack = np.zeros(len(snr), dtype=np.int64)
             for f in ids:
                 e = f % ens
                 c = (f // ens) % chans.shape[1]
@@ -148,13 +172,17 @@ def test_production_replay_matches_oracle(handle, policy, monkeypatch):
                 r = O.frame_chain_structured(p, vt, vr, chans[:, c], snr[si], sym[f].T, nz[f])
                 want_sym[si] += r.sym_err
                 want_bit[si] += r.bit_err
+                slack[si] += flip_budget(p, [r.eq])
             assert np.array_equal(res["sym_tot"], np.full(len(snr), chans.shape[1] * ens * p.N * (p.S - 1)))
             assert np.array_equal(res["bit_tot"], res["sym_tot"] * p.bits)
             if precision == 1:
                 assert np.array_equal(res["sym_err"], want_sym) and np.array_equal(res["bit_err"], want_bit)
             else:
-                assert np.all(np.abs(res["sym_err"] - want_sym) <= 3 + 0.002 * want_sym)
-                assert np.all(np.abs(res["bit_err"] - want_bit) <= 4 + 0.002 * want_bit)
+                # fp32: only symbols within the fp32 tolerance of a decision boundary may flip (a flip moves one level:
+                # one symbol error, at most two bit errors in the natural map, one in Gray)
+                assert np.all(np.abs(res["sym_err"] - want_sym) <= slack), (res["sym_err"], want_sym, slack)
+                assert np.all(np.abs(res["bit_err"] - want_bit) <= 2 * slack), (res["bit_err"], want_bit, slack)
+                OBSERVED["prod"] = max(OBSERVED["prod"], float(np.max(np.abs(res["sym_err"] - want_sym) / np.maximum(slack, 1))))
 
 
 @pytest.mark.parametrize("name,N,cp,bits,nv,precision", [("WOLA", 256, 16, 4, 7, 0), ("wtx", 256, 22, 4, 2, 0), ("CPW", 512, 32, 6, 3, 0),
@@ -225,17 +253,20 @@ def test_production_replay_cluster_kernel(handle, name, nn, policy, monkeypatch)
         sym, nz = handle.ber_draws(s, chans.shape[0], 77, 0, ids)
         want_sym = np.zeros(len(snr), dtype=np.int64)
         want_bit = np.zeros(len(snr), dtype=np.int64)
+        slack = np.zeros(len(snr), dtype=np.int64)
         for f in ids:
             c = (f // ens) % chans.shape[1]
             si = f // (ens * chans.shape[1])
             r = O.frame_chain_structured(p, vt, vr, chans[:, c], snr[si], sym[f].T, nz[f])
             want_sym[si] += r.sym_err
             want_bit[si] += r.bit_err
+            slack[si] += flip_budget(p, [r.eq])
         if precision == 1:
             assert np.array_equal(res["sym_err"], want_sym) and np.array_equal(res["bit_err"], want_bit)
         else:
-            assert np.all(np.abs(res["sym_err"] - want_sym) <= 5 + 0.003 * want_sym), (res["sym_err"], want_sym)
-            assert np.all(np.abs(res["bit_err"] - want_bit) <= 8 + 0.003 * want_bit), (res["bit_err"], want_bit)
+            assert np.all(np.abs(res["sym_err"] - want_sym) <= slack), (res["sym_err"], want_sym, slack)
+            assert np.all(np.abs(res["bit_err"] - want_bit) <= 3 * slack), (res["bit_err"], want_bit, slack)
+            OBSERVED["prod"] = max(OBSERVED["prod"], float(np.max(np.abs(res["sym_err"] - want_sym) / np.maximum(slack, 1))))
 
 
 @pytest.mark.parametrize("name,N,cp,ttx,trx,bits", [("wtx", 256, 16, 8, 0, 4), ("CPW", 256, 16, 8, 10, 4),
@@ -600,3 +631,44 @@ def test_guard_band(handle, name, N, cp, ttx, trx, bits, guard, precision):
     assert abs(int(res["sym_err"][0]) - want_s) <= tol and abs(int(res["bit_err"][0]) - want_b) <= tol + 2
     with pytest.raises(W.WofdmError):
         handle.ber_run(W.params_from_name(name, N, cp, ttx, trx, bits=8, guard=guard), vt, vr, h, [18.0], 1)
+
+
+def test_in_process_multi_device_handle_matches_one_device():
+    """wofdm_create(&h, 0): ONE process that owns every visible GPU and splits each job's frames over them itself (this is
+    the MEX gateway's handle; ber_host.cu: wofdm_ber_run_multi's sub-shards).  Counters must be identical to the one-device
+    run -- draws depend on the global frame id only.  Needs >= 2 devices (the driver's multi-GPU box; skipped on one)."""
+    import ctypes
+    n = ctypes.c_int(0)
+    assert W.capi.load().wofdm_device_count(ctypes.byref(n)) == 0
+    if n.value < 2:
+        pytest.skip("one visible device")
+    p = O.system_params("WOLA", 256, 16, 8, 10, S=16, bits=4, noise_norm=0, constellation=0)
+    vt, vr, _, _ = O.perturbed_windows(p, seed=2)
+    chan = O.synth_channels(7, 21, seed=4)
+    snr = np.array([3.0, 15.0, 27.0])
+    with W.Handle([0]) as h1, W.Handle(None) as hall:
+        for precision in (0, 1):
+            s = to_sys(p, precision)
+            a = h1.ber_run(s, vt, vr, chan, snr, 11, seed=5)
+            b = hall.ber_run(s, vt, vr, chan, snr, 11, seed=5)
+            for k in a:
+                assert np.array_equal(a[k], b[k]), (precision, k)
+        s = to_sys(p, 0)
+        wins_t, wins_r = [vt, O.rc_window_tx(p)], [vr, O.rc_window_rx(p)]
+        a = h1.ber_run_multi(s, wins_t, wins_r, chan, snr, 11, seed=6)
+        b = hall.ber_run_multi(s, wins_t, wins_r, chan, snr, 11, seed=6)
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k
+        # the interference path of a multi-device handle runs on its first device
+        Pa = h1.interf_power(to_sys(p, 1), vt, vr, chan)
+        Pb = hall.interf_power(to_sys(p, 1), vt, vr, chan)
+        assert np.array_equal(Pa, Pb)
+
+
+def test_zz_report_observed_fp32_slack():
+    """Not a check of its own: prints what the fp32 parity tests above actually needed, so that their budgets stay honest
+    (run with -s to see it; the asserts keep a regression from hiding inside the budgets)."""
+    print(f"\nfp32 parity, observed over this run: most decisions of one frame that could legitimately differ = {OBSERVED['unsafe']}, "
+          f"largest per-symbol deviation = {OBSERVED['dev']:.2e} (budget {FP32_SYM_TOL:.0e}), "
+          f"largest production |counter - oracle| / flip budget = {OBSERVED['prod']:.2f}")
+    assert OBSERVED["dev"] <= FP32_SYM_TOL
