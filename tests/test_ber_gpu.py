@@ -633,6 +633,30 @@ def test_guard_band(handle, name, N, cp, ttx, trx, bits, guard, precision):
         handle.ber_run(W.params_from_name(name, N, cp, ttx, trx, bits=8, guard=guard), vt, vr, h, [18.0], 1)
 
 
+@pytest.mark.parametrize("which", ["n256", "multi", "n512", "n1024"])
+def test_relaxed_barriers_against_debug_build(which):
+    """The tensor-core kernel drops the barrier at the end of a frame, lets only the MMA-issuing warps wait for the stream
+    (bar.arrive / bar.sync) and reuses its shared-memory buffers from frame to frame.  compute-sanitizer is closed on this
+    GPU pool (profiles/r2_racecheck_attempt.txt), so the check is a second build of the library, libwofdm_dbg.so, in which
+    all of that is a full CTA / cluster barrier (ber_tconv2.cuh: TCV2_DEBUG_BARRIERS): jobs with several frames per CTA
+    (tools/sanitize_k1.py) must give bit-identical counters in both builds, run after run."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    dbg = os.path.join(root, "w-ofdm-optimization_b200", "libwofdm_dbg.so")
+    assert os.path.exists(dbg), "libwofdm_dbg.so is built by `make -C w-ofdm-optimization_b200/csrc` (__graft_entry__.build)"
+    outs = []
+    for lib in (None, dbg, None):
+        env = dict(os.environ)
+        env.pop("WOFDM_LIB", None)
+        if lib:
+            env["WOFDM_LIB"] = lib
+        r = subprocess.run([sys.executable, os.path.join(root, "tools", "sanitize_k1.py"), which], env=env, capture_output=True,
+                           text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append([l for l in r.stdout.splitlines() if l.startswith("COUNTERS")])
+    assert outs[0] and outs[0] == outs[1] == outs[2], outs
+
+
 def test_in_process_multi_device_handle_matches_one_device():
     """wofdm_create(&h, 0): ONE process that owns every visible GPU and splits each job's frames over them itself (this is
     the MEX gateway's handle; ber_host.cu: wofdm_ber_run_multi's sub-shards).  Counters must be identical to the one-device

@@ -33,6 +33,9 @@ namespace wofdm {
 #ifndef TCV2_NISSUE
 #define TCV2_NISSUE 4
 #endif
+#ifndef TCV2_DEBUG_BARRIERS
+#define TCV2_DEBUG_BARRIERS 0          // 1 (libwofdm_dbg.so): every relaxed synchronisation of the kernel replaced by a full barrier --
+#endif                                 // the reference the race test compares the production build with (compute-sanitizer is closed here)
 constexpr int TCV2_BAR_STREAM = 14;      // named barrier: "the split stream of this frame is complete"
 
 __host__ __device__ constexpr int tconv2_wtx_len(int stride, int tail_tx) { return (stride + tail_tx + 3) & ~3; }
@@ -396,8 +399,9 @@ ber_tconv2_kernel(const BerParams prm) {
         const int irank = (warp_u - (int)issuer) & (NW - 1);          // warp-uniform: issuing warps have irank < TCV2_NISSUE
         const bool is_issuer = irank < TCV2_NISSUE;
         ++issuer;
+        if (TCV2_DEBUG_BARRIERS) __syncthreads();
         if (is_issuer) {
-            asm volatile("bar.sync %0, %1;" :: "n"(TCV2_BAR_STREAM), "n"(NT) : "memory");
+            if (!TCV2_DEBUG_BARRIERS) asm volatile("bar.sync %0, %1;" :: "n"(TCV2_BAR_STREAM), "n"(NT) : "memory");
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (tcv_elect_one()) {
 #pragma unroll
@@ -415,7 +419,7 @@ ber_tconv2_kernel(const BerParams prm) {
             }
             __syncwarp();
         } else {
-            asm volatile("bar.arrive %0, %1;" :: "n"(TCV2_BAR_STREAM), "n"(NT) : "memory");
+            if (!TCV2_DEBUG_BARRIERS) asm volatile("bar.arrive %0, %1;" :: "n"(TCV2_BAR_STREAM), "n"(NT) : "memory");
         }
         // ---- noise, in receiver layout and in registers (ber_kernel.cuh: noise_draw48): the 16 samples this thread's FFT
         //      rows gather, and its extras; |n|^2 partial
@@ -623,6 +627,7 @@ ber_tconv2_kernel(const BerParams prm) {
         // No barrier here: what the next frame's prologue and Tx stage overwrite (the split stream over r, the symbol words,
         // the taps operand, the exchange regions over the parked noise) was last read before the pilot barriers above by
         // every thread; geq, red and the tensor-memory accumulators are rewritten only behind the next frame's own barriers.
+        if (TCV2_DEBUG_BARRIERS) frame_sync<CL>();
       }   // window pairs
         f += df;
         if constexpr (!VERIFY) {
