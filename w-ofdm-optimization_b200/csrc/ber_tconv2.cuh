@@ -25,6 +25,7 @@
 // tails within the outer register rows (ber_host.cu:choose_variant checks).
 #pragma once
 #include <cuda_fp16.h>
+#include <cstdio>
 #include "ber_kernel.cuh"
 #include "ber_tconv.cuh"
 
@@ -32,6 +33,21 @@ namespace wofdm {
 
 #ifndef TCV2_NISSUE
 #define TCV2_NISSUE 4
+#endif
+// transform group `slot` of a CTA works on its OFDM symbol S - 1 - slot: the pilot (symbol 0), whose receiver everybody waits
+// for, then sits in the warp with the highest index, which the warp schedulers serve first
+#ifndef TCV2_REVERSE_SLOTS
+#define TCV2_REVERSE_SLOTS 1
+#endif
+#define TCV2_SLOT_SYMBOL(slot, S) (TCV2_REVERSE_SLOTS ? (S) - 1 - (slot) : (slot))
+// development aid: per-warp clock() stamps at the phase boundaries of a few frames of CTA 0, printed from the device
+#ifndef TCV2_TRACE
+#define TCV2_TRACE 0
+#endif
+#if TCV2_TRACE
+#define TCV2_STAMP(k) do { if (trace_on && lane == 0) trace_buf[warp * 12 + (k)] = clock64(); } while (0)
+#else
+#define TCV2_STAMP(k) do { } while (0)
 #endif
 #ifndef TCV2_DEBUG_BARRIERS
 #define TCV2_DEBUG_BARRIERS 0          // 1 (libwofdm_dbg.so): every relaxed synchronisation of the kernel replaced by a full barrier --
@@ -220,7 +236,16 @@ ber_tconv2_kernel(const BerParams prm) {
         si = (int)(q / prm.C);       ci = (int)(q - (long long)si * prm.C);
         ds = (int)(dq / prm.C);      dc = (int)(dq - (long long)ds * prm.C);
     }
+#if TCV2_TRACE
+    __shared__ long long trace_buf[16 * 12];
+    int trace_it = 0;
+#endif
     for (long long j = fslot; j < prm.n_frames; j += nslots) {
+#if TCV2_TRACE
+        const bool trace_on = blockIdx.x == 0 && trace_it >= 3 && trace_it < 6;
+        ++trace_it;
+        TCV2_STAMP(0);
+#endif
         if constexpr (VERIFY) { ci = (int)f; si = (int)f; }
         const T snr_lin = reinterpret_cast<const T*>(prm.snr_lin)[si];
       // every window pair of the plan on this frame's symbols (drawn once), each with its own noise stream
@@ -272,8 +297,8 @@ ber_tconv2_kernel(const BerParams prm) {
             }
             frame_sync<CL>();
         } else {
-            const int s = slot;
-            const bool act = s < S;
+            const bool act = slot < S;
+            const int s = TCV2_SLOT_SYMBOL(slot, S);
             const int se = act ? s : S - 1;     // idle slots shadow the last symbol (identical stores)
             const bool first = sb + se == 0;    // the frame's first symbol has no predecessor
             C2 v[16];
@@ -352,7 +377,9 @@ ber_tconv2_kernel(const BerParams prm) {
                     }
                 }
             }
+            TCV2_STAMP(1);
             frame_sync<CL>();                   // every symbol's tail is in place
+            TCV2_STAMP(2);
             // the falling tail of the previous symbol: same buffer, or the previous CTA's (behind its kept samples)
             const uint32_t* const th = (CL > 1 && se == 0) ? prev_uh + sec : sh;
             const uint32_t* const tl = (CL > 1 && se == 0) ? prev_ul + sec : sl;
@@ -387,6 +414,7 @@ ber_tconv2_kernel(const BerParams prm) {
             // "I have taken what I need from my neighbour's stream": awaited before anybody parks r over a stream
             asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
         }
+        TCV2_STAMP(3);
         // the tensor core reads shared memory through the async proxy
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -421,13 +449,14 @@ ber_tconv2_kernel(const BerParams prm) {
         } else {
             if (!TCV2_DEBUG_BARRIERS) asm volatile("bar.arrive %0, %1;" :: "n"(TCV2_BAR_STREAM), "n"(NT) : "memory");
         }
+        TCV2_STAMP(4);
         // ---- noise, in receiver layout and in registers (ber_kernel.cuh: noise_draw48): the 16 samples this thread's FFT
         //      rows gather, and its extras; |n|^2 partial
         C2 nz[16], nx[N48_MAXLEV];
         C2 pr2 = mk2<T>(0, 0), pn2 = mk2<T>(0, 0);
         {
             const bool act = slot < S;
-            const int se = act ? slot : S - 1;
+            const int se = act ? TCV2_SLOT_SYMBOL(slot, S) : S - 1;
             const int sg = sb + se;                                      // symbol index in the frame
             const int xas = ng.xa + (sg == prm.S - 1 ? ng.tailx : 0);    // extras of this symbol (uniform per transform group)
             const int nlev = (xas + TPF - 1) / TPF;
@@ -477,8 +506,10 @@ ber_tconv2_kernel(const BerParams prm) {
                 for (int lev = 0; lev < N48_MAXLEV; ++lev) pn2 = csq_acc(nx[lev], pn2);
             }
         }
+        TCV2_STAMP(5);
         // ---- the channel output, once: frame-wide signal power, r parked over the dead split stream
         tcv_mbar_wait(tcv_smem_u32(bar), phase);
+        TCV2_STAMP(6);
         phase ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if constexpr (CL > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -524,7 +555,9 @@ ber_tconv2_kernel(const BerParams prm) {
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        TCV2_STAMP(7);
         frame_sync<CL>();                          // r and the power partials are complete
+        TCV2_STAMP(8);
         const T g = noise_gain(block_total<CL * NW>(red), snr_lin, block_total<CL * NW>(red + 32));
 
         // =========================== receiver ===========================
@@ -532,8 +565,8 @@ ber_tconv2_kernel(const BerParams prm) {
         // q[n] = o[(n + shift) mod N]; Y = DFT(q)   (receiver.py:13-133)
         unsigned bit_cnt = 0, sym_cnt = 0;
         {
-            const int s = slot;
-            const bool act = s < S;
+            const bool act = slot < S;
+            const int s = TCV2_SLOT_SYMBOL(slot, S);
             const int se = act ? s : S - 1;
             C2 v[16];
             // r of stream sample i: half (i >> 1) & 1, chunk i >> 2, element i & 1 -- constant i mod 4 for all of this thread's samples
@@ -568,12 +601,14 @@ ber_tconv2_kernel(const BerParams prm) {
             const uint32_t w[4] = {wv.x, wv.y, wv.z, wv.w};
             // pilot (wofdm_simulation.py:223): the pilot's threads publish Y0, then every thread turns one bin into the
             // equaliser tap G[k] = X0[k] / Y0[k] (lattice units)
+            TCV2_STAMP(9);
             if (rank == 0) {
                 if (se == 0) {
 #pragma unroll
                     for (int q = 0; q < 16; ++q) geq[t + q * TPF] = v[q];
                 }
                 __syncthreads();
+                TCV2_STAMP(10);
                 const unsigned char* pil = reinterpret_cast<const unsigned char*>(symw);
                 for (int k = tid; k < N; k += NT) {
                     const C2 y0 = geq[k];
@@ -615,6 +650,21 @@ ber_tconv2_kernel(const BerParams prm) {
         }
         bit_cnt = warp_sum(bit_cnt);
         sym_cnt = warp_sum(sym_cnt);
+#if TCV2_TRACE
+        TCV2_STAMP(11);
+        if (trace_on) {
+            __syncthreads();
+            if (tid == 0) {
+                const long long t0 = trace_buf[0];
+                for (int w = 0; w < NW; ++w) {
+                    printf("TRACE it %d warp %d:", trace_it - 1, w);
+                    for (int k = 0; k < 12; ++k) printf(" %lld", trace_buf[w * 12 + k] - t0);
+                    printf("\n");
+                }
+            }
+            __syncthreads();
+        }
+#endif
         if (lane == 0) {
             if constexpr (VERIFY) {
                 atomicAdd(reinterpret_cast<unsigned long long*>(prm.bit_err_f) + f, (unsigned long long)bit_cnt);
