@@ -222,7 +222,7 @@ void fill_sys(BerParams& p, const wofdm_sys_t& s, int L) {
 int prepare_kernel(wofdm_ctx* h, const BerVariant& v, size_t smem, int sm_count, int* blocks_per_sm, long long* max_ctas) {
     WOFDM_CUDA(h, cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int nb = 0;
-    WOFDM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, v.fn, v.NT, smem));
+    WOFDM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, v.fn, v.launch_threads, smem));
     if (v.ntile > 0) {
         // the occupancy calculator counts a kernel that allocates tensor memory as one CTA per SM; these kernels take
         // 256 of the 512 columns (N = 256; all of them at N = 512), so registers, shared memory and tensor memory together decide
@@ -232,7 +232,7 @@ int prepare_kernel(wofdm_ctx* h, const BerVariant& v, size_t smem, int sm_count,
         WOFDM_CUDA(h, cudaGetDevice(&dev));
         WOFDM_CUDA(h, cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
         WOFDM_CUDA(h, cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev));
-        const int by_smem = (int)((size_t)smem_sm / (smem + 1024)), by_regs = regs_sm / (((fa.numRegs + 7) & ~7) * v.NT);
+        const int by_smem = (int)((size_t)smem_sm / (smem + 1024)), by_regs = regs_sm / (((fa.numRegs + 7) & ~7) * v.launch_threads);
         const int by_tmem = 512 / (int)tconv_tmem_cols(v.ntile);
         nb = std::max(nb, std::min(by_smem, std::min(by_regs, by_tmem)));
     }
@@ -243,7 +243,7 @@ int prepare_kernel(wofdm_ctx* h, const BerVariant& v, size_t smem, int sm_count,
     long long cap = (long long)nb * sm_count;
     if (v.CL > 1) {
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(v.CL * sm_count); cfg.blockDim = dim3(v.NT); cfg.dynamicSmemBytes = smem;
+        cfg.gridDim = dim3(v.CL * sm_count); cfg.blockDim = dim3(v.launch_threads); cfg.dynamicSmemBytes = smem;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = v.CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;

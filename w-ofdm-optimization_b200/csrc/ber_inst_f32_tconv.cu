@@ -14,7 +14,7 @@ struct TconvVariantImpl {
     static BerVariant make(const char* name) {
         BerVariant v;
         v.name = name; v.N = N; v.NT = NT; v.TC = 2 * NTILE; v.LB = TCV_LB; v.MINB = MINB; v.CL = 1; v.circ = false; v.txs = true; v.full = false;
-        v.ntile = NTILE; v.gen = 1;
+        v.ntile = NTILE; v.gen = 1; v.launch_threads = NT;
         v.fp64 = false; v.verify = V;
         v.layout = &tconv_smem_layout<N, NT, NTILE>;
         v.fn = reinterpret_cast<const void*>(&ber_tconv_kernel<N, NT, NTILE, MINB, V>);

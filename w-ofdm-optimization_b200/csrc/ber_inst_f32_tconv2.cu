@@ -10,11 +10,11 @@ struct Tconv2VariantImpl {
     // grid = CTAs (a multiple of CL); CL > 1 launches thread-block clusters of CL CTAs
     static cudaError_t launch(const BerParams& prm, int grid, size_t smem, cudaStream_t st) {
         if constexpr (CL == 1) {
-            ber_tconv2_kernel<N, NT, NTILE, MINB, V><<<grid, NT, smem, st>>>(prm);
+            ber_tconv2_kernel<N, NT, NTILE, MINB, V><<<grid, NT + tconv2_mma_warp_threads(N, NT), smem, st>>>(prm);   // (+ the MMA warp)
             return cudaGetLastError();
         } else {
             cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NT + tconv2_mma_warp_threads(N, NT)); cfg.dynamicSmemBytes = smem; cfg.stream = st;
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeClusterDimension;
             at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -25,7 +25,7 @@ struct Tconv2VariantImpl {
     static BerVariant make(const char* name) {
         BerVariant v;
         v.name = name; v.N = N; v.NT = NT; v.TC = 2 * NTILE; v.LB = TCV_LB; v.MINB = MINB; v.CL = CL; v.circ = false; v.txs = true; v.full = false;
-        v.ntile = NTILE; v.gen = 2;
+        v.ntile = NTILE; v.gen = 2; v.launch_threads = NT + tconv2_mma_warp_threads(N, NT);
         v.fp64 = false; v.verify = V;
         v.layout = &tconv2_smem_layout<N, NT, NTILE>;
         v.fn = reinterpret_cast<const void*>(&ber_tconv2_kernel<N, NT, NTILE, MINB, V, CL>);

@@ -14,6 +14,7 @@ struct BerVariant {
     bool txs;                  // accepts BerParams::tx_stream (channel-mask variant); the staged kernels always do
     bool full;                 // every register of every thread is a live stream sample (NT*TC == S*stride)
     int ntile;                 // > 0: channel convolution on the tensor cores (ber_tconv*.cuh), frames of up to 512*ntile samples
+    int launch_threads;        // threads per CTA at launch (NT, plus the MMA warp of ber_tconv2.cuh)
     int gen;                   // tensor-core kernels: 1 = ber_tconv.cuh (64-bit noise draws by position), 2 = ber_tconv2.cuh (48-bit draws)
     bool fp64, verify;
     BerSmem (*layout)(int S, int stride, int tail_tx, int tail_rx, int L, int chunk, int use_global);
@@ -40,7 +41,7 @@ struct BerVariantImpl {
     }
     static BerVariant make(const char* name) {
         BerVariant v;
-        v.name = name; v.N = N; v.NT = NT; v.TC = TC; v.LB = LB; v.MINB = MINB; v.CL = CL; v.circ = CIRC; v.txs = TXS || TC == 0; v.full = FULL; v.ntile = 0; v.gen = 0;
+        v.name = name; v.N = N; v.NT = NT; v.TC = TC; v.LB = LB; v.MINB = MINB; v.CL = CL; v.circ = CIRC; v.txs = TXS || TC == 0; v.full = FULL; v.ntile = 0; v.gen = 0; v.launch_threads = NT;
         v.fp64 = sizeof(T) == 8; v.verify = V;
         v.layout = &ber_smem_layout<T, N, NT, TC, LB>;
         v.fn = reinterpret_cast<const void*>(&ber_frame_kernel<T, N, NT, TC, LB, MINB, FULL, V, CL, CIRC, TXS>);

@@ -17,8 +17,9 @@
 //     codes directly, no decision table, bit errors by the GF(2)-linear Gray map of the XOR.
 //   * 48 random bits per complex noise sample instead of 64: a 32-bit radius word and a 16-bit angle (65 536 phases),
 //     three Philox4x32-10 calls per eight samples.
-//   * Only the warps that issue the MMAs wait for the whole stream to be written (bar.sync); all others announce their
-//     part (bar.arrive) and start drawing noise.  MMA descriptors advance by one addition.
+//   * A dedicated ninth (seventeenth) warp issues the MMAs: it alone waits for the whole stream to be written (bar.sync)
+//     and then sits in front of the tensor core's queue, while the working warps announce their part (bar.arrive) and
+//     draw their noise.  MMA descriptors advance by one addition.
 //
 // fp32; N = 256: one CTA of 256 threads per frame, two CTAs per SM (256 of the 512 tensor-memory columns each);
 // N = 512: one CTA of 512 threads per frame and SM.  S <= 16 symbols in one Tx pass, L <= TCV_LB, prefix / suffix /
@@ -31,9 +32,6 @@
 
 namespace wofdm {
 
-#ifndef TCV2_NISSUE
-#define TCV2_NISSUE 4
-#endif
 // transform group `slot` of a CTA works on its OFDM symbol S - 1 - slot: the pilot (symbol 0), whose receiver everybody waits
 // for, then sits in the warp with the highest index, which the warp schedulers serve first
 #ifndef TCV2_REVERSE_SLOTS
@@ -54,6 +52,13 @@ namespace wofdm {
 #endif                                 // the reference the race test compares the production build with (compute-sanitizer is closed here)
 constexpr int TCV2_BAR_STREAM = 14;      // named barrier: "the split stream of this frame is complete"
 
+// N <= 512: the CTA has one more warp that only issues the MMAs.  The register file then leaves the working threads 96
+// registers (two CTAs of 288 threads, or one of 544, per SM), which the N = 256 kernel fits without spills and the N = 512
+// kernel with ~60 bytes of them (measured: 2.06e8 -> 2.12e8 OFDM symbols/s all the same).  N = 1024 (clusters) spills
+// 200 bytes under that cap (8.6e7 -> 6.8e7), so there four of the working warps, rotating from frame to frame, issue a
+// quarter of the frame's MMAs each before they draw their noise.
+__host__ __device__ constexpr int tconv2_mma_warp_threads(int N, int NT) { return (N <= 512 && NT <= 512) ? 32 : 0; }
+constexpr int TCV2_NISSUE = 4;
 __host__ __device__ constexpr int tconv2_wtx_len(int stride, int tail_tx) { return (stride + tail_tx + 3) & ~3; }
 __host__ __device__ constexpr int tconv2_wrx_len(int N, int tail_rx) { return (N + tail_rx + 3) & ~3; }
 
@@ -94,7 +99,7 @@ __host__ __device__ inline BerSmem tconv2_smem_layout(int S, int stride, int tai
 // L - 1 samples of convolution history (PULLED, a few dozen words), the per-warp power partials and the pilot's equaliser
 // taps are PUSHED into both CTAs, so every read is local.
 template <int N, int NT, int NTILE, int MINB, bool VERIFY, int CL = 1>
-__global__ void __launch_bounds__(NT, MINB)
+__global__ void __launch_bounds__(NT + tconv2_mma_warp_threads(N, NT), MINB)
 ber_tconv2_kernel(const BerParams prm) {
     using T = float;
     using C2 = float2;
@@ -152,7 +157,7 @@ ber_tconv2_kernel(const BerParams prm) {
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(tcv_smem_u32(bar)), "r"(TCV2_NISSUE) : "memory");   // one commit per issuing warp and frame
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(tcv_smem_u32(bar)), "r"(tconv2_mma_warp_threads(N, NT) ? 1 : TCV2_NISSUE) : "memory");   // one commit per issuing warp and frame
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < P::NTW; i += NT) tw[i] = reinterpret_cast<const C2*>(prm.tw)[i];
@@ -205,6 +210,8 @@ ber_tconv2_kernel(const BerParams prm) {
     const int tp = TG == 1 ? 0 : (warp_u >> 3);                // this warp's tile set: tiles tp, tp + TG, ...
     const uint32_t tlane = tmem + ((uint32_t)((warp_u & 3) * 32) << 16) + (uint32_t)(4 * ((warp_u >> 2) & 1));
     uint32_t phase = 0, issuer = blockIdx.x;
+    constexpr bool MMAW = tconv2_mma_warp_threads(N, NT) > 0;       // a dedicated MMA warp (warp NW)
+    constexpr int NTB = NT + tconv2_mma_warp_threads(N, NT);        // threads that meet at the "stream complete" barrier
     // MMA descriptors of tile 0, K step 0 (tile: +2048 B = +128 in the address field, K step: +32 B = +2; B operand: +256 B = +16)
     const uint64_t d_ahi = tcv_desc(tcv_smem_u32(ahi), 16, 128), d_alo = tcv_desc(tcv_smem_u32(alo), 16, 128);
     const uint64_t d_bhl = tcv_desc(tcv_smem_u32(bt), 128, 768), d_bh0 = tcv_desc(tcv_smem_u32(bt), 128, 1536);
@@ -226,6 +233,64 @@ ber_tconv2_kernel(const BerParams prm) {
         }
     }
     const long long fslot = blockIdx.x / CL, nslots = gridDim.x / CL;   // frames in flight on the grid
+#if TCV2_TRACE
+    __shared__ long long trace_buf[17 * 12];
+    int trace_it = 0;
+#endif
+    if (MMAW && warp == NW) {
+        // ===== the MMA warp: the CTA's extra warp issues every tcgen05.mma of the kernel and nothing else =====
+        // An issuing thread sits in front of the tensor core's short queue for as long as the convolution takes (~40 cycles per
+        // MMA, bound by the operand reads: ~2200 cycles per frame at N = 256).  Measured with the issue spread over four of
+        // the eight working warps: those four reached the power barrier ~1900 cycles after the others, every frame.  Here
+        // the working warps only announce their stores (bar.arrive) and draw their noise while this warp waits for the
+        // stream (bar.sync), issues, and otherwise just keeps the CTA's / cluster's barrier sequence.
+        for (long long j = fslot; j < prm.n_frames; j += nslots) {
+            for (int var = 0; var < nvar; ++var) {
+#if TCV2_TRACE
+                const bool trace_on = blockIdx.x == 0 && trace_it >= 3 && trace_it < 6;
+                ++trace_it;
+                TCV2_STAMP(0);
+#endif
+                frame_sync<CL>();                                         // Tx: every symbol's tail is in place
+                TCV2_STAMP(1);
+                if constexpr (CL > 1) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+                if (TCV2_DEBUG_BARRIERS) __syncthreads();
+                else asm volatile("bar.sync %0, %1;" :: "n"(TCV2_BAR_STREAM), "n"(NTB) : "memory");   // the split stream is complete
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                TCV2_STAMP(2);
+                if (tcv_elect_one()) {
+#pragma unroll
+                    for (int ti = 0; ti < NTILE; ++ti) {
+                        const uint32_t tacc = tmem + (uint32_t)(16 * ti);
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            tcv_mma(tacc, d_ahi + (uint64_t)(ti * 128 + k * 2), d_bhl + (uint64_t)(k * 16), k != 0);
+                            tcv_mma(tacc, d_alo + (uint64_t)(ti * 128 + k * 2), d_bh0 + (uint64_t)(k * 16), 1u);
+                        }
+                    }
+                    // completes when all of the frame's MMAs have
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(tcv_smem_u32(bar)) : "memory");
+                }
+                __syncwarp();
+                TCV2_STAMP(3);
+#if TCV2_TRACE
+                if (trace_on) { tcv_mbar_wait(tcv_smem_u32(bar), phase); TCV2_STAMP(4); }
+                phase ^= 1u;
+#endif
+                if constexpr (CL > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+                frame_sync<CL>();                                         // power partials
+                if (rank == 0) __syncthreads();                           // pilot published
+                frame_sync<CL>();                                         // equaliser taps
+#if TCV2_TRACE
+                if (trace_on) { __syncthreads(); __syncthreads(); }
+#endif
+                if (TCV2_DEBUG_BARRIERS) frame_sync<CL>();
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        frame_sync<CL>();
+        return;
+    }
     long long f = prm.frame_begin + fslot * prm.frame_step;
     const long long df = nslots * prm.frame_step;
     long long fe = 0, de = 0;
@@ -236,10 +301,6 @@ ber_tconv2_kernel(const BerParams prm) {
         si = (int)(q / prm.C);       ci = (int)(q - (long long)si * prm.C);
         ds = (int)(dq / prm.C);      dc = (int)(dq - (long long)ds * prm.C);
     }
-#if TCV2_TRACE
-    __shared__ long long trace_buf[16 * 12];
-    int trace_it = 0;
-#endif
     for (long long j = fslot; j < prm.n_frames; j += nslots) {
 #if TCV2_TRACE
         const bool trace_on = blockIdx.x == 0 && trace_it >= 3 && trace_it < 6;
@@ -422,14 +483,14 @@ ber_tconv2_kernel(const BerParams prm) {
         // =========================== channel + AWGN ===========================
         // r = conv(h, u) (wofdm_simulation.py:206-209) on the tensor cores; y = r + sqrt(Pr*10^(-snr/10)/Pn) n with Pr, Pn
         // summed over the whole frame (:135-138; noise_norm 1: over the full convolution, main_BER_calculation.m:260-261,289-292)
-        // One elected lane of each of TCV2_NISSUE warps (rotating from frame to frame) waits for the whole stream and issues
-        // its share of the frame's MMAs; every other warp only announces its stores and goes on to the noise draws.
+        // The MMA warp (above) waits for the whole stream and issues the frame's MMAs; the working warps only announce their
+        // stores and go on to the noise draws.  Without an MMA warp (NT = 512), TCV2_NISSUE working warps do its job first.
         const int irank = (warp_u - (int)issuer) & (NW - 1);          // warp-uniform: issuing warps have irank < TCV2_NISSUE
-        const bool is_issuer = irank < TCV2_NISSUE;
+        const bool is_issuer = !MMAW && irank < TCV2_NISSUE;
         ++issuer;
         if (TCV2_DEBUG_BARRIERS) __syncthreads();
         if (is_issuer) {
-            if (!TCV2_DEBUG_BARRIERS) asm volatile("bar.sync %0, %1;" :: "n"(TCV2_BAR_STREAM), "n"(NT) : "memory");
+            if (!TCV2_DEBUG_BARRIERS) asm volatile("bar.sync %0, %1;" :: "n"(TCV2_BAR_STREAM), "n"(NTB) : "memory");
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (tcv_elect_one()) {
 #pragma unroll
@@ -442,12 +503,11 @@ ber_tconv2_kernel(const BerParams prm) {
                         tcv_mma(tacc, d_alo + (uint64_t)(ti * 128 + k * 2), d_bh0 + (uint64_t)(k * 16), 1u);
                     }
                 }
-                // completes when all of this warp's MMAs have
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(tcv_smem_u32(bar)) : "memory");
             }
             __syncwarp();
-        } else {
-            if (!TCV2_DEBUG_BARRIERS) asm volatile("bar.arrive %0, %1;" :: "n"(TCV2_BAR_STREAM), "n"(NT) : "memory");
+        } else if (!TCV2_DEBUG_BARRIERS) {
+            asm volatile("bar.arrive %0, %1;" :: "n"(TCV2_BAR_STREAM), "n"(NTB) : "memory");
         }
         TCV2_STAMP(4);
         // ---- noise, in receiver layout and in registers (ber_kernel.cuh: noise_draw48): the 16 samples this thread's FFT
@@ -656,7 +716,7 @@ ber_tconv2_kernel(const BerParams prm) {
             __syncthreads();
             if (tid == 0) {
                 const long long t0 = trace_buf[0];
-                for (int w = 0; w < NW; ++w) {
+                for (int w = 0; w <= NW; ++w) {
                     printf("TRACE it %d warp %d:", trace_it - 1, w);
                     for (int k = 0; k < 12; ++k) printf(" %lld", trace_buf[w * 12 + k] - t0);
                     printf("\n");
