@@ -118,12 +118,16 @@ __device__ __forceinline__ bool tcv_elect_one() {
 }
 __device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cast<const uint32_t*>(&h); }
 __device__ __forceinline__ __half2 bits_h2(uint32_t w) { return *reinterpret_cast<const __half2*>(&w); }
-// u = hi + lo
+// u = hi + lo.  The residual v - hi comes from the mixed-precision FMA (fp16 x fp16 + fp32, SASS FHFMA): hi * (-1) + v with
+// one rounding = the fp32 difference, one instruction per component instead of unpack + subtract.
 __device__ __forceinline__ void split_h2(float2 v, uint32_t& hi, uint32_t& lo) {
     const __half2 a = __floats2half2_rn(v.x, v.y);
-    const float2 d = sub2(v, __half22float2(a));
     hi = h2_bits(a);
-    lo = h2_bits(__floats2half2_rn(d.x, d.y));
+    const unsigned short al = (unsigned short)(hi & 0xffffu), ah = (unsigned short)(hi >> 16), mone = 0xbc00u;   // -1.0
+    float dx, dy;
+    asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(dx) : "h"(al), "h"(mone), "f"(v.x));
+    asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(dy) : "h"(ah), "h"(mone), "f"(v.y));
+    lo = h2_bits(__floats2half2_rn(dx, dy));
 }
 __device__ __forceinline__ float2 join_h2(uint32_t hi, uint32_t lo) { return add2(__half22float2(bits_h2(hi)), __half22float2(bits_h2(lo))); }
 

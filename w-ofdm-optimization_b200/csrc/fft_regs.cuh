@@ -7,7 +7,8 @@
 // (natural order), which is the layout symbol generation, CP/CS insertion and the equaliser use.
 //
 // Twiddles come from a table built on the host in double precision (see fft_twiddle_count):
-//   section P_p (p = 1..a-1), entry [m*16^p + k] = exp(-2*pi*i * k*m / 16^(p+1)), m < 16, k < 16^p
+//   section P_1 (a >= 2),     entry [k*TW1_PITCH + m] = exp(-2*pi*i * k*m / 256),  k < 16, m < 16 (a thread's 15 factors are one row)
+//   section P_2 (a >= 3),     entry [m*256 + k] = exp(-2*pi*i * k*m / 4096),       m < 16, k < 256
 //   section F   (if r > 1),   entry [m*(N/r) + j] = exp(-2*pi*i * j*m / N),       m < r,  j < N/r
 // DIR = -1 forward (unscaled), DIR = +1 inverse (unscaled; the caller folds 1/N into the Tx window).
 // Replaces the dense IDFT/DFT products of the reference (python/ofdm_utils/transmitter.py:38-58,
@@ -17,18 +18,21 @@
 
 namespace wofdm {
 
+constexpr int TW1_PITCH = 18;     // row pitch of the first twiddle section (16 entries + 2: rows 144 B apart, 128-bit loads without bank conflicts)
 template <int N> struct FftPlan {
     static constexpr int a = (N % 4096 == 0) ? 3 : (N % 256 == 0) ? 2 : (N % 16 == 0) ? 1 : 0;
     static constexpr int p16 = (a == 3) ? 4096 : (a == 2) ? 256 : (a == 1) ? 16 : 1;
     static constexpr int r = N / p16;
     static constexpr int TPF = N / 16;                 // threads per transform
-    static constexpr int XLEN = N + N / 16;            // padded exchange buffer (elements)
-    static constexpr int NTW = ((a >= 2) ? 256 : 0) + ((a >= 3) ? 4096 : 0) + ((r > 1) ? N : 0);
+    static constexpr int XLEN = N + N / 8;             // padded exchange buffer (elements)
+    static constexpr int NTW = ((a >= 2) ? 16 * TW1_PITCH : 0) + ((a >= 3) ? 4096 : 0) + ((r > 1) ? N : 0);
     static_assert(N >= 16 && (N & (N - 1)) == 0 && N <= 4096, "N must be a power of two in [16, 4096]");
     static_assert(r == 1 || r == 2 || r == 4 || r == 8, "unsupported factorisation");
 };
 
-__host__ __device__ constexpr int fft_pad(int i) { return i + (i >> 4); }
+// two pad elements per 16: a thread's 16 consecutive points of the first exchange start 16-byte aligned (vector stores),
+// and both the stores (lane stride 18) and the transposed loads (lane stride 1) stay free of bank conflicts
+__host__ __device__ constexpr int fft_pad(int i) { return i + 2 * (i >> 4); }
 
 // multiply by exp(DIR * 2*pi*i * E / 16), E compile time
 template <typename T, int DIR, int E> __device__ __forceinline__ V2<T> mul_w16(V2<T> a) {
@@ -118,6 +122,26 @@ template <int TPF, int NB> __device__ __forceinline__ void fft_group_sync(int gr
     else __syncthreads();
 }
 
+// 16 consecutive complex values, 16-byte aligned: 128-bit accesses (eight for float2, one per element for double2)
+__device__ __forceinline__ void store16(float2* dst, const float2 (&v)[16]) {
+    float4* d = reinterpret_cast<float4*>(dst);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d[i] = make_float4(v[2 * i].x, v[2 * i].y, v[2 * i + 1].x, v[2 * i + 1].y);
+}
+__device__ __forceinline__ void store16(double2* dst, const double2 (&v)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) dst[i] = v[i];
+}
+__device__ __forceinline__ void load16(float2 (&w)[16], const float2* src) {
+    const float4* s = reinterpret_cast<const float4*>(src);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float4 q = s[i]; w[2 * i] = make_float2(q.x, q.y); w[2 * i + 1] = make_float2(q.z, q.w); }
+}
+__device__ __forceinline__ void load16(double2 (&w)[16], const double2* src) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) w[i] = src[i];
+}
+
 // One transform per group of N/16 threads; EVERY thread of the CTA must call this (it contains
 // barriers).  xb: this group's exchange buffer (FftPlan<N>::XLEN elements, shared memory), private
 // to the group; tw: twiddle table (FftPlan<N>::NTW elements).  Memory that aliases xb and is
@@ -134,29 +158,37 @@ __device__ __forceinline__ void fft_regs(V2<T> (&v)[16], const int t, V2<T>* __r
         const int Ns = (p == 0) ? 1 : (p == 1) ? 16 : 256;
         const int k = t & (Ns - 1);
         if (p > 0) {
-            V2<T> w[15];                  // fetched before the barrier: they do not depend on the exchange
+            V2<T> w[16];                  // fetched before the barrier: they do not depend on the exchange
+            if (p == 1) {
+                load16(w, tw + tw_off + k * TW1_PITCH);
+            } else {
 #pragma unroll
-            for (int m = 1; m < 16; ++m) w[m - 1] = tw[tw_off + m * Ns + k];
+                for (int m = 1; m < 16; ++m) w[m] = tw[tw_off + m * Ns + k];
+            }
             fft_group_sync<TPF, NB>(group);
-            {   // fft_pad(t + m TPF) = fft_pad(t) + m (TPF + TPF/16): one address, immediate offsets
+            {   // fft_pad(t + m TPF) = fft_pad(t) + m (TPF + TPF/8): one address, immediate offsets
                 const V2<T>* const xr = xb + fft_pad(t);
 #pragma unroll
-                for (int m = 0; m < 16; ++m) v[m] = xr[m * (TPF + TPF / 16)];
+                for (int m = 0; m < 16; ++m) v[m] = xr[m * (TPF + TPF / 8)];
             }
 #pragma unroll
-            for (int m = 1; m < 16; ++m) v[m] = tw_apply<T, DIR>(v[m], w[m - 1]);
-            tw_off += 16 * Ns;
+            for (int m = 1; m < 16; ++m) v[m] = tw_apply<T, DIR>(v[m], w[m]);
+            tw_off += p == 1 ? 16 * TW1_PITCH : 16 * Ns;
         }
         dft16<T, DIR>(v);
         const bool last = (p == P::a - 1);
         if (!(last && P::r == 1)) {
             fft_group_sync<TPF, NB>(group);        // the group has finished reading the previous layout (also of an earlier call)
             const int base = (t - k) * 16 + k;
-            {   // base = 16 Ns j + k, k < Ns: fft_pad(base + m Ns) = fft_pad(base) + m (Ns = 1) or + m (Ns + Ns/16)
+            {   // base = 16 Ns j + k, k < Ns: fft_pad(base + m Ns) = fft_pad(base) + m (Ns = 1) or + m (Ns + Ns/8)
                 V2<T>* const xw = xb + fft_pad(base);
-                const int step = Ns == 1 ? 1 : Ns + Ns / 16;
+                if (Ns == 1) {
+                    store16(xw, v);           // 16 consecutive points, 16-byte aligned: vector stores
+                } else {
+                    const int step = Ns + Ns / 8;
 #pragma unroll
-                for (int m = 0; m < 16; ++m) xw[m * step] = v[m];
+                    for (int m = 0; m < 16; ++m) xw[m * step] = v[m];
+                }
             }
         }
     }
@@ -166,7 +198,7 @@ __device__ __forceinline__ void fft_regs(V2<T> (&v)[16], const int t, V2<T>* __r
         if constexpr (TPF % 16 == 0) {
             const V2<T>* const xr = xb + fft_pad(t);
 #pragma unroll
-            for (int q = 0; q < 16; ++q) v[q] = xr[q * (TPF + TPF / 16)];
+            for (int q = 0; q < 16; ++q) v[q] = xr[q * (TPF + TPF / 8)];
         } else {
 #pragma unroll
             for (int q = 0; q < 16; ++q) v[q] = xb[fft_pad(t + q * TPF)];

@@ -65,13 +65,23 @@ std::vector<double> build_twiddles(int N) {
     std::vector<double> tw;
     const double two_pi = 6.283185307179586476925286766559;
     int Ns = 16;
-    for (int p = 1; p < a; ++p, Ns *= 16)
+    for (int p = 1; p < a; ++p, Ns *= 16) {
+        if (p == 1) {                        // rows of TW1_PITCH = 18: thread k's factors m = 0..15 side by side (fft_regs.cuh)
+            for (int k = 0; k < 16; ++k)
+                for (int m = 0; m < wofdm::TW1_PITCH; ++m) {
+                    const double ang = m < 16 ? -two_pi * (double)(k * m) / 256.0 : 0.0;
+                    tw.push_back(m < 16 ? std::cos(ang) : 0.0);
+                    tw.push_back(m < 16 ? std::sin(ang) : 0.0);
+                }
+            continue;
+        }
         for (int m = 0; m < 16; ++m)
             for (int k = 0; k < Ns; ++k) {
                 const double ang = -two_pi * (double)(k * m) / (double)(16 * Ns);
                 tw.push_back(std::cos(ang));
                 tw.push_back(std::sin(ang));
             }
+    }
     if (r > 1)
         for (int m = 0; m < r; ++m)
             for (int j = 0; j < N / r; ++j) {
