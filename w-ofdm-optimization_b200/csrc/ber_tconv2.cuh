@@ -57,7 +57,13 @@ constexpr int TCV2_BAR_STREAM = 14;      // named barrier: "the split stream of 
 // kernel with ~60 bytes of them (measured: 2.06e8 -> 2.12e8 OFDM symbols/s all the same).  N = 1024 (clusters) spills
 // 200 bytes under that cap (8.6e7 -> 6.8e7), so there four of the working warps, rotating from frame to frame, issue a
 // quarter of the frame's MMAs each before they draw their noise.
-__host__ __device__ constexpr int tconv2_mma_warp_threads(int N, int NT) { return (N <= 512 && NT <= 512) ? 32 : 0; }
+#ifndef TCV2_MMAW_MAXN
+#define TCV2_MMAW_MAXN 512
+#endif
+__host__ __device__ constexpr int tconv2_mma_warp_threads(int N, int NT) { return (N <= TCV2_MMAW_MAXN && NT <= 512) ? 32 : 0; }
+// (Registers: ptxas derives 96 per thread from __launch_bounds__(288, 2) and that is what the hardware grants -- the register
+//  file is allocated to an even number of warps per CTA: a build forced to 112 registers ran one CTA per SM, 7.9 ms instead
+//  of 6.0, and the 544-thread kernel at 117 failed to launch.)
 constexpr int TCV2_NISSUE = 4;
 __host__ __device__ constexpr int tconv2_wtx_len(int stride, int tail_tx) { return (stride + tail_tx + 3) & ~3; }
 __host__ __device__ constexpr int tconv2_wrx_len(int N, int tail_rx) { return (N + tail_rx + 3) & ~3; }
