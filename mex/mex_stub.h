@@ -15,6 +15,8 @@ size_t mxGetM(const mxArray*);
 size_t mxGetN(const mxArray*);
 size_t mxGetNumberOfElements(const mxArray*);
 bool mxIsChar(const mxArray*);
+bool mxIsCell(const mxArray*);
+mxArray* mxGetCell(const mxArray*, size_t);
 bool mxIsComplex(const mxArray*);
 int mxGetString(const mxArray*, char*, mwSize);
 mxArray* mxCreateDoubleMatrix(mwSize, mwSize, mxComplexity);
