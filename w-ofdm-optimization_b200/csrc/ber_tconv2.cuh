@@ -518,8 +518,10 @@ ber_tconv2_kernel(const BerParams prm) {
         TCV2_STAMP(4);
         // ---- noise, in receiver layout and in registers (ber_kernel.cuh: noise_draw48): the 16 samples this thread's FFT
         //      rows gather, and its extras; |n|^2 partial
-        C2 nz[16], nx[N48_MAXLEV];
-        C2 pr2 = mk2<T>(0, 0), pn2 = mk2<T>(0, 0);
+        // (only the extras of levels 0 and 1 can be overlap-add samples the receiver gathers, tail_rx / 2 <= TPF; the others
+        //  count in the noise power and are dropped)
+        C2 nz[16], nx[2];
+        C2 pr2 = mk2<T>(0, 0), pn2 = mk2<T>(0, 0), pnx = mk2<T>(0, 0);
         {
             const bool act = slot < S;
             const int se = act ? TCV2_SLOT_SYMBOL(slot, S) : S - 1;
@@ -534,7 +536,8 @@ ber_tconv2_kernel(const BerParams prm) {
 #pragma unroll
                 for (int lev = 0; lev < N48_MAXLEV; ++lev) {
                     const int x = xt + lev * TPF;
-                    nx[lev] = x < xas ? to_v2<T>(nin[n48_extra_offset(prm, ng, x)]) : mk2<T>(0, 0);
+                    const C2 e = x < xas ? to_v2<T>(nin[n48_extra_offset(prm, ng, x)]) : mk2<T>(0, 0);
+                    if (lev < 2) nx[lev] = e; else pnx = csq_acc(e, pnx);
                 }
             } else {
                 const uint32_t q0 = (uint32_t)(sg * TPF + t) * 9u;
@@ -547,29 +550,33 @@ ber_tconv2_kernel(const BerParams prm) {
                     gauss_quad48(cb.x, cb.y, cc.z, nz[8 * gq + 4], nz[8 * gq + 5]);
                     gauss_quad48(cb.z, cb.w, cc.w, nz[8 * gq + 6], nz[8 * gq + 7]);
                 }
-#pragma unroll
-                for (int lev = 0; lev < N48_MAXLEV; ++lev) nx[lev] = mk2<T>(0, 0);
+                nx[0] = nx[1] = mk2<T>(0, 0);
                 if (nlev > 0) {                                          // uniform per transform group
                     const uint4 c6 = noise48_call(prm, f, q0 + 6, var);
                     gauss_quad48(c6.y, c6.z, c6.x, nx[0], nx[1]);
+                    if (xt >= xas) nx[0] = mk2<T>(0, 0);
+                    if (xt + TPF >= xas) nx[1] = mk2<T>(0, 0);
                     if (nlev > 2) {
                         const uint4 c7 = noise48_call(prm, f, q0 + 7, var);
-                        gauss_quad48(c7.x, c7.y, c6.w, nx[2], nx[3]);
+                        C2 e2, e3;
+                        gauss_quad48(c7.x, c7.y, c6.w, e2, e3);
+                        if (xt + 2 * TPF < xas) pnx = csq_acc(e2, pnx);
+                        if (xt + 3 * TPF < xas) pnx = csq_acc(e3, pnx);
                         if (nlev > 4) {
                             const uint4 c8 = noise48_call(prm, f, q0 + 8, var);
-                            gauss_quad48(c7.w, c8.x, c7.z, nx[4], nx[5]);
+                            gauss_quad48(c7.w, c8.x, c7.z, e2, e3);
+                            if (xt + 4 * TPF < xas) pnx = csq_acc(e2, pnx);
+                            if (xt + 5 * TPF < xas) pnx = csq_acc(e3, pnx);
                         }
                     }
-#pragma unroll
-                    for (int lev = 0; lev < N48_MAXLEV; ++lev)
-                        if (xt + lev * TPF >= xas) nx[lev] = mk2<T>(0, 0);
                 }
             }
             if (act) {
 #pragma unroll
                 for (int q = 0; q < 16; ++q) pn2 = csq_acc(nz[q], pn2);
-#pragma unroll
-                for (int lev = 0; lev < N48_MAXLEV; ++lev) pn2 = csq_acc(nx[lev], pn2);
+                pn2 = csq_acc(nx[0], pn2);
+                pn2 = csq_acc(nx[1], pn2);
+                pn2 = cadd(pn2, pnx);
             }
         }
         TCV2_STAMP(5);
