@@ -47,6 +47,9 @@ namespace wofdm {
 #else
 #define TCV2_STAMP(k) do { } while (0)
 #endif
+#ifndef TCV2_GT
+#define TCV2_GT 3
+#endif
 #ifndef TCV2_DEBUG_BARRIERS
 #define TCV2_DEBUG_BARRIERS 0          // 1 (libwofdm_dbg.so): every relaxed synchronisation of the kernel replaced by a full barrier --
 #endif                                 // the reference the race test compares the production build with (compute-sanitizer is closed here)
@@ -586,7 +589,7 @@ ber_tconv2_kernel(const BerParams prm) {
         phase ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if constexpr (CL > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-        constexpr int GT = 3;                      // tiles per batch of accumulator loads (one wait per batch)
+        constexpr int GT = TCV2_GT;                // tiles per batch of accumulator loads (one wait per batch)
         float4* const rst = reinterpret_cast<float4*>(rb) + wg * RCH + row;
 #pragma unroll
         for (int t0 = 0; t0 < NTH; t0 += GT) {
