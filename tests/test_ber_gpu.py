@@ -633,6 +633,40 @@ def test_guard_band(handle, name, N, cp, ttx, trx, bits, guard, precision):
         handle.ber_run(W.params_from_name(name, N, cp, ttx, trx, bits=8, guard=guard), vt, vr, h, [18.0], 1)
 
 
+@pytest.mark.parametrize("name,N,cp,nn", [("WOLA", 256, 16, 0), ("CPW", 256, 32, 1), ("WOLA", 1024, 64, 1), ("CP", 1024, 128, 0)])
+def test_long_channel_on_the_tensor_core_kernel(handle, name, N, cp, nn):
+    """BASELINE configs[4]: "L = 21 (optionally 84)".  Channels of up to 84 taps stay on the tensor-core kernel (84 samples of
+    convolution history in the Hankel operand, 22 MMAs per tile): verify mode against the oracle, production replay."""
+    sc = N // 256
+    ttx, trx = (0, 0) if name == "CP" else (8 * sc, 10 * sc)
+    L = 84
+    p = O.system_params(name, N, cp, ttx, trx, S=16, bits=4 if N == 256 else 6, noise_norm=nn, constellation=nn)
+    vt, vr, _, _ = O.perturbed_windows(p, seed=N + cp)
+    rng = np.random.default_rng(L + N)
+    frames = []
+    for k in range(2):
+        h = O.synth_channels(1, L, seed=60 + k)[:, 0]
+        n = O.noise_len(p, L)
+        frames.append((h, 12.0 + 15 * k, rng.integers(0, 1 << p.bits, size=(N, 16)), rng.standard_normal(n) + 1j * rng.standard_normal(n)))
+    check_frames(handle, p, vt, vr, frames, 0)
+    s = to_sys(p, 0)
+    chans = O.synth_channels(2, L, seed=70)
+    snr = np.array([10.0, 26.0])
+    plan = handle.ber_plan(s, vt, vr, chans, snr)
+    assert "f32t2" in plan.kernel and "_l84" in plan.kernel, plan.kernel
+    plan.close()
+    ens = 2
+    res = handle.ber_run(s, vt, vr, chans, snr, ens, seed=31)
+    F = len(snr) * 2 * ens
+    sym, nz = handle.ber_draws(s, L, 31, 0, np.arange(F))
+    want, slack = np.zeros(2, dtype=np.int64), np.zeros(2, dtype=np.int64)
+    for f in range(F):
+        r = O.frame_chain_structured(p, vt, vr, chans[:, (f // ens) % 2], snr[f // (ens * 2)], sym[f].T, nz[f])
+        want[f // (ens * 2)] += r.sym_err
+        slack[f // (ens * 2)] += flip_budget(p, [r.eq])
+    assert np.all(np.abs(res["sym_err"] - want) <= slack), (res["sym_err"], want, slack)
+
+
 @pytest.mark.parametrize("which", ["n256", "multi", "n512", "n1024"])
 def test_relaxed_barriers_against_debug_build(which):
     """The tensor-core kernel drops the barrier at the end of a frame, lets only the MMA-issuing warps wait for the stream

@@ -99,14 +99,17 @@ int choose_variant(wofdm_ctx* h, const wofdm_sys_t& s, int L, bool verify, bool 
                 if (v.gen != tconv_gen) continue;
                 if (v.CL > 1 && want_txs) continue;                  // (the masked Tx stream is a one-CTA-per-frame feature)
                 // second generation: a receiver thread holds at most N48_MAXLEV noise samples besides its 16 FFT rows
-                if (v.gen == 2 && (stride - s.N + (s.noise_norm == 1 ? s.tail_tx + L - 1 : 0) + tpf - 1) / tpf > N48_MAXLEV) continue;
+                if (v.gen == 2 && (stride - s.N + (s.noise_norm == 1 ? s.tail_tx + L - 1 : 0) + tpf - 1) / tpf > (v.LB > TCV_LB ? N48_MAXLEV : N48_MAXLEV_SHORT)) continue;
                 if (s.cp > 2 * tpf || s.cs > 2 * tpf || s.tail_tx > 2 * tpf || s.tail_rx / 2 > tpf || s.shift > tpf) continue;
-                const int need = std::max(s.noise_norm == 1 ? body + L - 1 : sec_cta, body + TCV_ZERO);
+                const int need = std::max(s.noise_norm == 1 ? body + L - 1 : sec_cta, body + (v.gen == 2 ? tconv2_zero(v.LB) : TCV_ZERO));
                 if (need > 512 * v.ntile || sec_cta <= 512 * (v.ntile - 2)) continue;   // (the kernel range-checks its last two tiles only)
                 if (nvar > 1 && v.gen != 2) continue;                // (several window pairs per launch: ber_tconv2.cuh only)
                 const BerSmem lay = v.layout(S_cta, stride, s.tail_tx, s.tail_rx, L, v.gen == 2 ? nvar : 0, 0);
                 if (lay.bytes > smem_cap) continue;
-                if (!best.var || best.var->ntile == 0 || v.ntile < best.var->ntile) { best.var = &v; best.lay = lay; best.chunk = 0; }
+                // fewest taps of history first (MMAs per tile), then fewest tiles
+                if (!best.var || best.var->ntile == 0 || v.LB < best.var->LB || (v.LB == best.var->LB && v.ntile < best.var->ntile)) {
+                    best.var = &v; best.lay = lay; best.chunk = 0;
+                }
                 continue;
             }
             if (best.var && best.var->ntile > 0) continue;

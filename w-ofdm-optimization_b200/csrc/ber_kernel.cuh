@@ -189,10 +189,12 @@ __device__ __forceinline__ void noise_pair(const BerParams& prm, long long f, ui
 //   x >= XA           last symbol, noise_norm = 1: the tail_tx + L - 1 samples behind the frame (full-convolution sums)
 // base = (N - hh - shift) mod TPF puts every overlap-add sample into the thread that needs it.
 // 48 random bits per complex sample: a 32-bit radius word and a 16-bit angle (65 536 phases).  Philox calls of (s, t):
-// counter index ((s TPF + t) 9 + c); c = 3 g + {0, 1, 2} serve the main samples q = 8 g + e: radius = word e of (call 3g,
-// call 3g+1), angle = half e & 1 of word e >> 1 of call 3g+2; c = 6, 7, 8 give the words V[0..9) of the extras: levels
-// 2 j, 2 j + 1 take their angles from the halves of V[3 j] and their radii from V[3 j + 1], V[3 j + 2].
-constexpr int N48_MAXLEV = 6;
+// counter index ((s TPF + t) N48_CALLS + c); c = 3 g + {0, 1, 2} serve the main samples q = 8 g + e: radius = word e of
+// (call 3g, call 3g+1), angle = half e & 1 of word e >> 1 of call 3g+2; c = 6, 7, ... give the words V[0..) of the extras:
+// levels 2 j, 2 j + 1 take their angles from the halves of V[3 j] and their radii from V[3 j + 1], V[3 j + 2].
+constexpr int N48_MAXLEV = 16;                                   // extra levels a symbol may have (pairs of two)
+constexpr int N48_MAXLEV_SHORT = 6;                             // ... in the kernels for L <= 21 (inline draws)
+constexpr int N48_CALLS = 6 + (3 * (N48_MAXLEV / 2) + 3) / 4;     // Philox calls reserved per (symbol, thread): 12
 // (var: window pair of a multi-variant launch; its noise stream is that of a single launch with variant + var)
 __device__ __forceinline__ uint4 noise48_call(const BerParams& prm, long long f, uint32_t q, int var = 0) {
     return philox4x32_10_rk(make_uint4((uint32_t)f, (uint32_t)((unsigned long long)f >> 32), q, STREAM_NOISE + prm.variant + (uint32_t)var), prm.rk);
@@ -250,7 +252,7 @@ __device__ __forceinline__ float2 noise_draw48(const BerParams& prm, long long f
         const int ia = 3 * j, ir = 3 * j + 1 + (lev & 1);
         cr = 6 + (ir >> 2); wr = ir & 3; ca = 6 + (ia >> 2); wa = ia & 3; half = lev & 1;
     }
-    const uint32_t q0 = (uint32_t)(s * g.tpf + t) * 9u;
+    const uint32_t q0 = (uint32_t)(s * g.tpf + t) * (uint32_t)N48_CALLS;
     const uint32_t uw = u4_word(noise48_call(prm, f, q0 + (uint32_t)cr), wr), aw = u4_word(noise48_call(prm, f, q0 + (uint32_t)ca), wa);
     float2 n0, n1;
     gauss_quad48(uw, uw, aw, n0, n1);

@@ -22,7 +22,7 @@
 //     draw their noise.  MMA descriptors advance by one addition.
 //
 // fp32; N = 256: one CTA of 256 threads per frame, two CTAs per SM (256 of the 512 tensor-memory columns each);
-// N = 512: one CTA of 512 threads per frame and SM.  S <= 16 symbols in one Tx pass, L <= TCV_LB, prefix / suffix /
+// N = 512: one CTA of 512 threads per frame and SM.  S <= 16 symbols in one Tx pass, L <= LB (21 or 84), prefix / suffix /
 // tails within the outer register rows (ber_host.cu:choose_variant checks).
 #pragma once
 #include <cuda_fp16.h>
@@ -68,16 +68,40 @@ __host__ __device__ constexpr int tconv2_mma_warp_threads(int N, int NT) { retur
 //  file is allocated to an even number of warps per CTA: a build forced to 112 registers ran one CTA per SM, 7.9 ms instead
 //  of 6.0, and the 544-thread kernel at 117 failed to launch.)
 constexpr int TCV2_NISSUE = 4;
+// Taps: the Hankel operand's row r holds the samples 4r - PAD .. 4r + 3, PAD = LB - 1 rounded up to 4 (r stays 16-byte
+// aligned behind the pad): (PAD + 4) / 8 K steps of 16 halves, two MMAs (hi, lo stream half) each.  LB = 21: PAD 20, 3 K
+// steps, 6 MMAs per tile of 512 samples; LB = 84 (configs[4] "optionally 84 taps"): PAD 84, 11 K steps, 22 MMAs.
+__host__ __device__ constexpr int tconv2_pad(int LB) { return (LB - 1 + 3) & ~3; }
+__host__ __device__ constexpr int tconv2_ksteps(int LB) { return (tconv2_pad(LB) + 4) / 8; }
+__host__ __device__ constexpr int tconv2_tbl(int LB) { return (tconv2_pad(LB) + 4) / 4 * 128; }   // bytes of one taps table (8 columns x K halves)
+__host__ __device__ constexpr int tconv2_zero(int LB) { return (LB - 1 + 3 + 4) & ~3; }             // zero samples written behind the stream
+// |n|^2 of a thread's extras of level 2 and above (words V[3j .. 3j+2] of pair j >= 1, ber_kernel.cuh: noise_draw48): they
+// only count in the noise power.  Kept out of line: the common shapes have at most two levels and the kernel is register bound.
+__device__ __forceinline__ float2 n48_more_extras(const BerParams& prm, long long f, uint32_t q0, int var, int nlev, int xt, int tpf, int xas) {
+    float2 pnx = make_float2(0.f, 0.f);
+#pragma unroll 1
+    for (int jp = 1; 2 * jp < nlev; ++jp) {
+        const int w0 = 3 * jp;
+        const uint4 ca = noise48_call(prm, f, q0 + 6 + (uint32_t)(w0 >> 2), var);
+        const uint4 cb = noise48_call(prm, f, q0 + 6 + (uint32_t)((w0 + 2) >> 2), var);
+        const uint32_t aw = u4_word(ca, w0 & 3), u0 = u4_word((w0 + 1) >> 2 == w0 >> 2 ? ca : cb, (w0 + 1) & 3), u1 = u4_word(cb, (w0 + 2) & 3);
+        float2 e2, e3;
+        gauss_quad48(u0, u1, aw, e2, e3);
+        if (xt + 2 * jp * tpf < xas) pnx = csq_acc(e2, pnx);
+        if (xt + (2 * jp + 1) * tpf < xas) pnx = csq_acc(e3, pnx);
+    }
+    return pnx;
+}
 __host__ __device__ constexpr int tconv2_wtx_len(int stride, int tail_tx) { return (stride + tail_tx + 3) & ~3; }
 __host__ __device__ constexpr int tconv2_wrx_len(int N, int tail_rx) { return (N + tail_rx + 3) & ~3; }
 
-template <int N, int NT, int NTILE>
+template <int N, int NT, int NTILE, int LB = TCV_LB>
 __host__ __device__ inline BerSmem tconv2_smem_layout(int S, int stride, int tail_tx, int tail_rx, int L, int nvar, int use_global) {
     using P = FftPlan<N>;
     constexpr int FPP = NT / P::TPF;
     BerSmem m;
-    m.pad = TCV_PAD;
-    m.flen = tconv_alen(NTILE);
+    m.pad = tconv2_pad(LB);
+    m.flen = tconv2_pad(LB) + NTILE * 512;
     m.xlen = FPP * P::XLEN;
     int o = 0;
     o += m.flen * 4;                 m.off_lo = o;        // ahi
@@ -87,7 +111,7 @@ __host__ __device__ inline BerSmem tconv2_smem_layout(int S, int stride, int tai
     o += m.xlen * 8;                 m.off_tw = o;
     o += P::NTW * 8;                 m.off_geq = o;
     o += N * 8;                      m.off_bt = o;
-    o += 3 * 768;                    m.off_wtx = o;       // [T_hi | T_lo | zeros], 8 rows x 48 halves each
+    o += 3 * tconv2_tbl(LB);         m.off_wtx = o;       // [T_hi | T_lo | zeros], 8 columns x K halves each
     const int nv = nvar > 1 ? nvar : 1;                   // window pairs evaluated per frame (BerParams::nvar)
     o += nv * tconv2_wtx_len(stride, tail_tx) * 4;   m.off_wrx = o;
     o += nv * tconv2_wrx_len(N, tail_rx) * 4;        m.off_red = o;
@@ -107,7 +131,7 @@ __host__ __device__ inline BerSmem tconv2_smem_layout(int S, int stride, int tai
 // three times per frame through distributed shared memory: the second CTA takes the first one's last Tx tail and the
 // L - 1 samples of convolution history (PULLED, a few dozen words), the per-warp power partials and the pilot's equaliser
 // taps are PUSHED into both CTAs, so every read is local.
-template <int N, int NT, int NTILE, int MINB, bool VERIFY, int CL = 1>
+template <int N, int NT, int NTILE, int MINB, bool VERIFY, int CL = 1, int LB = TCV_LB>
 __global__ void __launch_bounds__(NT + tconv2_mma_warp_threads(N, NT), MINB)
 ber_tconv2_kernel(const BerParams prm) {
     using T = float;
@@ -137,13 +161,14 @@ ber_tconv2_kernel(const BerParams prm) {
     const int npow = (prm.noise_norm == 1 && last_rank) ? body + L - 1 : sec;   // samples inside the frame-wide power sums
 
     const int nvar = (!VERIFY && prm.nvar > 1) ? prm.nvar : 1;     // window pairs evaluated on every frame's symbols
-    const BerSmem lay = tconv2_smem_layout<N, NT, NTILE>(S, stride, beta, prm.tail_rx, L, nvar, 0);
+    constexpr int PAD = tconv2_pad(LB), KS = tconv2_ksteps(LB), TBL = tconv2_tbl(LB), ZERO = tconv2_zero(LB);
+    const BerSmem lay = tconv2_smem_layout<N, NT, NTILE, LB>(S, stride, beta, prm.tail_rx, L, nvar, 0);
     uint32_t* const ahi = reinterpret_cast<uint32_t*>(smem_raw);
     uint32_t* const alo = reinterpret_cast<uint32_t*>(smem_raw + lay.off_lo);
-    uint32_t* const uh = ahi + TCV_PAD;         // uh[i], ul[i]: split stream sample i
-    uint32_t* const ul = alo + TCV_PAD;
-    C2* const rb = reinterpret_cast<C2*>(smem_raw + TCV_PAD * 4);   // channel output r[i], over the dead split stream (keeps ahi's zero pad)
-    static_assert((TCV_PAD * 4) % 16 == 0, "r is stored in 16-byte pairs");
+    uint32_t* const uh = ahi + PAD;         // uh[i], ul[i]: split stream sample i
+    uint32_t* const ul = alo + PAD;
+    C2* const rb = reinterpret_cast<C2*>(smem_raw + PAD * 4);   // channel output r[i], over the dead split stream (keeps ahi's zero pad)
+    static_assert((PAD * 4) % 16 == 0, "r is stored in 16-byte pairs");
     C2* const xbuf = reinterpret_cast<C2*>(smem_raw + lay.off_x);  // FFT exchange, one region per transform group
     C2* tw = reinterpret_cast<C2*>(smem_raw + lay.off_tw);
     C2* geq = reinterpret_cast<C2*>(smem_raw + lay.off_geq);
@@ -191,8 +216,8 @@ ber_tconv2_kernel(const BerParams prm) {
             qtx[i] = ft ? cscale(wflat * TCV_XSCALE, q) : q;
         }
     };
-    for (int i = tid; i < TCV_PAD; i += NT) ahi[i] = 0u;
-    for (int i = tid; i < 768 / 4; i += NT) reinterpret_cast<uint32_t*>(bt + 1536)[i] = 0u;
+    for (int i = tid; i < PAD; i += NT) ahi[i] = 0u;
+    for (int i = tid; i < TBL / 4; i += NT) reinterpret_cast<uint32_t*>(bt + 2 * TBL)[i] = 0u;
     for (int i = tid; i < (1 << prm.bits); i += NT) qlut[i] = mk2<T>((T)(2 * (i >> hb) - (m - 1)), (T)(2 * (i & (m - 1)) - (m - 1)));
     build_qtx(0);
     if (tid == 0 && prm.bits < 8) { qlut[255] = mk2<T>(0, 0); qtx[255] = mk2<T>(0, 0); }
@@ -223,7 +248,7 @@ ber_tconv2_kernel(const BerParams prm) {
     constexpr int NTB = NT + tconv2_mma_warp_threads(N, NT);        // threads that meet at the "stream complete" barrier
     // MMA descriptors of tile 0, K step 0 (tile: +2048 B = +128 in the address field, K step: +32 B = +2; B operand: +256 B = +16)
     const uint64_t d_ahi = tcv_desc(tcv_smem_u32(ahi), 16, 128), d_alo = tcv_desc(tcv_smem_u32(alo), 16, 128);
-    const uint64_t d_bhl = tcv_desc(tcv_smem_u32(bt), 128, 768), d_bh0 = tcv_desc(tcv_smem_u32(bt), 128, 1536);
+    const uint64_t d_bhl = tcv_desc(tcv_smem_u32(bt), 128, TBL), d_bh0 = tcv_desc(tcv_smem_u32(bt), 128, 2 * TBL);
     // channel output r, parked over the dead split stream in two halves: R[wg] holds outputs 2 wg, 2 wg + 1 of every operand
     // row as one 16-byte chunk per row -- consecutive lanes store consecutive chunks (no bank conflicts) and a receiver
     // thread's samples i = i0 + q TPF all have the same i mod 4, i.e. the same half and chunk slot: base + immediate
@@ -272,7 +297,7 @@ ber_tconv2_kernel(const BerParams prm) {
                     for (int ti = 0; ti < NTILE; ++ti) {
                         const uint32_t tacc = tmem + (uint32_t)(16 * ti);
 #pragma unroll
-                        for (int k = 0; k < 3; ++k) {
+                        for (int k = 0; k < KS; ++k) {
                             tcv_mma(tacc, d_ahi + (uint64_t)(ti * 128 + k * 2), d_bhl + (uint64_t)(k * 16), k != 0);
                             tcv_mma(tacc, d_alo + (uint64_t)(ti * 128 + k * 2), d_bh0 + (uint64_t)(k * 16), 1u);
                         }
@@ -325,10 +350,9 @@ ber_tconv2_kernel(const BerParams prm) {
         const T* const wtx = wtx_all + var * WTXL;
         const T* const wrx = wrx_all + var * WRXL;
         // ---- taps operand of this frame: n = 2o + comp (o < 4), K pair jj = sample offset in the row, tap l = LB-1 + o - jj
-        if (tid < 8 * 24) {
-          if (var == 0) {
-            const int n = tid / 24, jj = tid % 24;
-            const int o = n >> 1, l = TCV_LB - 1 + o - jj;
+        auto build_tap = [&](int e) {
+            const int n = e / (PAD + 4), jj = e % (PAD + 4);
+            const int o = n >> 1, l = PAD + o - jj;
             C2 tpv = mk2<T>(0, 0);
             if (l >= 0 && l < L) tpv = reinterpret_cast<const C2*>(prm.chan)[(size_t)ci * L + l];
             tpv = cscale(TCV_HSCALE, tpv);
@@ -337,13 +361,25 @@ ber_tconv2_kernel(const BerParams prm) {
             split_h2(v, hi, lo);
             const int off = (jj >> 2) * 128 + n * 16 + (jj & 3) * 4;
             *reinterpret_cast<uint32_t*>(bt + off) = hi;
-            *reinterpret_cast<uint32_t*>(bt + 768 + off) = lo;
-          }
-        } else if (tid < 8 * 24 + TCV_PAD) {
-            alo[tid - 8 * 24] = 0u;                                              // (r of the previous frame lay over it)
-        } else if (tid - (8 * 24 + TCV_PAD) < TCV_ZERO) {
-            const int i = body + tid - (8 * 24 + TCV_PAD);                       // the linear convolution sees zeros behind the stream
-            uh[i] = 0u; ul[i] = 0u;
+            *reinterpret_cast<uint32_t*>(bt + TBL + off) = lo;
+        };
+        constexpr int NTAP = 8 * (PAD + 4);
+        if constexpr (NTAP + PAD + ZERO <= NT) {                             // (LB = 21) one element per thread
+            if (tid < NTAP) {
+                if (var == 0) build_tap(tid);
+            } else if (tid < NTAP + PAD) {
+                alo[tid - NTAP] = 0u;                                        // (r of the previous frame lay over it)
+            } else if (tid - (NTAP + PAD) < ZERO) {
+                const int i = body + tid - (NTAP + PAD);                     // the linear convolution sees zeros behind the stream
+                uh[i] = 0u; ul[i] = 0u;
+            }
+        } else {
+            if (var == 0)
+                for (int e = tid; e < NTAP; e += NT) build_tap(e);
+            for (int e = NT - 1 - tid; e < PAD + ZERO; e += NT) {           // (the last threads: the first ones build the taps)
+                if (e < PAD) alo[e] = 0u;
+                else { const int i = body + e - PAD; uh[i] = 0u; ul[i] = 0u; }
+            }
         }
 
         // =========================== transmitter ===========================
@@ -479,8 +515,8 @@ ber_tconv2_kernel(const BerParams prm) {
             }
         }
         if constexpr (CL > 1) {
-            // convolution history: the last TCV_PAD stream samples of the previous CTA (none of them is a head)
-            if (rank > 0 && tid < TCV_PAD) { ahi[tid] = prev_uh[sec - TCV_PAD + tid]; alo[tid] = prev_ul[sec - TCV_PAD + tid]; }
+            // convolution history: the last PAD stream samples of the previous CTA (none of them is a head)
+            if (rank > 0 && tid < PAD) { ahi[tid] = prev_uh[sec - PAD + tid]; alo[tid] = prev_ul[sec - PAD + tid]; }
             // "I have taken what I need from my neighbour's stream": awaited before anybody parks r over a stream
             asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
         }
@@ -507,7 +543,7 @@ ber_tconv2_kernel(const BerParams prm) {
                     if (ti % TCV2_NISSUE != irank) continue;              // the issuing warps share the tiles round-robin
                     const uint32_t tacc = tmem + (uint32_t)(16 * ti);
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) {
+                    for (int k = 0; k < KS; ++k) {
                         tcv_mma(tacc, d_ahi + (uint64_t)(ti * 128 + k * 2), d_bhl + (uint64_t)(k * 16), k != 0);
                         tcv_mma(tacc, d_alo + (uint64_t)(ti * 128 + k * 2), d_bh0 + (uint64_t)(k * 16), 1u);
                     }
@@ -543,7 +579,7 @@ ber_tconv2_kernel(const BerParams prm) {
                     if (lev < 2) nx[lev] = e; else pnx = csq_acc(e, pnx);
                 }
             } else {
-                const uint32_t q0 = (uint32_t)(sg * TPF + t) * 9u;
+                const uint32_t q0 = (uint32_t)(sg * TPF + t) * (uint32_t)N48_CALLS;
 #pragma unroll
                 for (int gq = 0; gq < 2; ++gq) {
                     const uint4 ca = noise48_call(prm, f, q0 + 3 * gq, var), cb = noise48_call(prm, f, q0 + 3 * gq + 1, var);
@@ -559,7 +595,10 @@ ber_tconv2_kernel(const BerParams prm) {
                     gauss_quad48(c6.y, c6.z, c6.x, nx[0], nx[1]);
                     if (xt >= xas) nx[0] = mk2<T>(0, 0);
                     if (xt + TPF >= xas) nx[1] = mk2<T>(0, 0);
-                    if (nlev > 2) {
+                    // further level pairs (long prefixes; the last symbol under MATLAB's full-convolution sums): rare, out of line
+                    if constexpr (LB > TCV_LB) {
+                        if (nlev > 2) pnx = n48_more_extras(prm, f, q0, var, nlev, xt, TPF, xas);
+                    } else if (nlev > 2) {                               // (at most N48_MAXLEV_SHORT = 6 levels: ber_host.cu)
                         const uint4 c7 = noise48_call(prm, f, q0 + 7, var);
                         C2 e2, e3;
                         gauss_quad48(c7.x, c7.y, c6.w, e2, e3);
