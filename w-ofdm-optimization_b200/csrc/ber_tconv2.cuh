@@ -63,7 +63,22 @@ constexpr int TCV2_BAR_STREAM = 14;      // named barrier: "the split stream of 
 #ifndef TCV2_MMAW_MAXN
 #define TCV2_MMAW_MAXN 512
 #endif
-__host__ __device__ constexpr int tconv2_mma_warp_threads(int N, int NT) { return (N <= TCV2_MMAW_MAXN && NT <= 512) ? 32 : 0; }
+// Register reallocation (setmaxnreg): the MMA warp is launched inside a whole warp group of four (setmaxnreg is a warp-group
+// instruction: with an incomplete group -- the MMA warp and one idle warp were tried -- the release never completes and the
+// working warps spin in their request); the three other warps are idle register donors.  The group shrinks to 24 registers
+// and the working warps grow from what the launch grants to tconv2_work_regs: NT = 256: 384 threads x 80 at launch ->
+// 256 x 104 + 128 x 24 (5.91 -> 5.83 ms per 202 500 frames).  The donors walk through the MMA warp's barrier
+// sequence and issue nothing.
+#ifndef TCV2_SETMAXNREG
+#define TCV2_SETMAXNREG 1
+#endif
+// (NT = 512: measured slower, 4.64 ms against 4.51 per 60 000 frames -- 20 warps of 112 registers against 17 of 96 with ~60
+//  bytes of spills; it keeps the lone MMA warp)
+__host__ __device__ constexpr bool tconv2_setmaxnreg(int NT) { return TCV2_SETMAXNREG && NT == 256; }
+__host__ __device__ constexpr int tconv2_mma_warp_threads(int N, int NT) {
+    return (N <= TCV2_MMAW_MAXN && NT <= 512) ? (tconv2_setmaxnreg(NT) ? 128 : 32) : 0;
+}
+__host__ __device__ constexpr int tconv2_work_regs(int NT) { return NT == 256 ? 104 : 112; }   // (NT = 512: 640 x 96 -> 512 x 112 + 128 x 24)
 // (Registers: ptxas derives 96 per thread from __launch_bounds__(288, 2) and that is what the hardware grants -- the register
 //  file is allocated to an even number of warps per CTA: a build forced to 112 registers ran one CTA per SM, 7.9 ms instead
 //  of 6.0, and the 544-thread kernel at 117 failed to launch.)
@@ -271,7 +286,8 @@ ber_tconv2_kernel(const BerParams prm) {
     __shared__ long long trace_buf[17 * 12];
     int trace_it = 0;
 #endif
-    if (MMAW && warp == NW) {
+    if (MMAW && warp >= NW) {
+        if constexpr (tconv2_setmaxnreg(NT)) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;" ::: "memory");
         // ===== the MMA warp: the CTA's extra warp issues every tcgen05.mma of the kernel and nothing else =====
         // An issuing thread sits in front of the tensor core's short queue for as long as the convolution takes (~40 cycles per
         // MMA, bound by the operand reads: ~2200 cycles per frame at N = 256).  Measured with the issue spread over four of
@@ -292,7 +308,7 @@ ber_tconv2_kernel(const BerParams prm) {
                 else asm volatile("bar.sync %0, %1;" :: "n"(TCV2_BAR_STREAM), "n"(NTB) : "memory");   // the split stream is complete
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 TCV2_STAMP(2);
-                if (tcv_elect_one()) {
+                if (warp_u == NW && tcv_elect_one()) {
 #pragma unroll
                     for (int ti = 0; ti < NTILE; ++ti) {
                         const uint32_t tacc = tmem + (uint32_t)(16 * ti);
@@ -325,6 +341,7 @@ ber_tconv2_kernel(const BerParams prm) {
         frame_sync<CL>();
         return;
     }
+    if constexpr (MMAW && tconv2_setmaxnreg(NT)) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(tconv2_work_regs(NT)) : "memory");
     long long f = prm.frame_begin + fslot * prm.frame_step;
     const long long df = nslots * prm.frame_step;
     long long fe = 0, de = 0;
