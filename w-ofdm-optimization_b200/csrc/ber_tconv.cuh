@@ -111,6 +111,24 @@ __device__ __forceinline__ void tcv_ld4(uint32_t taddr, float2& a, float2& b) {
     a = make_float2(__uint_as_float(v0), __uint_as_float(v1));
     b = make_float2(__uint_as_float(v2), __uint_as_float(v3));
 }
+// eight / sixteen accumulator columns of this thread's row
+__device__ __forceinline__ void tcv_ld8(uint32_t taddr, float2& a, float2& b, float2& c, float2& d) {
+    uint32_t v[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr) : "memory");
+    a = make_float2(__uint_as_float(v[0]), __uint_as_float(v[1]));
+    b = make_float2(__uint_as_float(v[2]), __uint_as_float(v[3]));
+    c = make_float2(__uint_as_float(v[4]), __uint_as_float(v[5]));
+    d = make_float2(__uint_as_float(v[6]), __uint_as_float(v[7]));
+}
+__device__ __forceinline__ void tcv_ld16(uint32_t taddr, float2 (&c)[8]) {
+    uint32_t v[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]) : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c[i] = make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+}
 __device__ __forceinline__ bool tcv_elect_one() {
     uint32_t pred;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));

@@ -53,6 +53,9 @@ namespace wofdm {
 #ifndef TCV2_DEBUG_BARRIERS
 #define TCV2_DEBUG_BARRIERS 0          // 1 (libwofdm_dbg.so): every relaxed synchronisation of the kernel replaced by a full barrier --
 #endif                                 // the reference the race test compares the production build with (compute-sanitizer is closed here)
+#ifndef TCV2_REBALANCE
+#define TCV2_REBALANCE 1
+#endif
 constexpr int TCV2_BAR_STREAM = 14;      // named barrier: "the split stream of this frame is complete"
 
 // N <= 512: the CTA has one more warp that only issues the MMAs.  The register file then leaves the working threads 96
@@ -74,9 +77,12 @@ constexpr int TCV2_BAR_STREAM = 14;      // named barrier: "the split stream of 
 #endif
 // (NT = 512: measured slower, 4.64 ms against 4.51 per 60 000 frames -- 20 warps of 112 registers against 17 of 96 with ~60
 //  bytes of spills; it keeps the lone MMA warp)
-__host__ __device__ constexpr bool tconv2_setmaxnreg(int NT) { return TCV2_SETMAXNREG && NT == 256; }
+#ifndef TCV2_SETMAXNREG_1024
+#define TCV2_SETMAXNREG_1024 0     // (measured: 104 bytes of spills at 112 registers, 11.85 ms against 11.22)
+#endif
+__host__ __device__ constexpr bool tconv2_setmaxnreg(int N, int NT) { return TCV2_SETMAXNREG && (NT == 256 || (TCV2_SETMAXNREG_1024 && N == 1024)); }
 __host__ __device__ constexpr int tconv2_mma_warp_threads(int N, int NT) {
-    return (N <= TCV2_MMAW_MAXN && NT <= 512) ? (tconv2_setmaxnreg(NT) ? 128 : 32) : 0;
+    return tconv2_setmaxnreg(N, NT) ? 128 : (N <= TCV2_MMAW_MAXN && NT <= 512) ? 32 : 0;
 }
 __host__ __device__ constexpr int tconv2_work_regs(int NT) { return NT == 256 ? 104 : 112; }   // (NT = 512: 640 x 96 -> 512 x 112 + 128 x 24)
 // (Registers: ptxas derives 96 per thread from __launch_bounds__(288, 2) and that is what the hardware grants -- the register
@@ -126,7 +132,7 @@ __host__ __device__ inline BerSmem tconv2_smem_layout(int S, int stride, int tai
     o += m.xlen * 8;                 m.off_tw = o;
     o += P::NTW * 8;                 m.off_geq = o;
     o += N * 8;                      m.off_bt = o;
-    o += 3 * tconv2_tbl(LB);         m.off_wtx = o;       // [T_hi | T_lo | zeros], 8 columns x K halves each
+    o += 4 * tconv2_tbl(LB);         m.off_wtx = o;       // taps blocks [A0 | A1 | B0 | B1] (below), 8 columns x K halves each
     const int nv = nvar > 1 ? nvar : 1;                   // window pairs evaluated per frame (BerParams::nvar)
     o += nv * tconv2_wtx_len(stride, tail_tx) * 4;   m.off_wrx = o;
     o += nv * tconv2_wrx_len(N, tail_rx) * 4;        m.off_red = o;
@@ -232,7 +238,7 @@ ber_tconv2_kernel(const BerParams prm) {
         }
     };
     for (int i = tid; i < PAD; i += NT) ahi[i] = 0u;
-    for (int i = tid; i < TBL / 4; i += NT) reinterpret_cast<uint32_t*>(bt + 2 * TBL)[i] = 0u;
+    for (int i = tid; i < 2 * TBL / 4; i += NT) reinterpret_cast<uint32_t*>(bt + 2 * TBL)[i] = 0u;   // (B0, B1: their rows 4..7 stay zero)
     for (int i = tid; i < (1 << prm.bits); i += NT) qlut[i] = mk2<T>((T)(2 * (i >> hb) - (m - 1)), (T)(2 * (i & (m - 1)) - (m - 1)));
     build_qtx(0);
     if (tid == 0 && prm.bits < 8) { qlut[255] = mk2<T>(0, 0); qtx[255] = mk2<T>(0, 0); }
@@ -257,13 +263,17 @@ ber_tconv2_kernel(const BerParams prm) {
     const int wg = (warp >> 2) & 1, row = (warp & 3) * 32 + lane;
     const int warp_u = __shfl_sync(0xffffffffu, warp, 0);      // the warp index as a value the compiler knows to be warp-uniform
     const int tp = TG == 1 ? 0 : (warp_u >> 3);                // this warp's tile set: tiles tp, tp + TG, ...
-    const uint32_t tlane = tmem + ((uint32_t)((warp_u & 3) * 32) << 16) + (uint32_t)(4 * ((warp_u >> 2) & 1));
+    const uint32_t tlane = tmem + ((uint32_t)((warp_u & 3) * 32) << 16) + (uint32_t)(8 * ((warp_u >> 2) & 1));
     uint32_t phase = 0, issuer = blockIdx.x;
     constexpr bool MMAW = tconv2_mma_warp_threads(N, NT) > 0;       // a dedicated MMA warp (warp NW)
     constexpr int NTB = NT + tconv2_mma_warp_threads(N, NT);        // threads that meet at the "stream complete" barrier
     // MMA descriptors of tile 0, K step 0 (tile: +2048 B = +128 in the address field, K step: +32 B = +2; B operand: +256 B = +16)
     const uint64_t d_ahi = tcv_desc(tcv_smem_u32(ahi), 16, 128), d_alo = tcv_desc(tcv_smem_u32(alo), 16, 128);
-    const uint64_t d_bhl = tcv_desc(tcv_smem_u32(bt), 128, TBL), d_bh0 = tcv_desc(tcv_smem_u32(bt), 128, 2 * TBL);
+    // Taps operand (16 columns = two core matrices of 8 rows, TBL bytes apart): the accumulator columns a thread reads are kept
+    // together -- column 8 g + r (g = output pair, r = 2 (o & 1) + comp) takes hi.T_hi + lo.T_hi and column 8 g + 4 + r the
+    // correction hi.T_lo, so one tcgen05.ld.x8 fetches a thread's two outputs with their corrections.  Blocks A_g (hi
+    // stream: rows 0..3 = T_hi, rows 4..7 = T_lo of pair g) and B_g (lo stream: rows 0..3 = T_hi, rows 4..7 = zeros).
+    const uint64_t d_bhl = tcv_desc(tcv_smem_u32(bt), 128, TBL), d_bh0 = tcv_desc(tcv_smem_u32(bt + 2 * TBL), 128, TBL);
     // channel output r, parked over the dead split stream in two halves: R[wg] holds outputs 2 wg, 2 wg + 1 of every operand
     // row as one 16-byte chunk per row -- consecutive lanes store consecutive chunks (no bank conflicts) and a receiver
     // thread's samples i = i0 + q TPF all have the same i mod 4, i.e. the same half and chunk slot: base + immediate
@@ -287,7 +297,7 @@ ber_tconv2_kernel(const BerParams prm) {
     int trace_it = 0;
 #endif
     if (MMAW && warp >= NW) {
-        if constexpr (tconv2_setmaxnreg(NT)) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;" ::: "memory");
+        if constexpr (tconv2_setmaxnreg(N, NT)) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;" ::: "memory");
         // ===== the MMA warp: the CTA's extra warp issues every tcgen05.mma of the kernel and nothing else =====
         // An issuing thread sits in front of the tensor core's short queue for as long as the convolution takes (~40 cycles per
         // MMA, bound by the operand reads: ~2200 cycles per frame at N = 256).  Measured with the issue spread over four of
@@ -341,7 +351,7 @@ ber_tconv2_kernel(const BerParams prm) {
         frame_sync<CL>();
         return;
     }
-    if constexpr (MMAW && tconv2_setmaxnreg(NT)) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(tconv2_work_regs(NT)) : "memory");
+    if constexpr (MMAW && tconv2_setmaxnreg(N, NT)) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(tconv2_work_regs(NT)) : "memory");
     long long f = prm.frame_begin + fslot * prm.frame_step;
     const long long df = nslots * prm.frame_step;
     long long fe = 0, de = 0;
@@ -376,9 +386,10 @@ ber_tconv2_kernel(const BerParams prm) {
             const C2 v = (n & 1) ? mk2<T>(tpv.y, tpv.x) : mk2<T>(tpv.x, -tpv.y);     // multiplies (Re u, Im u)
             uint32_t hi, lo;
             split_h2(v, hi, lo);
-            const int off = (jj >> 2) * 128 + n * 16 + (jj & 3) * 4;
+            const int off = (n >> 2) * TBL + (jj >> 2) * 128 + (n & 3) * 16 + (jj & 3) * 4;
             *reinterpret_cast<uint32_t*>(bt + off) = hi;
-            *reinterpret_cast<uint32_t*>(bt + TBL + off) = lo;
+            *reinterpret_cast<uint32_t*>(bt + off + 64) = lo;
+            *reinterpret_cast<uint32_t*>(bt + 2 * TBL + off) = hi;
         };
         constexpr int NTAP = 8 * (PAD + 4);
         if constexpr (NTAP + PAD + ZERO <= NT) {                             // (LB = 21) one element per thread
@@ -646,6 +657,46 @@ ber_tconv2_kernel(const BerParams prm) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if constexpr (CL > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
         constexpr int GT = TCV2_GT;                // tiles per batch of accumulator loads (one wait per batch)
+        if constexpr (!MMAW && TCV2_REBALANCE) {
+            // The working warps issue the MMAs (N = 1024): the four issuing warps of this frame reach this point ~2000 cycles
+            // after the others (phase traces: they sat in front of the tensor core's queue), and everybody would wait for
+            // them at the power barrier.  So they skip this pass: the tiles of a tensor-memory lane quarter -- which only the
+            // four warps w = quarter (mod 4) can read -- go to the three warps of the quarter that did not issue (exactly one
+            // did: the issuers are four consecutive warps), all 16 columns of a row in one tcgen05.ld.x16.
+            static_assert(NW == 16, "four warps per tensor-memory lane quarter");
+            if (!is_issuer) {
+                const int wi = ((int)(issuer - 1u) + ((warp_u - (int)(issuer - 1u)) & 3)) & (NW - 1);   // the quarter's issuing warp
+                const int k = warp_u >> 2, ki = wi >> 2;
+                const int r3 = k - (k > ki ? 1 : 0);                               // my rank among the quarter's three others
+                const uint32_t tq = tmem + ((uint32_t)((warp_u & 3) * 32) << 16);
+                float4* const rq = reinterpret_cast<float4*>(rb) + row;
+                constexpr int NPW = (NTILE + 2) / 3;                                // tiles per warp
+                constexpr int GR = 2;                                               // tiles per batch of loads
+#pragma unroll
+                for (int i0 = 0; i0 < NPW; i0 += GR) {
+                    C2 c[GR][8];
+#pragma unroll
+                    for (int u = 0; u < GR; ++u)
+                        if (i0 + u < NPW) tcv_ld16(tq + (uint32_t)(16 * min(3 * (i0 + u) + r3, NTILE - 1)), c[u]);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int u = 0; u < GR; ++u) {
+                        if (i0 + u < NPW) {
+                            const int tt = 3 * (i0 + u) + r3, p = 512 * tt + 4 * row;
+                            if (tt < NTILE) {
+#pragma unroll
+                                for (int wq = 0; wq < 2; ++wq) {
+                                    const C2 r0 = cadd(c[u][4 * wq], c[u][4 * wq + 2]), r1 = cadd(c[u][4 * wq + 1], c[u][4 * wq + 3]);
+                                    if (p + 2 * wq < npow) pr2 = csq_acc(r0, pr2);
+                                    if (p + 2 * wq + 1 < npow) pr2 = csq_acc(r1, pr2);
+                                    if (p + 2 * wq < sec) rq[wq * RCH + 128 * tt] = make_float4(r0.x, r0.y, r1.x, r1.y);   // (a sample past the frame is never gathered)
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        } else {
         float4* const rst = reinterpret_cast<float4*>(rb) + wg * RCH + row;
 #pragma unroll
         for (int t0 = 0; t0 < NTH; t0 += GT) {
@@ -654,8 +705,12 @@ ber_tconv2_kernel(const BerParams prm) {
             for (int u = 0; u < GT; ++u) {
                 if (t0 + u < NTH) {
                     const int tt = min(TG * (t0 + u) + tp, NTILE - 1);      // (a set's tile past the frame: result masked below)
-                    tcv_ld4(tlane + (uint32_t)(16 * tt), a0[u], a1[u]);
-                    tcv_ld4(tlane + (uint32_t)(16 * tt + 8), b0[u], b1[u]);
+                    if constexpr (N == 512) {        // (register bound: an x8 load's eight consecutive registers cost spills there)
+                        tcv_ld4(tlane + (uint32_t)(16 * tt), a0[u], a1[u]);
+                        tcv_ld4(tlane + (uint32_t)(16 * tt + 4), b0[u], b1[u]);
+                    } else {
+                        tcv_ld8(tlane + (uint32_t)(16 * tt), a0[u], a1[u], b0[u], b1[u]);
+                    }
                 }
             }
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -675,6 +730,7 @@ ber_tconv2_kernel(const BerParams prm) {
                     }
                 }
             }
+        }
         }
         T pr = warp_sum(pr2.x + pr2.y), pn = warp_sum(pn2.x + pn2.y);
         if (lane == 0) {
