@@ -56,6 +56,23 @@ namespace wofdm {
 #ifndef TCV2_REBALANCE
 #define TCV2_REBALANCE 1
 #endif
+// The frame's tiles complete in tconv2_nseg(N) segments, one mbarrier each: the accumulator pass starts on the first tiles while
+// the tensor core still works on the last ones.  Segment k is signalled once tile seg_end(k) -- the first tile of the NEXT
+// segment -- is complete too: that tile reads the last PAD samples of its predecessor's stream as convolution history, and
+// r is parked over the stream.
+// Measured (ms per launch, one against three segments): N = 512: 4.55 -> 4.41 (the MMAs outlast the noise draws there);
+// N = 256: 5.79 -> 5.88 (they do not: only the extra waits remain); N = 1024: 10.83 either way.
+#ifndef TCV2_NSEG_512
+#define TCV2_NSEG_512 3
+#endif
+constexpr int TCV2_MAXSEG = 4;
+__host__ __device__ constexpr int tconv2_nseg(int N) { return N == 512 ? TCV2_NSEG_512 : 1; }
+__host__ __device__ constexpr int tconv2_seg_end(int nseg, int ntile, int k) { return (ntile * (k + 1) + nseg - 1) / nseg; }   // tiles < seg_end(k): segments 0..k
+__host__ __device__ constexpr int tconv2_seg_of(int nseg, int ntile, int tt) {
+    int k = 0;
+    while (k < nseg - 1 && tt >= tconv2_seg_end(nseg, ntile, k)) ++k;
+    return k;
+}
 constexpr int TCV2_BAR_STREAM = 14;      // named barrier: "the split stream of this frame is complete"
 
 // N <= 512: the CTA has one more warp that only issues the MMAs.  The register file then leaves the working threads 96
@@ -140,7 +157,7 @@ __host__ __device__ inline BerSmem tconv2_smem_layout(int S, int stride, int tai
     o += 2 * 256 * 8;                         m.off_gmask = o;      // lattice points: Rx (pilot) copy, Tx copy (carries the flat window value)
     o += P::TPF * 32;                         m.off_symw = o;
     o += S * P::TPF * 16;                     m.off_bar = o;
-    o += 16;
+    o += 8 * TCV2_MAXSEG + 8;
     m.off_hf = m.off_taps = m.off_dlut = 0;
     m.bytes = ((size_t)o + 15) & ~(size_t)15;
     (void)L; (void)use_global;
@@ -162,6 +179,8 @@ ber_tconv2_kernel(const BerParams prm) {
     static_assert(NT == 256 || NT == 512, "eight warps read a tile's accumulators");
     constexpr int TG = NT / 256, NTH = (NTILE + TG - 1) / TG;             // tile sets; tiles per thread
     constexpr uint32_t TMEM_COLS = tconv_tmem_cols(NTILE);
+    constexpr int NSEG = tconv2_nseg(N);
+    static_assert(NSEG <= TCV2_MAXSEG, "one mbarrier per segment");
     static_assert(16 * NTILE <= (int)TMEM_COLS, "accumulators of a frame must fit tensor memory");
     static_assert(CL * NW <= 32, "per-warp power partials of all CTAs must fit the reduction scratch");
 
@@ -203,7 +222,7 @@ ber_tconv2_kernel(const BerParams prm) {
     uint4* gmask = reinterpret_cast<uint4*>(smem_raw + lay.off_gmask);
     uint4* symw = reinterpret_cast<uint4*>(smem_raw + lay.off_symw);
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw + lay.off_bar);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + lay.off_bar + 8);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + lay.off_bar + 8 * TCV2_MAXSEG);
     C2* const xb = xbuf + slot * P::XLEN;
 
     // ---- one-time: tensor memory, barrier, tables ----
@@ -212,7 +231,8 @@ ber_tconv2_kernel(const BerParams prm) {
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(tcv_smem_u32(bar)), "r"(tconv2_mma_warp_threads(N, NT) ? 1 : TCV2_NISSUE) : "memory");   // one commit per issuing warp and frame
+        for (int k = 0; k < NSEG; ++k)       // one commit per issuing warp, segment and frame
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(tcv_smem_u32(bar + k)), "r"(tconv2_mma_warp_threads(N, NT) ? 1 : TCV2_NISSUE) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < P::NTW; i += NT) tw[i] = reinterpret_cast<const C2*>(prm.tw)[i];
@@ -327,14 +347,17 @@ ber_tconv2_kernel(const BerParams prm) {
                             tcv_mma(tacc, d_ahi + (uint64_t)(ti * 128 + k * 2), d_bhl + (uint64_t)(k * 16), k != 0);
                             tcv_mma(tacc, d_alo + (uint64_t)(ti * 128 + k * 2), d_bh0 + (uint64_t)(k * 16), 1u);
                         }
+                        // completes when all MMAs issued so far have
+#pragma unroll
+                        for (int sgm = 0; sgm < NSEG; ++sgm)
+                            if (ti == (tconv2_seg_end(NSEG, NTILE, sgm) < NTILE - 1 ? tconv2_seg_end(NSEG, NTILE, sgm) : NTILE - 1))
+                                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(tcv_smem_u32(bar + sgm)) : "memory");
                     }
-                    // completes when all of the frame's MMAs have
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(tcv_smem_u32(bar)) : "memory");
                 }
                 __syncwarp();
                 TCV2_STAMP(3);
 #if TCV2_TRACE
-                if (trace_on) { tcv_mbar_wait(tcv_smem_u32(bar), phase); TCV2_STAMP(4); }
+                if (trace_on) { tcv_mbar_wait(tcv_smem_u32(bar + NSEG - 1), phase); TCV2_STAMP(4); }
                 phase ^= 1u;
 #endif
                 if constexpr (CL > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -568,15 +591,19 @@ ber_tconv2_kernel(const BerParams prm) {
             if (tcv_elect_one()) {
 #pragma unroll
                 for (int ti = 0; ti < NTILE; ++ti) {
-                    if (ti % TCV2_NISSUE != irank) continue;              // the issuing warps share the tiles round-robin
-                    const uint32_t tacc = tmem + (uint32_t)(16 * ti);
+                    if (ti % TCV2_NISSUE == irank) {                      // the issuing warps share the tiles round-robin
+                        const uint32_t tacc = tmem + (uint32_t)(16 * ti);
 #pragma unroll
-                    for (int k = 0; k < KS; ++k) {
-                        tcv_mma(tacc, d_ahi + (uint64_t)(ti * 128 + k * 2), d_bhl + (uint64_t)(k * 16), k != 0);
-                        tcv_mma(tacc, d_alo + (uint64_t)(ti * 128 + k * 2), d_bh0 + (uint64_t)(k * 16), 1u);
+                        for (int k = 0; k < KS; ++k) {
+                            tcv_mma(tacc, d_ahi + (uint64_t)(ti * 128 + k * 2), d_bhl + (uint64_t)(k * 16), k != 0);
+                            tcv_mma(tacc, d_alo + (uint64_t)(ti * 128 + k * 2), d_bh0 + (uint64_t)(k * 16), 1u);
+                        }
                     }
+#pragma unroll
+                    for (int sgm = 0; sgm < NSEG; ++sgm)
+                        if (ti == (tconv2_seg_end(NSEG, NTILE, sgm) < NTILE - 1 ? tconv2_seg_end(NSEG, NTILE, sgm) : NTILE - 1))
+                            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(tcv_smem_u32(bar + sgm)) : "memory");
                 }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(tcv_smem_u32(bar)) : "memory");
             }
             __syncwarp();
         } else if (!TCV2_DEBUG_BARRIERS) {
@@ -651,10 +678,14 @@ ber_tconv2_kernel(const BerParams prm) {
         }
         TCV2_STAMP(5);
         // ---- the channel output, once: frame-wide signal power, r parked over the dead split stream
-        tcv_mbar_wait(tcv_smem_u32(bar), phase);
+        int seg_waited = 0;                        // (compile-time in the unrolled passes below)
+        auto wait_tiles = [&](int tmax) {          // tiles 0..tmax are complete (and nobody reads their stream any more)
+            const int k = tconv2_seg_of(NSEG, NTILE, tmax < NTILE - 1 ? tmax : NTILE - 1);
+            for (; seg_waited <= k; ++seg_waited) tcv_mbar_wait(tcv_smem_u32(bar + seg_waited), phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        };
+        wait_tiles(0);
         TCV2_STAMP(6);
-        phase ^= 1u;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if constexpr (CL > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
         constexpr int GT = TCV2_GT;                // tiles per batch of accumulator loads (one wait per batch)
         if constexpr (!MMAW && TCV2_REBALANCE) {
@@ -675,6 +706,7 @@ ber_tconv2_kernel(const BerParams prm) {
 #pragma unroll
                 for (int i0 = 0; i0 < NPW; i0 += GR) {
                     C2 c[GR][8];
+                    wait_tiles(3 * (i0 + GR - 1) + 2);
 #pragma unroll
                     for (int u = 0; u < GR; ++u)
                         if (i0 + u < NPW) tcv_ld16(tq + (uint32_t)(16 * min(3 * (i0 + u) + r3, NTILE - 1)), c[u]);
@@ -701,6 +733,7 @@ ber_tconv2_kernel(const BerParams prm) {
 #pragma unroll
         for (int t0 = 0; t0 < NTH; t0 += GT) {
             C2 a0[GT], a1[GT], b0[GT], b1[GT];
+            wait_tiles(TG * (t0 + GT - 1) + TG - 1);
 #pragma unroll
             for (int u = 0; u < GT; ++u) {
                 if (t0 + u < NTH) {
@@ -732,6 +765,7 @@ ber_tconv2_kernel(const BerParams prm) {
             }
         }
         }
+        phase ^= 1u;
         T pr = warp_sum(pr2.x + pr2.y), pn = warp_sum(pn2.x + pn2.y);
         if (lane == 0) {
             // warp partials go to slot rank*NW + warp of EVERY CTA of the frame: same order, same gain everywhere
