@@ -53,6 +53,12 @@ namespace wofdm {
 #ifndef TCV2_DEBUG_BARRIERS
 #define TCV2_DEBUG_BARRIERS 0          // 1 (libwofdm_dbg.so): every relaxed synchronisation of the kernel replaced by a full barrier --
 #endif                                 // the reference the race test compares the production build with (compute-sanitizer is closed here)
+// Kernels whose working warps issue the MMAs (N = 1024): 1 = the issue is staggered over all warps -- four groups of four
+// warps issue a quarter of the tiles each, group g after g quarters of its noise draws -- so nobody sits in front of the
+// tensor core's queue for the whole convolution.  Each group has its own "stream complete" named barrier (14 - g).
+#ifndef TCV2_STAGGER
+#define TCV2_STAGGER 0     // (measured: 10.97 ms against 10.84 with the issuers skipping the accumulator pass -- the kernel is throughput bound)
+#endif
 #ifndef TCV2_REBALANCE
 #define TCV2_REBALANCE 1
 #endif
@@ -186,7 +192,8 @@ ber_tconv2_kernel(const BerParams prm) {
 
     extern __shared__ __align__(128) unsigned char tcv_smem[];
     unsigned char* const smem_raw = tcv_smem;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x;    // (tried: an identity shuffle to stop ptxas re-deriving the index from %tid.x -- 12 S2R instead of 22, 6.27 ms against 5.79)
+    const int warp = tid >> 5, lane = tid & 31;
     const int slot = tid / TPF, t = tid % TPF;
     int rank = 0;
     if constexpr (CL > 1) rank = (int)cooperative_groups::this_cluster().block_rank();
@@ -232,7 +239,7 @@ ber_tconv2_kernel(const BerParams prm) {
     }
     if (tid == 0) {
         for (int k = 0; k < NSEG; ++k)       // one commit per issuing warp, segment and frame
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(tcv_smem_u32(bar + k)), "r"(tconv2_mma_warp_threads(N, NT) ? 1 : TCV2_NISSUE) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(tcv_smem_u32(bar + k)), "r"(tconv2_mma_warp_threads(N, NT) ? 1 : (TCV2_STAGGER && !TCV2_DEBUG_BARRIERS) ? NT / 32 : TCV2_NISSUE) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < P::NTW; i += NT) tw[i] = reinterpret_cast<const C2*>(prm.tw)[i];
@@ -401,7 +408,8 @@ ber_tconv2_kernel(const BerParams prm) {
         const T* const wrx = wrx_all + var * WRXL;
         // ---- taps operand of this frame: n = 2o + comp (o < 4), K pair jj = sample offset in the row, tap l = LB-1 + o - jj
         auto build_tap = [&](int e) {
-            const int n = e / (PAD + 4), jj = e % (PAD + 4);
+            // (a warp covers one 16-byte K chunk of all 8 rows: its stores spread over the banks)
+            const int n = (e >> 2) & 7, jj = (e >> 5) * 4 + (e & 3);
             const int o = n >> 1, l = PAD + o - jj;
             C2 tpv = mk2<T>(0, 0);
             if (l >= 0 && l < L) tpv = reinterpret_cast<const C2*>(prm.chan)[(size_t)ci * L + l];
@@ -584,8 +592,46 @@ ber_tconv2_kernel(const BerParams prm) {
         const int irank = (warp_u - (int)issuer) & (NW - 1);          // warp-uniform: issuing warps have irank < TCV2_NISSUE
         const bool is_issuer = !MMAW && irank < TCV2_NISSUE;
         ++issuer;
+        constexpr bool STAG = !MMAW && TCV2_STAGGER && !TCV2_DEBUG_BARRIERS;
+        const int igrp = irank >> 2;                                    // staggered issue: this warp's group
+        auto issue_group = [&](auto gc) {                               // group g's quarter of the tiles, shared round-robin by its four warps
+            constexpr int g = decltype(gc)::value;
+            (void)g;
+            if constexpr (STAG) {
+                if (igrp == g) {
+                    asm volatile("bar.sync %0, %1;" :: "n"(TCV2_BAR_STREAM - g), "n"(NTB) : "memory");
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (tcv_elect_one()) {
+                        constexpr int g0 = NTILE * g / 4, g1 = NTILE * (g + 1) / 4;
+#pragma unroll
+                        for (int ti = g0; ti < g1; ++ti) {
+                            if (((ti - g0) & 3) == (irank & 3)) {
+                                const uint32_t tacc = tmem + (uint32_t)(16 * ti);
+#pragma unroll
+                                for (int k = 0; k < KS; ++k) {
+                                    tcv_mma(tacc, d_ahi + (uint64_t)(ti * 128 + k * 2), d_bhl + (uint64_t)(k * 16), k != 0);
+                                    tcv_mma(tacc, d_alo + (uint64_t)(ti * 128 + k * 2), d_bh0 + (uint64_t)(k * 16), 1u);
+                                }
+                            }
+                        }
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(tcv_smem_u32(bar)) : "memory");
+                    }
+                    __syncwarp();
+                }
+            }
+        };
+        if constexpr (STAG) {
+            static_assert(NW == 16 && NSEG == 1, "four groups of four warps, one commit per warp");
+            // "my part of the stream is stored" to the three groups this warp is not in
+            if (igrp != 0) asm volatile("bar.arrive %0, %1;" :: "n"(TCV2_BAR_STREAM), "n"(NTB) : "memory");
+            if (igrp != 1) asm volatile("bar.arrive %0, %1;" :: "n"(TCV2_BAR_STREAM - 1), "n"(NTB) : "memory");
+            if (igrp != 2) asm volatile("bar.arrive %0, %1;" :: "n"(TCV2_BAR_STREAM - 2), "n"(NTB) : "memory");
+            if (igrp != 3) asm volatile("bar.arrive %0, %1;" :: "n"(TCV2_BAR_STREAM - 3), "n"(NTB) : "memory");
+            issue_group(std::integral_constant<int, 0>{});
+        }
         if (TCV2_DEBUG_BARRIERS) __syncthreads();
-        if (is_issuer) {
+        if (STAG) {
+        } else if (is_issuer) {
             if (!TCV2_DEBUG_BARRIERS) asm volatile("bar.sync %0, %1;" :: "n"(TCV2_BAR_STREAM), "n"(NTB) : "memory");
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (tcv_elect_one()) {
@@ -643,6 +689,7 @@ ber_tconv2_kernel(const BerParams prm) {
                     gauss_quad48(ca.z, ca.w, cc.y, nz[8 * gq + 2], nz[8 * gq + 3]);
                     gauss_quad48(cb.x, cb.y, cc.z, nz[8 * gq + 4], nz[8 * gq + 5]);
                     gauss_quad48(cb.z, cb.w, cc.w, nz[8 * gq + 6], nz[8 * gq + 7]);
+                    if (gq == 0) issue_group(std::integral_constant<int, 1>{}); else issue_group(std::integral_constant<int, 2>{});
                 }
                 nx[0] = nx[1] = mk2<T>(0, 0);
                 if (nlev > 0) {                                          // uniform per transform group
@@ -668,6 +715,8 @@ ber_tconv2_kernel(const BerParams prm) {
                     }
                 }
             }
+            if constexpr (VERIFY) { issue_group(std::integral_constant<int, 1>{}); issue_group(std::integral_constant<int, 2>{}); }
+            issue_group(std::integral_constant<int, 3>{});
             if (act) {
 #pragma unroll
                 for (int q = 0; q < 16; ++q) pn2 = csq_acc(nz[q], pn2);
@@ -688,7 +737,7 @@ ber_tconv2_kernel(const BerParams prm) {
         TCV2_STAMP(6);
         if constexpr (CL > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
         constexpr int GT = TCV2_GT;                // tiles per batch of accumulator loads (one wait per batch)
-        if constexpr (!MMAW && TCV2_REBALANCE) {
+        if constexpr (!MMAW && TCV2_REBALANCE && !STAG) {
             // The working warps issue the MMAs (N = 1024): the four issuing warps of this frame reach this point ~2000 cycles
             // after the others (phase traces: they sat in front of the tensor core's queue), and everybody would wait for
             // them at the power barrier.  So they skip this pass: the tiles of a tensor-memory lane quarter -- which only the
