@@ -174,7 +174,10 @@ WOFDM_API int wofdm_ber_draws(wofdm_handle h, const wofdm_sys_t* sys, int L, uin
 /* ---- interference power ------------------------------------------------------------------ */
 /* Replaces interf_power (python/ofdm_utils/interf_calc.py:20-113) per channel realisation:
  * P[k + N*c] = sum_{j!=k} |A_0[k,j]|^2 + sum_{m>=1} sum_j |A_m[k,j]|^2,  A_m = Rx_mat . H_m(h_c) . Tx_mat.
- * mode 0 = fp64 (DMMA), 1 = TF32-split tensor cores.  chan: complex L x C, P: N x C column-major. */
+ * mode 0 = fp64 (DMMA), one contraction per channel and slice; 1 = TF32-split tensor cores (fp32 grade); 2 = fp64,
+ * Hermitian form in the taps: A_m(c) = sum_l h_c[l] G_{m,l}, so the L impulse responses G go through the mode-0
+ * contraction once per window pair and every channel costs L^2 MACs per sub-carrier (P_k = h^H Q_k h) -- the mode for
+ * many channels (C > L; L <= 88).  chan: complex L x C, P: N x C column-major. */
 WOFDM_API int wofdm_interf_power(wofdm_handle h, const wofdm_sys_t* sys, const double* win_tx, const double* win_rx,
                        const double* chan, int L, int C, int mode, double* P);
 /* MATLAB semantics (calculate_interference, matlab/main_interference_calculation.m:177-225):

@@ -16,7 +16,7 @@ def main():
     variants = {"CP": 1, "wtx": 2, "CPwtx": 2, "wrx": 2, "CPwrx": 2, "WOLA": 7, "CPW": 7}
     h = W.Handle([0])
     out = {}
-    for mode in (0, 1):
+    for mode in (0, 1, 2):
         calls, flops, t0 = 0, 0.0, None
         for rep in range(2):                      # first pass = warm-up (arena growth, module load)
             calls, flops = 0, 0.0

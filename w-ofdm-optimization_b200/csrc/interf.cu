@@ -295,6 +295,9 @@ int interf_upload(wofdm_ctx* h, const wofdm_sys_t* sys, const double* win_tx, co
     return WOFDM_OK;
 }
 
+static int interf_run_quad(wofdm_handle h, const wofdm_sys_t* sys, const double* win_tx, const double* win_rx,
+                           const double* chan, int L, int C, int scalar, double* P);
+
 static int interf_run(wofdm_handle h, const wofdm_sys_t* sys, const double* win_tx, const double* win_rx,
                       const double* chan, int L, int C, int mode, int scalar, double* P) {
     NvtxRange nvtx_("wofdm_interf_power");
@@ -302,8 +305,9 @@ static int interf_run(wofdm_handle h, const wofdm_sys_t* sys, const double* win_
     int rc = validate_sys(h, sys, L);
     if (rc) return rc;
     if (!win_tx || !win_rx || !chan || !P || C < 1) return fail(h, WOFDM_EINVAL, "bad buffer");
-    if (mode != 0 && mode != 1) return fail(h, WOFDM_EINVAL, "mode must be 0 (fp64) or 1 (TF32-split)");
+    if (mode != 0 && mode != 1 && mode != 2) return fail(h, WOFDM_EINVAL, "mode must be 0 (fp64), 1 (TF32-split) or 2 (fp64, Hermitian form in the taps)");
     if (sys->N % 64) return fail(h, WOFDM_EUNSUPPORTED, "interference path needs N to be a multiple of 64");
+    if (mode == 2) return interf_run_quad(h, sys, win_tx, win_rx, chan, L, C, scalar, P);
     if (mode == 1 && sys->N % TF32_TN) return fail(h, WOFDM_EUNSUPPORTED, "TF32-split interference path needs N to be a multiple of 256");
     DeviceCtx& d = h->devs[0];
     WOFDM_CUDA(h, cudaSetDevice(d.dev));
@@ -358,6 +362,281 @@ static int interf_run(wofdm_handle h, const wofdm_sys_t* sys, const double* win_
         if (cudaEventElapsedTime(&ms, h->interf_ev[2], h->interf_ev[3]) == cudaSuccess) h->interf_ms[2] = ms;
     }
     h->interf_k_isi = k_isi; h->interf_kp = v.Kp;
+    return WOFDM_OK;
+}
+
+// ---- K2 mode 2: the interference power as a Hermitian form in the channel taps ---------------------------------------
+// H_m(h) is linear in the taps, so A_m(c) = sum_l h_c[l] G_{m,l} with G_{m,l} = Rx_mat . H_m(e_l) . Tx_mat the response to
+// the unit impulse at tap l, and
+//     P_k(c) = sum_{l,l'} h_c[l] conj(h_c[l']) Q_k[l,l'],   Q_k[l,l'] = sum_m sum_{j (!= k for m = 0)} G_{m,l}[k,j] conj(G_{m,l'}[k,j]).
+// The window pair costs L impulse responses through the SAME band product and tensor-core contraction as mode 0 (store
+// epilogue) plus N small Gram matrices; every channel realisation then costs L^2 complex MACs per sub-carrier instead of a
+// 2N x K x N GEMM per slice, and nothing per channel travels through HBM but its taps and its row of P.  Same
+// arithmetic type (fp64), same off-diagonal mask before squaring, so no cancellation the direct form does not have.
+// (interf_calc.py:91-100 evaluates ONE channel per call; the 250-channel sweeps of BASELINE configs[3] / the 10 000
+// channels of configs[4] are where this pays: the cost no longer grows with the number of channels.)
+// In real arithmetic (Q_k is Hermitian): P_k(c) = w_c . q_k over F = L (L + 1) features, two per tap pair p = (l, l' <= l):
+//   q_k[2p] = Re Q_k[l,l'], q_k[2p+1] = Im Q_k[l,l'];   w_c[2p] = 2 Re(h_l conj h_l'), w_c[2p+1] = -2 Im(h_l conj h_l')
+//   (l = l': |h_l|^2 and 0), so all channels and sub-carriers are ONE real product P = W . Q^T  (C x F x N).
+__host__ __device__ inline int quad_features(int L) { return ((L * (L + 1) + 15) / 16) * 16; }   // padded to the K tile
+__device__ __forceinline__ void quad_pair(int p, int& l, int& lp) {
+    l = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
+    while ((l + 1) * (l + 2) / 2 <= p) ++l;
+    while (l * (l + 1) / 2 > p) --l;
+    lp = p - l * (l + 1) / 2;
+}
+// One CTA per sub-carrier k; X[l*Ms + ms] = [Re G; Im G] (2N x N) from gemm_power_f64<true>.  qf: [N][F].
+// Q_k = Z Z^H with Z[l][(ms, j)] the k-th rows of the impulse responses (the diagonal entry of slice 0 masked): a thread
+// owns a 4 x 4 block of tap pairs (32 fp64 accumulators: 16 shared-memory loads per 64 FMAs) and every G-th column of the
+// staged tile; the G column groups of a block meet in shared memory at the end.
+template <int JT>
+__global__ void __launch_bounds__(256) quad_q_kernel(const double* __restrict__ X, double* __restrict__ qf, int N, int L, int Ms, int F) {
+    extern __shared__ __align__(16) double qsm[];            // [LB4*4*Ms*2][JT + 1] (odd pitch), then the block sums [nblk][32]
+    constexpr int JP = JT + 1;
+    const int k = blockIdx.x;
+    const size_t mat = (size_t)2 * N * N;
+    const int LB4 = (L + 3) / 4, nblk = LB4 * (LB4 + 1) / 2, LP = 4 * LB4;
+    int G = 1;
+    while (2 * G * nblk <= 256 && 2 * G <= 8) G *= 2;        // column groups per block: 1, 2, 4 or 8
+    double* const qsum = qsm + (size_t)LP * Ms * 2 * JP;
+    const int blk = threadIdx.x / G, grp = threadIdx.x % G;
+    const bool live = blk < nblk;
+    int br = 0, bc = 0;                                       // block row >= block column
+    if (live) quad_pair(blk, br, bc);
+    double ar[4][4], ai[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ar[i][j] = ai[i][j] = 0.0;
+    for (int j0 = 0; j0 < N; j0 += JT) {
+        __syncthreads();
+        constexpr int UL = 6;                                 // loads in flight per thread (the tile is L2 / HBM latency bound)
+        for (int e0 = threadIdx.x; e0 < LP * Ms * 2 * JT; e0 += 256 * UL) {
+            double v[UL];
+#pragma unroll
+            for (int u = 0; u < UL; ++u) {
+                const int e = e0 + 256 * u, j = e % JT, row = e / JT, part = row & 1, sl = row >> 1;   // sl = l * Ms + ms
+                v[u] = 0.0;
+                if (sl < L * Ms) v[u] = __ldg(X + (size_t)sl * mat + (size_t)(part * N + k) * N + j0 + j);
+            }
+#pragma unroll
+            for (int u = 0; u < UL; ++u) {
+                const int e = e0 + 256 * u, j = e % JT, row = e / JT, sl = row >> 1;
+                if (e < LP * Ms * 2 * JT) qsm[row * JP + j] = (sl % Ms == 0 && j0 + j == k) ? 0.0 : v[u];   // slice 0: off-diagonal entries only
+            }
+        }
+        __syncthreads();
+        if (live) {
+            for (int ms = 0; ms < Ms; ++ms) {
+                const double* xb = qsm + (size_t)((4 * br * Ms + ms) * 2) * JP;       // row l = 4 br + i: xb + i * Ms * 2 * JP (re), + JP (im)
+                const double* yb = qsm + (size_t)((4 * bc * Ms + ms) * 2) * JP;
+                for (int j = grp; j < JT; j += G) {
+                    double xr[4], xi[4], yr[4], yi[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        xr[i] = xb[(size_t)i * Ms * 2 * JP + j]; xi[i] = xb[(size_t)i * Ms * 2 * JP + JP + j];
+                        yr[i] = yb[(size_t)i * Ms * 2 * JP + j]; yi[i] = yb[(size_t)i * Ms * 2 * JP + JP + j];
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {     // G_l conj(G_l')
+                            ar[i][jj] = fma(xr[i], yr[jj], fma(xi[i], yi[jj], ar[i][jj]));
+                            ai[i][jj] = fma(xi[i], yr[jj], fma(-xr[i], yi[jj], ai[i][jj]));
+                        }
+                }
+            }
+        }
+    }
+    // the G column groups of a block are G consecutive lanes: butterfly sum, then group 0 publishes the block
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            for (int st = 1; st < G; st <<= 1) {
+                ar[i][jj] += __shfl_xor_sync(0xffffffffu, ar[i][jj], st);
+                ai[i][jj] += __shfl_xor_sync(0xffffffffu, ai[i][jj], st);
+            }
+            if (live && grp == 0) {
+                qsum[blk * 32 + (i * 4 + jj) * 2] = ar[i][jj];
+                qsum[blk * 32 + (i * 4 + jj) * 2 + 1] = ai[i][jj];
+            }
+        }
+    __syncthreads();
+    for (int e = threadIdx.x; e < nblk * 16; e += 256) {
+        int r, c;
+        quad_pair(e / 16, r, c);
+        const int l = 4 * r + (e % 16) / 4, lp = 4 * c + (e % 4);
+        if (l < L && lp <= l)
+            *reinterpret_cast<double2*>(qf + (size_t)k * F + 2 * (l * (l + 1) / 2 + lp)) = make_double2(qsum[2 * e], qsum[2 * e + 1]);
+    }
+    for (int f = L * (L + 1) + threadIdx.x; f < F; f += 256) qf[(size_t)k * F + f] = 0.0;
+}
+
+// wf: [C][F], the channels' tap-pair features
+__global__ void __launch_bounds__(256) quad_w_kernel(const double2* __restrict__ chan, double* __restrict__ wf, int L, int C, int F) {
+    const int c = blockIdx.y, npair = L * (L + 1) / 2;
+    const double2* h = chan + (size_t)c * L;
+    for (int p = blockIdx.x * 256 + threadIdx.x; 2 * p < F; p += gridDim.x * 256) {
+        double2 w = make_double2(0.0, 0.0);
+        if (p < npair) {
+            int l, lp;
+            quad_pair(p, l, lp);
+            const double2 a = h[l], b = h[lp];
+            if (l == lp) w.x = a.x * a.x + a.y * a.y;
+            else { w.x = 2.0 * (a.x * b.x + a.y * b.y); w.y = -2.0 * (a.y * b.x - a.x * b.y); }
+        }
+        *reinterpret_cast<double2*>(wf + (size_t)c * F + 2 * p) = w;
+    }
+}
+
+// P[c][k] = sum_f wf[c][f] qf[k][f]: a TS x TS tile per CTA (64, or 32 when 64 would leave most SMs idle), RT x RT outputs
+// per thread, F in tiles of 16 (plain FP64 FMAs: the product is C x L(L+1) x N, 0.06 GFLOP for the 250 channels of
+// configs[3]).  scalar: the row sum over k instead.
+template <int TS>
+__global__ void __launch_bounds__(256) quad_eval_kernel(const double* __restrict__ wf, const double* __restrict__ qf,
+                                                        double* __restrict__ P, int N, int C, int F, int scalar) {
+    constexpr int RT = TS / 16;
+    __shared__ double ws[16][TS + 4], qs[16][TS + 4];
+    const int c0 = blockIdx.x * TS, k0 = blockIdx.y * TS;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;          // outputs: channels c0 + RT ty + i, sub-carriers k0 + RT tx + j
+    // loads: TS rows x 16 features per operand = TS * 16 / 256 doubles per thread
+    constexpr int LV = TS / 16;                                      // consecutive features per thread (4 or 2)
+    const int lr = threadIdx.x / (16 / LV), lf = (threadIdx.x % (16 / LV)) * LV;
+    double acc[RT][RT];
+#pragma unroll
+    for (int i = 0; i < RT; ++i)
+#pragma unroll
+        for (int j = 0; j < RT; ++j) acc[i][j] = 0.0;
+    for (int f0 = 0; f0 < F; f0 += 16) {
+        double a[LV], b[LV];
+#pragma unroll
+        for (int i = 0; i < LV; ++i) {
+            a[i] = c0 + lr < C ? wf[(size_t)(c0 + lr) * F + f0 + lf + i] : 0.0;
+            b[i] = k0 + lr < N ? qf[(size_t)(k0 + lr) * F + f0 + lf + i] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < LV; ++i) { ws[lf + i][lr] = a[i]; qs[lf + i][lr] = b[i]; }
+        __syncthreads();
+#pragma unroll
+        for (int f = 0; f < 16; ++f) {
+            double wv[RT], qv[RT];
+#pragma unroll
+            for (int i = 0; i < RT; ++i) { wv[i] = ws[f][RT * ty + i]; qv[i] = qs[f][RT * tx + i]; }
+#pragma unroll
+            for (int i = 0; i < RT; ++i)
+#pragma unroll
+                for (int j = 0; j < RT; ++j) acc[i][j] = fma(wv[i], qv[j], acc[i][j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < RT; ++i) {
+        const int c = c0 + RT * ty + i;
+        if (c >= C) continue;
+        if (scalar) {
+            double sum = 0.0;
+#pragma unroll
+            for (int j = 0; j < RT; ++j) if (k0 + RT * tx + j < N) sum += acc[i][j];
+            atomicAdd(&P[c], sum);
+        } else {
+#pragma unroll
+            for (int j = 0; j < RT; ++j) if (k0 + RT * tx + j < N) P[(size_t)c * N + k0 + RT * tx + j] = acc[i][j];
+        }
+    }
+}
+
+static int interf_run_quad(wofdm_handle h, const wofdm_sys_t* sys, const double* win_tx, const double* win_rx,
+                           const double* chan, int L, int C, int scalar, double* P) {
+    DeviceCtx& d = h->devs[0];
+    WOFDM_CUDA(h, cudaSetDevice(d.dev));
+    for (auto& e : h->interf_ev)
+        if (!e) WOFDM_CUDA(h, cudaEventCreate(&e));
+    WOFDM_CUDA(h, cudaEventRecord(h->interf_ev[0], d.stream));
+    static cudaEvent_t dbg[4] = {nullptr, nullptr, nullptr, nullptr};
+    const bool dbg_on = getenv("WOFDM_DEBUG") != nullptr;
+    if (dbg_on) for (auto& e : dbg) if (!e) cudaEventCreate(&e);
+    const int N = sys->N, n_tx = N + sys->cp + sys->cs, n_rx = n_tx - sys->tail_tx, n_w = N + sys->tail_rx;
+    const int Kp = ((2 * n_rx + 63) / 64) * 64;
+    const int M = 1 + (L - 1 + sys->tail_tx + n_rx - 1) / n_rx;
+    const int Ms = scalar ? std::min(M, 2) : M;
+    const int k_isi = interf_isi_k(L, sys->tail_tx, n_rx, Kp);
+    if (L > 88) return fail(h, WOFDM_EUNSUPPORTED, "mode 2: at most 88 taps (253 blocks of 4 x 4 tap pairs per CTA)");
+    const size_t mat = (size_t)2 * N * N * 8;
+    const int F = quad_features(L);
+    const size_t pbytes = scalar ? (size_t)C * 8 : (size_t)C * N * 8;
+    const size_t need = (size_t)(n_tx + n_w) * 8 + (size_t)L * C * 16 + (size_t)L * L * 16 + (size_t)n_tx * N * 16 +
+                        (size_t)2 * N * Kp * 8 + (size_t)L * Ms * Kp * N * 8 + (size_t)L * Ms * mat + (size_t)(N + C) * F * 8 + pbytes + 4096;
+    int rc = arena_reserve(h, d, need);
+    if (rc) return rc;
+    double* d_vtx = static_cast<double*>(arena_take(d, (size_t)n_tx * 8));
+    double* d_vrx = static_cast<double*>(arena_take(d, (size_t)n_w * 8));
+    double2* d_chan = static_cast<double2*>(arena_take(d, (size_t)L * C * 16));
+    double2* d_imp = static_cast<double2*>(arena_take(d, (size_t)L * L * 16));
+    double2* d_T = static_cast<double2*>(arena_take(d, (size_t)n_tx * N * 16));
+    double* d_R = static_cast<double*>(arena_take(d, (size_t)2 * N * Kp * 8));
+    double* d_B = static_cast<double*>(arena_take(d, (size_t)L * Ms * Kp * N * 8));
+    double* d_X = static_cast<double*>(arena_take(d, (size_t)L * Ms * mat));
+    double* d_Q = static_cast<double*>(arena_take(d, (size_t)N * F * 8));
+    double* d_W = static_cast<double*>(arena_take(d, (size_t)C * F * 8));
+    double* d_P = static_cast<double*>(arena_take(d, pbytes));
+    if (!d_vtx || !d_vrx || !d_chan || !d_imp || !d_T || !d_R || !d_B || !d_X || !d_Q || !d_W || !d_P) return fail(h, WOFDM_ENOMEM, "arena exhausted");
+    std::vector<double> imp((size_t)L * L * 2, 0.0);
+    for (int l = 0; l < L; ++l) imp[((size_t)l * L + l) * 2] = 1.0;          // "channel" l = the unit impulse at tap l
+    WOFDM_CUDA(h, cudaMemcpyAsync(d_vtx, win_tx, (size_t)n_tx * 8, cudaMemcpyHostToDevice, d.stream));
+    WOFDM_CUDA(h, cudaMemcpyAsync(d_vrx, win_rx, (size_t)n_w * 8, cudaMemcpyHostToDevice, d.stream));
+    WOFDM_CUDA(h, cudaMemcpyAsync(d_chan, chan, (size_t)L * C * 16, cudaMemcpyHostToDevice, d.stream));
+    WOFDM_CUDA(h, cudaMemcpyAsync(d_imp, imp.data(), (size_t)L * L * 16, cudaMemcpyHostToDevice, d.stream));
+    build_tx_matrix<<<n_tx, 256, 0, d.stream>>>(d_T, d_vtx, N, sys->cp, n_tx);
+    build_rx_matrix<<<N, 256, 0, d.stream>>>(d_R, d_vrx, N, sys->tail_rx, sys->rm, sys->shift, n_rx, Kp);
+    WOFDM_CUDA(h, cudaEventRecord(h->interf_ev[1], d.stream));
+    const int slices = L * Ms;
+    build_b<false><<<dim3((N + 255) / 256, (Kp / 2 + BB - 1) / BB, slices), 256, (size_t)(L + 2 * BB) * sizeof(double2), d.stream>>>(
+        d_B, d_T, d_imp, L, N, n_tx, n_rx, n_rx, Kp, Ms, M, 0, scalar, k_isi);
+    WOFDM_CUDA(h, cudaGetLastError());
+    WOFDM_CUDA(h, cudaEventRecord(h->interf_ev[2], d.stream));
+    constexpr size_t smem = (size_t)(2 * BM * AS + 2 * BK * BS) * sizeof(double);
+    WOFDM_CUDA(h, cudaFuncSetAttribute(gemm_power_f64<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gemm_power_f64<true><<<dim3(N / BN, 2 * N / BM, slices), 256, smem, d.stream>>>(d_R, d_B, d_X, N, Kp, Ms, 0, 0, k_isi);
+    WOFDM_CUDA(h, cudaGetLastError());
+    WOFDM_CUDA(h, cudaEventRecord(h->interf_ev[3], d.stream));
+    // Gram matrices of the impulse responses and the channels' tap-pair features, then every channel in one product
+    const int LB4 = (L + 3) / 4;
+    auto q_smem = [&](int jt) { return ((size_t)4 * LB4 * Ms * 2 * (jt + 1) + (size_t)LB4 * (LB4 + 1) / 2 * 32) * sizeof(double); };
+    if (q_smem(64) <= 160 * 1024 && N % 64 == 0) {          // 64 columns per staged tile where they fit (fewer barriers), else 32
+        WOFDM_CUDA(h, cudaFuncSetAttribute(quad_q_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)q_smem(64)));
+        quad_q_kernel<64><<<N, 256, q_smem(64), d.stream>>>(d_X, d_Q, N, L, Ms, F);
+    } else {
+        WOFDM_CUDA(h, cudaFuncSetAttribute(quad_q_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)q_smem(32)));
+        quad_q_kernel<32><<<N, 256, q_smem(32), d.stream>>>(d_X, d_Q, N, L, Ms, F);
+    }
+    if (dbg_on) cudaEventRecord(dbg[0], d.stream);
+    quad_w_kernel<<<dim3((F / 2 + 255) / 256, C), 256, 0, d.stream>>>(d_chan, d_W, L, C, F);
+    if (dbg_on) cudaEventRecord(dbg[1], d.stream);
+    WOFDM_CUDA(h, cudaGetLastError());
+    if (scalar) WOFDM_CUDA(h, cudaMemsetAsync(d_P, 0, pbytes, d.stream));
+    if (((C + 63) / 64) * ((N + 63) / 64) >= 148)
+        quad_eval_kernel<64><<<dim3((C + 63) / 64, (N + 63) / 64), 256, 0, d.stream>>>(d_W, d_Q, d_P, N, C, F, scalar);
+    else
+        quad_eval_kernel<32><<<dim3((C + 31) / 32, (N + 31) / 32), 256, 0, d.stream>>>(d_W, d_Q, d_P, N, C, F, scalar);
+    if (dbg_on) cudaEventRecord(dbg[2], d.stream);
+    WOFDM_CUDA(h, cudaGetLastError());
+    h->launches += 7;
+    WOFDM_CUDA(h, cudaMemcpyAsync(P, d_P, pbytes, cudaMemcpyDeviceToHost, d.stream));
+    WOFDM_CUDA(h, cudaEventRecord(h->interf_ev[4], d.stream));
+    WOFDM_CUDA(h, cudaStreamSynchronize(d.stream));
+    float ms = 0.f;
+    h->interf_ms[0] = h->interf_ms[1] = h->interf_ms[2] = -1.0;
+    if (cudaEventElapsedTime(&ms, h->interf_ev[0], h->interf_ev[4]) == cudaSuccess) h->interf_ms[0] = ms;
+    if (cudaEventElapsedTime(&ms, h->interf_ev[1], h->interf_ev[2]) == cudaSuccess) h->interf_ms[1] = ms;
+    if (cudaEventElapsedTime(&ms, h->interf_ev[2], h->interf_ev[3]) == cudaSuccess) h->interf_ms[2] = ms;
+    if (dbg_on) {
+        float t[6];
+        cudaEventElapsedTime(&t[0], h->interf_ev[0], h->interf_ev[1]); cudaEventElapsedTime(&t[1], h->interf_ev[3], dbg[0]);
+        cudaEventElapsedTime(&t[2], dbg[0], dbg[1]); cudaEventElapsedTime(&t[3], dbg[1], dbg[2]); cudaEventElapsedTime(&t[4], dbg[2], h->interf_ev[4]);
+        fprintf(stderr, "[wofdm] mode 2: upload+builders %.3f, Q %.3f, W %.3f, eval %.3f, download %.3f ms\n", t[0], t[1], t[2], t[3], t[4]);
+    }
+    h->interf_k_isi = k_isi; h->interf_kp = Kp;
     return WOFDM_OK;
 }
 

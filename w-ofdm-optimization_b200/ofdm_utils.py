@@ -115,13 +115,16 @@ def simulation_fun(data: tuple, seed: int = 0, handle=None):
 
 
 def interf_power(sys_design: str, window_data: list, dft_len: int, cp_len: int, tail_tx: int, tail_rx: int,
-                 channel_path: str = "channels/vehicularA.npy", per_channel: bool = False, mode: int = 0, handle=None):
+                 channel_path: str = "channels/vehicularA.npy", per_channel: bool = False, mode=None, handle=None):
     """Drop-in for ofdm_utils.interf_power.  Default: the reference's behaviour -- the MEAN impulse response of the
     stored set (interf_calc.py:80-83) -> (P_opt, P_rc), each (N,), or a single (N,) vector for 'CP'.
-    per_channel=True evaluates every realisation: arrays of shape (C, N)."""
+    per_channel=True evaluates every realisation: arrays of shape (C, N).  mode None: fp64, the direct contraction
+    (0) for up to L channels, the Hermitian form in the taps (2) for more."""
     h = handle or default_handle()
     chann = np.load(channel_path)
     chan = chann if per_channel else chann.mean(axis=1)[:, None]
+    if mode is None:
+        mode = 2 if (chan.shape[1] > chan.shape[0] and chan.shape[0] <= 88) else 0
     if sys_design == "CP":                                             # interf_calc.py:57-73
         s = capi.params_from_name("CP", dft_len, cp_len, 0, 0)
         P = h.interf_power(s, np.ones(s.n_tx), np.ones(s.N), chan, mode=mode)
