@@ -212,6 +212,14 @@ WOFDM_API int wofdm_ber_run_masked(wofdm_handle h, const wofdm_sys_t* sys, const
  * u = a*(tail_tx+1) + b for Rx-tail variable a and Tx-tail variable b (OptimizerTxRx's flatten order; Tx-only and
  * Rx-only systems have tail_rx = 0 or tail_tx = 0 and the index is b or a).  *n_var (may be NULL) returns n_var. */
 WOFDM_API int wofdm_window_hessian(wofdm_handle h, const wofdm_sys_t* sys, const double* chan, int L, double* H, int* n_var);
+/* The two parts of that quadratic form for ARBITRARY basis windows: basis_tx = n_tb windows of n_tx samples, basis_rx = n_rb
+ * windows of N + tail_rx samples (row-major), variable u = a*n_tb + b, n_var = n_rb*n_tb:
+ *   H_ici[u,u'] = 2 Re <offdiag A0_u, offdiag A0_u'>,   H_isi[u,u'] = 2 Re <AS_u, AS_u'>   (wofdm_window_hessian = their sum
+ * on the reduced bases).  With the FULL window as the variable (basis = identity) and the other side's window fixed (one
+ * row) these are quad_objective_tx / _rx of matlab/window_optimization.m:596-680:
+ *   HTx (or HRx) = alpha * H_ici + (1 - alpha) * diag(row sums of H_isi)       (H2 = real(diag(diag(B2' B2 C C'))), :628-631). */
+WOFDM_API int wofdm_window_hessian_parts(wofdm_handle h, const wofdm_sys_t* sys, const double* chan, int L,
+                               const double* basis_tx, int n_tb, const double* basis_rx, int n_rb, double* H_ici, double* H_isi);
 
 /* ---- Channel generation (next-row 8f-4) ------------------------------------------------------------------
  * ITU-R tapped-delay-line channels with GMEDS_1 Rayleigh fading on the device: channel_model.gen_chan

@@ -215,7 +215,7 @@ static void do_run_sim_mc(int nlhs, mxArray* plhs[], int nrhs, const mxArray* pr
 //   -- the quadratic form of the interference power (ICI + ISI) in the REDUCED window variables (tail coefficients), as
 //      python's OptimizerTx/Rx/TxRx.gen_hessian builds it.  channel: ONE impulse response.  (quad_objective_tx / _rx of
 //      matlab/window_optimization.m:596-680 work in the full window variable with the other window fixed, weight the
-//      two terms with alpha and keep only the diagonal of the ISI term: that variant is not mirrored.)
+//      two terms with alpha and keep only the diagonal of the ISI term: 'quad_objective_tx' / 'quad_objective_rx' below.)
 static void do_window_hessian(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     if (nrhs < 6) mexErrMsgIdAndTxt("wofdm:nargin", "window_hessian needs 6 arguments");
     (void)nlhs;
@@ -233,6 +233,43 @@ static void do_window_hessian(int nlhs, mxArray* plhs[], int nrhs, const mxArray
     plhs[0] = mxCreateDoubleMatrix((mwSize)n_var, (mwSize)n_var, mxREAL);
     int nv = 0;
     check(wofdm_window_hessian(handle(), &s, chan.data(), L, mxGetPr(plhs[0]), &nv), "wofdm_window_hessian");
+}
+
+// HTx = wofdm_mex('quad_objective_tx', typeOFDM, numSubcar, cpLength, tailTx, tailRx, windowRx, channel, alpha)
+// HRx = wofdm_mex('quad_objective_rx', typeOFDM, numSubcar, cpLength, tailTx, tailRx, windowTx, channel, alpha)
+//   -- quad_objective_tx / _rx of matlab/window_optimization.m:596-680: the FULL window of one side is the variable
+//      (n_tx, or N + tailRx, entries), the other side's window (diagonal matrix or vector) is fixed:
+//      H = 2 (alpha H1 + (1 - alpha) H2), H1 the off-diagonal ICI term, H2 = real(diag(diag(.))) of the ISI term (:628-631).
+//      channel: ONE impulse response (the script passes array_ici_isi of the mean channel; the device builds those matrices).
+static void do_quad_objective(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[], bool tx_side) {
+    if (nrhs < 8) mexErrMsgIdAndTxt("wofdm:nargin", "quad_objective_tx / _rx need 8 arguments");
+    (void)nlhs;
+    char name[16];
+    if (!mxIsChar(prhs[0]) || mxGetString(prhs[0], name, sizeof(name))) mexErrMsgIdAndTxt("wofdm:type", "typeOFDM must be a string");
+    wofdm_sys_t s;
+    memset(&s, 0, sizeof(s));
+    s.bits = 4; s.S = 2; s.precision = 1;
+    if (wofdm_params_from_name(name, (int)mxGetScalar(prhs[1]), (int)mxGetScalar(prhs[2]), (int)mxGetScalar(prhs[3]),
+                               (int)mxGetScalar(prhs[4]), &s) != WOFDM_OK)
+        mexErrMsgIdAndTxt("wofdm:type", "unknown typeOFDM '%s'", name);
+    const size_t n_tx = (size_t)(s.N + s.cp + s.cs), n_w = (size_t)(s.N + s.tail_rx);
+    const size_t n = tx_side ? n_tx : n_w;                       // variables: the full window of this side
+    const std::vector<double> fixed = diag_of(prhs[5], tx_side ? n_w : n_tx);
+    const int L = (int)mxGetNumberOfElements(prhs[6]);
+    const std::vector<double> chan = interleave(prhs[6], (size_t)L, 1, 0);
+    const double alpha = mxGetScalar(prhs[7]);
+    std::vector<double> eye(n * n, 0.0), hc(n * n), hs(n * n);
+    for (size_t i = 0; i < n; ++i) eye[i * n + i] = 1.0;
+    check(wofdm_window_hessian_parts(handle(), &s, chan.data(), L, tx_side ? eye.data() : fixed.data(), tx_side ? (int)n : 1,
+                                     tx_side ? fixed.data() : eye.data(), tx_side ? 1 : (int)n, hc.data(), hs.data()),
+          "wofdm_window_hessian_parts");
+    plhs[0] = mxCreateDoubleMatrix((mwSize)n, (mwSize)n, mxREAL);
+    double* H = mxGetPr(plhs[0]);
+    for (size_t i = 0; i < n; ++i) {
+        double row = 0.0;
+        for (size_t j = 0; j < n; ++j) { row += hs[i * n + j]; H[i + j * n] = alpha * hc[i * n + j]; }
+        H[i + i * n] += (1.0 - alpha) * row;
+    }
 }
 
 // channels = wofdm_mex('gen_channels', standard, numTaps, dopplerFreq, samplingRate, frameDuration, noFrames, nSets [, seed])
@@ -287,12 +324,14 @@ static void do_calculate_interference(int nlhs, mxArray* plhs[], int nrhs, const
 extern "C" void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     char cmd[32];
     if (nrhs < 1 || !mxIsChar(prhs[0]) || mxGetString(prhs[0], cmd, sizeof(cmd)))
-        mexErrMsgIdAndTxt("wofdm:usage", "first argument: 'run_simulation', 'run_simulation_sweep', 'run_simulation_sweep_multi', 'run_sim_mc', 'calculate_interference', 'window_hessian' or 'gen_channels'");
+        mexErrMsgIdAndTxt("wofdm:usage", "first argument: 'run_simulation', 'run_simulation_sweep', 'run_simulation_sweep_multi', 'run_sim_mc', 'calculate_interference', 'window_hessian', 'quad_objective_tx', 'quad_objective_rx' or 'gen_channels'");
     if (!strcmp(cmd, "run_simulation")) do_run_simulation(nlhs, plhs, nrhs - 1, prhs + 1, false);
     else if (!strcmp(cmd, "run_simulation_sweep")) do_run_simulation(nlhs, plhs, nrhs - 1, prhs + 1, true);
     else if (!strcmp(cmd, "run_simulation_sweep_multi")) do_run_simulation_multi(nlhs, plhs, nrhs - 1, prhs + 1);
     else if (!strcmp(cmd, "run_sim_mc")) do_run_sim_mc(nlhs, plhs, nrhs - 1, prhs + 1);
     else if (!strcmp(cmd, "window_hessian")) do_window_hessian(nlhs, plhs, nrhs - 1, prhs + 1);
+    else if (!strcmp(cmd, "quad_objective_tx")) do_quad_objective(nlhs, plhs, nrhs - 1, prhs + 1, true);
+    else if (!strcmp(cmd, "quad_objective_rx")) do_quad_objective(nlhs, plhs, nrhs - 1, prhs + 1, false);
     else if (!strcmp(cmd, "gen_channels")) do_gen_channels(nlhs, plhs, nrhs - 1, prhs + 1);
     else if (!strcmp(cmd, "calculate_interference")) do_calculate_interference(nlhs, plhs, nrhs - 1, prhs + 1);
     else mexErrMsgIdAndTxt("wofdm:usage", "unknown command '%s'", cmd);

@@ -66,6 +66,59 @@ def test_device_matches_golden_and_oracle(name):
         print(f"{name}: {Hd.shape[0]} variables, device call {dt * 1e3:.2f} ms")
 
 
+@pytest.mark.parametrize("name,side", [("WOLA", "tx"), ("WOLA", "rx"), ("wtx", "tx"), ("CPwrx", "rx")])
+def test_matlab_quad_objective_oracle(name, side):
+    """quad_objective_tx / _rx (matlab/window_optimization.m:596-680; MATLAB only: parity unpinned): the three loops as
+    written against their vector form, and against the identity the device path uses -- with the full window as the
+    variable, H = alpha H_ici + (1 - alpha) diag(row sums of H_isi), H_ici / H_isi the Gram parts of window_hessian."""
+    a, b = tails(name, 2, 2)
+    p = O.system_params(name, 16, 4, a, b)
+    vt, vr, _, _ = O.perturbed_windows(p, seed=3)
+    hch = O.synth_channels(1, 5, seed=2)[:, 0]
+    fixed = vr if side == "tx" else vt
+    Hl = O.quad_objective_matlab(p, side, fixed, hch, 0.3, loops=True)
+    Hv = O.quad_objective_matlab(p, side, fixed, hch, 0.3)
+    n = p.n_tx if side == "tx" else p.N + p.tail_rx
+    assert Hl.shape == (n, n) and np.allclose(Hl, Hl.T)
+    assert np.abs(Hl - Hv).max() <= 1e-12 * np.abs(Hl).max()
+    x0, xs = [], []
+    for i in range(n):
+        e = np.zeros(n)
+        e[i] = 1.0
+        A = O.interf_matrices(p, e, fixed, hch) if side == "tx" else O.interf_matrices(p, fixed, e, hch)
+        x0.append((A[0] - np.diag(np.diag(A[0]))).ravel())
+        xs.append(A[1:].sum(axis=0).ravel())
+    x0, xs = np.array(x0), np.array(xs)
+    Hc, Hs = 2.0 * (x0 @ x0.conj().T).real, 2.0 * (xs @ xs.conj().T).real
+    assert np.abs(Hl - (0.3 * Hc + 0.7 * np.diag(Hs.sum(axis=1)))).max() <= 1e-12 * np.abs(Hl).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,N,cp,ttx,trx,L", [("WOLA", 64, 8, 2, 2, 9), ("wtx", 64, 8, 4, 0, 9), ("CPW", 256, 16, 8, 10, 21)])
+def test_device_matlab_quad_objective(name, N, cp, ttx, trx, L):
+    """The MATLAB-signature mirrors (full window as the variable) through wofdm_window_hessian_parts against the oracle."""
+    import wofdm_b200 as W
+    from wofdm_b200 import ofdm_utils as U
+    p = O.system_params(name, N, cp, ttx, trx)
+    vt, vr, _, _ = O.perturbed_windows(p, seed=N)
+    hch = O.synth_channels(4, L, seed=5).mean(axis=1)
+    with W.Handle([0]) as h:
+        t0 = time.perf_counter()
+        HTx = U.quad_objective_tx(np.diag(vr), N, trx, cp, name, ttx, hch, 0.5, handle=h)
+        dt = time.perf_counter() - t0
+        want = O.quad_objective_matlab(p, "tx", vr, hch, 0.5)
+        assert HTx.shape == (p.n_tx, p.n_tx)
+        assert np.abs(HTx - want).max() <= 1e-9 * np.abs(want).max()
+        print(f"{name} N={N}: HTx {HTx.shape[0]} variables, device call {dt * 1e3:.1f} ms")
+        if N == 64:
+            HRx = U.quad_objective_rx(vt, N, trx, cp, name, ttx, hch, 0.25, handle=h)
+            want = O.quad_objective_matlab(p, "rx", vt, hch, 0.25)
+            assert np.abs(HRx - want).max() <= 1e-9 * np.abs(want).max()
+            Hc, Hs = h.window_hessian_parts(W.params_from_name(name, N, cp, ttx, trx), hch,
+                                            *[np.array(x) for x in O.window_basis(p)])
+            assert np.abs(Hc + Hs - O.window_hessian(p, hch)).max() <= 1e-9 * np.abs(Hc + Hs).max()   # parts on the reduced bases = wofdm_window_hessian
+
+
 @pytest.mark.gpu
 def test_bad_system_names_raise():
     from wofdm_b200 import optimizers as OPT

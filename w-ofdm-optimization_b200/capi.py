@@ -97,6 +97,7 @@ SIGNATURES = {
     "wofdm_ber_run_masked": (C.c_int, [C.c_void_p, _P(SysT), _dp, _dp, _dp, C.c_int, C.c_int, _dp, C.c_int, C.c_int64, C.c_uint64,
                                        C.c_uint32, C.c_int, _i64p, _i64p, _i64p, _i64p]),
     "wofdm_window_hessian": (C.c_int, [C.c_void_p, _P(SysT), _dp, C.c_int, _dp, _P(C.c_int)]),
+    "wofdm_window_hessian_parts": (C.c_int, [C.c_void_p, _P(SysT), _dp, C.c_int, _dp, C.c_int, _dp, C.c_int, _dp, _dp]),
     "wofdm_channel_profile": (C.c_int, [C.c_char_p]),
     "wofdm_gen_channels": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
                                      C.c_uint64, _dp, _dp]),
@@ -371,6 +372,21 @@ class Handle:
         self._check(rc)
         assert nv.value == n_var
         return H
+
+    def window_hessian_parts(self, s, chan, basis_tx, basis_rx):
+        """The ICI and ISI parts of the quadratic form for arbitrary basis windows (wofdm_window_hessian_parts):
+        basis_tx (n_tb, n_tx), basis_rx (n_rb, N + tail_rx) -> (H_ici, H_isi), each (n_var, n_var), u = a*n_tb + b."""
+        ch = _cplx(np.ravel(chan))
+        bt = np.ascontiguousarray(np.atleast_2d(basis_tx), dtype=np.float64)
+        br = np.ascontiguousarray(np.atleast_2d(basis_rx), dtype=np.float64)
+        if bt.shape[1] != s.n_tx or br.shape[1] != s.N + s.tail_rx:
+            raise WofdmError(EINVAL, f"basis windows must have {s.n_tx} (Tx) and {s.N + s.tail_rx} (Rx) samples")
+        n_var = bt.shape[0] * br.shape[0]
+        Hc, Hs = np.empty((n_var, n_var)), np.empty((n_var, n_var))
+        rc = load().wofdm_window_hessian_parts(self._h, C.byref(s), _ptr(ch, _dp), ch.size, _ptr(bt, _dp), bt.shape[0],
+                                               _ptr(br, _dp), br.shape[0], _ptr(Hc, _dp), _ptr(Hs, _dp))
+        self._check(rc)
+        return Hc, Hs
 
     def gen_channels(self, standard, L, doppler_freq, sampling_rate, frame_duration, no_frames=1, n_sets=1, seed=0,
                      phases=None):

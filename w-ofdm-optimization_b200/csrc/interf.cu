@@ -493,9 +493,11 @@ __global__ void __launch_bounds__(256) quad_w_kernel(const double2* __restrict__
 // P[c][k] = sum_f wf[c][f] qf[k][f]: a TS x TS tile per CTA (64, or 32 when 64 would leave most SMs idle), RT x RT outputs
 // per thread, F in tiles of 16 (plain FP64 FMAs: the product is C x L(L+1) x N, 0.06 GFLOP for the 250 channels of
 // configs[3]).  scalar: the row sum over k instead.
+// (also the Gram product of the window Hessian's parts: ldw / ldq = row pitches, F = features contracted, scale on the way out)
 template <int TS>
 __global__ void __launch_bounds__(256) quad_eval_kernel(const double* __restrict__ wf, const double* __restrict__ qf,
-                                                        double* __restrict__ P, int N, int C, int F, int scalar) {
+                                                        double* __restrict__ P, int N, int C, int F, int scalar,
+                                                        size_t ldw, size_t ldq, double scale) {
     constexpr int RT = TS / 16;
     __shared__ double ws[16][TS + 4], qs[16][TS + 4];
     const int c0 = blockIdx.x * TS, k0 = blockIdx.y * TS;
@@ -512,8 +514,8 @@ __global__ void __launch_bounds__(256) quad_eval_kernel(const double* __restrict
         double a[LV], b[LV];
 #pragma unroll
         for (int i = 0; i < LV; ++i) {
-            a[i] = c0 + lr < C ? wf[(size_t)(c0 + lr) * F + f0 + lf + i] : 0.0;
-            b[i] = k0 + lr < N ? qf[(size_t)(k0 + lr) * F + f0 + lf + i] : 0.0;
+            a[i] = c0 + lr < C ? wf[(size_t)(c0 + lr) * ldw + f0 + lf + i] : 0.0;
+            b[i] = k0 + lr < N ? qf[(size_t)(k0 + lr) * ldq + f0 + lf + i] : 0.0;
         }
         __syncthreads();
 #pragma unroll
@@ -538,10 +540,10 @@ __global__ void __launch_bounds__(256) quad_eval_kernel(const double* __restrict
             double sum = 0.0;
 #pragma unroll
             for (int j = 0; j < RT; ++j) if (k0 + RT * tx + j < N) sum += acc[i][j];
-            atomicAdd(&P[c], sum);
+            atomicAdd(&P[c], scale * sum);
         } else {
 #pragma unroll
-            for (int j = 0; j < RT; ++j) if (k0 + RT * tx + j < N) P[(size_t)c * N + k0 + RT * tx + j] = acc[i][j];
+            for (int j = 0; j < RT; ++j) if (k0 + RT * tx + j < N) P[(size_t)c * N + k0 + RT * tx + j] = scale * acc[i][j];
         }
     }
 }
@@ -616,9 +618,9 @@ static int interf_run_quad(wofdm_handle h, const wofdm_sys_t* sys, const double*
     WOFDM_CUDA(h, cudaGetLastError());
     if (scalar) WOFDM_CUDA(h, cudaMemsetAsync(d_P, 0, pbytes, d.stream));
     if (((C + 63) / 64) * ((N + 63) / 64) >= 148)
-        quad_eval_kernel<64><<<dim3((C + 63) / 64, (N + 63) / 64), 256, 0, d.stream>>>(d_W, d_Q, d_P, N, C, F, scalar);
+        quad_eval_kernel<64><<<dim3((C + 63) / 64, (N + 63) / 64), 256, 0, d.stream>>>(d_W, d_Q, d_P, N, C, F, scalar, F, F, 1.0);
     else
-        quad_eval_kernel<32><<<dim3((C + 31) / 32, (N + 31) / 32), 256, 0, d.stream>>>(d_W, d_Q, d_P, N, C, F, scalar);
+        quad_eval_kernel<32><<<dim3((C + 31) / 32, (N + 31) / 32), 256, 0, d.stream>>>(d_W, d_Q, d_P, N, C, F, scalar, F, F, 1.0);
     if (dbg_on) cudaEventRecord(dbg[2], d.stream);
     WOFDM_CUDA(h, cudaGetLastError());
     h->launches += 7;
@@ -674,50 +676,41 @@ __global__ void __launch_bounds__(256) gram_offdiag(const double* __restrict__ X
     (void)n_tb;
 }
 
-static int window_hessian_run(wofdm_handle h, const wofdm_sys_t* sys, const double* chan, int L, double* H_out, int* n_var_out) {
-    NvtxRange nvtx_("wofdm_window_hessian");
-    if (!h) return WOFDM_EINVAL;
-    int rc = validate_sys(h, sys, L);
-    if (rc) return rc;
-    if (!chan || !H_out) return fail(h, WOFDM_EINVAL, "bad buffer");
-    if (sys->N % 64) return fail(h, WOFDM_EUNSUPPORTED, "interference path needs N to be a multiple of 64");
+// slice 0 of every stored [Re A; Im A]: the diagonal entries leave the sums (off-diagonal interference only)
+__global__ void zero_diag_kernel(double* __restrict__ X, int n_var, int N) {
+    const int u = blockIdx.x;
+    double* x = X + (size_t)u * 2 * ((size_t)2 * N * N);
+    for (int k = threadIdx.x; k < N; k += blockDim.x) { x[(size_t)k * N + k] = 0.0; x[(size_t)(N + k) * N + k] = 0.0; }
+}
+
+// bt: n_tb Tx windows (n_tx each), br: n_rb Rx windows (N + tail_rx each), host.  H_out (sum of the parts, gram_offdiag) or
+// the parts H_ici / H_isi (Gram products through quad_eval_kernel); n_var = n_rb * n_tb, u = a * n_tb + b.
+static int window_hessian_core(wofdm_handle h, const wofdm_sys_t* sys, const double* chan, int L, const double* bt_h, int n_tb,
+                               const double* br_h, int n_rb, double* H_out, double* H_ici, double* H_isi) {
     DeviceCtx& d = h->devs[0];
     WOFDM_CUDA(h, cudaSetDevice(d.dev));
     const int N = sys->N, n_tx = N + sys->cp + sys->cs, n_rx = n_tx - sys->tail_tx, n_w = N + sys->tail_rx;
-    const int n_tb = sys->tail_tx + 1, n_rb = sys->tail_rx / 2 + 1, n_var = n_tb * n_rb;
-    if (n_var_out) *n_var_out = n_var;
+    const int n_var = n_tb * n_rb;
     const int Kp = ((2 * n_rx + 63) / 64) * 64;
     const int M = 1 + (L - 1 + sys->tail_tx + n_rx - 1) / n_rx;
     const int Ms = 2;                                          // slice 0 and the sum of the ISI slices
     const int k_isi = interf_isi_k(L, sys->tail_tx, n_rx, Kp);
-    // basis windows = columns of reduce_variable_tx / _rx (optimization_tools/utils.py:13-73)
-    std::vector<double> bt((size_t)n_tb * n_tx), br((size_t)n_rb * n_w), e(std::max(n_tb, n_rb));
-    for (int b = 0; b < n_tb; ++b) {
-        std::fill(e.begin(), e.end(), 0.0); e[b] = 1.0;
-        rc = wofdm_expand_window_tx(sys, e.data(), bt.data() + (size_t)b * n_tx);
-        if (rc) return fail(h, rc, "expand_window_tx");
-    }
-    for (int a = 0; a < n_rb; ++a) {
-        std::fill(e.begin(), e.end(), 0.0); e[a] = 1.0;
-        rc = wofdm_expand_window_rx(sys, e.data(), br.data() + (size_t)a * n_w);
-        if (rc) return fail(h, rc, "expand_window_rx");
-    }
     const size_t matb = (size_t)2 * N * N * 8;
-    const size_t need = bt.size() * 8 + br.size() * 8 + (size_t)L * 16 + (size_t)n_tx * N * 16 + (size_t)2 * N * Kp * 8 +
-                        (size_t)n_tb * Ms * Kp * N * 8 + (size_t)n_var * Ms * matb + (size_t)n_var * n_var * 8;
-    rc = arena_reserve(h, d, need);
+    const size_t need = (size_t)n_tb * n_tx * 8 + (size_t)n_rb * n_w * 8 + (size_t)L * 16 + (size_t)n_tx * N * 16 + (size_t)2 * N * Kp * 8 +
+                        (size_t)n_tb * Ms * Kp * N * 8 + (size_t)n_var * Ms * matb + (size_t)2 * n_var * n_var * 8;
+    int rc = arena_reserve(h, d, need);
     if (rc) return rc;
-    double* d_bt = static_cast<double*>(arena_take(d, bt.size() * 8));
-    double* d_br = static_cast<double*>(arena_take(d, br.size() * 8));
+    double* d_bt = static_cast<double*>(arena_take(d, (size_t)n_tb * n_tx * 8));
+    double* d_br = static_cast<double*>(arena_take(d, (size_t)n_rb * n_w * 8));
     double2* d_chan = static_cast<double2*>(arena_take(d, (size_t)L * 16));
     double2* d_T = static_cast<double2*>(arena_take(d, (size_t)n_tx * N * 16));
     double* d_R = static_cast<double*>(arena_take(d, (size_t)2 * N * Kp * 8));
     double* d_B = static_cast<double*>(arena_take(d, (size_t)n_tb * Ms * Kp * N * 8));
     double* d_X = static_cast<double*>(arena_take(d, (size_t)n_var * Ms * matb));
-    double* d_H = static_cast<double*>(arena_take(d, (size_t)n_var * n_var * 8));
+    double* d_H = static_cast<double*>(arena_take(d, (size_t)2 * n_var * n_var * 8));
     if (!d_bt || !d_br || !d_chan || !d_T || !d_R || !d_B || !d_X || !d_H) return fail(h, WOFDM_ENOMEM, "arena exhausted");
-    WOFDM_CUDA(h, cudaMemcpyAsync(d_bt, bt.data(), bt.size() * 8, cudaMemcpyHostToDevice, d.stream));
-    WOFDM_CUDA(h, cudaMemcpyAsync(d_br, br.data(), br.size() * 8, cudaMemcpyHostToDevice, d.stream));
+    WOFDM_CUDA(h, cudaMemcpyAsync(d_bt, bt_h, (size_t)n_tb * n_tx * 8, cudaMemcpyHostToDevice, d.stream));
+    WOFDM_CUDA(h, cudaMemcpyAsync(d_br, br_h, (size_t)n_rb * n_w * 8, cudaMemcpyHostToDevice, d.stream));
     WOFDM_CUDA(h, cudaMemcpyAsync(d_chan, chan, (size_t)L * 16, cudaMemcpyHostToDevice, d.stream));
     // B_{b,ms} = H_ms . Tx_mat(t_b) for every Tx basis window
     for (int b = 0; b < n_tb; ++b) {
@@ -735,12 +728,62 @@ static int window_hessian_run(wofdm_handle h, const wofdm_sys_t* sys, const doub
             d_R, d_B, d_X + (size_t)a * n_tb * Ms * 2 * N * N, N, Kp, Ms, 0, 0, k_isi);
     }
     WOFDM_CUDA(h, cudaGetLastError());
-    gram_offdiag<<<n_var * (n_var + 1) / 2, 256, 0, d.stream>>>(d_X, d_H, n_var, N, n_tb);
-    WOFDM_CUDA(h, cudaGetLastError());
     h->launches += 2 * n_tb + 2 * n_rb + 1;
-    WOFDM_CUDA(h, cudaMemcpyAsync(H_out, d_H, (size_t)n_var * n_var * 8, cudaMemcpyDeviceToHost, d.stream));
+    if (H_out) {
+        gram_offdiag<<<n_var * (n_var + 1) / 2, 256, 0, d.stream>>>(d_X, d_H, n_var, N, n_tb);
+        WOFDM_CUDA(h, cudaGetLastError());
+        WOFDM_CUDA(h, cudaMemcpyAsync(H_out, d_H, (size_t)n_var * n_var * 8, cudaMemcpyDeviceToHost, d.stream));
+    } else {
+        // the parts, each one Gram product of the stored matrices (rows of pitch 2 mat: [slice 0 | ISI sum])
+        const size_t mat = (size_t)2 * N * N;
+        zero_diag_kernel<<<n_var, 256, 0, d.stream>>>(d_X, n_var, N);
+        const dim3 g((n_var + 63) / 64, (n_var + 63) / 64);
+        quad_eval_kernel<64><<<g, 256, 0, d.stream>>>(d_X, d_X, d_H, n_var, n_var, (int)mat, 0, 2 * mat, 2 * mat, 2.0);
+        quad_eval_kernel<64><<<g, 256, 0, d.stream>>>(d_X + mat, d_X + mat, d_H + (size_t)n_var * n_var, n_var, n_var, (int)mat, 0, 2 * mat, 2 * mat, 2.0);
+        WOFDM_CUDA(h, cudaGetLastError());
+        h->launches += 2;
+        WOFDM_CUDA(h, cudaMemcpyAsync(H_ici, d_H, (size_t)n_var * n_var * 8, cudaMemcpyDeviceToHost, d.stream));
+        WOFDM_CUDA(h, cudaMemcpyAsync(H_isi, d_H + (size_t)n_var * n_var, (size_t)n_var * n_var * 8, cudaMemcpyDeviceToHost, d.stream));
+    }
     WOFDM_CUDA(h, cudaStreamSynchronize(d.stream));
     return WOFDM_OK;
+}
+
+static int window_hessian_run(wofdm_handle h, const wofdm_sys_t* sys, const double* chan, int L, double* H_out, int* n_var_out) {
+    NvtxRange nvtx_("wofdm_window_hessian");
+    if (!h) return WOFDM_EINVAL;
+    int rc = validate_sys(h, sys, L);
+    if (rc) return rc;
+    if (!chan || !H_out) return fail(h, WOFDM_EINVAL, "bad buffer");
+    if (sys->N % 64) return fail(h, WOFDM_EUNSUPPORTED, "interference path needs N to be a multiple of 64");
+    const int N = sys->N, n_tx = N + sys->cp + sys->cs, n_w = N + sys->tail_rx;
+    const int n_tb = sys->tail_tx + 1, n_rb = sys->tail_rx / 2 + 1;
+    if (n_var_out) *n_var_out = n_tb * n_rb;
+    // basis windows = columns of reduce_variable_tx / _rx (optimization_tools/utils.py:13-73)
+    std::vector<double> bt((size_t)n_tb * n_tx), br((size_t)n_rb * n_w), e(std::max(n_tb, n_rb));
+    for (int b = 0; b < n_tb; ++b) {
+        std::fill(e.begin(), e.end(), 0.0); e[b] = 1.0;
+        rc = wofdm_expand_window_tx(sys, e.data(), bt.data() + (size_t)b * n_tx);
+        if (rc) return fail(h, rc, "expand_window_tx");
+    }
+    for (int a = 0; a < n_rb; ++a) {
+        std::fill(e.begin(), e.end(), 0.0); e[a] = 1.0;
+        rc = wofdm_expand_window_rx(sys, e.data(), br.data() + (size_t)a * n_w);
+        if (rc) return fail(h, rc, "expand_window_rx");
+    }
+    return window_hessian_core(h, sys, chan, L, bt.data(), n_tb, br.data(), n_rb, H_out, nullptr, nullptr);
+}
+
+static int window_hessian_parts_run(wofdm_handle h, const wofdm_sys_t* sys, const double* chan, int L, const double* basis_tx,
+                                    int n_tb, const double* basis_rx, int n_rb, double* H_ici, double* H_isi) {
+    NvtxRange nvtx_("wofdm_window_hessian_parts");
+    if (!h) return WOFDM_EINVAL;
+    int rc = validate_sys(h, sys, L);
+    if (rc) return rc;
+    if (!chan || !basis_tx || !basis_rx || !H_ici || !H_isi || n_tb < 1 || n_rb < 1) return fail(h, WOFDM_EINVAL, "bad buffer");
+    if (sys->N % 64) return fail(h, WOFDM_EUNSUPPORTED, "interference path needs N to be a multiple of 64");
+    if ((size_t)2 * sys->N * sys->N % 16) return fail(h, WOFDM_EUNSUPPORTED, "N");
+    return window_hessian_core(h, sys, chan, L, basis_tx, n_tb, basis_rx, n_rb, nullptr, H_ici, H_isi);
 }
 
 }  // namespace wofdm
@@ -771,6 +814,11 @@ int wofdm_interf_last_timing(wofdm_handle h, double* total_ms, double* band_ms, 
 
 int wofdm_window_hessian(wofdm_handle h, const wofdm_sys_t* sys, const double* chan, int L, double* H, int* n_var) {
     return window_hessian_run(h, sys, chan, L, H, n_var);
+}
+
+int wofdm_window_hessian_parts(wofdm_handle h, const wofdm_sys_t* sys, const double* chan, int L, const double* basis_tx, int n_tb,
+                               const double* basis_rx, int n_rb, double* H_ici, double* H_isi) {
+    return window_hessian_parts_run(h, sys, chan, L, basis_tx, n_tb, basis_rx, n_rb, H_ici, H_isi);
 }
 
 }  // extern "C"

@@ -189,3 +189,29 @@ def calculate_interference(cpLength, typeOFDM, windowTx, windowRx, numSubcar, ta
     s = capi.params_from_name(typeOFDM, int(numSubcar), int(cpLength), int(tailTx), int(tailRx))
     mean_ir = np.asarray(channels).mean(axis=0)                       # :196
     return float(h.interf_power(s, _diag(windowTx), _diag(windowRx), mean_ir[:, None], mode=mode, scalar=True)[0])
+
+
+def _quad_objective(side, typeOFDM, window_fixed, numSubcar, cpLength, tailTx, tailRx, channel, alpha, handle=None):
+    h = handle or default_handle()
+    s = capi.params_from_name(typeOFDM, int(numSubcar), int(cpLength), int(tailTx), int(tailRx))
+    fixed = _diag(window_fixed)
+    if side == "tx":
+        Hc, Hs = h.window_hessian_parts(s, channel, np.eye(s.n_tx), fixed[None, :])
+    else:
+        Hc, Hs = h.window_hessian_parts(s, channel, fixed[None, :], np.eye(s.N + s.tail_rx))
+    return float(alpha) * Hc + (1.0 - float(alpha)) * np.diag(Hs.sum(axis=1))
+
+
+def quad_objective_tx(windowRx, numSubcar, tailRx, cpLength, typeOFDM, tailTx, channel, alpha, handle=None):
+    """HTx of quad_objective_tx (matlab/window_optimization.m:596-634): the full Tx window (n_tx entries) is the variable,
+    windowRx (diagonal matrix or vector) is fixed; H = 2 (alpha H1 + (1 - alpha) H2) with H1 the off-diagonal ICI term and
+    H2 = real(diag(diag(B2' B2 C C'))) (:628-631).  The script hands over array_ici_isi of the mean channel
+    (:224-229); here `channel` is that impulse response and the device builds the matrices; prefixRemovalLength,
+    circularShiftLength and csLength follow from calculate_parameters for typeOFDM."""
+    return _quad_objective("tx", typeOFDM, windowRx, numSubcar, cpLength, tailTx, tailRx, channel, alpha, handle)
+
+
+def quad_objective_rx(windowTx, numSubcar, tailRx, cpLength, typeOFDM, tailTx, channel, alpha, handle=None):
+    """HRx of quad_objective_rx (matlab/window_optimization.m:637-680): the full Rx window (N + tailRx entries) is the
+    variable, windowTx is fixed."""
+    return _quad_objective("rx", typeOFDM, windowTx, numSubcar, cpLength, tailTx, tailRx, channel, alpha, handle)
