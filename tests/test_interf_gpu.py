@@ -114,6 +114,23 @@ def test_hermitian_form_many_channels(handle, name, N, C, L):
     assert np.allclose(S2, S0, rtol=1e-10)
 
 
+@pytest.mark.parametrize("L,C", [(1, 3), (2, 1), (5, 70), (21, 1), (88, 2)])
+def test_hermitian_form_edge_shapes(handle, L, C):
+    """mode 2 with one tap, one channel, fewer channels than taps, the longest channel it takes (88 taps)."""
+    p = O.system_params("WOLA", 64, 8, 2, 2)
+    vt, vr, _, _ = O.perturbed_windows(p, seed=L)
+    chans = O.synth_channels(C, L, seed=C)
+    P2 = handle.interf_power(to_sys(p), vt, vr, chans, mode=2)
+    for c in range(min(C, 3)):
+        want = O.interf_power_dense(p, vt, vr, chans[:, c])
+        # (channels inside the prefix leave rounding noise only, ~1e-28 of the signal: absolute floor)
+        assert np.max(np.abs(P2[c] - want)) <= 1e-9 * np.max(want) + 1e-24, c
+    with pytest.raises(W.WofdmError):
+        handle.interf_power(to_sys(p), vt, vr, O.synth_channels(2, 89, seed=1), mode=2)
+    with pytest.raises(W.WofdmError):
+        handle.interf_power(to_sys(p), vt, vr, chans, mode=3)
+
+
 @pytest.mark.parametrize("name", ["WOLA", "wtx", "CPW", "CP"])
 def test_tf32_split_tensor_path(handle, name):
     """mode 1: tcgen05 kind::tf32 with the 3xTF32 split; fp32-grade accuracy against the fp64 path / oracle.

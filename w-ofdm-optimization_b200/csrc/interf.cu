@@ -605,6 +605,7 @@ static int interf_run_quad(wofdm_handle h, const wofdm_sys_t* sys, const double*
     // Gram matrices of the impulse responses and the channels' tap-pair features, then every channel in one product
     const int LB4 = (L + 3) / 4;
     auto q_smem = [&](int jt) { return ((size_t)4 * LB4 * Ms * 2 * (jt + 1) + (size_t)LB4 * (LB4 + 1) / 2 * 32) * sizeof(double); };
+    if (q_smem(32) > 220 * 1024) return fail(h, WOFDM_EUNSUPPORTED, "mode 2: the impulse responses of this many taps and slices do not fit shared memory (use mode 0)");
     if (q_smem(64) <= 160 * 1024 && N % 64 == 0) {          // 64 columns per staged tile where they fit (fewer barriers), else 32
         WOFDM_CUDA(h, cudaFuncSetAttribute(quad_q_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)q_smem(64)));
         quad_q_kernel<64><<<N, 256, q_smem(64), d.stream>>>(d_X, d_Q, N, L, Ms, F);
