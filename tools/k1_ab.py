@@ -14,7 +14,8 @@ scale = N // 256
 h = W.Handle([0])
 rng = np.random.default_rng(0)
 C = 250
-chan = (rng.standard_normal((21, C)) + 1j * rng.standard_normal((21, C))) * np.exp(-np.arange(21) / 4)[:, None]
+LT = int(os.environ.get("K1AB_L", "21"))       # channel taps
+chan = (rng.standard_normal((LT, C)) + 1j * rng.standard_normal((LT, C))) * np.exp(-np.arange(LT) / 4)[:, None]
 snr = np.linspace(-20, 50, 30)
 stream = torch.cuda.Stream()
 torch.cuda.set_stream(stream)
