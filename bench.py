@@ -13,7 +13,7 @@ per GPU (ensemble 27 x 16 -> 3.24 M frames = 51.8 M OFDM symbols per GPU and ste
 region is seconds, not milliseconds, long.  Weak scaling: the ensemble grows with N, frames are sharded by global frame
 id, one all-reduce of the int64 counters per step.
 Beside the headline the line carries: `e2e` (host buffers through the C-ABI), `roofline`, `cpu_baseline`, and the
-secondary objects `matlab_convention` (the same batch in MATLAB's conventions), `configs4` (N=1024 stress case), `k2`
+secondary objects `matlab_convention` (the same batch in MATLAB's conventions), `configs4` / `configs4_l84` (N=1024 stress case), `k2`
 (interference power, configs[3] shapes, fp64 and TF32-split, channels sharded over the ranks) and, for N > 1, `strong`
 (the N=1 batch sharded over N GPUs).  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement".
 """
@@ -490,6 +490,14 @@ def main():
                               "workload": WORKLOAD4, "kernel": j4.plan.kernel, "frames_per_gpu_per_step": j4.frames_rank,
                               "frac": a4 / peak_tflops, "achieved_tflops": a4, "flops_per_symbol": sum(f4)}
         j4.plan.close()
+        # (2b) the same with the 84-tap channels configs[4] names as its option ("L = 21 (optionally 84)")
+        j84 = Job(torch, dist, W, capi, h, dict(CFG4, L=84, name=WORKLOAD4.replace("L=21", "L=84")), world, rank, 1, args.scaling)
+        ms_8, kms_8, _ = j84.timed(stream, flush, 3, 3, 6500)
+        a8, f8 = j84.roofline_tflops(kms_8)
+        extras["configs4_l84"] = {"value": j84.symbols_job() * 3 / (ms_8 * 1e-3), "unit": UNIT, "ms_per_step": ms_8 / 3, "steps": 3,
+                                  "workload": WORKLOAD4.replace("L=21", "L=84"), "kernel": j84.plan.kernel,
+                                  "frac": a8 / peak_tflops, "achieved_tflops": a8, "flops_per_symbol": sum(f8)}
+        j84.plan.close()
         # (3) strong scaling: the one-GPU batch sharded over the GPUs (N = 1: identical to the headline, skipped)
         if world > 1 and args.scaling == "weak":
             js = Job(torch, dist, W, capi, h, dict(CFG), world, rank, args.reps, "strong")
