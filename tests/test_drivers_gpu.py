@@ -173,7 +173,50 @@ def test_channel_mask_variant_replay(handle, name, cp, bits):
     for res, w in ((plain, want[0]), (masked, want[1])):
         assert np.all(np.abs(res["sym_err"] - w[:, 0]) <= 3 + 0.003 * w[:, 0]), (res["sym_err"], w[:, 0])
         assert np.all(np.abs(res["bit_err"] - w[:, 1]) <= 5 + 0.003 * w[:, 1]), (res["bit_err"], w[:, 1])
+    # the Tx side is the dense tensor-core product (mask_gemm.cu); the per-symbol FFT kernel (mask_kernel.cuh) is the same
+    # linear map evaluated another way: counters agree up to decisions on a boundary
+    os.environ["WOFDM_MASK_FFT"] = "1"
+    try:
+        fft = handle.ber_run_masked(s, vt, vr, chans, snr, ens, seed=5, variant=1, roll_off=10)
+    finally:
+        del os.environ["WOFDM_MASK_FFT"]
+    assert np.all(np.abs(fft["sym_err"] - masked["sym_err"]) <= 2), (fft["sym_err"], masked["sym_err"])
+    assert np.all(np.abs(fft["bit_err"] - masked["bit_err"]) <= 3), (fft["bit_err"], masked["bit_err"])
     # the MATLAB-signature mirror returns [berMasked, ber]
     bm, b0 = U.run_sim_mc(3, p.cp, p.cs, ttx, trx, np.diag(vt), np.diag(vr), chans[:, 0], 20.0, 64, p.rm, p.shift, 256, bits,
                           16, 10, seed=1, handle=handle)
     assert 0.0 <= b0 < 0.5 and 0.0 <= bm < 0.5
+
+
+@pytest.mark.parametrize("name,N,cp,ttx,trx,bits,guard", [("CP", 128, 8, 0, 0, 2, 0), ("CPW", 512, 32, 16, 20, 4, 128),
+                                                           ("wtx", 256, 16, 8, 0, 6, 0), ("WOLA", 256, 30, 8, 10, 4, 64)])
+def test_channel_mask_product_against_fft_kernel(handle, tmp_path, name, N, cp, ttx, trx, bits, guard):
+    """The masked Tx stream two ways: the dense tensor-core product (mask_gemm.cu: the matrices of main_channel_mask.m:384-417
+    multiplied out once, fp16 hi + lo against the exact lattice points) and the per-symbol FFT kernel (mask_kernel.cuh).
+    Streams of the first frames agree to fp32 rounding; the K1 kernel that gathers from the product's output itself gives
+    the counters of the assembled stream bit for bit; counters of the two Tx kernels differ by boundary decisions only."""
+    s = W.params_from_name(name, N, cp, ttx, trx, bits=bits, S=16, noise_norm=1, constellation=1, guard=guard)
+    vt, vr = W.capi.rc_window_tx(s), W.capi.rc_window_rx(s)
+    chans = O.synth_channels(6, 21, seed=N + cp)
+    snr = np.array([6.0, 18.0, 30.0, 42.0])
+    ens = 3
+    res, dumps = {}, {}
+    try:
+        for mode in ("fft", "gemm"):
+            os.environ["WOFDM_MASK_FFT"] = "1" if mode == "fft" else "0"
+            os.environ["WOFDM_MASK_DUMP"] = str(tmp_path / (mode + ".bin"))
+            res[mode] = handle.ber_run_masked(s, vt, vr, chans, snr, ens, seed=9, variant=1, roll_off=10)
+            dumps[mode] = np.fromfile(tmp_path / (mode + ".bin"), dtype=np.float32)
+            del os.environ["WOFDM_MASK_DUMP"]
+        res["gather"] = handle.ber_run_masked(s, vt, vr, chans, snr, ens, seed=9, variant=1, roll_off=10)
+    finally:
+        os.environ.pop("WOFDM_MASK_FFT", None)
+        os.environ.pop("WOFDM_MASK_DUMP", None)
+    a, b = dumps["fft"], dumps["gemm"]
+    assert a.size == b.size == 2 * 4 * (ttx + 16 * (N + cp + s.cs - ttx))
+    assert np.abs(a - b).max() <= 4e-6 * np.abs(a).max(), (np.abs(a - b).max(), np.abs(a).max())
+    for k in ("bit_err", "sym_err", "bit_tot", "sym_tot"):
+        assert np.array_equal(res["gather"][k], res["gemm"][k]), k
+    assert np.all(np.abs(res["fft"]["sym_err"] - res["gemm"]["sym_err"]) <= 2), (res["fft"]["sym_err"], res["gemm"]["sym_err"])
+    assert np.all(np.abs(res["fft"]["bit_err"] - res["gemm"]["bit_err"]) <= 4), (res["fft"]["bit_err"], res["gemm"]["bit_err"])
+    assert res["gemm"]["sym_err"][0] > res["gemm"]["sym_err"][-1]

@@ -1,5 +1,6 @@
-"""Throughput of the channel-mask BER variant (matlab/main_channel_mask.m): masked chain (tx_mask_kernel + staged K1) and
-the unmasked guard-band chain on the same symbols; wall time of the C-ABI calls with host buffers."""
+"""Throughput of the channel-mask BER variant (matlab/main_channel_mask.m): masked chain (mask product on the tensor cores,
+mask_gemm.cu, + the K1 kernel that gathers from its output; WOFDM_MASK_FFT=1: the per-symbol FFT kernel) and the unmasked
+guard-band chain on the same symbols; wall time of the C-ABI calls with host buffers."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np

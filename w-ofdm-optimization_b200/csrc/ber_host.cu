@@ -7,6 +7,7 @@
 
 #include "host_common.h"
 #include "mask_kernel.cuh"
+#include "mask_gemm.h"
 #include "ber_tconv2.cuh"
 
 using namespace wofdm;
@@ -71,7 +72,7 @@ void fill_split(BerParams& prm, const BerVariant& v) {
 // win_tx (may be NULL): the circular-interior kernels need it flat between the tails; no_circ excludes them
 int choose_variant(wofdm_ctx* h, const wofdm_sys_t& s, int L, bool verify, bool force_staged, size_t smem_cap,
                    Choice* out, const double* win_tx = nullptr, bool no_circ = false, bool want_txs = false,
-                   bool no_tconv = false, int nvar = 1) {
+                   bool no_tconv = false, int nvar = 1, bool want_txy = false) {
     const int stride = s.N + s.cp + s.cs - s.tail_tx;
     const int sec = s.S * stride;
     const bool fp64 = s.precision == 1;
@@ -97,6 +98,7 @@ int choose_variant(wofdm_ctx* h, const wofdm_sys_t& s, int L, bool verify, bool 
                 const int tpf = s.N / 16, S_cta = s.S / v.CL, sec_cta = sec / v.CL, body = s.tail_tx + sec_cta;
                 if (no_tconv || S_cta > v.NT / tpf || L > v.LB) continue;
                 if (v.gen != tconv_gen) continue;
+                if (v.txy != want_txy) continue;                     // (the mask product's consumers serve the channel-mask variant only)
                 if (v.CL > 1 && want_txs) continue;                  // (the masked Tx stream is a one-CTA-per-frame feature)
                 // second generation: a receiver thread holds at most N48_MAXLEV noise samples besides its 16 FFT rows
                 if (v.gen == 2 && (stride - s.N + (s.noise_norm == 1 ? s.tail_tx + L - 1 : 0) + tpf - 1) / tpf > (v.LB > TCV_LB ? N48_MAXLEV : N48_MAXLEV_SHORT)) continue;
@@ -699,8 +701,9 @@ static void host_fft_pow2(std::vector<double>& a, int n) {
     }
 }
 
-// Channel-mask variant (include/wofdm.h): frames in batches -- tx_mask_kernel writes the masked Tx streams of a batch
-// to HBM, the staged K1 kernel reads them (BerParams::tx_stream) and does channel, noise, Rx and counting as always.
+// Channel-mask variant (include/wofdm.h): frames in batches -- the masked Tx streams of a batch are written to HBM (the dense
+// tensor-core product of mask_gemm.cu, or tx_mask_kernel with WOFDM_MASK_FFT=1), a K1 kernel reads them
+// (BerParams::tx_stream) and does channel, noise, Rx and counting as always.
 int wofdm_ber_run_masked(wofdm_handle h, const wofdm_sys_t* sys, const double* win_tx, const double* win_rx,
                          const double* chan, int L, int C, const double* snr_db, int n_snr, int64_t ensemble,
                          uint64_t seed, uint32_t variant, int roll_off,
@@ -719,7 +722,18 @@ int wofdm_ber_run_masked(wofdm_handle h, const wofdm_sys_t* sys, const double* w
     DeviceCtx& d = h->devs[0];
     WOFDM_CUDA(h, cudaSetDevice(d.dev));
     Choice ch, prod;
-    rc = choose_variant(h, *sys, L, false, false, d.smem_optin, &ch, nullptr, true, true);   // a tx_stream kernel (tuned or staged) runs it
+    // Tx side: the dense tensor-core product of mask_gemm.cu; WOFDM_MASK_FFT=1 keeps the per-symbol FFT kernel (mask_kernel.cuh)
+    const char* mask_env = getenv("WOFDM_MASK_FFT");
+    const bool use_gemm = !(mask_env && atoi(mask_env) == 1);
+    const char* dump_env = getenv("WOFDM_MASK_DUMP");
+    // a second-generation tensor-core kernel that gathers its stream from the product's output itself (no assembled copy in
+    // HBM) where the frame fits one, else a tx_stream kernel (tuned or staged)
+    bool fused = false;
+    if (use_gemm && !(dump_env && *dump_env)) {
+        rc = choose_variant(h, *sys, L, false, false, d.smem_optin, &ch, nullptr, true, true, false, 1, true);
+        fused = rc == WOFDM_OK && ch.var->txy;
+    }
+    if (!fused) rc = choose_variant(h, *sys, L, false, false, d.smem_optin, &ch, nullptr, true, true);
     if (rc) return rc;
     if (ch.var->CL > 1) return fail(h, WOFDM_EUNSUPPORTED, "no channel-mask variant for cluster kernels");
     rc = choose_variant(h, *sys, L, false, false, d.smem_optin, &prod, win_tx);     // noise numbering of wofdm_ber_run / _draws
@@ -729,42 +743,55 @@ int wofdm_ber_run_masked(wofdm_handle h, const wofdm_sys_t* sys, const double* w
     long long max_ctas = 0;
     rc = prepare_kernel(h, *ch.var, ch.lay.bytes, d.sm_count, &nb, &max_ctas);
     if (rc) return rc;
-    // g = IDFT_M(ifftshift(windowRC)), main_channel_mask.m:404-412, 477-493
-    std::vector<double> wrc(M, 0.0);
-    {
-        const int wl = M / 2, rest = M - wl - 2 * roll_off, zl = rest / 2;
-        for (int i = 0; i < roll_off; ++i) {
-            const double ax = -(roll_off + 1) / 2.0 + 1.0 + i;
-            const double v = std::sin(1.5707963267948966 * (0.5 + ax / roll_off));
-            wrc[zl + i] = v * v;
-            wrc[zl + roll_off + wl + (roll_off - 1 - i)] = v * v;
+    std::vector<double> gd;
+    if (!use_gemm) {
+        // g = IDFT_M(ifftshift(windowRC)), main_channel_mask.m:404-412, 477-493
+        std::vector<double> wrc(M, 0.0);
+        {
+            const int wl = M / 2, rest = M - wl - 2 * roll_off, zl = rest / 2;
+            for (int i = 0; i < roll_off; ++i) {
+                const double ax = -(roll_off + 1) / 2.0 + 1.0 + i;
+                const double v = std::sin(1.5707963267948966 * (0.5 + ax / roll_off));
+                wrc[zl + i] = v * v;
+                wrc[zl + roll_off + wl + (roll_off - 1 - i)] = v * v;
+            }
+            for (int i = 0; i < wl; ++i) wrc[zl + roll_off + i] = 1.0;
         }
-        for (int i = 0; i < wl; ++i) wrc[zl + roll_off + i] = 1.0;
-    }
-    std::vector<double> gd(2 * (size_t)M);
-    for (int n = 0; n < M; ++n) {
-        double re = 0.0, im = 0.0;
-        for (int k = 0; k < M; ++k) {                        // ifftshift: shifted[k] = wrc[(k + M/2) mod M] (odd M: floor)
-            const double w = wrc[(k + M / 2) % M];
-            if (w == 0.0) continue;
-            const double a = 6.283185307179586476925286766559 * (double)(((long long)k * n) % M) / (double)M;
-            re += w * std::cos(a); im += w * std::sin(a);
+        gd.resize(2 * (size_t)M);
+        std::vector<double> phc(M), phs(M);
+        for (int i = 0; i < M; ++i) {
+            const double a = 6.283185307179586476925286766559 * (double)i / (double)M;
+            phc[i] = std::cos(a); phs[i] = std::sin(a);
         }
-        gd[2 * n] = re / M; gd[2 * n + 1] = im / M;
+        for (int n = 0; n < M; ++n) {
+            double re = 0.0, im = 0.0;
+            int idx = 0;                                         // k n mod M
+            for (int k = 0; k < M; ++k) {                        // ifftshift: shifted[k] = wrc[(k + M/2) mod M] (odd M: floor)
+                const double w = wrc[(k + M / 2) % M];
+                if (w != 0.0) { re += w * phc[idx]; im += w * phs[idx]; }
+                idx += n;
+                if (idx >= M) idx -= M;
+            }
+            gd[2 * n] = re / M; gd[2 * n + 1] = im / M;
+        }
     }
     // the circular convolution (mod M) of an n_tx-sample symbol = a linear one with the periodic extension of g on
     // [-(n_tx-1), M-1]: Gp = FFT_P of that sequence laid out circularly in P = 8N >= 4 n_tx - 3 points, times 1/P
     const int P = 8 * N;
-    std::vector<double> gc(2 * (size_t)P, 0.0);
-    for (int mm = -(n_tx - 1); mm <= M - 1; ++mm) {
-        const int gi = ((mm % M) + M) % M, ci = ((mm % P) + P) % P;
-        gc[2 * ci] = gd[2 * gi]; gc[2 * ci + 1] = gd[2 * gi + 1];
-    }
-    host_fft_pow2(gc, P);
-    std::vector<float> g(2 * (size_t)P);
-    for (size_t i = 0; i < g.size(); ++i) g[i] = (float)(gc[i] / P);
+    std::vector<float> g(2 * (size_t)P, 0.f);
     std::vector<unsigned char> twp;
-    cast_any(false, build_twiddles(P), twp);
+    if (!use_gemm) {
+        std::vector<double> gc(2 * (size_t)P, 0.0);
+        for (int mm = -(n_tx - 1); mm <= M - 1; ++mm) {
+            const int gi = ((mm % M) + M) % M, ci = ((mm % P) + P) % P;
+            gc[2 * ci] = gd[2 * gi]; gc[2 * ci + 1] = gd[2 * gi + 1];
+        }
+        host_fft_pow2(gc, P);
+        for (size_t i = 0; i < g.size(); ++i) g[i] = (float)(gc[i] / P);
+        cast_any(false, build_twiddles(P), twp);
+    } else {
+        twp.resize(16);
+    }
     HostTables t;
     build_tables(*sys, win_tx, win_rx, t, ch.var->ntile > 0);   // (tx_mask_kernel shares the table: a common factor of its stream)
     std::vector<unsigned char> hchan, hsnr;
@@ -774,12 +801,14 @@ int wofdm_ber_run_masked(wofdm_handle h, const wofdm_sys_t* sys, const double* w
     cast_any(false, lin, hsnr);
     const long long total = (long long)n_snr * C * ensemble;
     const size_t body = (size_t)sys->tail_tx + (size_t)sys->S * stride;
-    const long long batch = std::min<long long>(total, 8192);
+    const long long batch = std::min<long long>(total, use_gemm ? 16384 : 8192);
     const size_t scratch_elems = (size_t)ch.lay.pad + body + 64;
     const int grid_ber = (int)std::min<long long>(batch, max_ctas);
     const size_t scratch_bytes = ch.use_global ? (size_t)grid_ber * 2 * scratch_elems * sizeof(float2) : 0;
+    MaskGemm mg;
+    const size_t mg_bytes = use_gemm ? mask_gemm_plan(*sys, batch, mg) : 0;
     rc = arena_reserve(h, d, t.wtx.size() + t.wrx.size() + t.tw.size() + twp.size() + hchan.size() + hsnr.size() + g.size() * 4 +
-                                 (size_t)n_snr * 16 + (size_t)batch * body * sizeof(float2) + scratch_bytes);
+                                 (size_t)n_snr * 16 + (fused ? 16 : (size_t)batch * body * sizeof(float2)) + scratch_bytes + mg_bytes + 8192);
     if (rc) return rc;
     auto put = [&](const void* src, size_t bytes, void** dst) -> cudaError_t {
         *dst = arena_take(d, std::max<size_t>(bytes, 16));
@@ -795,9 +824,13 @@ int wofdm_ber_run_masked(wofdm_handle h, const wofdm_sys_t* sys, const double* w
     WOFDM_CUDA(h, put(g.data(), g.size() * 4, &d_g));
     WOFDM_CUDA(h, put(twp.data(), twp.size(), &d_twp));
     WOFDM_CUDA(h, put(nullptr, (size_t)n_snr * 16, &d_cnt));
-    WOFDM_CUDA(h, put(nullptr, (size_t)batch * body * sizeof(float2), &d_stream));
+    WOFDM_CUDA(h, put(nullptr, fused ? 16 : (size_t)batch * body * sizeof(float2), &d_stream));
     if (scratch_bytes) WOFDM_CUDA(h, put(nullptr, scratch_bytes, &d_scr));
     WOFDM_CUDA(h, cudaMemsetAsync(d_cnt, 0, (size_t)n_snr * 16, d.stream));
+    if (use_gemm) {
+        rc = mask_gemm_setup(h, d, mg, roll_off, static_cast<const float*>(d_wtx));
+        if (rc) return rc;
+    }
 
     MaskParams mp;
     memset(&mp, 0, sizeof(mp));
@@ -823,12 +856,17 @@ int wofdm_ber_run_masked(wofdm_handle h, const wofdm_sys_t* sys, const double* w
     prm.counters = static_cast<unsigned long long*>(d_cnt);
     prm.scratch = d_scr; prm.scratch_elems = (long long)scratch_elems;
     prm.tx_stream = static_cast<const float2*>(d_stream);
+    if (fused) { prm.tx_y = mg.Y; prm.tx_yp = mg.Yp; }
     size_t msm = 0;
     for (long long f0 = 0; f0 < total; f0 += batch) {
         const long long nf = std::min(batch, total - f0);
         mp.frame_begin = f0; mp.frame_step = 1; mp.n_frames = nf;
         const int mgrid = (int)std::min<long long>(nf, (long long)d.sm_count);
         cudaError_t e = cudaSuccess;
+        if (use_gemm) {
+            rc = mask_gemm_batch(h, d, mg, seed, f0, nf, fused ? nullptr : static_cast<float2*>(d_stream));
+            if (rc) return rc;
+        } else
         switch (N) {
             case 128: msm = MaskSmem<128>::bytes(sys->S, stride, sys->tail_tx);
                       e = cudaFuncSetAttribute(tx_mask_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm);
@@ -842,6 +880,16 @@ int wofdm_ber_run_masked(wofdm_handle h, const wofdm_sys_t* sys, const double* w
         }
         WOFDM_CUDA(h, e);
         WOFDM_CUDA(h, cudaGetLastError());
+        if (f0 == 0) {
+            // development aid: WOFDM_MASK_DUMP=<file> writes the masked Tx streams of the first (up to 4) frames as raw float32 pairs
+            const char* dump = dump_env;
+            if (dump && *dump) {
+                std::vector<float> hs(2 * body * (size_t)std::min<long long>(nf, 4));
+                WOFDM_CUDA(h, cudaMemcpyAsync(hs.data(), d_stream, hs.size() * 4, cudaMemcpyDeviceToHost, d.stream));
+                WOFDM_CUDA(h, cudaStreamSynchronize(d.stream));
+                if (FILE* fp = fopen(dump, "wb")) { fwrite(hs.data(), 4, hs.size(), fp); fclose(fp); }
+            }
+        }
         prm.frame_begin = f0; prm.frame_step = 1; prm.n_frames = nf;
         WOFDM_CUDA(h, ch.var->launch(prm, (int)std::min<long long>(nf, max_ctas), ch.lay.bytes, d.stream));
         h->launches += 2;

@@ -5,12 +5,12 @@
 #include "ber_tconv2.cuh"
 namespace wofdm {
 namespace {
-template <int N, int NT, int NTILE, int MINB, bool V, int CL = 1, int LB = TCV_LB>
+template <int N, int NT, int NTILE, int MINB, bool V, int CL = 1, int LB = TCV_LB, bool TXY = false>
 struct Tconv2VariantImpl {
     // grid = CTAs (a multiple of CL); CL > 1 launches thread-block clusters of CL CTAs
     static cudaError_t launch(const BerParams& prm, int grid, size_t smem, cudaStream_t st) {
         if constexpr (CL == 1) {
-            ber_tconv2_kernel<N, NT, NTILE, MINB, V, 1, LB><<<grid, NT + tconv2_mma_warp_threads(N, NT), smem, st>>>(prm);   // (+ the MMA warp)
+            ber_tconv2_kernel<N, NT, NTILE, MINB, V, 1, LB, TXY><<<grid, NT + tconv2_mma_warp_threads(N, NT), smem, st>>>(prm);   // (+ the MMA warp)
             return cudaGetLastError();
         } else {
             cudaLaunchConfig_t cfg = {};
@@ -19,16 +19,16 @@ struct Tconv2VariantImpl {
             at[0].id = cudaLaunchAttributeClusterDimension;
             at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             cfg.attrs = at; cfg.numAttrs = 1;
-            return cudaLaunchKernelEx(&cfg, ber_tconv2_kernel<N, NT, NTILE, MINB, V, CL, LB>, prm);
+            return cudaLaunchKernelEx(&cfg, ber_tconv2_kernel<N, NT, NTILE, MINB, V, CL, LB, TXY>, prm);
         }
     }
     static BerVariant make(const char* name) {
         BerVariant v;
         v.name = name; v.N = N; v.NT = NT; v.TC = 2 * NTILE; v.LB = LB; v.MINB = MINB; v.CL = CL; v.circ = false; v.txs = true; v.full = false;
-        v.ntile = NTILE; v.gen = 2; v.launch_threads = NT + tconv2_mma_warp_threads(N, NT);
+        v.ntile = NTILE; v.gen = 2; v.txy = TXY; v.launch_threads = NT + tconv2_mma_warp_threads(N, NT);
         v.fp64 = false; v.verify = V;
         v.layout = &tconv2_smem_layout<N, NT, NTILE, LB>;
-        v.fn = reinterpret_cast<const void*>(&ber_tconv2_kernel<N, NT, NTILE, MINB, V, CL, LB>);
+        v.fn = reinterpret_cast<const void*>(&ber_tconv2_kernel<N, NT, NTILE, MINB, V, CL, LB, TXY>);
         v.launch = &launch;
         return v;
     }
@@ -45,7 +45,14 @@ struct Tconv2VariantImpl {
 #define WOFDM_VARIANT_TCONV2_LB(N, NT, NTILE, MINB, CL, LB)                                                   \
     out.push_back(Tconv2VariantImpl<N, NT, NTILE, MINB, false, CL, LB>::make("ber_f32t2_n" #N "_t" #NT "_tiles" #NTILE "_b" #MINB "_cl" #CL "_l" #LB)); \
     out.push_back(Tconv2VariantImpl<N, NT, NTILE, MINB, true, CL, LB>::make("ber_f32t2_n" #N "_t" #NT "_tiles" #NTILE "_b" #MINB "_cl" #CL "_l" #LB "_verify"));
+// channel-mask chain: the Tx stream gathered from the mask product's output (BerParams::tx_y, tconv2_load_masked)
+#define WOFDM_VARIANT_TCONV2_TXY(N, NT, NTILE, MINB)                                                          \
+    out.push_back(Tconv2VariantImpl<N, NT, NTILE, MINB, false, 1, TCV_LB, true>::make("ber_f32t2_n" #N "_t" #NT "_tiles" #NTILE "_b" #MINB "_txy"));
 void register_ber_f32_tconv2(std::vector<BerVariant>& out) {
+    WOFDM_VARIANT_TCONV2_TXY(256, 256, 9, 2)
+    WOFDM_VARIANT_TCONV2_TXY(256, 256, 10, 2)
+    WOFDM_VARIANT_TCONV2_TXY(512, 512, 18, 1)
+    WOFDM_VARIANT_TCONV2_TXY(512, 512, 19, 1)
     WOFDM_VARIANT_TCONV2(256, 256, 9, 2)
     WOFDM_VARIANT_TCONV2(256, 256, 10, 2)
     WOFDM_VARIANT_TCONV2(512, 512, 18, 1)

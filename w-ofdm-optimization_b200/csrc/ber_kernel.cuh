@@ -81,6 +81,10 @@ struct BerParams {
     // staged policy with use_global: 2 * scratch_elems V2<T> per CTA
     void* scratch;
     long long scratch_elems;
+    // TXY instantiations of ber_tconv2.cuh (channel-mask chain): instead of tx_stream, the mask product's output (mask_gemm.cu),
+    // one column of tx_yp floats per symbol (local frame j, symbol s: column j*S + s); the loader does the overlap-adds itself
+    const float* tx_y;
+    int tx_yp;
 };
 
 // ---- constellation helpers (oracle/wofdm_oracle.py: idx_to_levels / levels_to_idx) --------------

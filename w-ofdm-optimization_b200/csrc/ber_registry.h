@@ -16,6 +16,7 @@ struct BerVariant {
     int ntile;                 // > 0: channel convolution on the tensor cores (ber_tconv*.cuh), frames of up to 512*ntile samples
     int launch_threads;        // threads per CTA at launch (NT, plus the MMA warp of ber_tconv2.cuh)
     int gen;                   // tensor-core kernels: 1 = ber_tconv.cuh (64-bit noise draws by position), 2 = ber_tconv2.cuh (48-bit draws)
+    bool txy = false;          // ber_tconv2.cuh: takes the Tx stream from the mask product's output (BerParams::tx_y) and nothing else
     bool fp64, verify;
     BerSmem (*layout)(int S, int stride, int tail_tx, int tail_rx, int L, int chunk, int use_global);
     const void* fn;

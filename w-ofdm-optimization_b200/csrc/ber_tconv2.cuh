@@ -139,6 +139,46 @@ __device__ __forceinline__ float2 n48_more_extras(const BerParams& prm, long lon
 __host__ __device__ constexpr int tconv2_wtx_len(int stride, int tail_tx) { return (stride + tail_tx + 3) & ~3; }
 __host__ __device__ constexpr int tconv2_wrx_len(int N, int tail_rx) { return (N + tail_rx + 3) & ~3; }
 
+// Channel-mask chain (TXY instantiations): the frame's serialised Tx stream gathered from the mask product's output
+// (mask_gemm.cu, BerParams::tx_y: y_s = column s of the frame, samples (Re, Im) interleaved).  Symbol s keeps its samples
+// 0..n_tx-1 and takes the filter tail of symbol s-1 at its start, filtered[s][i] = y_s[i] + y_{s-1}[n_tx + i] (i < n_tx - 1; the
+// last tail is dropped, main_channel_mask.m:413-416); the filtered symbols are overlap-added with the frame stride (tx2rx,
+// :420-431).  Four stream samples per thread and round: up to 16 loads in flight (the loader is latency bound otherwise).
+template <int NT>
+static __device__ __forceinline__ void tconv2_load_masked(const float* __restrict__ y0, int yp, int S, int stride, int n_tx, int body,
+                                                          uint32_t* __restrict__ uh, uint32_t* __restrict__ ul, int tid) {
+    constexpr int U = 4;
+    for (int p0 = tid; p0 < body; p0 += U * NT) {
+        float2 a[U], b[U], c[U], d[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int p = p0 + u * NT;
+            a[u] = b[u] = c[u] = d[u] = make_float2(0.f, 0.f);
+            if (p < body) {
+                const int s = min(p / stride, S), i = p - s * stride;
+                const float* ys = y0 + (size_t)s * yp;
+                if (s < S) {
+                    a[u] = __ldg(reinterpret_cast<const float2*>(ys + 2 * i));
+                    if (s >= 1 && i < n_tx - 1) b[u] = __ldg(reinterpret_cast<const float2*>(ys - yp + 2 * (n_tx + i)));
+                }
+                if (s >= 1 && stride + i < n_tx) {
+                    c[u] = __ldg(reinterpret_cast<const float2*>(ys - yp + 2 * (stride + i)));
+                    if (s >= 2 && stride + i < n_tx - 1) d[u] = __ldg(reinterpret_cast<const float2*>(ys - 2 * yp + 2 * (n_tx + stride + i)));
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int p = p0 + u * NT;
+            if (p < body) {
+                uint32_t hi, lo;
+                split_h2(cscale(TCV_XSCALE, cadd(cadd(a[u], b[u]), cadd(c[u], d[u]))), hi, lo);
+                uh[p] = hi; ul[p] = lo;
+            }
+        }
+    }
+}
+
 template <int N, int NT, int NTILE, int LB = TCV_LB>
 __host__ __device__ inline BerSmem tconv2_smem_layout(int S, int stride, int tail_tx, int tail_rx, int L, int nvar, int use_global) {
     using P = FftPlan<N>;
@@ -175,7 +215,7 @@ __host__ __device__ inline BerSmem tconv2_smem_layout(int S, int stride, int tai
 // three times per frame through distributed shared memory: the second CTA takes the first one's last Tx tail and the
 // L - 1 samples of convolution history (PULLED, a few dozen words), the per-warp power partials and the pilot's equaliser
 // taps are PUSHED into both CTAs, so every read is local.
-template <int N, int NT, int NTILE, int MINB, bool VERIFY, int CL = 1, int LB = TCV_LB>
+template <int N, int NT, int NTILE, int MINB, bool VERIFY, int CL = 1, int LB = TCV_LB, bool TXY = false>
 __global__ void __launch_bounds__(NT + tconv2_mma_warp_threads(N, NT), MINB)
 ber_tconv2_kernel(const BerParams prm) {
     using T = float;
@@ -454,11 +494,15 @@ ber_tconv2_kernel(const BerParams prm) {
                 }
                 symw[e] = make_uint4(w[0], w[1], w[2], w[3]);
             }
-            const float2* src = prm.tx_stream + (size_t)j * body;
-            for (int i = tid; i < body; i += NT) {
-                uint32_t hi, lo;
-                split_h2(cscale(TCV_XSCALE, src[i]), hi, lo);
-                uh[i] = hi; ul[i] = lo;
+            if constexpr (TXY) {             // (its own instantiations: the production kernels stay as they are)
+                tconv2_load_masked<NT>(prm.tx_y + (size_t)j * S * prm.tx_yp, prm.tx_yp, S, stride, n_tx, body, uh, ul, tid);
+            } else {
+                const float2* src = prm.tx_stream + (size_t)j * body;
+                for (int i = tid; i < body; i += NT) {
+                    uint32_t hi, lo;
+                    split_h2(cscale(TCV_XSCALE, src[i]), hi, lo);
+                    uh[i] = hi; ul[i] = lo;
+                }
             }
             frame_sync<CL>();
         } else {
