@@ -13,7 +13,7 @@ per GPU (ensemble 27 x 16 -> 3.24 M frames = 51.8 M OFDM symbols per GPU and ste
 region is seconds, not milliseconds, long.  Weak scaling: the ensemble grows with N, frames are sharded by global frame
 id, one all-reduce of the int64 counters per step.
 Beside the headline the line carries: `e2e` (host buffers through the C-ABI), `roofline`, `cpu_baseline`, and the
-secondary objects `matlab_convention` (the same batch in MATLAB's conventions), `configs4` / `configs4_l84` (N=1024 stress case), `k2`
+secondary objects `matlab_convention` (the same batch in MATLAB's conventions), `configs4` / `configs4_l84` (N=1024 stress case), `mask_chain`, `k2`
 (interference power, configs[3] shapes, fp64 and TF32-split, channels sharded over the ranks) and, for N > 1, `strong`
 (the N=1 batch sharded over N GPUs).  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement".
 """
@@ -526,6 +526,27 @@ def main():
                 with open(tp) as fh:
                     k2["traffic"] = json.load(fh)
         extras["k2"] = k2
+        # (5) the channel-mask BER variant (matlab/main_channel_mask.m): guard band N/4 + DFT-domain RC mask, the mask as a
+        #     dense tcgen05 product.  One device per call: every rank runs the same call, rank 0 reports its own wall time.
+        import time as _time
+        import numpy as _np
+        sm_ = W.params_from_name("wtx", 256, 16, 8, 0, bits=4, S=16, noise_norm=1, constellation=1, guard=64)
+        rng_ = _np.random.default_rng(0)
+        ch_ = (rng_.standard_normal((21, 250)) + 1j * rng_.standard_normal((21, 250))) * _np.exp(-_np.arange(21) / 4)[:, None]
+        snr_ = _np.linspace(-20, 50, 30)
+        vt_, vr_ = capi.rc_window_tx(sm_), capi.rc_window_rx(sm_)
+        ens_ = 16
+        for _ in range(2):
+            h.ber_run_masked(sm_, vt_, vr_, ch_, snr_, ens_, seed=1, variant=1)
+        t0_ = _time.perf_counter()
+        for k_ in range(3):
+            rm_ = h.ber_run_masked(sm_, vt_, vr_, ch_, snr_, ens_, seed=2 + k_, variant=1)
+        dt_ = (_time.perf_counter() - t0_) / 3
+        extras["mask_chain"] = {"value": 30 * 250 * ens_ * 16 / dt_, "unit": UNIT, "ms_per_call": dt_ * 1e3, "frames_per_call": 30 * 250 * ens_,
+                                "api": "wofdm_ber_run_masked (ctypes, host buffers in, int64 counters out; wall time)",
+                                "workload": "main_channel_mask.m run_sim_mc: wtx N=256 cp=16 tail_tx=8 16-QAM, 128 active sub-carriers (guard 64), "
+                                            "RC mask roll-off 10 bins, 250 channels x 30 SNR points x ensemble 16, MATLAB conventions (parity unpinned)",
+                                "ber": [float(rm_["bit_err"][k] / rm_["bit_tot"][k]) for k in (0, 10, 15, 20, 29)]}
     if rank == 0:
         line.update(extras)
         if world == 1 and not args.no_cpu_baseline:
