@@ -188,14 +188,15 @@ def test_channel_mask_variant_replay(handle, name, cp, bits):
     assert 0.0 <= b0 < 0.5 and 0.0 <= bm < 0.5
 
 
-@pytest.mark.parametrize("name,N,cp,ttx,trx,bits,guard", [("CP", 128, 8, 0, 0, 2, 0), ("CPW", 512, 32, 16, 20, 4, 128),
-                                                           ("wtx", 256, 16, 8, 0, 6, 0), ("WOLA", 256, 30, 8, 10, 4, 64)])
-def test_channel_mask_product_against_fft_kernel(handle, tmp_path, name, N, cp, ttx, trx, bits, guard):
+@pytest.mark.parametrize("name,N,cp,ttx,trx,bits,guard,S", [("CP", 128, 8, 0, 0, 2, 0, 16), ("CPW", 512, 32, 16, 20, 4, 128, 16),
+                                                             ("wtx", 256, 16, 8, 0, 6, 0, 16), ("WOLA", 256, 30, 8, 10, 4, 64, 7),
+                                                             ("CPwtx", 256, 10, 8, 0, 4, 100, 2)])
+def test_channel_mask_product_against_fft_kernel(handle, tmp_path, name, N, cp, ttx, trx, bits, guard, S):
     """The masked Tx stream two ways: the dense tensor-core product (mask_gemm.cu: the matrices of main_channel_mask.m:384-417
     multiplied out once, fp16 hi + lo against the exact lattice points) and the per-symbol FFT kernel (mask_kernel.cuh).
     Streams of the first frames agree to fp32 rounding; the K1 kernel that gathers from the product's output itself gives
     the counters of the assembled stream bit for bit; counters of the two Tx kernels differ by boundary decisions only."""
-    s = W.params_from_name(name, N, cp, ttx, trx, bits=bits, S=16, noise_norm=1, constellation=1, guard=guard)
+    s = W.params_from_name(name, N, cp, ttx, trx, bits=bits, S=S, noise_norm=1, constellation=1, guard=guard)
     vt, vr = W.capi.rc_window_tx(s), W.capi.rc_window_rx(s)
     chans = O.synth_channels(6, 21, seed=N + cp)
     snr = np.array([6.0, 18.0, 30.0, 42.0])
@@ -213,10 +214,30 @@ def test_channel_mask_product_against_fft_kernel(handle, tmp_path, name, N, cp, 
         os.environ.pop("WOFDM_MASK_FFT", None)
         os.environ.pop("WOFDM_MASK_DUMP", None)
     a, b = dumps["fft"], dumps["gemm"]
-    assert a.size == b.size == 2 * 4 * (ttx + 16 * (N + cp + s.cs - ttx))
+    assert a.size == b.size == 2 * 4 * (ttx + S * (N + cp + s.cs - ttx))
     assert np.abs(a - b).max() <= 4e-6 * np.abs(a).max(), (np.abs(a - b).max(), np.abs(a).max())
     for k in ("bit_err", "sym_err", "bit_tot", "sym_tot"):
         assert np.array_equal(res["gather"][k], res["gemm"][k]), k
     assert np.all(np.abs(res["fft"]["sym_err"] - res["gemm"]["sym_err"]) <= 2), (res["fft"]["sym_err"], res["gemm"]["sym_err"])
     assert np.all(np.abs(res["fft"]["bit_err"] - res["gemm"]["bit_err"]) <= 4), (res["fft"]["bit_err"], res["gemm"]["bit_err"])
     assert res["gemm"]["sym_err"][0] > res["gemm"]["sym_err"][-1]
+
+
+def test_channel_mask_product_over_several_batches(handle):
+    """More frames than one batch of the mask product holds (16 384): the last, shorter batch reuses the operand buffers."""
+    s = W.params_from_name("wtx", 256, 16, 8, 0, bits=4, S=16, noise_norm=1, constellation=1, guard=64)
+    vt, vr = W.capi.rc_window_tx(s), W.capi.rc_window_rx(s)
+    chans = O.synth_channels(25, 21, seed=3)
+    snr = np.linspace(0.0, 40.0, 30)
+    ens = 24                                                 # 18 000 frames
+    got = handle.ber_run_masked(s, vt, vr, chans, snr, ens, seed=11, variant=1, roll_off=10)
+    os.environ["WOFDM_MASK_FFT"] = "1"
+    try:
+        ref = handle.ber_run_masked(s, vt, vr, chans, snr, ens, seed=11, variant=1, roll_off=10)
+    finally:
+        del os.environ["WOFDM_MASK_FFT"]
+    assert np.all(got["sym_tot"] == 25 * ens * 128 * 15)
+    assert np.all(np.abs(got["sym_err"] - ref["sym_err"]) <= 3 + 2e-5 * ref["sym_err"]), (got["sym_err"], ref["sym_err"])
+    assert np.all(np.abs(got["bit_err"] - ref["bit_err"]) <= 5 + 2e-5 * ref["bit_err"]), (got["bit_err"], ref["bit_err"])
+    again = handle.ber_run_masked(s, vt, vr, chans, snr, ens, seed=11, variant=1, roll_off=10)
+    assert np.array_equal(again["bit_err"], got["bit_err"]) and np.array_equal(again["sym_err"], got["sym_err"])

@@ -495,6 +495,11 @@ ber_tconv2_kernel(const BerParams prm) {
                 symw[e] = make_uint4(w[0], w[1], w[2], w[3]);
             }
             if constexpr (TXY) {             // (its own instantiations: the production kernels stay as they are)
+                // the frame this CTA takes next: its S columns of Y are contiguous -- one bulk prefetch into L2 (the loader is
+                // bound by the latency of its gather, and the product wrote Y through to HBM)
+                if (tid == 0 && j + nslots < prm.n_frames)
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(prm.tx_y + (size_t)(j + nslots) * S * prm.tx_yp),
+                                 "r"((uint32_t)(S * prm.tx_yp * 4)) : "memory");
                 tconv2_load_masked<NT>(prm.tx_y + (size_t)j * S * prm.tx_yp, prm.tx_yp, S, stride, n_tx, body, uh, ul, tid);
             } else {
                 const float2* src = prm.tx_stream + (size_t)j * body;

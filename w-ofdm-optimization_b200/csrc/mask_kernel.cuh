@@ -68,7 +68,10 @@ __global__ void __launch_bounds__(256) tx_mask_kernel(const MaskParams p) {
     __syncthreads();
     BerParams draw = {};                                   // only what load_sym_idx reads
     draw.seed = p.seed; philox_round_keys(p.seed, draw.rk); draw.bits = p.bits; draw.S = S;
-    const int half = (S + FPPP - 1) / FPPP;                // symbols per big-transform slot: slot g takes g*half + pass
+    // symbols per big-transform slot: slot g takes g*half + pass.  At least two, so that symbols filtered at the same time are
+    // never neighbours (their stream segments overlap by the Tx tail; S <= FPPP used to put neighbours side by side -- found by
+    // the comparison with the mask product, tests/test_drivers_gpu.py::test_channel_mask_product_against_fft_kernel)
+    const int half = max(2, (S + FPPP - 1) / FPPP);
     for (long long j = blockIdx.x; j < p.n_frames; j += gridDim.x) {
         const long long f = p.frame_begin + j * p.frame_step;
         for (int i = tid; i < body; i += NT) us[i] = make_float2(0.f, 0.f);
