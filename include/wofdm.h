@@ -197,7 +197,10 @@ WOFDM_API int wofdm_interf_last_timing(wofdm_handle h, double* total_ms, double*
  * whose windowed symbols pass the DFT-domain raised-cosine mask of length 2 n_tx - 1 (dft_rc_filt, :398-417, roll_off
  * as `rollOff`, 10 in the reference); the filter tail of each symbol is added to the next one.  Same arguments, draws
  * (the symbol stream does not depend on `variant`) and counters as wofdm_ber_run, whose result with the same sys is
- * the UNMASKED ber of that script.  fp32, N = 128 / 256 / 512, one device (the first of the handle). */
+ * the UNMASKED ber of that script.  fp32, N = 128 / 256 / 512; the frames are split over the devices of the handle
+ * (contiguous ranges of the global frame id: counters do not depend on the split).  The Tx side is one dense tensor-core
+ * product (csrc/mask_gemm.cu: the script's matrices multiplied out once); WOFDM_MASK_FFT=1 in the environment selects
+ * the per-symbol FFT kernel (csrc/mask_kernel.cuh) instead. */
 WOFDM_API int wofdm_ber_run_masked(wofdm_handle h, const wofdm_sys_t* sys, const double* win_tx, const double* win_rx,
                          const double* chan, int L, int C, const double* snr_db, int n_snr, int64_t ensemble,
                          uint64_t seed, uint32_t variant, int roll_off,

@@ -717,6 +717,13 @@ def test_in_process_multi_device_handle_matches_one_device():
         b = hall.ber_run_multi(s, wins_t, wins_r, chan, snr, 11, seed=6)
         for k in a:
             assert np.array_equal(a[k], b[k]), k
+        # the channel-mask chain: contiguous frame ranges per device, its mask product and K1 on each of them
+        sg = W.params_from_name("wtx", 256, 16, 8, 0, bits=4, S=16, noise_norm=1, constellation=1, guard=64)
+        wt, wr = W.capi.rc_window_tx(sg), W.capi.rc_window_rx(sg)
+        a = h1.ber_run_masked(sg, wt, wr, chan, snr, 37, seed=7, variant=1)
+        b = hall.ber_run_masked(sg, wt, wr, chan, snr, 37, seed=7, variant=1)
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k
         # the interference path of a multi-device handle runs on its first device
         Pa = h1.interf_power(to_sys(p, 1), vt, vr, chan)
         Pb = hall.interf_power(to_sys(p, 1), vt, vr, chan)

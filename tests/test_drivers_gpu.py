@@ -143,16 +143,16 @@ def test_production_ser_against_the_reference_itself(handle, name):
         assert np.all(np.abs(z) <= 3.5), (name, w, z, ref[w], mean)
 
 
-@pytest.mark.parametrize("name,cp,bits", [("wtx", 16, 4), ("WOLA", 22, 4), ("CP", 16, 2), ("CPW", 16, 6)])
-def test_channel_mask_variant_replay(handle, name, cp, bits):
+@pytest.mark.parametrize("name,cp,bits,S", [("wtx", 16, 4, 16), ("WOLA", 22, 4, 16), ("CP", 16, 2, 16), ("CPW", 16, 6, 16), ("WOLA", 16, 4, 3)])
+def test_channel_mask_variant_replay(handle, name, cp, bits, S):
     """matlab/main_channel_mask.m: guard band N/4 + DFT-domain RC mask.  The production counters of the
     masked chain, replayed through the oracle's line-by-line restatement (frame_chain_masked) from the exported draws;
     the unmasked counters of the same symbols through frame_chain_structured.  (MATLAB-only path: parity unpinned.)"""
     ttx = 8 if name in U.TX_SYSTEMS else 0
     trx = 10 if name in U.RX_SYSTEMS else 0
-    p = O.system_params(name, 256, cp, ttx, trx, S=16, bits=bits, noise_norm=1, constellation=1, guard=64)
+    p = O.system_params(name, 256, cp, ttx, trx, S=S, bits=bits, noise_norm=1, constellation=1, guard=64)
     vt, vr, _, _ = O.perturbed_windows(p, seed=cp)
-    s = W.SysT(N=p.N, cp=p.cp, cs=p.cs, tail_tx=p.tail_tx, tail_rx=p.tail_rx, rm=p.rm, shift=p.shift, bits=bits, S=16,
+    s = W.SysT(N=p.N, cp=p.cp, cs=p.cs, tail_tx=p.tail_tx, tail_rx=p.tail_rx, rm=p.rm, shift=p.shift, bits=bits, S=S,
                noise_norm=1, constellation=1, precision=0, guard=64)
     chans = O.synth_channels(2, 21, seed=cp)
     snr = np.array([14.0, 32.0])
@@ -169,7 +169,7 @@ def test_channel_mask_variant_replay(handle, name, cp, bits):
         b = O.frame_chain_masked(p, vt, vr, chans[:, c], snr[si], sym[f].T, nz1[f], roll_off=10)
         want[0, si] += (a.sym_err, a.bit_err)
         want[1, si] += (b.sym_err, b.bit_err)
-    assert np.all(masked["sym_tot"] == 2 * ens * 128 * 15) and np.all(masked["bit_tot"] == masked["sym_tot"] * bits)
+    assert np.all(masked["sym_tot"] == 2 * ens * 128 * (S - 1)) and np.all(masked["bit_tot"] == masked["sym_tot"] * bits)
     for res, w in ((plain, want[0]), (masked, want[1])):
         assert np.all(np.abs(res["sym_err"] - w[:, 0]) <= 3 + 0.003 * w[:, 0]), (res["sym_err"], w[:, 0])
         assert np.all(np.abs(res["bit_err"] - w[:, 1]) <= 5 + 0.003 * w[:, 1]), (res["bit_err"], w[:, 1])

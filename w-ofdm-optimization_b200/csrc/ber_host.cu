@@ -719,8 +719,8 @@ int wofdm_ber_run_masked(wofdm_handle h, const wofdm_sys_t* sys, const double* w
     if (N != 128 && N != 256 && N != 512) return fail(h, WOFDM_EUNSUPPORTED, "the channel-mask variant is built for N = 128, 256, 512");
     if (roll_off < 1 || M / 2 + 2 * roll_off > M) return fail(h, WOFDM_EINVAL, "roll_off does not fit the mask");
     if (2 * n_tx > 3 * N + 1) return fail(h, WOFDM_EUNSUPPORTED, "cp + cs too long for the mask kernel (n_tx <= 1.5 N)");
-    DeviceCtx& d = h->devs[0];
-    WOFDM_CUDA(h, cudaSetDevice(d.dev));
+    DeviceCtx& d0 = h->devs[0];              // (variant selection: the devices of a handle are alike)
+    WOFDM_CUDA(h, cudaSetDevice(d0.dev));
     Choice ch, prod;
     // Tx side: the dense tensor-core product of mask_gemm.cu; WOFDM_MASK_FFT=1 keeps the per-symbol FFT kernel (mask_kernel.cuh)
     const char* mask_env = getenv("WOFDM_MASK_FFT");
@@ -730,18 +730,18 @@ int wofdm_ber_run_masked(wofdm_handle h, const wofdm_sys_t* sys, const double* w
     // HBM) where the frame fits one, else a tx_stream kernel (tuned or staged)
     bool fused = false;
     if (use_gemm && !(dump_env && *dump_env)) {
-        rc = choose_variant(h, *sys, L, false, false, d.smem_optin, &ch, nullptr, true, true, false, 1, true);
+        rc = choose_variant(h, *sys, L, false, false, d0.smem_optin, &ch, nullptr, true, true, false, 1, true);
         fused = rc == WOFDM_OK && ch.var->txy;
     }
-    if (!fused) rc = choose_variant(h, *sys, L, false, false, d.smem_optin, &ch, nullptr, true, true);
+    if (!fused) rc = choose_variant(h, *sys, L, false, false, d0.smem_optin, &ch, nullptr, true, true);
     if (rc) return rc;
     if (ch.var->CL > 1) return fail(h, WOFDM_EUNSUPPORTED, "no channel-mask variant for cluster kernels");
-    rc = choose_variant(h, *sys, L, false, false, d.smem_optin, &prod, win_tx);     // noise numbering of wofdm_ber_run / _draws
+    rc = choose_variant(h, *sys, L, false, false, d0.smem_optin, &prod, win_tx);     // noise numbering of wofdm_ber_run / _draws
     if (rc) return rc;
     if (prod.var->CL > 1) return fail(h, WOFDM_EUNSUPPORTED, "no channel-mask variant for cluster kernels");
     int nb = 0;
     long long max_ctas = 0;
-    rc = prepare_kernel(h, *ch.var, ch.lay.bytes, d.sm_count, &nb, &max_ctas);
+    rc = prepare_kernel(h, *ch.var, ch.lay.bytes, d0.sm_count, &nb, &max_ctas);
     if (rc) return rc;
     std::vector<double> gd;
     if (!use_gemm) {
@@ -805,9 +805,21 @@ int wofdm_ber_run_masked(wofdm_handle h, const wofdm_sys_t* sys, const double* w
     const size_t scratch_elems = (size_t)ch.lay.pad + body + 64;
     const int grid_ber = (int)std::min<long long>(batch, max_ctas);
     const size_t scratch_bytes = ch.use_global ? (size_t)grid_ber * 2 * scratch_elems * sizeof(float2) : 0;
+    // every device of the handle takes a contiguous range of the frames (frame ids are global: same draws, same counters as
+    // on one device); its work is enqueued on its own stream, the counters meet on the host
+    const int nd = (int)std::min<long long>((long long)h->devs.size(), std::max<long long>(1, total / 64));
+    std::vector<std::vector<unsigned long long>> cnts(nd, std::vector<unsigned long long>((size_t)n_snr * 2, 0ull));
+    std::vector<void*> d_cnts(nd, nullptr);
+    auto run_dev = [&](DeviceCtx& d, long long f_lo, long long f_hi, void** d_cnt_out) -> int {
+    WOFDM_CUDA(h, cudaSetDevice(d.dev));
+    if (&d != &d0) {
+        int nb_ = 0; long long mc_ = 0;
+        const int rcp = prepare_kernel(h, *ch.var, ch.lay.bytes, d.sm_count, &nb_, &mc_);
+        if (rcp) return rcp;
+    }
     MaskGemm mg;
     const size_t mg_bytes = use_gemm ? mask_gemm_plan(*sys, batch, mg) : 0;
-    rc = arena_reserve(h, d, t.wtx.size() + t.wrx.size() + t.tw.size() + twp.size() + hchan.size() + hsnr.size() + g.size() * 4 +
+    int rc = arena_reserve(h, d, t.wtx.size() + t.wrx.size() + t.tw.size() + twp.size() + hchan.size() + hsnr.size() + g.size() * 4 +
                                  (size_t)n_snr * 16 + (fused ? 16 : (size_t)batch * body * sizeof(float2)) + scratch_bytes + mg_bytes + 8192);
     if (rc) return rc;
     auto put = [&](const void* src, size_t bytes, void** dst) -> cudaError_t {
@@ -858,8 +870,8 @@ int wofdm_ber_run_masked(wofdm_handle h, const wofdm_sys_t* sys, const double* w
     prm.tx_stream = static_cast<const float2*>(d_stream);
     if (fused) { prm.tx_y = mg.Y; prm.tx_yp = mg.Yp; }
     size_t msm = 0;
-    for (long long f0 = 0; f0 < total; f0 += batch) {
-        const long long nf = std::min(batch, total - f0);
+    for (long long f0 = f_lo; f0 < f_hi; f0 += batch) {
+        const long long nf = std::min(batch, f_hi - f0);
         mp.frame_begin = f0; mp.frame_step = 1; mp.n_frames = nf;
         const int mgrid = (int)std::min<long long>(nf, (long long)d.sm_count);
         cudaError_t e = cudaSuccess;
@@ -894,11 +906,27 @@ int wofdm_ber_run_masked(wofdm_handle h, const wofdm_sys_t* sys, const double* w
         WOFDM_CUDA(h, ch.var->launch(prm, (int)std::min<long long>(nf, max_ctas), ch.lay.bytes, d.stream));
         h->launches += 2;
     }
-    std::vector<unsigned long long> cnt((size_t)n_snr * 2);
-    WOFDM_CUDA(h, cudaMemcpyAsync(cnt.data(), d_cnt, cnt.size() * 8, cudaMemcpyDeviceToHost, d.stream));
-    WOFDM_CUDA(h, cudaStreamSynchronize(d.stream));
+    *d_cnt_out = d_cnt;
+    return WOFDM_OK;
+    };   // run_dev
+    for (int i = 0; i < nd; ++i) {
+        rc = run_dev(h->devs[i], total * i / nd, total * (i + 1) / nd, &d_cnts[i]);
+        if (rc) break;
+    }
+    // (the downloads into pageable memory block the host: only after every device has its work)
+    for (int i = 0; i < nd; ++i) {           // (also after a failure: nothing of this call stays in flight)
+        cudaSetDevice(h->devs[i].dev);
+        cudaError_t es = cudaSuccess;
+        if (!rc && d_cnts[i]) es = cudaMemcpyAsync(cnts[i].data(), d_cnts[i], (size_t)n_snr * 16, cudaMemcpyDeviceToHost, h->devs[i].stream);
+        if (es == cudaSuccess) es = cudaStreamSynchronize(h->devs[i].stream);
+        if (es != cudaSuccess && !rc) rc = fail(h, WOFDM_ECUDA, std::string("wofdm_ber_run_masked: ") + cudaGetErrorString(es));
+    }
+    cudaSetDevice(d0.dev);
+    if (rc) return rc;
     for (int i = 0; i < n_snr; ++i) {
-        bit_err[i] = (int64_t)cnt[2 * i]; sym_err[i] = (int64_t)cnt[2 * i + 1];
+        unsigned long long be = 0, se = 0;
+        for (int k = 0; k < nd; ++k) { be += cnts[k][2 * i]; se += cnts[k][2 * i + 1]; }
+        bit_err[i] = (int64_t)be; sym_err[i] = (int64_t)se;
         sym_tot[i] = (int64_t)C * ensemble * (N - 2 * sys->guard) * (sys->S - 1);
         bit_tot[i] = sym_tot[i] * sys->bits;
     }
