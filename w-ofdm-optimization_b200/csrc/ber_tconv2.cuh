@@ -140,31 +140,25 @@ __host__ __device__ constexpr int tconv2_wtx_len(int stride, int tail_tx) { retu
 __host__ __device__ constexpr int tconv2_wrx_len(int N, int tail_rx) { return (N + tail_rx + 3) & ~3; }
 
 // Channel-mask chain (TXY instantiations): the frame's serialised Tx stream gathered from the mask product's output
-// (mask_gemm.cu, BerParams::tx_y: y_s = column s of the frame, samples (Re, Im) interleaved).  Symbol s keeps its samples
-// 0..n_tx-1 and takes the filter tail of symbol s-1 at its start, filtered[s][i] = y_s[i] + y_{s-1}[n_tx + i] (i < n_tx - 1; the
-// last tail is dropped, main_channel_mask.m:413-416); the filtered symbols are overlap-added with the frame stride (tx2rx,
-// :420-431).  Four stream samples per thread and round: up to 16 loads in flight (the loader is latency bound otherwise).
+// (mask_gemm.cu, BerParams::tx_y: column s of the frame = the filtered symbol f_s, n_tx samples (Re, Im) interleaved, the
+// filter tail of symbol s-1 already inside, main_channel_mask.m:413-416).  The filtered symbols are overlap-added with the
+// frame stride (tx2rx, :420-431): stream[s stride + i] = f_s[i] + f_{s-1}[stride + i].  Four stream samples per thread and
+// round: eight loads in flight (the loader is latency bound otherwise).
 template <int NT>
 static __device__ __forceinline__ void tconv2_load_masked(const float* __restrict__ y0, int yp, int S, int stride, int n_tx, int body,
                                                           uint32_t* __restrict__ uh, uint32_t* __restrict__ ul, int tid) {
     constexpr int U = 4;
     for (int p0 = tid; p0 < body; p0 += U * NT) {
-        float2 a[U], b[U], c[U], d[U];
+        float2 a[U], c[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int p = p0 + u * NT;
-            a[u] = b[u] = c[u] = d[u] = make_float2(0.f, 0.f);
+            a[u] = c[u] = make_float2(0.f, 0.f);
             if (p < body) {
                 const int s = min(p / stride, S), i = p - s * stride;
                 const float* ys = y0 + (size_t)s * yp;
-                if (s < S) {
-                    a[u] = __ldg(reinterpret_cast<const float2*>(ys + 2 * i));
-                    if (s >= 1 && i < n_tx - 1) b[u] = __ldg(reinterpret_cast<const float2*>(ys - yp + 2 * (n_tx + i)));
-                }
-                if (s >= 1 && stride + i < n_tx) {
-                    c[u] = __ldg(reinterpret_cast<const float2*>(ys - yp + 2 * (stride + i)));
-                    if (s >= 2 && stride + i < n_tx - 1) d[u] = __ldg(reinterpret_cast<const float2*>(ys - 2 * yp + 2 * (n_tx + stride + i)));
-                }
+                if (s < S) a[u] = __ldg(reinterpret_cast<const float2*>(ys + 2 * i));
+                if (s >= 1 && stride + i < n_tx) c[u] = __ldg(reinterpret_cast<const float2*>(ys - yp + 2 * (stride + i)));
             }
         }
 #pragma unroll
@@ -172,7 +166,7 @@ static __device__ __forceinline__ void tconv2_load_masked(const float* __restric
             const int p = p0 + u * NT;
             if (p < body) {
                 uint32_t hi, lo;
-                split_h2(cscale(TCV_XSCALE, cadd(cadd(a[u], b[u]), cadd(c[u], d[u]))), hi, lo);
+                split_h2(cscale(TCV_XSCALE, cadd(a[u], c[u])), hi, lo);
                 uh[p] = hi; ul[p] = lo;
             }
         }

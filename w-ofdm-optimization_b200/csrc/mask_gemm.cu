@@ -13,6 +13,15 @@
 //
 //     [Re y; Im y] (2M rows, interleaved) = A (2M x 2 nact, real form of Mm) . [Re a; Im a]  for all symbols of a batch at once.
 //
+// dft_rc_filt then keeps samples 0..n_tx-1 of y_s in symbol s and adds the other n_tx - 1 to the start of symbol s+1 (:413-416).
+// That is linear too and goes into the product's K dimension: with Mm = [Mtop; Mbot] (rows 0..n_tx-1 and n_tx..M-1, a zero row
+// appended), the filtered symbol is
+//
+//     f_s = y_s[0..n_tx) + y_{s-1}[n_tx..M) = [Mtop | Mbot] [a_s; a_{s-1}]          (a_{-1} = 0)
+//
+// -- the same number of MACs (n_tx x 2 nact instead of M x nact), half the output.  The B operand holds, per column (frame, s),
+// the lattice points of symbol s followed by those of symbol s-1.
+//
 // The lattice points are small odd integers -- exact in fp16 -- and A is split A = hi + lo in fp16 behind a power-of-two
 // scale (relative error ~2^-22 per entry, fp32 accumulation in tensor memory): two MMAs per K step give fp32-grade
 // results, 1.2 Mflop per symbol.  Kernels:
@@ -21,10 +30,9 @@
 //   mask_sym_kernel                          the Philox symbol draws of K1 (load_sym_idx) -> lattice points as fp16 B tiles
 //   mask_gemm_f16                            persistent, warp-specialised: bulk-copy producer, one MMA thread, four epilogue
 //                                            warps; two 128 x 256 accumulators in tensor memory, three 64 KB stages
-//   mask_assemble_kernel                     (K1 kernels other than ber_tconv2.cuh, which gathers from Y itself:) symbol s
-//                                            keeps samples 0..n_tx-1, the filter's tail is added to the start of
-//                                            symbol s+1 (:413-416), symbols are overlap-added with the frame stride (tx2rx,
-//                                            :420-431): the serialised stream K1 reads (BerParams::tx_stream)
+//   mask_assemble_kernel                     (K1 kernels other than ber_tconv2.cuh, which gathers from Y itself:) the filtered
+//                                            symbols overlap-added with the frame stride (tx2rx, :420-431): the serialised
+//                                            stream K1 reads (BerParams::tx_stream)
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -148,9 +156,10 @@ __global__ void __launch_bounds__(256) mask_matrix_kernel(const double2* __restr
 }
 
 // real form, scaled by a power of two into the comfortable fp16 range and split hi + lo, straight into the UMMA tiles:
-// A[2r][2c] = Re, A[2r][2c+1] = -Im, A[2r+1][2c] = Im, A[2r+1][2c+1] = Re; rows >= 2M and columns >= 2 nact are zero
+// A[2r][2c] = Re, A[2r][2c+1] = -Im, A[2r+1][2c] = Im, A[2r+1][2c+1] = Re of Mm[r][c] in columns [0, Kp/2) (r < n_tx: Mtop) and of
+// Mm[n_tx + r][c] in columns [Kp/2, Kp) (Mbot); rows >= 2 n_tx, row n_tx - 1 of Mbot and the K padding are zero
 __global__ void __launch_bounds__(256) mask_split_kernel(const double2* __restrict__ Mm, const unsigned* __restrict__ maxbits, __half* __restrict__ At,
-                                                         float* __restrict__ scale_out, int M, int nact, int Kp, int RT) {
+                                                         float* __restrict__ scale_out, int M, int n_tx, int nact, int Kp, int RT) {
     const float mx = __uint_as_float(*maxbits);
     const int ex = mx > 0.f ? 11 - ilogbf(mx) : 0;         // largest entry lands in [2^11, 2^12)
     const double sc = ldexp(1.0, ex);
@@ -160,9 +169,10 @@ __global__ void __launch_bounds__(256) mask_split_kernel(const double2* __restri
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int R = (int)(i / Kp), k = (int)(i % Kp);
         double x = 0.0;
-        if (R < 2 * M && k < 2 * nact) {
-            const double2 v = Mm[(size_t)(R >> 1) * nact + (k >> 1)];
-            x = (R & 1) ? ((k & 1) ? v.x : v.y) : ((k & 1) ? -v.y : v.x);
+        const int part = k >= Kp / 2, kk = k - part * (Kp / 2), row = (R >> 1) + part * n_tx;
+        if (R < 2 * n_tx && row < M && kk < 2 * nact) {
+            const double2 v = Mm[(size_t)row * nact + (kk >> 1)];
+            x = (R & 1) ? ((kk & 1) ? v.x : v.y) : ((kk & 1) ? -v.y : v.x);
         }
         x *= sc;
         const __half hi = __float2half_rn((float)x);
@@ -173,31 +183,45 @@ __global__ void __launch_bounds__(256) mask_split_kernel(const double2* __restri
     }
 }
 
-// the symbols of the batch, exactly as K1 draws them (load_sym_idx): thread (frame, s, t) holds the 16 level codes of bins
-// t + q TPF and stores the lattice points of the active ones as (Re, Im) fp16 pairs of column frame * S + s
+// the symbols of the batch, exactly as K1 draws them (load_sym_idx): one CTA per frame; thread (s, t) holds the 16 level codes
+// of bins t + q TPF and parks the lattice points of the active ones, (Re, Im) fp16 pairs, in shared memory; the frame's columns
+// then leave as 16-byte chunks (four sub-carriers; consecutive lanes = consecutive columns of a core matrix): into the first
+// half of column frame * S + s (a_s) and into the second half of the next symbol's column (a_{s-1} there; symbol 0's second
+// half stays zero)
 template <int N>
 __global__ void __launch_bounds__(256) mask_sym_kernel(const BerParams draw, long long f0, long long nf, int S, int guard, int nact,
                                                        __half* __restrict__ Bt, int nk) {
     constexpr int TPF = N / 16;
+    extern __shared__ __align__(16) __half2 lat[];         // [S][rowp]
+    const int khalf = nk * KB / 2;
     const int hb = draw.bits >> 1, m = 1 << hb;
-    const long long total = nf * S * TPF;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int t = (int)(i % TPF);
-        const long long col = i / TPF;
-        const int s = (int)(col % S);
-        const long long fl = col / S;
-        uint32_t w[4];
-        load_sym_idx<N, false>(draw, f0 + fl, s, t, w);
+    const int nchunk = (nact + 3) / 4, rowp = 4 * nchunk + 4;
+    for (int e = threadIdx.x; e < S * rowp; e += blockDim.x) lat[e] = __floats2half2_rn(0.f, 0.f);
+    __syncthreads();
+    for (long long fl = blockIdx.x; fl < nf; fl += gridDim.x) {
+        for (int e = threadIdx.x; e < S * TPF; e += blockDim.x) {
+            const int s = e / TPF, t = e % TPF;
+            uint32_t w[4];
+            load_sym_idx<N, false>(draw, f0 + fl, s, t, w);
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            const int bin = t + q * TPF;
-            const int c = ((bin + N / 2) & (N - 1)) - guard;
-            if (c >= 0 && c < nact) {
-                const int code = sym_byte(w, q);
-                const __half2 v = __floats2half2_rn((float)(2 * (code >> hb) - (m - 1)), (float)(2 * (code & (m - 1)) - (m - 1)));
-                *reinterpret_cast<__half2*>(Bt + b_off(col, 2 * c, nk)) = v;
+            for (int q = 0; q < 16; ++q) {
+                const int bin = t + q * TPF;
+                const int c = ((bin + N / 2) & (N - 1)) - guard;
+                if (c >= 0 && c < nact) {
+                    const int code = sym_byte(w, q);
+                    lat[s * rowp + c] = __floats2half2_rn((float)(2 * (code >> hb) - (m - 1)), (float)(2 * (code & (m - 1)) - (m - 1)));
+                }
             }
         }
+        __syncthreads();
+        for (int e = threadIdx.x; e < S * nchunk; e += blockDim.x) {
+            const int s = e % S, kc = e / S;
+            const uint4 v = *reinterpret_cast<const uint4*>(lat + s * rowp + 4 * kc);
+            const long long col = fl * S + s;
+            *reinterpret_cast<uint4*>(Bt + b_off(col, 8 * kc, nk)) = v;
+            if (s + 1 < S) *reinterpret_cast<uint4*>(Bt + b_off(col + 1, khalf + 8 * kc, nk)) = v;
+        }
+        __syncthreads();
     }
 }
 
@@ -318,9 +342,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) mask_gemm_f16(const __half* __res
     if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(2 * TN) : "memory");
 }
 
-// stream[f][p], p = s stride + i: symbol s keeps its samples 0..n_tx-1 and takes the filter tail of symbol s-1 at its start
-// (filtered[s][i] = y_s[i] + y_{s-1}[n_tx + i], i < n_tx - 1; the last symbol's tail is dropped); the filtered symbols are
-// overlap-added with the frame stride (stream[s stride + i] += filtered[s-1][stride + i] while stride + i < n_tx)
+// stream[f][p], p = s stride + i: the filtered symbols (columns of Y) overlap-added with the frame stride,
+// stream[s stride + i] = f_s[i] + f_{s-1}[stride + i] (the second term while stride + i < n_tx; s = S: the last symbol's tail)
 __global__ void __launch_bounds__(256) mask_assemble_kernel(const float* __restrict__ Y, float2* __restrict__ stream, long long nf, int S, int stride,
                                                             int n_tx, int tail_tx, int Yp) {
     const int body = tail_tx + S * stride;
@@ -329,19 +352,11 @@ __global__ void __launch_bounds__(256) mask_assemble_kernel(const float* __restr
         const long long fl = e / body;
         const int p = (int)(e - fl * body);
         const int s = min(p / stride, S), i = p - s * stride;
-        const float* y0 = Y + (size_t)(fl * S) * Yp;
-        auto y = [&](int ss, int idx) -> float2 { return *reinterpret_cast<const float2*>(y0 + (size_t)ss * Yp + 2 * idx); };
-        float2 v = make_float2(0.f, 0.f);
-        if (s < S) {
-            v = y(s, i);
-            if (s >= 1 && i < n_tx - 1) v = cadd(v, y(s - 1, n_tx + i));
-        }
-        if (s >= 1 && stride + i < n_tx) {
-            float2 u = y(s - 1, stride + i);
-            if (s >= 2 && stride + i < n_tx - 1) u = cadd(u, y(s - 2, n_tx + stride + i));
-            v = cadd(v, u);
-        }
-        stream[e] = v;
+        const float* ys = Y + (size_t)(fl * S + s) * Yp;
+        float2 a = make_float2(0.f, 0.f), c = make_float2(0.f, 0.f);
+        if (s < S) a = *reinterpret_cast<const float2*>(ys + 2 * i);
+        if (s >= 1 && stride + i < n_tx) c = *reinterpret_cast<const float2*>(ys - Yp + 2 * (stride + i));
+        stream[e] = cadd(a, c);
     }
 }
 
@@ -352,8 +367,8 @@ size_t mask_gemm_plan(const wofdm_sys_t& sys, long long batch, MaskGemm& mg) {
     mg.N = sys.N; mg.S = sys.S; mg.cp = sys.cp; mg.bits = sys.bits; mg.guard = sys.guard; mg.tail_tx = sys.tail_tx;
     mg.n_tx = sys.N + sys.cp + sys.cs; mg.stride = mg.n_tx - sys.tail_tx; mg.M = 2 * mg.n_tx - 1;
     mg.nact = sys.N - 2 * sys.guard;
-    mg.Kp = (2 * mg.nact + KB - 1) / KB * KB; mg.nk = mg.Kp / KB;
-    mg.RT = (2 * mg.M + TM - 1) / TM; mg.Yp = mg.RT * TM;
+    mg.Kp = 2 * ((2 * mg.nact + KB - 1) / KB * KB); mg.nk = mg.Kp / KB;          // [a_s | a_{s-1}], each half padded to the K block
+    mg.RT = (2 * mg.n_tx + TM - 1) / TM; mg.Yp = mg.RT * TM;
     mg.batch = batch;
     const size_t cols = (size_t)((batch * sys.S + TN - 1) / TN) * TN;
     return (size_t)mg.RT * mg.nk * 2 * A_BYTES + cols * mg.Kp * 2 + cols * mg.Yp * 4 + (size_t)mg.M * 16 + (size_t)mg.M * mg.nact * 16 + 4096;
@@ -377,7 +392,7 @@ int mask_gemm_setup(wofdm_ctx* h, DeviceCtx& d, MaskGemm& mg, int roll_off, cons
     const int ne = mg.M * mg.nact;
     mask_matrix_kernel<<<(ne + 255) / 256, 256, (size_t)mg.N * 16, d.stream>>>(mg.g, d_wtx, mg.Mm, mg.maxbits, mg.N, mg.n_tx, mg.cp, mg.guard, mg.M, mg.nact);
     WOFDM_CUDA(h, cudaGetLastError());
-    mask_split_kernel<<<2 * d.sm_count, 256, 0, d.stream>>>(mg.Mm, mg.maxbits, mg.At, mg.scale, mg.M, mg.nact, mg.Kp, mg.RT);
+    mask_split_kernel<<<2 * d.sm_count, 256, 0, d.stream>>>(mg.Mm, mg.maxbits, mg.At, mg.scale, mg.M, mg.n_tx, mg.nact, mg.Kp, mg.RT);
     WOFDM_CUDA(h, cudaGetLastError());
     WOFDM_CUDA(h, cudaFuncSetAttribute(mask_gemm_f16, cudaFuncAttributeMaxDynamicSharedMemorySize, NSTAGE * STAGE_BYTES));
     h->launches += 3;
@@ -390,11 +405,13 @@ int mask_gemm_batch(wofdm_ctx* h, DeviceCtx& d, const MaskGemm& mg, uint64_t see
     memset(&draw, 0, sizeof(draw));
     draw.seed = seed; philox_round_keys(seed, draw.rk); draw.bits = mg.bits; draw.S = mg.S;
     const long long ncols = nf * mg.S;
-    const int grid_s = (int)std::min<long long>((ncols * (mg.N / 16) + 255) / 256, (long long)d.sm_count * 16);
+    const int grid_s = (int)std::min<long long>(nf, (long long)d.sm_count * 8);
+    const size_t sm_s = (size_t)mg.S * (4 * ((mg.nact + 3) / 4) + 4) * sizeof(__half2);
+    if (sm_s > 48 * 1024) return fail(h, WOFDM_EUNSUPPORTED, "mask product: too many symbols per frame for the symbol kernel");
     switch (mg.N) {
-        case 128: mask_sym_kernel<128><<<grid_s, 256, 0, d.stream>>>(draw, f0, nf, mg.S, mg.guard, mg.nact, mg.Bt, mg.nk); break;
-        case 256: mask_sym_kernel<256><<<grid_s, 256, 0, d.stream>>>(draw, f0, nf, mg.S, mg.guard, mg.nact, mg.Bt, mg.nk); break;
-        case 512: mask_sym_kernel<512><<<grid_s, 256, 0, d.stream>>>(draw, f0, nf, mg.S, mg.guard, mg.nact, mg.Bt, mg.nk); break;
+        case 128: mask_sym_kernel<128><<<grid_s, 256, sm_s, d.stream>>>(draw, f0, nf, mg.S, mg.guard, mg.nact, mg.Bt, mg.nk); break;
+        case 256: mask_sym_kernel<256><<<grid_s, 256, sm_s, d.stream>>>(draw, f0, nf, mg.S, mg.guard, mg.nact, mg.Bt, mg.nk); break;
+        case 512: mask_sym_kernel<512><<<grid_s, 256, sm_s, d.stream>>>(draw, f0, nf, mg.S, mg.guard, mg.nact, mg.Bt, mg.nk); break;
         default: return fail(h, WOFDM_EUNSUPPORTED, "the channel-mask variant is built for N = 128, 256, 512");
     }
     WOFDM_CUDA(h, cudaGetLastError());

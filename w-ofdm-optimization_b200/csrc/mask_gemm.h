@@ -9,12 +9,13 @@ struct MaskGemm {
     int N, S, n_tx, stride, tail_tx, cp, bits, guard;
     int M;              // 2 n_tx - 1: length of the mask's circular convolution
     int nact;           // active sub-carriers N - 2 guard
-    int Kp, nk;         // K = 2 nact (Re, Im interleaved) rounded up to the K block; K blocks
-    int RT, Yp;         // row tiles of 128; floats per column of Y (= RT * 128 >= 2 M)
+    int Kp, nk;         // K = 2 halves of 2 nact (Re, Im interleaved; symbols s and s-1), each rounded up to the K block; K blocks
+    int RT, Yp;         // row tiles of 128; floats per column of Y (= RT * 128 >= 2 n_tx)
     long long batch;    // frames per batch (columns = batch * S, rounded up to the column tile)
     __half* At;         // mask matrix, [RT][nk][hi | lo][128 x 64] K-major UMMA tiles
     __half* Bt;         // lattice points of the batch's symbols, [CT][nk][256 x 64] tiles
-    float* Y;           // [columns][Yp]: the masked symbol of column (frame, s), samples (Re, Im) interleaved
+    float* Y;           // [columns][Yp]: the filtered symbol of column (frame, s) -- its n_tx samples with the filter tail of symbol
+                        // s-1 added -- (Re, Im) interleaved
     float* scale;       // [2]: power-of-two scale of At and its inverse (set on the device)
     double2* g;         // [M] impulse response of the mask
     double2* Mm;        // [M][nact] the matrix in fp64 before the split
