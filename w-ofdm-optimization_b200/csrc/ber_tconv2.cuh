@@ -50,6 +50,9 @@ namespace wofdm {
 #ifndef TCV2_GT
 #define TCV2_GT 3
 #endif
+#ifndef TCV2_TXY_U
+#define TCV2_TXY_U 8      // stream samples per thread and round of the masked chain's loader (tconv2_load_masked)
+#endif
 #ifndef TCV2_DEBUG_BARRIERS
 #define TCV2_DEBUG_BARRIERS 0          // 1 (libwofdm_dbg.so): every relaxed synchronisation of the kernel replaced by a full barrier --
 #endif                                 // the reference the race test compares the production build with (compute-sanitizer is closed here)
@@ -142,12 +145,12 @@ __host__ __device__ constexpr int tconv2_wrx_len(int N, int tail_rx) { return (N
 // Channel-mask chain (TXY instantiations): the frame's serialised Tx stream gathered from the mask product's output
 // (mask_gemm.cu, BerParams::tx_y: column s of the frame = the filtered symbol f_s, n_tx samples (Re, Im) interleaved, the
 // filter tail of symbol s-1 already inside, main_channel_mask.m:413-416).  The filtered symbols are overlap-added with the
-// frame stride (tx2rx, :420-431): stream[s stride + i] = f_s[i] + f_{s-1}[stride + i].  Four stream samples per thread and
-// round: eight loads in flight (the loader is latency bound otherwise).
+// frame stride (tx2rx, :420-431): stream[s stride + i] = f_s[i] + f_{s-1}[stride + i].  TCV2_TXY_U stream samples per thread
+// and round, two loads each in flight (the loader is latency bound otherwise).
 template <int NT>
 static __device__ __forceinline__ void tconv2_load_masked(const float* __restrict__ y0, int yp, int S, int stride, int n_tx, int body,
                                                           uint32_t* __restrict__ uh, uint32_t* __restrict__ ul, int tid) {
-    constexpr int U = 4;
+    constexpr int U = TCV2_TXY_U;
     for (int p0 = tid; p0 < body; p0 += U * NT) {
         float2 a[U], c[U];
 #pragma unroll
