@@ -241,3 +241,27 @@ def test_channel_mask_product_over_several_batches(handle):
     assert np.all(np.abs(got["bit_err"] - ref["bit_err"]) <= 5 + 2e-5 * ref["bit_err"]), (got["bit_err"], ref["bit_err"])
     again = handle.ber_run_masked(s, vt, vr, chans, snr, ens, seed=11, variant=1, roll_off=10)
     assert np.array_equal(again["bit_err"], got["bit_err"]) and np.array_equal(again["sym_err"], got["sym_err"])
+
+
+def test_channel_mask_long_frames(handle):
+    """Frames of 48 symbols with every sub-carrier active: the mask product's symbol kernel needs more than the default 48 KB
+    of shared memory, K1 is the staged kernel (more symbols than one Tx pass).  Replayed through the oracle like the
+    reference-sized frames of test_channel_mask_variant_replay."""
+    S, bits = 48, 4
+    p = O.system_params("wtx", 256, 16, 8, 0, S=S, bits=bits, noise_norm=1, constellation=1, guard=0)
+    vt, vr, _, _ = O.perturbed_windows(p, seed=1)
+    s = W.SysT(N=p.N, cp=p.cp, cs=p.cs, tail_tx=p.tail_tx, tail_rx=p.tail_rx, rm=p.rm, shift=p.shift, bits=bits, S=S,
+               noise_norm=1, constellation=1, precision=0, guard=0)
+    chans = O.synth_channels(2, 21, seed=6)
+    snr = np.array([12.0, 28.0])
+    masked = handle.ber_run_masked(s, vt, vr, chans, snr, 1, seed=5, variant=1, roll_off=10)
+    F = len(snr) * 2
+    sym, nz1 = handle.ber_draws(s, 21, 5, 1, np.arange(F))
+    want = np.zeros((len(snr), 2), dtype=np.int64)
+    for f in range(F):
+        c, si = f % 2, f // 2
+        b = O.frame_chain_masked(p, vt, vr, chans[:, c], snr[si], sym[f].T, nz1[f], roll_off=10)
+        want[si] += (b.sym_err, b.bit_err)
+    assert np.all(masked["sym_tot"] == 2 * 256 * (S - 1))
+    assert np.all(np.abs(masked["sym_err"] - want[:, 0]) <= 3 + 0.003 * want[:, 0]), (masked["sym_err"], want[:, 0])
+    assert np.all(np.abs(masked["bit_err"] - want[:, 1]) <= 5 + 0.003 * want[:, 1]), (masked["bit_err"], want[:, 1])

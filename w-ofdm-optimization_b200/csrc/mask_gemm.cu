@@ -407,7 +407,11 @@ int mask_gemm_batch(wofdm_ctx* h, DeviceCtx& d, const MaskGemm& mg, uint64_t see
     const long long ncols = nf * mg.S;
     const int grid_s = (int)std::min<long long>(nf, (long long)d.sm_count * 8);
     const size_t sm_s = (size_t)mg.S * (4 * ((mg.nact + 3) / 4) + 4) * sizeof(__half2);
-    if (sm_s > 48 * 1024) return fail(h, WOFDM_EUNSUPPORTED, "mask product: too many symbols per frame for the symbol kernel");
+    if (sm_s > d.smem_optin) return fail(h, WOFDM_EUNSUPPORTED, "mask product: too many symbols per frame for the symbol kernel");
+    if (sm_s > 48 * 1024) {                 // (long frames: more than the default dynamic shared memory)
+        const void* fn = mg.N == 128 ? (const void*)mask_sym_kernel<128> : mg.N == 256 ? (const void*)mask_sym_kernel<256> : (const void*)mask_sym_kernel<512>;
+        WOFDM_CUDA(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_s));
+    }
     switch (mg.N) {
         case 128: mask_sym_kernel<128><<<grid_s, 256, sm_s, d.stream>>>(draw, f0, nf, mg.S, mg.guard, mg.nact, mg.Bt, mg.nk); break;
         case 256: mask_sym_kernel<256><<<grid_s, 256, sm_s, d.stream>>>(draw, f0, nf, mg.S, mg.guard, mg.nact, mg.Bt, mg.nk); break;
