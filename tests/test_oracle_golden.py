@@ -98,3 +98,25 @@ def test_decision_tie_rule_is_first_minimum():
     pts = O.qam_points(4, 0)
     x = np.array([0 + 0j, -2 - 2j, 2 + 2j, 0.0 + 3j, 5 + 5j, -7 - 0j])
     assert np.array_equal(O.hard_decision(x, 4, 0), O.hard_decision_argmin(x, pts))
+
+
+@pytest.mark.parametrize("name,cp,guard,S", [("wtx", 16, 64, 16), ("WOLA", 22, 64, 5), ("CP", 10, 0, 3), ("CPW", 32, 100, 2)])
+def test_mask_product_form_equals_the_filter_chain(name, cp, guard, S):
+    """The algebra behind csrc/mask_gemm.cu: the DFT-domain mask of main_channel_mask.m:398-417 (mask_symbols, restated line
+    by line) equals one constant matrix applied to the lattice points, with the filter tail of the previous symbol folded
+    into the K dimension."""
+    ttx = 8 if name in ("wtx", "WOLA", "CPW", "CPwtx") else 0
+    trx = 10 if name in ("WOLA", "CPW", "wrx", "CPwrx") else 0
+    p = O.system_params(name, 256, cp, ttx, trx, S=S, bits=4, noise_norm=1, constellation=1, guard=guard)
+    v_tx, _, _, _ = O.perturbed_windows(p, seed=cp)
+    rng = np.random.default_rng(cp)
+    sym_idx = rng.integers(0, 16, size=(p.N, S))
+    X = np.where(p.active[:, None], O.qam_points(p.bits, p.constellation)[sym_idx], 0.0)
+    x = np.fft.ifft(X, axis=0)
+    i = np.arange(p.n_tx)
+    want = O.mask_symbols(v_tx[:, None] * x[(i - p.cp) % p.N, :], 10)
+    nact = p.N - 2 * guard
+    bins = (np.arange(nact) + guard + p.N // 2) % p.N
+    got = O.mask_symbols_product(p, v_tx, X[bins, :], 10)
+    assert got.shape == want.shape == (p.n_tx, S)
+    assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max()
