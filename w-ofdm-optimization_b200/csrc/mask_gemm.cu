@@ -24,7 +24,7 @@
 //
 // The lattice points are small odd integers -- exact in fp16 -- and A is split A = hi + lo in fp16 behind a power-of-two
 // scale (relative error ~2^-22 per entry, fp32 accumulation in tensor memory): two MMAs per K step give fp32-grade
-// results, 1.2 Mflop per symbol.  Kernels:
+// results, 1.3 Mflop per symbol (N = 256, 128 active sub-carriers).  Kernels:
 //   mask_response_kernel, mask_matrix_kernel, mask_split_kernel   g and Mm in fp64 on the device (once per call), Mm split
 //                                            into pre-tiled hi | lo operands
 //   mask_sym_kernel                          the Philox symbol draws of K1 (load_sym_idx) -> lattice points as fp16 B tiles
