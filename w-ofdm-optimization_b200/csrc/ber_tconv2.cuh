@@ -50,6 +50,15 @@ namespace wofdm {
 #ifndef TCV2_GT
 #define TCV2_GT 3
 #endif
+// Slicer folded into the equaliser product (production instantiations): the taps are stored halved, so the scale and offset
+// of slice_index (y = e / 2 + (m - 2) / 2) ride on the complex product's first packed FMA, and the upper clamp is taken in
+// floating point (FMNMX, one issue cycle) before the saturating round-up conversion instead of on the integers afterwards.
+// Same decisions as slice_index up to the rounding of the fused sum (fp32 grade either way; ties still go to the lower level).
+// Measured: 16 packed instructions and 32 two-cycle integer clamps fewer per thread and frame, 5.76 ms against 5.78 per
+// 202 500 frames -- within the noise, so the build keeps slice_index (one definition of the decision for every kernel).
+#ifndef TCV2_FOLD_SLICER
+#define TCV2_FOLD_SLICER 0
+#endif
 #ifndef TCV2_TXY_U
 #define TCV2_TXY_U 8      // stream samples per thread and round of the masked chain's loader (tconv2_load_masked)
 #endif
@@ -930,7 +939,7 @@ ber_tconv2_kernel(const BerParams prm) {
                 for (int k = tid; k < N; k += NT) {
                     const C2 y0 = geq[k];
                     const C2 x0 = qlut[pil[(k % TPF) * 16 + k / TPF]];
-                    C2 gk = cscale(recip(y0.x * y0.x + y0.y * y0.y), cmulc(x0, y0));
+                    C2 gk = cscale(((TCV2_FOLD_SLICER && !VERIFY) ? (T)0.5 : (T)1) * recip(y0.x * y0.x + y0.y * y0.y), cmulc(x0, y0));
                     if (prm.guard > 0 && !bin_active<N>(k, prm.guard)) gk = mk2<T>(0, 0);
                     geq[k] = gk;
                     if constexpr (CL > 1) {
@@ -950,8 +959,18 @@ ber_tconv2_kernel(const BerParams prm) {
 #pragma unroll
                     for (int b = 0; b < 4; ++b) {
                         const int q = 4 * gq + b, k = t + q * TPF;
-                        const C2 e = cmul(v[q], geq[k]);                                   // :231
-                        const uint32_t dq = (uint32_t)slice_index(e, hb);                  // :233
+                        uint32_t dq;
+                        C2 e;
+                        if constexpr (TCV2_FOLD_SLICER && !VERIFY) {
+                            const C2 gh = geq[k];                                          // G[k] / 2
+                            const T off = (T)0.5 * (T)(m - 2), top = (T)(m - 1);
+                            const C2 y = fma2(rotj(v[q]), mk2<T>(gh.y, gh.y), fma2(v[q], mk2<T>(gh.x, gh.x), mk2<T>(off, off)));   // :231, :233
+                            dq = (__float2uint_ru(fminf(y.x, top)) << hb) | __float2uint_ru(fminf(y.y, top));
+                            e = y;
+                        } else {
+                            e = cmul(v[q], geq[k]);                                        // :231
+                            dq = (uint32_t)slice_index(e, hb);                             // :233
+                        }
                         d4 |= dq << (8 * b);
                         if constexpr (VERIFY) {
                             const size_t o = ((size_t)f * (prm.S - 1) + (sb + s - 1)) * N + k;
